@@ -1,0 +1,545 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s of the CBinfer change-based conv/pool path on B200 (BASELINE.json metric).
+
+Workload (config.workload): BASELINE.json configs[1] -- the scene-labeling CBinfer model (all five
+convs + both max-pools converted, feedback loop, fp32) on synthetic 640x480 video with 5 % block
+change per frame, `streams_per_gpu` independent video streams batched per GPU.
+
+A "step" is one frame of every resident stream through the whole model (one CUDA-graph replay).
+  value : frames/s with the frames already resident in HBM (device-timed, max over ranks)
+  e2e   : frames/s through the public module call with HOST (pinned) frames: per step one H2D copy
+          of the step's frames and one D2H read of the step's logits inside the timed region
+  roofline      : dominant kernel vs its HBM / tensor roofline (per-kernel CUDA-event timing)
+  cpu_baseline  : the reference's dense PyTorch CPU inference path on this box's host cores
+`--impl reference` times that CPU path alone on the same config.
+
+Launch: python bench.py --gpus N --steps K --warmup W      (N>1: via torch.distributed.run)
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams", type=int, default=8, help="video streams per GPU (batch)")
+    ap.add_argument("--height", type=int, default=480)
+    ap.add_argument("--width", type=int, default=640)
+    ap.add_argument("--rate", type=float, default=0.05, help="fraction of pixels changed per frame")
+    ap.add_argument("--mode", default="block", choices=["block", "iid"])
+    ap.add_argument("--dtype", default="f32", choices=["f32", "bf16", "f16"])
+    ap.add_argument("--gemm", default="auto", choices=["auto", "simt", "tc", "tc3x"])
+    ap.add_argument("--threshold-factor", type=float, default=0.02)
+    ap.add_argument("--no-extras", action="store_true", help="skip dense/latency/kernel/cpu legs")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampler (runs during the timed region)
+# ---------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            try:
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(index).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference arm / cpu baseline: dense PyTorch CPU inference (the reference's dense path)
+# ---------------------------------------------------------------------------------------------
+def cpu_dense_fps(args, seconds, warm=2):
+    import torch
+    from cbinfer_b200 import models, video
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)            # reference: sceneLabeling/modelConverter.py:4
+    base = models.sceneLabelingBaseline().float()
+    frames = video.sequence(1, args.height, args.width, 4, args.rate, args.mode)
+    times = []
+    with torch.no_grad():
+        for i in range(warm):
+            base(frames[i % 4])
+        t_end = time.perf_counter() + seconds
+        i = 0
+        while (time.perf_counter() < t_end and len(times) < 200) or len(times) < 3:
+            t0 = time.perf_counter()
+            base(frames[i % 4])
+            times.append(time.perf_counter() - t0)
+            i += 1
+    mean = sum(times) / len(times)
+    return {"value": 1.0 / mean, "best": 1.0 / min(times), "unit": "frames/s", "cores": cores,
+            "kind": "reference",
+            "sample": "%d frames %dx%d through the dense nn.Conv2d/ReLU/MaxPool2d scene CNN on torch CPU "
+                      "(the reference's dense inference path, evalTools.inferFrameset), fp32, "
+                      "%d threads" % (len(times), args.width, args.height, cores)}
+
+
+def cpu_cb_oracle_fps(args, frames_cpu, thresholds, base, max_seconds=10.0):
+    """the oracle's C port of the CB path (OpenMP) on a bounded sample -- reported, not a target."""
+    import numpy as np
+    import torch.nn as nn
+    from oracle import oracle as orc
+    L = orc.lib()
+    convs = [m for m in base.modules() if isinstance(m, nn.Conv2d)]
+    H, W = args.height, args.width
+    dims = [(H, W), (H // 2, W // 2), (H // 4, W // 4), (H // 4, W // 4), (H // 4, W // 4)]
+    st = []
+    for c, (h, w) in zip(convs, dims):
+        st.append(dict(
+            wt=np.ascontiguousarray(c.weight.detach().cpu().numpy()), b=c.bias.detach().cpu().numpy().copy(),
+            sin=np.full((c.in_channels, h, w), np.inf, np.float32),
+            sout=np.full((c.out_channels, h, w), np.inf, np.float32),
+            idx=np.zeros(h * w, np.int32), map=np.zeros(h * w, np.uint8), h=h, w=w))
+
+    def frame(x):
+        cur = x
+        for i, (c, s) in enumerate(zip(convs, st)):
+            k = c.kernel_size[0]
+            L.orc_cbconv_frame_fast_f32(orc._p(cur), orc._p(s["sin"]), orc._p(s["sout"]), orc._p(s["wt"]),
+                                        orc._p(s["b"]), orc._p(s["idx"]), orc._p(s["map"]), s["w"], s["h"],
+                                        c.in_channels, c.out_channels, k, k, float(thresholds[i]), 1,
+                                        int(i < 4))
+            cur = s["sout"]
+            if i < 2:      # dense 2x2 pool on the CPU side keeps the port simple
+                cur = np.ascontiguousarray(cur.reshape(cur.shape[0], s["h"] // 2, 2, s["w"] // 2, 2).max(axis=(2, 4)))
+        return cur
+
+    xs = [np.ascontiguousarray(f[0].numpy()) for f in frames_cpu]
+    frame(xs[0])
+    times = []
+    t_end = time.perf_counter() + max_seconds
+    i = 1
+    while time.perf_counter() < t_end and i < len(xs):
+        t0 = time.perf_counter()
+        frame(xs[i])
+        times.append(time.perf_counter() - t0)
+        i += 1
+    if not times:
+        return None
+    return {"value": len(times) / sum(times), "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": "%d frames through oracle/cbinfer_oracle.c orc_cbconv_frame_fast_f32 (OpenMP)" % len(times)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t0 = time.perf_counter()
+    per_step_budget = 120.0 / max(args.steps + args.warmup, 1)
+    r = cpu_dense_fps(args, seconds=min(60.0, per_step_budget * args.steps), warm=max(args.warmup, 1))
+    out = {
+        "impl": "reference", "metric": "frames/s", "value": r["value"], "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000.0 / r["value"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, streams=1),
+        "cpu_baseline": r,
+        "e2e": {"value": r["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(out))
+
+
+def workload_config(args, streams):
+    return {"workload": "sceneLabeling CBinfer CNN (5 CBConv2d + 2 CBPoolMax2d, feedback loop) on synthetic "
+                        "%dx%d video, %.0f%% %s change per frame" % (args.width, args.height, args.rate * 100, args.mode),
+            "streams_per_gpu": streams, "height": args.height, "width": args.width,
+            "change_rate": args.rate, "change_mode": args.mode, "threshold_factor": args.threshold_factor,
+            "gemm": args.gemm, "parallelism": "independent video streams sharded per GPU, no collective"}
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import cbinfer_b200 as cb
+    from cbinfer_b200 import models, video, conv2d_cg as cg
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    tdt = {"f32": torch.float32, "bf16": torch.bfloat16, "f16": torch.float16}[args.dtype]
+    S, H, W, K, Wm = args.streams, args.height, args.width, args.steps, max(args.warmup, 3)
+    torch.backends.cudnn.benchmark = True
+
+    # ---- model + synthetic video (each rank: its own streams, seeds offset by rank) ----------
+    base = models.sceneLabelingBaseline().to(dev).to(tdt)
+    model = models.sceneLabelingCBinfer(base, experimentIdx=6, threshold=0.1, convertAll=True,
+                                        clonePoolOutput=False)
+    for m in model.modules():
+        if type(m) is cb.CBConv2d:
+            m.gemmMode = args.gemm
+    nframes = K + Wm + 2
+    frames_cpu = video.sequence(S, H, W, nframes, args.rate, args.mode, seed=rank)
+    thresholds = models.calibrateThresholds(base, model, frames_cpu[0].to(dev).to(tdt),
+                                            factor=args.threshold_factor)
+    pinned = [f.to(tdt).pin_memory() for f in frames_cpu]
+    frames = [f.to(dev, non_blocking=True) for f in pinned]
+    torch.cuda.synchronize()
+
+    # ---- warm-up + CUDA graph of one step ---------------------------------------------------------
+    static_in = frames[0].clone()
+    with torch.no_grad():
+        model(static_in)                      # first frame: everything changed
+        static_in.copy_(frames[1])
+        model(static_in)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side), torch.no_grad():
+        model(static_in)
+    torch.cuda.current_stream().wait_stream(side)
+    with torch.cuda.graph(graph), torch.no_grad():
+        static_out = model(static_in)
+    my_launches_per_step = 5 * 3 + 2          # per CBConv2d: detect, dilate+compact, conv; per pool: 1
+
+    def step(t):
+        static_in.copy_(frames[t])
+        graph.replay()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    t = 2
+    for _ in range(Wm):
+        step(t)
+        t += 1
+    # ---- timed region: K steps, device-timed -----------------------------------------------------
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        step(t)
+        t += 1
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    elapsed_ms = e0.elapsed_time(e1)
+    if world > 1:
+        tt = torch.tensor([elapsed_ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(tt.item())
+    fps = world * S * K / (elapsed_ms * 1e-3)
+    counts = [int(m._scratch["count"].item()) for m in model.modules() if type(m) is cb.CBConv2d]
+    state_mb = sum(t.numel() * t.element_size() for t in cb.getStateTensors(model)) / 1e6
+
+    # ---- e2e: host frames -> H2D -> model -> D2H logits, every step ----------------------------
+    out_host = torch.empty(static_out.shape, dtype=static_out.dtype).pin_memory()
+    cb.clearMemory(model)        # fresh sequence through the public call (not the graph)
+    h2d = pinned[0].numel() * pinned[0].element_size()
+    d2h = out_host.numel() * out_host.element_size()
+
+    def e2e_step(i):
+        x = pinned[i].to(dev, non_blocking=True)
+        with torch.no_grad():
+            y = model(x)
+        out_host.copy_(y, non_blocking=True)
+
+    for i in range(Wm + 1):
+        e2e_step(i)
+    barrier()
+    e0.record()
+    for i in range(Wm + 1, Wm + 1 + K):
+        e2e_step(i)
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    if world > 1:
+        tt = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_ms = float(tt.item())
+    e2e_fps = world * S * K / (e2e_ms * 1e-3)
+
+    result = {
+        "metric": "frames/s", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.dtype, "data": "synthetic",
+        "config": dict(workload_config(args, S),
+                       l2="no flush: per-step working set = persistent state maps of %d streams = %.0f MB %s 126 MB L2"
+                          % (S, state_mb, ">" if state_mb > 126 else "<= (L2-resident!)"),
+                       thresholds=[round(x, 5) for x in thresholds],
+                       changed_pixels_last_frame=counts),
+        "clocks": clocks,
+        "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms / K, "path": "model(frame) eager, pinned H2D + D2H per step"},
+        "gpu_launches": my_launches_per_step * K,
+    }
+
+    # ---- extras on rank 0 at N=1: kernel table / roofline, dense cuDNN, single-stream latency, CPU ----
+    if rank == 0 and not args.no_extras:
+        try:
+            result.update(kernel_roofline(args, model, frames, dev, tdt))
+        except Exception as e:                                   # never lose the headline line
+            result["roofline_error"] = repr(e)
+        try:
+            result["dense_cudnn"] = dense_gpu(args, base, frames, dev)
+        except Exception as e:
+            result["dense_cudnn_error"] = repr(e)
+        if world == 1:
+            try:
+                result["single_stream"] = single_stream_latency(args, base, dev, tdt)
+            except Exception as e:
+                result["single_stream_error"] = repr(e)
+            try:
+                result["cpu_baseline"] = cpu_dense_fps(args, seconds=args.cpu_seconds)
+                if args.dtype == "f32":
+                    r = cpu_cb_oracle_fps(args, [f[:1].float() for f in frames_cpu[:12]], thresholds, base.float().cpu())
+                    base.to(dev)
+                    if r:
+                        result["cpu_cb_port"] = r
+            except Exception as e:
+                result["cpu_baseline_error"] = repr(e)
+    if rank == 0:
+        print(json.dumps(result))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def kernel_roofline(args, model, frames, dev, tdt):
+    """Per-kernel CUDA-event timing of the same frames (eager, one event pair per launch) and the
+    roofline of the dominant kernel.  Algorithmic bytes / FLOPs per launch: DESIGN.md section 4."""
+    import torch
+    import cbinfer_b200 as cb
+    from cbinfer_b200 import conv2d_cg as cg
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    bf16 = float(peaks.get("bf16_tflops", 1590.0))
+    src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+    es = 4 if args.dtype == "f32" else 2
+    rec = {}
+    cur = {"layer": None}
+    orig = {n: getattr(cg, n) for n in ("detect", "dilate_compact", "conv_update", "maxPool2d")}
+
+    def timed(name):
+        fn = orig[name]
+
+        def w(*a, **k):
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            r = fn(*a, **k)
+            a1.record()
+            rec.setdefault((cur["layer"], name), []).append((a0, a1))
+            return r
+        return w
+
+    hooks = []
+    for lname, m in model.named_children():
+        hooks.append(m.register_forward_pre_hook(lambda mod, inp, lname=lname: cur.__setitem__("layer", lname)))
+    for n in orig:
+        setattr(cg, n, timed(n))
+    try:
+        cb.clearMemory(model)
+        with torch.no_grad():
+            for i in range(0, 12):
+                model(frames[i])
+                if i == 1:
+                    rec.clear()               # drop the all-changed first frames
+        torch.cuda.synchronize()
+    finally:
+        for n, f in orig.items():
+            setattr(cg, n, f)
+        for h in hooks:
+            h.remove()
+    mods = dict(model.named_children())
+    table = []
+    for (lname, kname), evs in rec.items():
+        us = sum(a.elapsed_time(b) for a, b in evs) / len(evs) * 1e3
+        m = mods[lname]
+        row = {"layer": lname, "kernel": kname, "us": round(us, 2), "launches": len(evs)}
+        if type(m) is cb.CBConv2d:
+            B, Cin, Hh, Ww = m.prevInput.shape
+            P = B * Hh * Ww
+            n = int(m._scratch["count"].item())
+            k2 = m.kernel_size[0] * m.kernel_size[1]
+            if kname == "detect":
+                by = 2 * Cin * P * es + P // 8
+                row.update(bound="hbm", bytes=by, achieved=by / (us * 1e-6) / 1e9, peak=hbm, unit="GB/s")
+            elif kname == "dilate_compact":
+                by = P // 8 + 4 * n
+                row.update(bound="hbm", bytes=by, achieved=by / (us * 1e-6) / 1e9, peak=hbm, unit="GB/s")
+            elif kname == "conv_update":
+                fl = 2.0 * n * Cin * k2 * m.out_channels
+                by = min(n * k2, P) * Cin * es + m.out_channels * Cin * k2 * es + 4 * n + n * m.out_channels * es
+                pk = bf16 / 2 if args.dtype == "f32" else bf16
+                row.update(bound="tensor", flops=fl, bytes=by, achieved=fl / (us * 1e-6) / 1e12, peak=pk,
+                           unit="TFLOP/s", n=n, hbm_gbs=by / (us * 1e-6) / 1e9)
+        else:
+            row.update(bound="hbm")
+        if "achieved" in row:
+            row["frac"] = row["achieved"] / row["peak"]
+            row["achieved"] = round(row["achieved"], 2)
+        table.append(row)
+    table.sort(key=lambda r: -r["us"])
+    total = sum(r["us"] for r in table)
+    top = next((r for r in table if "achieved" in r), None)
+    out = {"kernels": table, "kernel_us_per_step": round(total, 1), "peaks_source": src}
+    if top:
+        out["roofline"] = {"kernel": "%s[%s]" % (top["kernel"], top["layer"]), "bound": top["bound"],
+                           "achieved": top["achieved"], "peak": top["peak"], "unit": top["unit"],
+                           "frac": top["frac"], "traffic": None,
+                           "share_of_step": top["us"] / total if total else None,
+                           "note": "fp32 data runs 3xTF32 (3 MMAs per product): peak = bf16 burst / 2, achieved counts "
+                                   "algorithmic FLOPs 2*n*K*Cout once" if top["bound"] == "tensor" and args.dtype == "f32" else ""}
+    return out
+
+
+def dense_gpu(args, base, frames, dev):
+    """dense cuDNN comparator on the same GPU, same batch: fp32 (TF32 off / on) and bf16."""
+    import torch
+    res = {}
+    S = frames[0].shape[0]
+    for name, tf32, dt, cl in (("fp32", False, torch.float32, False), ("tf32", True, torch.float32, False),
+                               ("tf32_channels_last", True, torch.float32, True),
+                               ("bf16_channels_last", True, torch.bfloat16, True)):
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        m = base.to(dt)
+        xs = [f.to(dt) for f in frames[:4]]
+        if cl:
+            m = m.to(memory_format=torch.channels_last)
+            xs = [x.contiguous(memory_format=torch.channels_last) for x in xs]
+        with torch.no_grad():
+            for i in range(5):
+                m(xs[i % 4])
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for i in range(20):
+                m(xs[i % 4])
+            b.record()
+            torch.cuda.synchronize()
+        res[name] = round(S * 20 / (a.elapsed_time(b) * 1e-3), 1)
+        base.to(frames[0].dtype).to(memory_format=torch.contiguous_format)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    res["unit"] = "frames/s"
+    res["batch"] = S
+    return res
+
+
+def single_stream_latency(args, base, dev, tdt):
+    """one stream (batch 1, the reference's own operating point): per-frame latency through a CUDA
+    graph with an L2 flush (256 MB write) before every timed frame."""
+    import torch
+    import cbinfer_b200 as cb
+    from cbinfer_b200 import models, video
+    model = models.sceneLabelingCBinfer(base, experimentIdx=6, threshold=0.1, convertAll=True,
+                                        clonePoolOutput=False)
+    for m in model.modules():
+        if type(m) is cb.CBConv2d:
+            m.gemmMode = args.gemm
+    fr = [f.to(dev).to(tdt) for f in video.sequence(1, args.height, args.width, 24, args.rate, args.mode, seed=77)]
+    models.calibrateThresholds(base, model, fr[0], factor=args.threshold_factor)
+    x = fr[0].clone()
+    with torch.no_grad():
+        model(x)
+        x.copy_(fr[1])
+        model(x)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side), torch.no_grad():
+        model(x)
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g), torch.no_grad():
+        model(x)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ms = []
+    for i in range(3, 24):
+        x.copy_(fr[i])
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        g.replay()
+        b.record()
+        torch.cuda.synchronize()
+        ms.append(a.elapsed_time(b))
+    ms = ms[3:]
+    ms.sort()
+    med = ms[len(ms) // 2]
+    return {"streams": 1, "ms_per_frame_median": round(med, 4), "frames_per_s": round(1000.0 / med, 1),
+            "l2_flush": "256 MB write before each timed frame", "frames": len(ms)}
+
+
+if __name__ == "__main__":
+    main()

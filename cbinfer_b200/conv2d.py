@@ -1,0 +1,299 @@
+"""CBConv2d / CBPoolMax2d -- the nn.Modules of the pycbinfer surface on the sm_100a backend.
+
+Mirrors the reference's ``pycbinfer/conv2d.py``: class ``CBPoolMax2d`` (:24-84) and class
+``CBConv2d`` (:87-304) with the same constructor arguments, flags (``withReLU``,
+``saveChangeMap``, ``propChangeIndexes``, ``gatherComputationStats``, ``finegrained``,
+``copyInput``, ``feedbackLoop``; :112-118), ``threshold`` attribute, state buffers
+(``prevInput``, ``prevOutput``, ``outputState``), ``clearMemory()`` / ``getStateTensors()``,
+``('changeIndexes', tensor, indices)`` tuple protocol (:180-187, :256-257) and ``__repr__``.
+
+What is different underneath (B200-first, not a translation):
+  * state lives pixel-major ([B,H,W,pitch], exposed as channels-last [B,C,H,W] views) so a changed
+    pixel's channels are one contiguous run for detection, gather, scatter and pooling;
+  * one frame of a layer is three launches -- detect, dilate+compact, fused gather/tcgen05
+    contraction/bias/ReLU/scatter -- with the change count kept on the device: no torch.nonzero,
+    no host sync, no X / Y / Y^T matrices (reference: ~10 launches + 1 sync, conv2d.py:222-251);
+  * batch > 1 = independent video streams (the reference is batch 1);
+  * CUDA only: the reference's CPU branches (conv2d.py:225-227,244-245,252-253) do not exist.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+from . import conv2d_cg as cg
+from .conv2d_cg import ChangeIndexes
+from .conv2d_fg import cbconvFG
+
+_INF = float("inf")
+
+
+def _parse_input(inp):
+    """tensor, or ('changeIndexes', tensor, indices) from an upstream CB layer (conv2d.py:180-187)."""
+    if type(inp) == tuple:
+        assert inp[0] == 'changeIndexes'
+        return inp[1].detach(), inp[2]
+    return inp.detach(), None
+
+
+class CBPoolMax2d(nn.Module):
+    def __init__(self, m):
+        super(CBPoolMax2d, self).__init__()
+        ks = m.kernel_size if isinstance(m.kernel_size, tuple) else (m.kernel_size,) * 2
+        st = m.stride if isinstance(m.stride, tuple) else (m.stride,) * 2
+        assert(ks == (2, 2) and st == (2, 2))
+        self.stride = st
+        self.kernel_size = ks
+        self.ceil_mode = m.ceil_mode
+        self.propChangeIndexes = False
+        self.cloneOutput = True   # reference returns outputState.clone() (conv2d.py:73)
+        self.register_buffer('outputState', torch.empty(0))
+        self._stateBuf = None
+        self.clearMemory()
+
+    def clearMemory(self):
+        self.outputState = self.outputState.new_empty(0)
+        self._stateBuf = None
+
+    def getStateTensors(self):
+        return [self.outputState] if hasattr(self, 'outputState') else []
+
+    def forward(self, inp):
+        assert(type(inp) == tuple and inp[0] == 'changeIndexes')
+        input = inp[1].detach()
+        changeIndexes = inp[2]
+        assert input.dim() == 4
+        _lib.require_cuda(input)
+        B, nc, h, w = input.shape
+        if not isinstance(changeIndexes, ChangeIndexes):
+            assert(changeIndexes.dim() == 1)
+            changeIndexes = ChangeIndexes.from_tensor(changeIndexes, (B, h, w))
+        if self.ceil_mode:
+            oh, ow = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+        else:
+            oh, ow = h // 2, w // 2
+        if list(self.outputState.shape) != [B, nc, oh, ow] or self.outputState.dtype != input.dtype \
+                or self.outputState.device != input.device:
+            # deviation (stated): the reference allocates only once a non-empty index list arrives
+            # (conv2d.py:53-62); deciding that needs a host sync, so the state is allocated up front.
+            self.outputState, self._stateBuf = cg.pixel_major((B, nc, oh, ow), input.dtype,
+                                                              input.device, _INF)
+        cg.maxPool2d(input, self.outputState, changeIndexes, self.kernel_size, self.stride)
+
+        output = self.outputState.clone() if self.cloneOutput else self.outputState
+        if self.propChangeIndexes:
+            return 'changeIndexes', output, changeIndexes
+        else:
+            return output
+
+    def __repr__(self):
+        s = ('{name} (k={kernel_size}, s={stride}, ceil_mode={ceil_mode}')
+        s += ', propChgIdxs={propChangeIndexes}'
+        s += ')'
+        return s.format(name=self.__class__.__name__, **self.__dict__)
+
+
+class CBConv2d(nn.Module):
+    #: contraction arithmetic per dtype (see include/cbinfer_b200.h): fp32 data defaults to the
+    #: fp32-accurate 3xTF32 tensor-core split, 16-bit data to kind::f16 with fp32 accumulation.
+    GEMM_MODES = {'simt': _lib.GEMM_SIMT_F32, 'tc': _lib.GEMM_TC, 'tc3x': _lib.GEMM_TC_3X}
+
+    def __init__(self, m, threshold):
+        super(CBConv2d, self).__init__()
+
+        assert(m.groups == 1 and m.transposed == False)
+        assert(m.output_padding == (0, 0) and m.padding == (m.kernel_size[-2] // 2, m.kernel_size[-1] // 2))
+        assert(m.dilation == (1, 1) and m.stride == (1, 1))
+        self.groups = m.groups
+        self.transposed = m.transposed
+        self.output_padding = m.output_padding
+        self.padding = m.padding
+        self.dilation = m.dilation
+        self.stride = m.stride
+        self.kernel_size = m.kernel_size
+        self.in_channels = m.in_channels
+        self.out_channels = m.out_channels
+
+        assert(m.weight is not None and m.bias is not None)
+        self.weight = m.weight
+        self.bias = m.bias
+
+        self.threshold = threshold
+
+        self.register_buffer('prevInput', self.weight.data.new_empty(0))
+        self.register_buffer('prevOutput', self.weight.data.new_empty(0))
+        self.clearMemory()
+
+        self.withReLU = False
+        self.saveChangeMap = False
+        self.propChangeIndexes = False
+        self.gatherComputationStats = False
+        self.finegrained = False
+        self.copyInput = True
+        self.feedbackLoop = False
+        self.gemmMode = 'auto'
+
+    # ---- state ---------------------------------------------------------------------------
+    def clearMemory(self):
+        # reference: fill_(-1e100).resize_(0) (conv2d.py:147-148; raises on torch >= 1.x)
+        self.prevInput = self.weight.data.new_empty(0)
+        self.prevOutput = self.weight.data.new_empty(0)
+        self._inBuf = None        # pixel-major storage behind prevInput / prevOutput
+        self._outBuf = None
+        self._scratch = None      # bitmaps, index list, count, compaction workspace
+        self._packed = None       # (key, packed weights, fp32 bias)
+        self.changeMap = None
+        if hasattr(self, 'compStats'):
+            self.compStats = None
+
+    def getStateTensors(self):
+        state = []
+        if hasattr(self, 'prevInput'):
+            state += [self.prevInput]
+        if hasattr(self, 'prevOutput'):
+            state += [self.prevOutput]
+        return state
+
+    def _gemm(self, dtype):
+        mode = getattr(self, 'gemmMode', 'auto')
+        if mode == 'auto':
+            return _lib.GEMM_TC_3X if dtype == torch.float32 else _lib.GEMM_TC
+        g = self.GEMM_MODES[mode]
+        if g == _lib.GEMM_TC_3X and dtype != torch.float32:
+            g = _lib.GEMM_TC
+        return g
+
+    def _weights(self, dtype, device):
+        gemm = self._gemm(dtype)
+        key = (self.weight.data_ptr(), self.weight._version, self.bias.data_ptr(),
+               self.bias._version, dtype, gemm, str(device))
+        if self._packed is None or self._packed[0] != key:
+            w = self.weight.detach().to(device=device, dtype=dtype)
+            self._packed = (key, cg.pack_weights(w, gemm),
+                            self.bias.detach().to(device=device, dtype=torch.float32).contiguous())
+        return gemm, self._packed[1], self._packed[2]
+
+    # ---- fine-grained path (conv2d.py:160-176) ---------------------------------------------
+    def forward_fg(self, inp):
+        input = inp.detach().contiguous()
+        _lib.require_cuda(input)
+        if self.prevInput.size() != input.size():
+            # init prevOutput with a dense convolution, as the reference does (conv2d.py:163-167)
+            self.prevOutput = F.conv2d(input, self.weight.detach(),
+                                       padding=tuple(s // 2 for s in self.weight.size()[2:]),
+                                       bias=self.bias.detach()).contiguous()
+            self.prevInput = input.clone()
+        else:
+            po = self.prevOutput.clone()                     # conv2d.py:169
+            # also performs prevInput = input (conv2d.py:175) in the same pass
+            self.prevOutput = cbconvFG(input, self.prevInput, po, self.weight, self.threshold)
+        outp = self.prevOutput
+        if self.withReLU:
+            outp = F.relu(outp)
+        return outp
+
+    # ---- coarse-grained path (conv2d.py:178-259) ---------------------------------------------
+    def forward_normal(self, inp):
+        input, changeIndexes = _parse_input(inp)
+        assert(input.dim() == 4)
+        assert(input.size(-3) == self.in_channels)
+        _lib.require_cuda(input)
+        B, _, H, W = input.shape
+        dev, dt = input.device, input.dtype
+
+        if self.prevInput.size() != input.size() or self.prevInput.dtype != dt or self._inBuf is None:
+            self.prevInput, self._inBuf = cg.pixel_major(input.shape, dt, dev, _INF)   # :192-194
+            self._scratch = None
+        outpSize = (B, self.out_channels, H, W)
+        if tuple(self.prevOutput.size()) != outpSize or self.prevOutput.dtype != dt or self._outBuf is None:
+            self.prevOutput, self._outBuf = cg.pixel_major(outpSize, dt, dev, _INF)    # :195-199
+        if self._scratch is None:
+            self._scratch = cg.alloc_scratch((B, H, W), dev, want_map=self.saveChangeMap)
+        if self.saveChangeMap and "dil_map" not in self._scratch:
+            self._scratch["dil_map"] = torch.zeros(B, H, W, dtype=torch.int8, device=dev)
+        s = self._scratch
+
+        if self.gatherComputationStats:
+            self._gatherStats(input)
+
+        if changeIndexes is None:
+            # reference: detect (feedback updates prevInput at changed pixels, :222-224), nonzero
+            # (:232), then prevInput.copy_(input) when not in feedback mode (:234-238).  Here the
+            # copy is part of the detection pass; copyInput=False (alias the input as state) is
+            # honoured as a copy -- the state always owns its memory.
+            cg.detect(input, self.prevInput, s["raw_bits"], self.threshold,
+                      _lib.UPDATE_CHANGED if self.feedbackLoop else _lib.UPDATE_ALL)
+            dil_map = s.get("dil_map") if self.saveChangeMap else None
+            cg.dilate_compact(s["raw_bits"], (B, H, W), self.kernel_size, s["idx"], s["count"],
+                              s["ws"], dil_bits=s["dil_bits"], dil_map=dil_map)
+            if self.saveChangeMap:
+                self.changeMap = dil_map[0] if B == 1 else dil_map
+            changeIndexes = ChangeIndexes(s["idx"], s["count"], (B, H, W), bits=s["dil_bits"])
+        else:
+            if not isinstance(changeIndexes, ChangeIndexes):
+                assert(changeIndexes.dim() == 1)
+                changeIndexes = ChangeIndexes.from_tensor(changeIndexes.detach(), (B, H, W))
+            if not self.feedbackLoop:
+                self.prevInput.copy_(input)                                            # :234-236
+            # (with feedbackLoop the reference never refreshes prevInput here either, :220,234)
+
+        gemm, packed, bias32 = self._weights(dt, dev)
+        cg.conv_update(self._inBuf, changeIndexes, packed, bias32, self._outBuf, self.in_channels,
+                       self.out_channels, self.kernel_size, self.withReLU, gemm)      # :242-251
+
+        if self.propChangeIndexes:
+            return 'changeIndexes', self.prevOutput, changeIndexes
+        else:
+            return self.prevOutput
+
+    def _gatherStats(self, input):
+        """op-count bookkeeping of conv2d.py:201-218 (dense torch ops, only when enabled)."""
+        changeTensor = (input - self.prevInput).abs().gt(self.threshold)
+        ones = torch.ones(changeTensor.size(-3), 1, self.weight.size(2), self.weight.size(3),
+                          device=input.device)
+        proped = F.conv2d(changeTensor.float(), ones, groups=changeTensor.size(-3)).gt(0)
+        opsPerValue = self.weight.size(0) * self.weight.size(2) * self.weight.size(3) * 2
+        nC = changeTensor.size(-3)
+        self.compStats = dict(
+            numInputChangesPerFeatureMap=changeTensor.sum() * opsPerValue,
+            numInputChanges=changeTensor.sum(-3).gt(0).sum() * nC * opsPerValue,
+            numInputPropedChangesPerFeatureMap=proped.sum() * opsPerValue,
+            numInputPropedChanges=proped.sum(-3).gt(0).sum() * nC * opsPerValue,
+            totalInputValues=changeTensor.size(-1) * changeTensor.size(-2) * nC * opsPerValue,
+        )
+
+    def forward(self, inp):
+        self._setDefaultValues()
+        with torch.no_grad():
+            if self.finegrained:
+                assert(self.feedbackLoop == False)
+                return self.forward_fg(inp)
+            else:
+                return self.forward_normal(inp)
+
+    def __repr__(self):
+        self._setDefaultValues()
+        s = ('{name} (th={threshold}, {in_channels}->{out_channels}, k={kernel_size}'
+             ', s={stride}, copyInput={copyInput}')
+        if self.padding != (0,) * len(self.padding):
+            s += ', pad={padding}'
+        if self.dilation != (1,) * len(self.dilation):
+            s += ', dilation={dilation}'
+        if self.output_padding != (0,) * len(self.output_padding):
+            s += ', outpad={output_padding}'
+        if self.groups != 1:
+            s += ', grp={groups}'
+        if self.bias is None:
+            s += ', bias=False'
+        if self.withReLU:
+            s += ', withReLU={withReLU}'
+        s += ', propChgIdxs={propChangeIndexes}'
+        s += ')'
+        return s.format(name=self.__class__.__name__, **self.__dict__)
+
+    def _setDefaultValues(self):
+        for name, val in (('saveChangeMap', False), ('propChangeIndexes', False),
+                          ('gatherComputationStats', False), ('finegrained', False),
+                          ('copyInput', True), ('feedbackLoop', False), ('gemmMode', 'auto')):
+            if not(hasattr(self, name)):
+                setattr(self, name, val)

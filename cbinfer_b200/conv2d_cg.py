@@ -1,0 +1,284 @@
+"""Coarse-grained change-based ops: python wrappers over the sm_100a C ABI.
+
+Mirrors the op surface of the reference's ``pycbinfer/conv2d_cg.py`` -- same function names,
+argument meaning and tensor layouts (planar NCHW, batch 1, int8 change maps, ascending int32
+indices) -- so code and tests written against the reference read the same here:
+
+    changeDetection      conv2d_cg.py:100-122      changePropagation   conv2d_cg.py:159-177
+    changeIndexesExtr    conv2d_cg.py:200-213      genXMatrix          conv2d_cg.py:239-261
+    matrixMult           conv2d_cg.py:342-349      updateOutput        conv2d_cg.py:292-313
+    maxPool2d            conv2d_cg.py:58-82
+
+Differences, all deliberate: no ``useHalf`` flag (the dtype is taken from the tensor), launch
+geometry lives in the library, the change count never has to visit the host
+(:class:`ChangeIndexes`), and every op is CUDA-only -- the reference's ``*_python`` CPU twins
+exist in this repo only inside ``oracle/`` as the parity checker.
+
+The fused per-frame path used by ``CBConv2d`` (``detect`` -> ``dilate_compact`` ->
+``conv_update``) is exposed as well.
+"""
+import torch
+
+from . import _lib
+from ._lib import C, check, dtype_code, require_cuda, stream_ptr
+
+
+def _strides4(t):
+    """(sb, sc, sy, sx) element strides of a [B,C,H,W] tensor."""
+    assert t.dim() == 4
+    return t.stride(0), t.stride(1), t.stride(2), t.stride(3)
+
+
+class ChangeIndexes(object):
+    """Device-resident change-index list: ``buffer[:count]`` holds ascending int32 pixel indices
+    ``b*H*W + y*W + x``.  It stands in for the exact-length tensor the reference passes between
+    layers (conv2d.py:256-257) without forcing the device->host sync ``torch.nonzero`` implies
+    (conv2d_cg.py:202): consumers in this package read ``count`` on the device; anything that
+    needs a real tensor (``len``, ``.tensor()``, indexing) synchronises on demand."""
+
+    def __init__(self, buffer, count, shape, bits=None):
+        self.buffer = buffer          # int32 [capacity]
+        self.count = count            # int32 [1] on the device
+        self.shape = shape            # (B, H, W) the indices refer to
+        self.bits = bits              # optional dilated bitmap the list was compacted from
+
+    @classmethod
+    def from_tensor(cls, idx, shape):
+        idx = idx.to(torch.int32).contiguous()
+        count = torch.full((1,), idx.numel(), dtype=torch.int32, device=idx.device)
+        return cls(idx, count, shape)
+
+    def tensor(self):
+        return self.buffer[: int(self.count.item())]
+
+    # tensor-like conveniences (all synchronise)
+    def __len__(self):
+        return int(self.count.item())
+
+    def numel(self):
+        return len(self)
+
+    def dim(self):
+        return 1
+
+    def size(self, d=None):
+        return torch.Size([len(self)]) if d is None else len(self)
+
+    def contiguous(self):
+        return self
+
+    @property
+    def data(self):
+        return self
+
+    @property
+    def is_cuda(self):
+        return self.buffer.is_cuda
+
+    def cpu(self):
+        return self.tensor().cpu()
+
+    def __getitem__(self, i):
+        return self.tensor()[i]
+
+
+# ---------------------------------------------------------------------------------------------
+# fused-path primitives (native pixel-major layout, batch-capable, no host sync)
+# ---------------------------------------------------------------------------------------------
+
+def detect(x, state, raw_bits, threshold, update_mode):
+    """cb_change_detect: raw (un-dilated) change bitmap of x vs state; updates state."""
+    require_cuda(x, state, raw_bits)
+    B, Cc, H, W = x.shape
+    assert state.shape == x.shape and state.dtype == x.dtype
+    check(C.cb_change_detect(stream_ptr(x.device), dtype_code(x), x.data_ptr(), *_strides4(x),
+                             state.data_ptr(), *_strides4(state), raw_bits.data_ptr(),
+                             B, Cc, H, W, float(threshold), int(update_mode)))
+
+
+def dilate_compact(raw_bits, shape, filtSize, idx, count, ws, dil_bits=None, dil_map=None):
+    """cb_dilate_compact: dilation by the filter footprint + ordered compaction."""
+    B, H, W = shape
+    check(C.cb_dilate_compact(stream_ptr(raw_bits.device), raw_bits.data_ptr(),
+                              dil_bits.data_ptr() if dil_bits is not None else None,
+                              dil_map.data_ptr() if dil_map is not None else None,
+                              idx.data_ptr(), count.data_ptr(), ws.data_ptr(), B, H, W,
+                              (filtSize[0] - 1) // 2, (filtSize[1] - 1) // 2))
+
+
+def alloc_scratch(shape, device, want_map=False):
+    """bitmaps / index buffer / count / compaction workspace for a [B,H,W] pixel grid."""
+    B, H, W = shape
+    nwords = C.cb_bitmap_words(B, H, W)
+    s = dict(
+        raw_bits=torch.zeros(max(nwords, 1), dtype=torch.int32, device=device),
+        dil_bits=torch.zeros(max(nwords, 1), dtype=torch.int32, device=device),
+        idx=torch.zeros(max(B * H * W, 1), dtype=torch.int32, device=device),
+        count=torch.zeros(1, dtype=torch.int32, device=device),
+        ws=torch.zeros(C.cb_compact_ws_bytes(B, H, W), dtype=torch.uint8, device=device),
+    )
+    if want_map:
+        s["dil_map"] = torch.zeros(B, H, W, dtype=torch.int8, device=device)
+    return s
+
+
+def pack_weights(weight, gemm):
+    """cb_pack_weights: [Cout,Cin,kH,kW] -> the layout cb_conv_update expects for `gemm`."""
+    require_cuda(weight)
+    Cout, Cin, kH, kW = weight.shape
+    w = weight.detach().contiguous()
+    nbytes = C.cb_packed_weight_bytes(dtype_code(w), gemm, Cout, Cin, kH, kW)
+    packed = torch.empty(nbytes + 256, dtype=torch.uint8, device=w.device)
+    off = (-packed.data_ptr()) % 256                       # TMA wants >=128-byte alignment
+    packed = packed[off: off + nbytes]
+    check(C.cb_pack_weights(stream_ptr(w.device), dtype_code(w), gemm, w.data_ptr(),
+                            packed.data_ptr(), Cout, Cin, kH, kW))
+    return packed
+
+
+def conv_update(state_buf, changes, packed_w, bias_f32, out_buf, Cin, Cout, filtSize, relu, gemm):
+    """cb_conv_update on pixel-major buffers [B,H,W,pitch]."""
+    B, H, W, Cp = state_buf.shape
+    assert out_buf.shape[:3] == state_buf.shape[:3]
+    check(C.cb_conv_update(stream_ptr(state_buf.device), dtype_code(state_buf), gemm,
+                           state_buf.data_ptr(), Cp, changes.buffer.data_ptr(),
+                           changes.count.data_ptr(), packed_w.data_ptr(), bias_f32.data_ptr(),
+                           out_buf.data_ptr(), out_buf.shape[3], B, H, W, Cin, Cout,
+                           filtSize[0], filtSize[1], int(bool(relu))))
+
+
+def pixel_major(shape, dtype, device, fill):
+    """Allocate a [B,C,H,W]-shaped *view* over a pixel-major [B,H,W,pitch] buffer whose pitch is
+    C rounded up to 16 bytes.  Real channels are set to `fill`, pad channels to 0 (they meet zero
+    weights in the contraction).  Returns (view, buffer)."""
+    B, Cc, H, W = shape
+    pitch = _lib.channel_pitch(dtype, Cc)
+    buf = torch.zeros(B, H, W, pitch, dtype=dtype, device=device)
+    view = buf[..., :Cc].permute(0, 3, 1, 2)
+    if fill != 0:
+        view.fill_(fill)
+    return view, buf
+
+
+# ---------------------------------------------------------------------------------------------
+# reference-named ops (planar layout, batch 1 unless noted)
+# ---------------------------------------------------------------------------------------------
+
+def changeDetection(input, prevInput, filtSize, threshold, updateInputState=False):
+    """conv2d_cg.py:100-122: int8 change map [H,W] (batch 1) / [B,H,W], dilated by filtSize;
+    with updateInputState the changed pixels of prevInput are overwritten in place."""
+    assert input.size() == prevInput.size() and input.dim() == 4
+    require_cuda(input, prevInput)
+    B, _, H, W = input.shape
+    s = alloc_scratch((B, H, W), input.device, want_map=True)
+    detect(input, prevInput, s["raw_bits"], threshold,
+           _lib.UPDATE_CHANGED if updateInputState else _lib.UPDATE_NONE)
+    dilate_compact(s["raw_bits"], (B, H, W), filtSize, s["idx"], s["count"], s["ws"],
+                   dil_map=s["dil_map"])
+    return s["dil_map"][0] if B == 1 else s["dil_map"]
+
+
+def _map_to_bits(changeMap):
+    H, W = changeMap.shape[-2:]
+    B = changeMap.numel() // (H * W)
+    m = changeMap.reshape(B, H, W).to(torch.int8).contiguous()
+    require_cuda(m)
+    bits = torch.zeros(max(C.cb_bitmap_words(B, H, W), 1), dtype=torch.int32, device=m.device)
+    check(C.cb_map_to_bits(stream_ptr(m.device), m.data_ptr(), bits.data_ptr(), B, H, W))
+    return bits, (B, H, W)
+
+
+def changePropagation(changeMap, filtSize):
+    """conv2d_cg.py:159-177: gather-dilate an int8/bool change map by filtSize."""
+    assert len(filtSize) == 2
+    if filtSize[0] == 1 and filtSize[1] == 1:
+        return changeMap
+    bits, shape = _map_to_bits(changeMap)
+    s = alloc_scratch(shape, changeMap.device, want_map=True)
+    dilate_compact(bits, shape, filtSize, s["idx"], s["count"], s["ws"], dil_map=s["dil_map"])
+    return s["dil_map"].reshape(changeMap.shape).to(changeMap.dtype)
+
+
+def changeIndexesExtr(changeMap, lazy=False):
+    """conv2d_cg.py:200-213: ascending int32 indices of the non-zero map cells.  With
+    ``lazy=True`` returns a :class:`ChangeIndexes` (no host sync)."""
+    bits, shape = _map_to_bits(changeMap)
+    s = alloc_scratch(shape, changeMap.device)
+    dilate_compact(bits, shape, (1, 1), s["idx"], s["count"], s["ws"])
+    ci = ChangeIndexes(s["idx"], s["count"], shape)
+    return ci if lazy else ci.tensor()
+
+
+changeIndexesExtr_python = changeIndexesExtr     # the reference's forward calls the *_python name
+
+
+def genXMatrix(input, changeIndexes, filtSize):
+    """conv2d_cg.py:239-261: im2col of the changed pixels, X[n, Cin*kH*kW] (planar input)."""
+    require_cuda(input)
+    inC, inH, inW = input.size(-3), input.size(-2), input.size(-1)
+    kH, kW = filtSize
+    idx = changeIndexes.tensor() if isinstance(changeIndexes, ChangeIndexes) else changeIndexes
+    idx = idx.to(torch.int32).contiguous()
+    n = idx.numel()
+    X = input.new_empty(n, inC * kH * kW)
+    if n > 0:
+        inp = input.contiguous()
+        check(C.cb_gen_xmatrix(stream_ptr(input.device), dtype_code(input), X.data_ptr(),
+                               inp.data_ptr(), idx.data_ptr(), kW, kH, inC, inW, inH, n))
+    return X
+
+
+def matrixMult(Xmatrix, weights, bias, activFun=None):
+    """conv2d_cg.py:342-349: Y = X . W.view(Cout,-1)^T + bias (fp32 accumulation)."""
+    if Xmatrix.numel() == 0:
+        return Xmatrix.clone()
+    require_cuda(Xmatrix, weights, bias)
+    n, K = Xmatrix.shape
+    Cout = weights.size(0)
+    Y = Xmatrix.new_empty(n, Cout)
+    w = weights.detach().contiguous().view(Cout, -1)
+    assert w.size(1) == K
+    check(C.cb_matrix_mult(stream_ptr(Xmatrix.device), dtype_code(Xmatrix),
+                           Xmatrix.contiguous().data_ptr(), w.data_ptr(),
+                           bias.detach().contiguous().data_ptr(), Y.data_ptr(), n, K, Cout))
+    if activFun is not None:
+        Y = activFun(Y)
+    return Y
+
+
+matrixMult_python = matrixMult
+
+
+def updateOutput(YMatrix, changeIndexes, prevOutput, withReLU=False):
+    """conv2d_cg.py:292-313: scatter Y^T[Cout,n] into the planar prevOutput (in place)."""
+    require_cuda(YMatrix, prevOutput)
+    outC, outH, outW = prevOutput.size(-3), prevOutput.size(-2), prevOutput.size(-1)
+    idx = changeIndexes.tensor() if isinstance(changeIndexes, ChangeIndexes) else changeIndexes
+    idx = idx.to(torch.int32).contiguous()
+    n = idx.numel()
+    if n > 0:
+        assert prevOutput.is_contiguous()
+        Yt = YMatrix.contiguous()
+        check(C.cb_update_output(stream_ptr(prevOutput.device), dtype_code(prevOutput),
+                                 Yt.data_ptr(), prevOutput.data_ptr(), idx.data_ptr(),
+                                 outW * outH, n, outC, int(bool(withReLU))))
+    return prevOutput
+
+
+def maxPool2d(input, outputState, changeIndexes, kernelSize=(2, 2), stride=(2, 2)):
+    """conv2d_cg.py:58-82: recompute the 2x2/stride-2 windows touched by the changed input
+    pixels into outputState (in place).  Any strides, batch >= 1."""
+    assert tuple(kernelSize) == (2, 2) and tuple(stride) == (2, 2)
+    require_cuda(input, outputState)
+    assert input.dim() == 4 and outputState.dim() == 4
+    B, Cc, H, W = input.shape
+    oH, oW = outputState.size(-2), outputState.size(-1)
+    if not isinstance(changeIndexes, ChangeIndexes):
+        changeIndexes = ChangeIndexes.from_tensor(changeIndexes, (B, H, W))
+    bits = changeIndexes.bits
+    check(C.cb_maxpool2x2(stream_ptr(input.device), dtype_code(input), input.data_ptr(),
+                          *_strides4(input), changeIndexes.buffer.data_ptr(),
+                          changeIndexes.count.data_ptr(),
+                          bits.data_ptr() if bits is not None else None,
+                          outputState.data_ptr(), *_strides4(outputState), B, Cc, H, W, oH, oW))
+    return outputState

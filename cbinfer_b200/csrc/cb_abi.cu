@@ -1,0 +1,239 @@
+// cb_abi.cu -- extern "C" entry points of libcbinfer_sm100.so (see include/cbinfer_b200.h).
+// sm_100a only: no other architecture, no CPU path, no dispatch to other backends.
+#include <stdarg.h>
+#include <string.h>
+
+#include "cb_common.cuh"
+#include "compact.cuh"
+#include "conv_simt.cuh"
+#include "conv_umma.cuh"
+#include "detect.cuh"
+#include "fg.cuh"
+#include "pool.cuh"
+#include "staged.cuh"
+
+namespace cb {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int sm_count() {
+  static thread_local int cached_dev = -1, cached = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev != cached_dev) {
+    cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
+    cached_dev = dev;
+  }
+  return cached > 0 ? cached : 148;
+}
+
+static inline unsigned grid_for(long long total, int threads, int per_sm = 8) {
+  long long blocks = (total + threads - 1) / threads;
+  long long cap = (long long)sm_count() * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (unsigned)blocks;
+}
+
+}  // namespace cb
+
+using namespace cb;
+
+#define CB_DISPATCH_DTYPE(dtype, ...)                                               \
+  switch (dtype) {                                                                  \
+    case CB_F32: { using T = float; constexpr int VEC = 4; (void)VEC; __VA_ARGS__; } break;           \
+    case CB_F16: { using T = __half; constexpr int VEC = 8; (void)VEC; __VA_ARGS__; } break;          \
+    case CB_BF16: { using T = __nv_bfloat16; constexpr int VEC = 8; (void)VEC; __VA_ARGS__; } break;  \
+    default: return cb::fail(2, "bad dtype %d", dtype);                             \
+  }
+
+extern "C" {
+
+int cb_version(void) { return 100; }
+
+const char* cb_last_error(void) { return cb::g_err; }
+
+int cb_device_info(int* sms, int* major, int* minor) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return cb::fail(3, "no CUDA device");
+  cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(minor, cudaDevAttrComputeCapabilityMinor, dev);
+  return 0;
+}
+
+int cb_bitmap_row_words(int W) { return (W + 31) / 32; }
+size_t cb_bitmap_words(int B, int H, int W) { return (size_t)B * H * ((W + 31) / 32); }
+size_t cb_compact_ws_bytes(int B, int H, int W) { return cb::compact_ws_bytes(cb_bitmap_words(B, H, W)); }
+int cb_channel_pitch(int dtype, int C) {
+  const int v = 16 / cb::esize(dtype);
+  return (C + v - 1) / v * v;
+}
+
+int cb_change_detect(void* stream, int dtype, const void* x, long long x_sb, long long x_sc,
+                     long long x_sy, long long x_sx, void* state, long long s_sb, long long s_sc,
+                     long long s_sy, long long s_sx, uint32_t* raw_bits, int B, int C, int H, int W,
+                     float threshold, int update_mode) {
+  CB_CHECK_ARG(x && state && raw_bits, "change_detect: null pointer");
+  CB_CHECK_ARG(B >= 0 && C > 0 && H >= 0 && W >= 0, "change_detect: bad shape");
+  CB_DISPATCH_DTYPE(dtype, return (launch_detect<T, VEC>((cudaStream_t)stream, x, x_sb, x_sc, x_sy,
+                                                        x_sx, state, s_sb, s_sc, s_sy, s_sx,
+                                                        raw_bits, B, C, H, W, threshold,
+                                                        update_mode)));
+  return 0;
+}
+
+int cb_dilate_compact(void* stream, const uint32_t* raw_bits, uint32_t* dil_bits, int8_t* dil_map,
+                      int32_t* idx, int32_t* count, void* ws, int B, int H, int W, int kHHalf,
+                      int kWHalf) {
+  CB_CHECK_ARG(raw_bits && idx && count && ws, "dilate_compact: null pointer");
+  CB_CHECK_ARG(raw_bits != dil_bits, "dilate_compact: dil_bits must not alias raw_bits");
+  CB_CHECK_ARG(kHHalf >= 0 && kWHalf >= 0 && kWHalf <= 31, "dilate_compact: kWHalf must be <= 31");
+  CB_CHECK_ARG((long long)B * H * W < (1ll << 31), "dilate_compact: more than 2^31 pixels");
+  const long long nwords = (long long)cb_bitmap_words(B, H, W);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (nwords == 0) {
+    cudaMemsetAsync(count, 0, sizeof(int32_t), s);
+    CB_CHECK_LAUNCH("dilate_compact(memset)");
+    return 0;
+  }
+  const int ntiles = (int)((nwords + kCompactThreads - 1) / kCompactThreads);
+  dilate_compact_kernel<<<ntiles, kCompactThreads, 0, s>>>(raw_bits, dil_bits, dil_map, idx, count,
+                                                          ws, B, H, W, (W + 31) / 32, kHHalf,
+                                                          kWHalf, nwords, ntiles);
+  CB_CHECK_LAUNCH("dilate_compact");
+  return 0;
+}
+
+int cb_map_to_bits(void* stream, const int8_t* map, uint32_t* bits, int B, int H, int W) {
+  CB_CHECK_ARG(map && bits, "map_to_bits: null pointer");
+  const long long nwords = (long long)cb_bitmap_words(B, H, W);
+  if (nwords == 0) return 0;
+  const long long blocks = (nwords + 7) / 8;
+  map_to_bits_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(map, bits, H, W,
+                                                                        (W + 31) / 32, nwords);
+  CB_CHECK_LAUNCH("map_to_bits");
+  return 0;
+}
+
+size_t cb_packed_weight_bytes(int dtype, int gemm, int Cout, int Cin, int kH, int kW) {
+  const int Cp = cb_channel_pitch(dtype, Cin);
+  if (gemm == CB_GEMM_SIMT_F32) {
+    const int CoutP = (Cout + 3) / 4 * 4;
+    return (size_t)kH * kW * Cp * CoutP * sizeof(float);
+  }
+  return cb::umma_packed_bytes(dtype, gemm, Cout, Cp, kH, kW);
+}
+
+int cb_pack_weights(void* stream, int dtype, int gemm, const void* weight, void* packed, int Cout,
+                    int Cin, int kH, int kW) {
+  CB_CHECK_ARG(weight && packed, "pack_weights: null pointer");
+  const int Cp = cb_channel_pitch(dtype, Cin);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (gemm == CB_GEMM_SIMT_F32) {
+    const int CoutP = (Cout + 3) / 4 * 4;
+    const long long total = (long long)kH * kW * Cp * CoutP;
+    CB_DISPATCH_DTYPE(dtype, (pack_weights_simt_kernel<T><<<grid_for(total, 256), 256, 0, s>>>(
+                                 (const T*)weight, (float*)packed, Cout, Cin, kH, kW, Cp, CoutP)));
+    CB_CHECK_LAUNCH("pack_weights");
+    return 0;
+  }
+  return cb::umma_pack_weights(s, dtype, gemm, weight, packed, Cout, Cin, Cp, kH, kW);
+}
+
+int cb_conv_update(void* stream, int dtype, int gemm, const void* state, int pitch_in,
+                   const int32_t* idx, const int32_t* count, const void* packed_w,
+                   const float* bias, void* out, int pitch_out, int B, int H, int W, int Cin,
+                   int Cout, int kH, int kW, int relu) {
+  CB_CHECK_ARG(state && idx && count && packed_w && bias && out, "conv_update: null pointer");
+  CB_CHECK_ARG(pitch_in == cb_channel_pitch(dtype, Cin), "conv_update: pitch_in %d != channel pitch %d",
+               pitch_in, cb_channel_pitch(dtype, Cin));
+  CB_CHECK_ARG(pitch_out >= Cout, "conv_update: pitch_out < Cout");
+  CB_CHECK_ARG((kH & 1) && (kW & 1), "conv_update: even kernel sizes unsupported (padding==k//2)");
+  CB_CHECK_ARG((long long)B * H * W < (1ll << 31), "conv_update: more than 2^31 pixels");
+  if (B == 0 || H == 0 || W == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (gemm == CB_GEMM_SIMT_F32) {
+    const int CoutP = (Cout + 3) / 4 * 4;
+    const unsigned grid = (unsigned)(sm_count() * 4);
+    CB_DISPATCH_DTYPE(dtype, (conv_simt_kernel<T><<<grid, SM_THREADS, 0, s>>>(
+                                 (const T*)state, pitch_in, idx, count, (const float*)packed_w, bias,
+                                 (T*)out, pitch_out, H, W, Cout, CoutP, kH, kW, relu)));
+    CB_CHECK_LAUNCH("conv_update(simt)");
+    return 0;
+  }
+  return cb::umma_conv_update(s, dtype, gemm, state, pitch_in, idx, count, packed_w, bias, out,
+                              pitch_out, B, H, W, Cin, Cout, kH, kW, relu);
+}
+
+int cb_maxpool2x2(void* stream, int dtype, const void* x, long long x_sb, long long x_sc,
+                  long long x_sy, long long x_sx, const int32_t* idx, const int32_t* count,
+                  const uint32_t* dil_bits, void* out, long long o_sb, long long o_sc,
+                  long long o_sy, long long o_sx, int B, int C, int H, int W, int oH, int oW) {
+  CB_CHECK_ARG(x && idx && count && out, "maxpool2x2: null pointer");
+  if (B == 0 || H == 0 || W == 0 || C == 0) return 0;
+  const unsigned grid = (unsigned)(sm_count() * 8);
+  CB_DISPATCH_DTYPE(dtype, (maxpool2x2_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
+                               (const T*)x, x_sb, x_sc, x_sy, x_sx, idx, count, dil_bits, (T*)out,
+                               o_sb, o_sc, o_sy, o_sx, C, H, W, oH, oW)));
+  CB_CHECK_LAUNCH("maxpool2x2");
+  return 0;
+}
+
+int cb_gen_xmatrix(void* stream, int dtype, void* columns, const void* input, const int32_t* idx,
+                   int kW, int kH, int C, int W, int H, int n) {
+  if (n <= 0) return 0;
+  CB_CHECK_ARG(columns && input && idx, "gen_xmatrix: null pointer");
+  const long long total = (long long)n * C * kH * kW;
+  CB_DISPATCH_DTYPE(dtype, (gen_xmatrix_kernel<T><<<grid_for(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(
+                               (T*)columns, (const T*)input, idx, kW, kH, C, W, H, n)));
+  CB_CHECK_LAUNCH("gen_xmatrix");
+  return 0;
+}
+
+int cb_matrix_mult(void* stream, int dtype, const void* X, const void* weight, const void* bias,
+                   void* Y, int n, int K, int Cout) {
+  if (n <= 0) return 0;
+  CB_CHECK_ARG(X && weight && bias && Y, "matrix_mult: null pointer");
+  dim3 grid((Cout + 31) / 32, (n + 31) / 32);
+  CB_CHECK_ARG(grid.y < 65536, "matrix_mult: n too large for the staged op");
+  CB_DISPATCH_DTYPE(dtype, (matrix_mult_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
+                               (const T*)X, (const T*)weight, (const T*)bias, (T*)Y, n, K, Cout)));
+  CB_CHECK_LAUNCH("matrix_mult");
+  return 0;
+}
+
+int cb_update_output(void* stream, int dtype, const void* Yt, void* output, const int32_t* idx,
+                     int numOutputPixel, int n, int Cout, int relu) {
+  if (n <= 0) return 0;
+  CB_CHECK_ARG(Yt && output && idx, "update_output: null pointer");
+  const long long total = (long long)n * Cout;
+  CB_DISPATCH_DTYPE(dtype, (update_output_kernel<T><<<grid_for(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(
+                               (const T*)Yt, (T*)output, idx, numOutputPixel, n, Cout, relu)));
+  CB_CHECK_LAUNCH("update_output");
+  return 0;
+}
+
+int cb_fg_update(void* stream, const float* x, float* prev, const float* weight, float* out,
+                 int32_t* count, int B, int Cin, int Cout, int H, int W, int kH, int kW,
+                 float threshold) {
+  CB_CHECK_ARG(x && prev && weight && out && count, "fg_update: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaMemsetAsync(count, 0, sizeof(int32_t), s);
+  const long long total = (long long)B * Cin * H * W;
+  if (total == 0) return 0;
+  fg_update_kernel<<<grid_for((total + 31) / 32 * 32, 256, 8), 256, 0, s>>>(x, prev, weight, out, count, B, Cin,
+                                                             Cout, H, W, kH, kW, threshold);
+  CB_CHECK_LAUNCH("fg_update");
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,177 @@
+// compact.cuh -- change propagation (dilation) + ordered compaction, bitmap domain.
+//
+// Replaces the scatter-dilate of changeDetection_kernel (reference cbconv2d_cg_backend.cu:62-72),
+// changePropagation_kernel (:101-124) and torch.nonzero(...).int() incl. its host sync
+// (conv2d_cg.py:200-213).
+//
+// One thread owns one bitmap word (32 pixels): vertical OR of the raw rows in the window,
+// horizontal dilation with funnel shifts across the neighbouring words, __popc for the count,
+// a block scan plus a single-pass chained ("decoupled look-back") scan across tiles for the
+// global offsets, then the set bits are expanded to ascending int32 pixel indices.
+// Traffic: P/8 bitmap bytes (re-read (2kH+1)*3 times out of L1/L2) + 4n index bytes.
+#pragma once
+#include "cb_common.cuh"
+
+namespace cb {
+
+constexpr int kCompactThreads = 256;           // words per tile
+
+struct CompactHeader {                         // first 16 bytes of the workspace
+  unsigned ticket, done, epoch, pad;
+};
+
+__host__ __device__ inline size_t compact_ws_bytes(size_t nwords) {
+  const size_t tiles = (nwords + kCompactThreads - 1) / kCompactThreads;
+  return sizeof(CompactHeader) + 8 * (tiles + 1);
+}
+
+// tile_state word: [63:34] tag (epoch-derived, never 0) | [33:32] status | [31:0] value
+__device__ __forceinline__ unsigned long long pack_state(unsigned tag, unsigned status, unsigned v) {
+  return ((unsigned long long)tag << 34) | ((unsigned long long)status << 32) | v;
+}
+
+__global__ void __launch_bounds__(kCompactThreads)
+dilate_compact_kernel(const uint32_t* __restrict__ raw, uint32_t* __restrict__ dil_bits,
+                      int8_t* __restrict__ dil_map, int32_t* __restrict__ idx,
+                      int32_t* __restrict__ count, void* ws, int B, int H, int W, int Wd, int kh,
+                      int kw, long long nwords, int ntiles) {
+  CompactHeader* hdr = reinterpret_cast<CompactHeader*>(ws);
+  volatile unsigned long long* tstate =
+      reinterpret_cast<volatile unsigned long long*>(reinterpret_cast<char*>(ws) + sizeof(CompactHeader));
+  __shared__ unsigned s_tile, s_epoch;
+  __shared__ int s_warp[kCompactThreads / 32];
+  __shared__ int s_base;
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) {
+    s_epoch = *reinterpret_cast<volatile unsigned*>(&hdr->epoch);
+    s_tile = atomicAdd(&hdr->ticket, 1u);      // ticket order == start order: look-back is safe
+  }
+  __syncthreads();
+  const int tile = (int)s_tile;
+  const unsigned tag = s_epoch % 0x3ffffffeu + 1u;
+
+  // ---- dilated word --------------------------------------------------------------------
+  const long long w = (long long)tile * kCompactThreads + tid;
+  unsigned d = 0;
+  int j = 0, y = 0;
+  long long r = 0;
+  if (w < nwords) {
+    j = (int)(w % Wd);
+    r = w / Wd;
+    y = (int)(r % H);
+    unsigned vp = 0, vc = 0, vn = 0;
+    const int y0 = max(0, y - kh), y1 = min(H - 1, y + kh);
+    const uint32_t* row = raw + (r - y + y0) * Wd + j;
+    for (int yy = y0; yy <= y1; ++yy, row += Wd) {
+      vc |= __ldg(row);
+      if (j > 0) vp |= __ldg(row - 1);
+      if (j + 1 < Wd) vn |= __ldg(row + 1);
+    }
+    d = vc;
+    for (int dx = 1; dx <= kw; ++dx) {
+      d |= (vc << dx) | (vp >> (32 - dx));     // source pixel dx to the left
+      d |= (vc >> dx) | (vn << (32 - dx));     // source pixel dx to the right
+    }
+    if (j == Wd - 1 && (W & 31)) d &= (1u << (W & 31)) - 1u;
+    if (dil_bits) dil_bits[w] = d;
+  }
+
+  // ---- block scan of popcounts -----------------------------------------------------------
+  const int cnt = __popc(d);
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int n = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += n;
+  }
+  if (lane == 31) s_warp[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    int v = lane < kCompactThreads / 32 ? s_warp[lane] : 0;
+    int inc2 = v;
+#pragma unroll
+    for (int o = 1; o < kCompactThreads / 32; o <<= 1) {
+      const int n = __shfl_up_sync(0xffffffffu, inc2, o);
+      if (lane >= o) inc2 += n;
+    }
+    if (lane < kCompactThreads / 32) s_warp[lane] = inc2 - v;   // exclusive warp offsets
+    const int total = __shfl_sync(0xffffffffu, inc2, kCompactThreads / 32 - 1);
+
+    // ---- chained scan across tiles (decoupled look-back), warp 0 ----------------------------
+    int exclusive = 0;
+    if (tile > 0) {
+      if (lane == 0) tstate[tile] = pack_state(tag, 1u, (unsigned)total);    // aggregate
+      int look = tile - 1;
+      while (true) {
+        const int t = look - lane;
+        unsigned long long st = 0;
+        if (t >= 0) {
+          do { st = tstate[t]; } while ((unsigned)(st >> 34) != tag);
+        }
+        const unsigned status = t >= 0 ? (unsigned)((st >> 32) & 3u) : 2u;   // before tile 0: prefix 0
+        const int val = t >= 0 ? (int)(unsigned)(st & 0xffffffffu) : 0;
+        const unsigned pm = __ballot_sync(0xffffffffu, status == 2u);
+        const int first = pm ? __ffs(pm) - 1 : 32;           // nearest tile with a full prefix
+        int part = lane <= first ? val : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        exclusive += part;
+        if (pm) break;
+        look -= 32;
+      }
+    }
+    if (lane == 0) {
+      __threadfence();
+      tstate[tile] = pack_state(tag, 2u, (unsigned)(exclusive + total));     // inclusive prefix
+      s_base = exclusive;
+      if (tile == ntiles - 1) *count = exclusive + total;
+    }
+  }
+  __syncthreads();
+
+  // ---- expand set bits to ascending pixel indices ------------------------------------------
+  if (w < nwords) {
+    int o = s_base + s_warp[wid] + (incl - cnt);
+    const int b = (int)(r / H);
+    const int pix0 = (int)(((long long)b * H + y) * W + j * 32);
+    unsigned dd = d;
+    while (dd) {
+      const int bit = __ffs(dd) - 1;
+      idx[o++] = pix0 + bit;
+      dd &= dd - 1;
+    }
+    if (dil_map) {
+      const int n = min(32, W - j * 32);
+      int8_t* m = dil_map + pix0;
+      for (int i = 0; i < n; ++i) m[i] = (int8_t)((d >> i) & 1u);
+    }
+  }
+
+  // ---- leave the workspace clean for the next launch ---------------------------------------
+  if (tid == 0) {
+    __threadfence();
+    const unsigned prev = atomicAdd(&hdr->done, 1u);
+    if (prev == (unsigned)ntiles - 1u) {
+      hdr->ticket = 0;
+      hdr->done = 0;
+      __threadfence();
+      *reinterpret_cast<volatile unsigned*>(&hdr->epoch) = s_epoch + 1u;
+    }
+  }
+}
+
+__global__ void map_to_bits_kernel(const int8_t* __restrict__ map, uint32_t* __restrict__ bits,
+                                   int H, int W, int Wd, long long nwords) {
+  const int lane = threadIdx.x & 31;
+  const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= nwords) return;
+  const int j = (int)(w % Wd);
+  const long long r = w / Wd;
+  const int x = j * 32 + lane;
+  const bool f = x < W && map[r * W + x] != 0;
+  const unsigned word = __ballot_sync(0xffffffffu, f);
+  if (lane == 0) bits[w] = word;
+}
+
+}  // namespace cb

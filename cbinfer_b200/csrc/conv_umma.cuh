@@ -1,0 +1,565 @@
+// conv_umma.cuh -- fused gather + tcgen05 contraction + bias/ReLU + scatter (the hot kernel).
+//
+// Replaces genXMatrix_kernel (reference cbconv2d_cg_backend.cu:138-161), the cuBLAS GEMM behind
+// matrixMult_python (conv2d_cg.py:342-349), the transpose copy (conv2d.py:247) and
+// updateOutput_kernel (cbconv2d_cg_backend.cu:175-189).  X, Y and Y^T never exist in memory.
+//
+// Implicit GEMM, D[128 x BN] (+)= A[128 x K] * B[BN x K]^T per tile:
+//   M : 128 changed pixels (rows of the index list; the count is read on the device)
+//   N : BN output channels
+//   K : kH*kW*Cp ordered (ky,kx,ci): every filter tap is a contiguous channel run of the
+//       pixel-major state, so one 16-byte chunk never straddles a tap.
+// Warp roles (192 threads):
+//   warps 0-3  gather producers: im2col rows of ONLY the changed receptive fields, 16-byte
+//              global loads -> 128B-swizzled K-major smem tile (the UMMA canonical layout);
+//              for fp32 data in 3xTF32 mode they also split every value into tf32 hi + lo.
+//              The same warps run the epilogue: tcgen05.ld accumulators from TMEM, + bias,
+//              ReLU, convert, scatter one contiguous channel run per pixel.
+//   warp 4     TMA producer for the (regular) weight tiles: cp.async.bulk.tensor.2d, SWIZZLE_128B.
+//   warp 5     MMA issuer: one elected thread issues tcgen05.mma (kind::tf32 / kind::f16) with
+//              the accumulator in TMEM; tcgen05.commit releases smem stages / signals the epilogue.
+// Stages are handed over with mbarriers (full/empty ring + tmem full/empty).
+#pragma once
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include "cb_common.cuh"
+
+namespace cb {
+
+constexpr int UM_BM = 128;                     // rows per tile (UMMA M, cta_group::1)
+constexpr int UM_PRODUCERS = 128;              // gather / epilogue threads (warps 0-3)
+constexpr int UM_THREADS = 192;
+constexpr int UM_ROW_BYTES = 128;              // K bytes per stage row = one swizzle-128B span
+
+// ---- PTX wrappers ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+// Bounded wait: a protocol bug traps (sticky error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok = 0;
+  long long t0 = 0;
+  for (uint32_t spins = 0;; ++spins) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if ((spins & 1023u) == 1023u) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ll) __trap();      // ~2 s at 2 GHz
+    }
+  }
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]; KIND 0: tf32, 1: f16/bf16
+template <int KIND>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                     uint32_t idesc, uint32_t accumulate) {
+  if (KIND == 0)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 UMMA):
+// start>>4 [0,14) | LBO>>4 = 1 [16,30) | SBO>>4 = 64 (8 rows x 128 B) [32,46) | version 1 [46,48)
+// | layout SWIZZLE_128B = 2 [61,64).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+// instruction descriptor: D=f32, A/B format fmt (0 f16, 1 bf16, 2 tf32), K-major both, N, M=128
+__host__ __device__ inline uint32_t umma_idesc(int fmt, int N) {
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(UM_BM >> 4) << 24);
+}
+
+// ---- configuration -----------------------------------------------------------------------------
+template <typename T, bool SPLIT3, int BN>
+struct UmmaCfg {
+  static constexpr int ES = sizeof(T);
+  static constexpr int VEC = 16 / ES;                        // elements per 16-byte chunk
+  static constexpr int BK = UM_ROW_BYTES / ES;               // K elements per stage
+  static constexpr int UK = 32 / ES;                         // K elements per tcgen05.mma
+  static constexpr int NSPLIT = SPLIT3 ? 2 : 1;
+  static constexpr int A_BYTES = UM_BM * UM_ROW_BYTES;       // 16 KB
+  static constexpr int B_BYTES = BN * UM_ROW_BYTES;
+  static constexpr int STAGE_BYTES = NSPLIT * (A_BYTES + B_BYTES);
+  static constexpr int STAGES = (96 * 1024 / STAGE_BYTES) < 2 ? 2
+                                : (96 * 1024 / STAGE_BYTES) > 6 ? 6 : (96 * 1024 / STAGE_BYTES);
+  static constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 2048 /*ctrl*/;
+};
+
+struct UmmaCtrl {                              // lives after the stage buffers
+  uint64_t full[8], empty[8], tmem_full, tmem_empty;
+  uint32_t tmem_base, pad;
+  int pix[UM_BM];
+  int yx[UM_BM];
+};
+static_assert(sizeof(UmmaCtrl) <= 2048, "ctrl block too large");
+
+template <typename T>
+__device__ __forceinline__ void store_chunk(uint8_t* a_hi, uint8_t* a_lo, uint32_t off, uint4 v,
+                                            bool split) {
+  if (split) {                                  // fp32 -> tf32 hi (exact) + lo (= v - hi, exact)
+    uint4 hi, lo;
+    hi.x = v.x & 0xFFFFE000u; hi.y = v.y & 0xFFFFE000u; hi.z = v.z & 0xFFFFE000u; hi.w = v.w & 0xFFFFE000u;
+    lo.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(hi.x));
+    lo.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(hi.y));
+    lo.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(hi.z));
+    lo.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(hi.w));
+    *reinterpret_cast<uint4*>(a_hi + off) = hi;
+    *reinterpret_cast<uint4*>(a_lo + off) = lo;
+  } else {
+    *reinterpret_cast<uint4*>(a_hi + off) = v;
+  }
+}
+
+// packed weights: [NSPLIT][CoutPad][KpPad] elements of T (K-major); tensor map dims {KpPad, NSPLIT*CoutPad}
+template <typename T, bool SPLIT3, int BN>
+__global__ void __launch_bounds__(UM_THREADS)
+conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__ state, int Cp,
+                 const int32_t* __restrict__ idx, const int32_t* __restrict__ count,
+                 const float* __restrict__ bias, T* __restrict__ out, int Op, int H, int W,
+                 int Cout, int CoutPad, int kH, int kW, int Kp, int relu) {
+  using C = UmmaCfg<T, SPLIT3, BN>;
+  const int n = *count;
+  const int mtiles = (n + UM_BM - 1) / UM_BM;
+  const int ntiles = CoutPad / BN;
+  const int total_tiles = mtiles * ntiles;
+  if ((int)blockIdx.x >= total_tiles) return;             // uniform: before any barrier / alloc
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~(uintptr_t)1023);
+  UmmaCtrl* ctrl = reinterpret_cast<UmmaCtrl*>(smem + C::STAGES * C::STAGE_BYTES);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int num_kb = (Kp + C::BK - 1) / C::BK;
+
+  if (tid == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&ctrl->full[s], UM_PRODUCERS + 1);
+      mbar_init(&ctrl->empty[s], 1);
+    }
+    mbar_init(&ctrl->tmem_full, 1);
+    mbar_init(&ctrl->tmem_empty, UM_PRODUCERS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) {                                         // TMEM allocation (one warp)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&ctrl->tmem_base)),
+                 "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp == 4 && lane == 0)
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&wmap)) : "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctrl->tmem_base;
+
+  const int ph = (kH - 1) / 2, pw = (kW - 1) / 2;
+  const int P = H * W;
+
+  if (warp < 4) {
+    // =============================== gather producers + epilogue ============================
+    uint32_t stage = 0, phase = 0, acc_phase = 0;
+    const int c = tid & 7;                                  // my 16-byte chunk column
+    const int r0 = tid >> 3;                                // my rows: r0 + 16*it
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int mt = tile / ntiles, nt = tile - mt * ntiles;
+      {                                                     // row table of this tile
+        const int j = mt * UM_BM + tid;
+        int pix = -1, yx = 0;
+        if (j < n) {
+          pix = __ldg(idx + j);
+          const int p = pix % P;
+          const int yy = p / W;
+          yx = (yy << 16) | (p - yy * W);
+        }
+        ctrl->pix[tid] = pix;
+        ctrl->yx[tid] = yx;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");       // producers only
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&ctrl->empty[stage], phase ^ 1u);
+        uint8_t* a_hi = smem + stage * C::STAGE_BYTES;
+        uint8_t* a_lo = a_hi + C::A_BYTES;                  // only used when SPLIT3
+        const int k = kb * C::BK + c * C::VEC;
+        const bool kvalid = k < Kp;
+        const int tap = k / Cp, ci = k - tap * Cp;
+        const int ky = tap / kW, kx = tap - ky * kW;
+        const int dy = ky - ph, dx = kx - pw;
+        const long long koff = ((long long)dy * W + dx) * Cp + ci;
+        uint4 v[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int r = r0 + 16 * it;
+          const int pix = ctrl->pix[r], yx = ctrl->yx[r];
+          const int iy = (yx >> 16) + dy, ix = (yx & 0xffff) + dx;
+          v[it] = make_uint4(0u, 0u, 0u, 0u);
+          if (kvalid && pix >= 0 && iy >= 0 && iy < H && ix >= 0 && ix < W)
+            v[it] = ld16(state + (long long)pix * Cp + koff);
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int r = r0 + 16 * it;
+          const uint32_t off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
+          store_chunk<T>(a_hi, a_lo, off, v[it], SPLIT3);
+        }
+        fence_proxy_async_smem();                            // generic writes -> async proxy (UMMA)
+        mbar_arrive(&ctrl->full[stage]);
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+      }
+      // ---- epilogue: TMEM -> registers -> bias / ReLU -> scatter -------------------------
+      mbar_wait(&ctrl->tmem_full, acc_phase);
+      tc_fence_after();
+      const int pix = ctrl->pix[tid];                       // TMEM lane == tile row == tid
+      const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+      T* orow = out + (long long)(pix < 0 ? 0 : pix) * Op;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        uint32_t acc[16];
+        tmem_ld16(trow + (uint32_t)c0, acc);
+        tmem_ld_wait();
+        const int co0 = nt * BN + c0;
+        if (pix >= 0 && co0 < Cout) {
+          float f[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int co = co0 + i;
+            float t = __uint_as_float(acc[i]) + (co < Cout ? __ldg(bias + co) : 0.f);
+            if (relu && t <= 0.f) t = 0.f;
+            f[i] = t;
+          }
+          if (co0 + 16 <= Cout && (Op % C::VEC) == 0) {      // full, 16-byte aligned run
+            if (sizeof(T) == 4) {
+#pragma unroll
+              for (int i = 0; i < 16; i += 4)
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(orow) + co0 + i) =
+                    make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; i += 8) {
+                T h[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) h[e] = from_float<T>(f[i + e]);
+                *reinterpret_cast<uint4*>(orow + co0 + i) = *reinterpret_cast<uint4*>(h);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (co0 + i < Cout) orow[co0 + i] = from_float<T>(f[i]);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&ctrl->tmem_empty);
+      acc_phase ^= 1u;
+      asm volatile("bar.sync 1, 128;" ::: "memory");       // row table is rewritten next tile
+    }
+  } else if (warp == 4) {
+    // =============================== TMA producer: weight tiles ==============================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % ntiles;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&ctrl->empty[stage], phase ^ 1u);
+          uint8_t* b_hi = smem + stage * C::STAGE_BYTES + C::NSPLIT * C::A_BYTES;
+          mbar_arrive_expect_tx(&ctrl->full[stage], (uint32_t)(C::NSPLIT * C::B_BYTES));
+          tma_load_2d(smem_u32(b_hi), &wmap, kb * C::BK, nt * BN, &ctrl->full[stage]);
+          if (SPLIT3)
+            tma_load_2d(smem_u32(b_hi + C::B_BYTES), &wmap, kb * C::BK, CoutPad + nt * BN,
+                        &ctrl->full[stage]);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else {
+    // =============================== MMA issuer ==============================================
+    if (lane == 0) {
+      constexpr int KIND = sizeof(T) == 4 ? 0 : 1;
+      const uint32_t idesc =
+          umma_idesc(sizeof(T) == 4 ? 2 : (std::is_same<T, __half>::value ? 0 : 1), BN);
+      uint32_t stage = 0, phase = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&ctrl->tmem_empty, acc_phase ^ 1u);        // epilogue drained the accumulator
+        tc_fence_after();
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&ctrl->full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t a_lo = a_hi + C::A_BYTES;
+          const uint32_t b_hi = a_hi + C::NSPLIT * C::A_BYTES;
+          const uint32_t b_lo = b_hi + C::B_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < C::BK / C::UK; ++ks) {
+            const uint32_t adv = (uint32_t)(ks * 32);        // 32 bytes of K per instruction
+            const uint32_t first = (kb | ks) ? 1u : 0u;
+            if (SPLIT3) {
+              umma<KIND>(tmem_base, umma_desc(a_lo + adv), umma_desc(b_hi + adv), idesc, first);
+              umma<KIND>(tmem_base, umma_desc(a_hi + adv), umma_desc(b_lo + adv), idesc, 1u);
+              umma<KIND>(tmem_base, umma_desc(a_hi + adv), umma_desc(b_hi + adv), idesc, 1u);
+            } else {
+              umma<KIND>(tmem_base, umma_desc(a_hi + adv), umma_desc(b_hi + adv), idesc, first);
+            }
+          }
+          umma_commit(&ctrl->empty[stage]);                  // frees the smem stage when done
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&ctrl->tmem_full);                       // accumulator complete
+        acc_phase ^= 1u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ---- weight packing ----------------------------------------------------------------------------
+// weight [Cout][Cin][kH][kW] (T) -> packed [NSPLIT][CoutPad][KpPad] (T), k = (ky*kW+kx)*Cp + ci.
+// fp32 + SPLIT3: plane 0 = tf32-truncated hi, plane 1 = lo = w - hi (exact).
+template <typename T>
+__global__ void pack_weights_umma_kernel(const T* __restrict__ w, T* __restrict__ packed, int Cout,
+                                         int Cin, int kH, int kW, int Cp, int CoutPad, int KpPad,
+                                         int split3) {
+  const long long plane = (long long)CoutPad * KpPad;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < plane;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % KpPad);
+    const int co = (int)(i / KpPad);
+    const int tap = k / Cp, ci = k - tap * Cp;
+    const int ky = tap / kW, kx = tap - ky * kW;
+    T v = from_float<T>(0.f);
+    if (co < Cout && ci < Cin && tap < kH * kW) v = w[(((long long)co * Cin + ci) * kH + ky) * kW + kx];
+    if (split3) {
+      const float f = to_float(v);
+      const float hi = __uint_as_float(__float_as_uint(f) & 0xFFFFE000u);
+      packed[i] = from_float<T>(hi);
+      packed[plane + i] = from_float<T>(f - hi);
+    } else {
+      packed[i] = v;
+    }
+  }
+}
+
+inline int umma_bn(int gemm, int Cout) {
+  const int maxbn = gemm == CB_GEMM_TC_3X ? 64 : 128;
+  int bn = 16;
+  while (bn < Cout && bn < maxbn) bn <<= 1;
+  return bn;
+}
+inline int umma_cout_pad(int gemm, int Cout) {
+  const int bn = umma_bn(gemm, Cout);
+  return (Cout + bn - 1) / bn * bn;
+}
+inline int umma_kp_pad(int dtype, int Cp, int kH, int kW) {
+  const int bk = UM_ROW_BYTES / esize(dtype);
+  return (kH * kW * Cp + bk - 1) / bk * bk;
+}
+
+inline size_t umma_packed_bytes(int dtype, int gemm, int Cout, int Cp, int kH, int kW) {
+  const int nsplit = (gemm == CB_GEMM_TC_3X && dtype == CB_F32) ? 2 : 1;
+  return (size_t)nsplit * umma_cout_pad(gemm, Cout) * umma_kp_pad(dtype, Cp, kH, kW) * esize(dtype);
+}
+
+inline int umma_pack_weights(cudaStream_t s, int dtype, int gemm, const void* weight, void* packed,
+                             int Cout, int Cin, int Cp, int kH, int kW) {
+  CB_CHECK_ARG(gemm == CB_GEMM_TC || gemm == CB_GEMM_TC_3X, "pack_weights: bad gemm mode %d", gemm);
+  const int split3 = (gemm == CB_GEMM_TC_3X && dtype == CB_F32) ? 1 : 0;
+  const int CoutPad = umma_cout_pad(gemm, Cout), KpPad = umma_kp_pad(dtype, Cp, kH, kW);
+  const long long plane = (long long)CoutPad * KpPad;
+  long long blocks = (plane + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  switch (dtype) {
+    case CB_F32:
+      pack_weights_umma_kernel<float><<<(unsigned)blocks, 256, 0, s>>>(
+          (const float*)weight, (float*)packed, Cout, Cin, kH, kW, Cp, CoutPad, KpPad, split3);
+      break;
+    case CB_F16:
+      pack_weights_umma_kernel<__half><<<(unsigned)blocks, 256, 0, s>>>(
+          (const __half*)weight, (__half*)packed, Cout, Cin, kH, kW, Cp, CoutPad, KpPad, 0);
+      break;
+    case CB_BF16:
+      pack_weights_umma_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, s>>>(
+          (const __nv_bfloat16*)weight, (__nv_bfloat16*)packed, Cout, Cin, kH, kW, Cp, CoutPad,
+          KpPad, 0);
+      break;
+    default: return fail(2, "pack_weights: bad dtype %d", dtype);
+  }
+  CB_CHECK_LAUNCH("pack_weights(umma)");
+  return 0;
+}
+
+// ---- host: tensor map + launch -----------------------------------------------------------------
+inline PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+template <typename T, bool SPLIT3, int BN>
+int launch_conv_umma(cudaStream_t s, int dtype, const void* state, int Cp, const int32_t* idx,
+                     const int32_t* count, const void* packed, const float* bias, void* out,
+                     int Op, int B, int H, int W, int Cout, int CoutPad, int kH, int kW, int relu) {
+  using C = UmmaCfg<T, SPLIT3, BN>;
+  const int Kp = kH * kW * Cp;
+  const int KpPad = umma_kp_pad(dtype, Cp, kH, kW);
+  auto enc = tensor_map_encoder();
+  if (!enc) return fail(3, "conv_update: cuTensorMapEncodeTiled unavailable");
+  alignas(64) CUtensorMap map;
+  const cuuint64_t gdim[2] = {(cuuint64_t)KpPad, (cuuint64_t)(C::NSPLIT * CoutPad)};
+  const cuuint64_t gstr[1] = {(cuuint64_t)KpPad * sizeof(T)};
+  const cuuint32_t box[2] = {(cuuint32_t)C::BK, (cuuint32_t)BN};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapDataType dt = dtype == CB_F32   ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                 : dtype == CB_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                                   : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUresult r = enc(&map, dt, 2, const_cast<void*>(packed), gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(3, "conv_update: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  auto kern = conv_umma_kernel<T, SPLIT3, BN>;
+  static thread_local int attr_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (attr_dev != dev) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) !=
+        cudaSuccess)
+      return fail(3, "conv_update: cannot reserve %d bytes of shared memory", C::SMEM_BYTES);
+    attr_dev = dev;
+  }
+  const long long max_tiles = (((long long)B * H * W + UM_BM - 1) / UM_BM) * (CoutPad / BN);
+  long long grid = (long long)sm_count() * 2;
+  if (grid > max_tiles) grid = max_tiles;
+  if (grid < 1) grid = 1;
+  kern<<<(unsigned)grid, UM_THREADS, C::SMEM_BYTES, s>>>(map, (const T*)state, Cp, idx, count, bias,
+                                                        (T*)out, Op, H, W, Cout, CoutPad, kH, kW,
+                                                        Kp, relu);
+  CB_CHECK_LAUNCH("conv_update(umma)");
+  return 0;
+}
+
+template <typename T, bool SPLIT3>
+int dispatch_bn(int bn, cudaStream_t s, int dtype, const void* state, int Cp, const int32_t* idx,
+                const int32_t* count, const void* packed, const float* bias, void* out, int Op,
+                int B, int H, int W, int Cout, int CoutPad, int kH, int kW, int relu) {
+#define CB_BN(N)                                                                              \
+  case N:                                                                                     \
+    return launch_conv_umma<T, SPLIT3, N>(s, dtype, state, Cp, idx, count, packed, bias, out, \
+                                          Op, B, H, W, Cout, CoutPad, kH, kW, relu);
+  switch (bn) {
+    CB_BN(16) CB_BN(32) CB_BN(64)
+    case 128:
+      if (!SPLIT3)
+        return launch_conv_umma<T, false, 128>(s, dtype, state, Cp, idx, count, packed, bias, out,
+                                               Op, B, H, W, Cout, CoutPad, kH, kW, relu);
+    default: return fail(2, "conv_update: unsupported N tile %d", bn);
+  }
+#undef CB_BN
+}
+
+inline int umma_conv_update(cudaStream_t s, int dtype, int gemm, const void* state, int Cp,
+                            const int32_t* idx, const int32_t* count, const void* packed,
+                            const float* bias, void* out, int Op, int B, int H, int W, int Cin,
+                            int Cout, int kH, int kW, int relu) {
+  (void)Cin;
+  CB_CHECK_ARG(gemm == CB_GEMM_TC || gemm == CB_GEMM_TC_3X, "conv_update: bad gemm mode %d", gemm);
+  CB_CHECK_ARG(H < 65536 && W < 65536, "conv_update: H, W must be < 65536");
+  CB_CHECK_ARG(((uintptr_t)state % 16) == 0 && ((uintptr_t)packed % 128) == 0,
+               "conv_update: state must be 16-byte and packed weights 128-byte aligned");
+  const int bn = umma_bn(gemm, Cout), CoutPad = umma_cout_pad(gemm, Cout);
+  const bool split3 = gemm == CB_GEMM_TC_3X && dtype == CB_F32;
+  switch (dtype) {
+    case CB_F32:
+      return split3 ? dispatch_bn<float, true>(bn, s, dtype, state, Cp, idx, count, packed, bias,
+                                               out, Op, B, H, W, Cout, CoutPad, kH, kW, relu)
+                    : dispatch_bn<float, false>(bn, s, dtype, state, Cp, idx, count, packed, bias,
+                                                out, Op, B, H, W, Cout, CoutPad, kH, kW, relu);
+    case CB_F16:
+      return dispatch_bn<__half, false>(bn, s, dtype, state, Cp, idx, count, packed, bias, out, Op,
+                                        B, H, W, Cout, CoutPad, kH, kW, relu);
+    case CB_BF16:
+      return dispatch_bn<__nv_bfloat16, false>(bn, s, dtype, state, Cp, idx, count, packed, bias,
+                                               out, Op, B, H, W, Cout, CoutPad, kH, kW, relu);
+    default: return fail(2, "conv_update: bad dtype %d", dtype);
+  }
+}
+
+}  // namespace cb

@@ -1,0 +1,163 @@
+// detect.cuh -- change detection: thresholded |x_t - x_{t-1}| -> 1 bit per pixel.
+//
+// Replaces the detection half of changeDetection[_1x1]_kernel
+// (reference pycbinfer/cbconv2d_cg_backend.cu:6-81, half: cbconv2d_cg_half_backend.cu:10-88).
+//
+// One warp owns 32 consecutive pixels of one image row (= one bitmap word).
+//   * vector path (pixel-major x and state): the warp streams the 32 pixels' channels as
+//     16-byte chunks, fully coalesced; per-chunk flags are folded to per-pixel flags with
+//     __ballot_sync + bit-range masks, then one ballot builds the bitmap word.
+//   * generic path (any strides, e.g. the user's planar NCHW frame): lane = pixel, loop over
+//     channels (coalesced across lanes for planar inputs).
+// HBM-bound: algorithmic bytes = 2*C*P*s read (+ P/8 bitmap, + feedback writes).
+#pragma once
+#include "cb_common.cuh"
+
+namespace cb {
+
+template <typename T, int VEC>
+__device__ __forceinline__ uint4 merge_tail(uint4 xv, const uint4& sv, int tail) {
+  T* xe = reinterpret_cast<T*>(&xv);
+  const T* se = reinterpret_cast<const T*>(&sv);
+#pragma unroll
+  for (int e = 0; e < VEC; ++e)
+    if (e >= tail) xe[e] = se[e];
+  return xv;
+}
+
+// x: pixel-major, pitch xp (elements); state: pixel-major, pitch sp.  Rows may be strided (sy).
+template <typename T, int VEC, int UPDATE>
+__global__ void __launch_bounds__(256)
+detect_vec_kernel(const T* __restrict__ x, long long x_sb, long long x_sy, int xp,
+                  T* __restrict__ st, long long s_sb, long long s_sy, int sp,
+                  uint32_t* __restrict__ bits, int B, int H, int W, int C, int Wd, T thr) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (warp >= (long long)B * H * Wd) return;
+  const int j = (int)(warp % Wd);
+  const long long r = warp / Wd;
+  const int y = (int)(r % H);
+  const int b = (int)(r / H);
+  const int x0 = j * 32;
+  const int npx = min(32, W - x0);
+  const T* xb = x + b * x_sb + y * x_sy + (long long)x0 * xp;
+  T* sb = st + b * s_sb + y * s_sy + (long long)x0 * sp;
+  const int cpv = (C + VEC - 1) / VEC;       // 16-byte chunks per pixel that hold real channels
+  const int tail = C % VEC;                  // valid elements of the last chunk (0 = all)
+  const int nq = npx * cpv;
+
+  bool mychg = false;                        // flag of pixel `lane`
+  const int plo = lane * cpv, phi = plo + cpv;
+  for (int q0 = 0; q0 < nq; q0 += 32) {
+    const int q = q0 + lane;
+    bool f = false;
+    if (q < nq) {
+      const int px = q / cpv, cc = q - px * cpv;
+      uint4 xv = ldg16(xb + (long long)px * xp + cc * VEC);
+      T* sptr = sb + (long long)px * sp + cc * VEC;
+      const uint4 sv = ld16(sptr);
+      if (tail && cc == cpv - 1) xv = merge_tail<T, VEC>(xv, sv, tail);
+      f = Chunk<T>::changed(sv, xv, thr);
+      if (UPDATE == CB_UPDATE_ALL) st16(sptr, xv);
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, f);
+    const int lo = max(plo, q0) - q0, hi = min(phi, q0 + 32) - q0;
+    if (hi > lo) {
+      const unsigned m = (hi - lo >= 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
+      mychg |= (bal & m) != 0u;
+    }
+  }
+  const unsigned word = __ballot_sync(0xffffffffu, mychg);
+  if (lane == 0) bits[warp] = word;
+
+  if (UPDATE == CB_UPDATE_CHANGED && word) {  // feedback: accept the new value at changed pixels
+    for (int q = lane; q < nq; q += 32) {
+      const int px = q / cpv, cc = q - px * cpv;
+      if ((word >> px) & 1u) {
+        uint4 xv = ldg16(xb + (long long)px * xp + cc * VEC);
+        T* sptr = sb + (long long)px * sp + cc * VEC;
+        if (tail && cc == cpv - 1) xv = merge_tail<T, VEC>(xv, ld16(sptr), tail);
+        st16(sptr, xv);
+      }
+    }
+  }
+}
+
+template <typename T, int UPDATE>
+__global__ void __launch_bounds__(256)
+detect_generic_kernel(const T* __restrict__ x, long long x_sb, long long x_sc, long long x_sy,
+                      long long x_sx, T* __restrict__ st, long long s_sb, long long s_sc,
+                      long long s_sy, long long s_sx, uint32_t* __restrict__ bits, int B, int H,
+                      int W, int C, int Wd, T thr) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (warp >= (long long)B * H * Wd) return;
+  const int j = (int)(warp % Wd);
+  const long long r = warp / Wd;
+  const int y = (int)(r % H);
+  const int b = (int)(r / H);
+  const int xx = j * 32 + lane;
+  bool f = false;
+  const T* xp = x + b * x_sb + y * x_sy + xx * x_sx;
+  T* sp = st + b * s_sb + y * s_sy + xx * s_sx;
+  if (xx < W) {
+    for (int c = 0; c < C; ++c) {
+      const T xv = xp[c * x_sc];
+      const T sv = sp[c * s_sc];
+      f |= value_changed(sv, xv, thr);
+      if (UPDATE == CB_UPDATE_ALL) sp[c * s_sc] = xv;
+    }
+    if (UPDATE == CB_UPDATE_CHANGED && f)
+      for (int c = 0; c < C; ++c) sp[c * s_sc] = xp[c * x_sc];
+  }
+  const unsigned word = __ballot_sync(0xffffffffu, f);
+  if (lane == 0) bits[warp] = word;
+}
+
+template <typename T> __host__ __device__ inline T thr_cast(float t);
+template <> __host__ __device__ inline float thr_cast<float>(float t) { return t; }
+template <> __host__ __device__ inline __half thr_cast<__half>(float t) { return __float2half_rn(t); }
+template <> __host__ __device__ inline __nv_bfloat16 thr_cast<__nv_bfloat16>(float t) {
+  return __float2bfloat16_rn(t);
+}
+
+template <typename T, int VEC>
+int launch_detect(cudaStream_t stream, const void* x, long long x_sb, long long x_sc,
+                  long long x_sy, long long x_sx, void* state, long long s_sb, long long s_sc,
+                  long long s_sy, long long s_sx, uint32_t* bits, int B, int C, int H, int W,
+                  float threshold, int update) {
+  const int Wd = (W + 31) / 32;
+  const long long warps = (long long)B * H * Wd;
+  if (warps == 0) return 0;
+  const int wpb = 8;
+  const long long blocks = (warps + wpb - 1) / wpb;
+  CB_CHECK_ARG(blocks < (1ll << 31), "change_detect: image too large");
+  const T thr = thr_cast<T>(threshold);
+  const size_t es = sizeof(T);
+  const bool vec_ok = x_sc == 1 && s_sc == 1 && (x_sx % VEC) == 0 && (s_sx % VEC) == 0 &&
+                      x_sx >= C && s_sx >= C && ((x_sy * es) % 16) == 0 && ((s_sy * es) % 16) == 0 &&
+                      ((x_sb * es) % 16) == 0 && ((s_sb * es) % 16) == 0 &&
+                      ((uintptr_t)x % 16) == 0 && ((uintptr_t)state % 16) == 0 &&
+                      x_sx < (1ll << 30) && s_sx < (1ll << 30);
+  dim3 grid((unsigned)blocks), block(wpb * 32);
+#define CB_DET(U)                                                                              \
+  if (vec_ok)                                                                                  \
+    detect_vec_kernel<T, VEC, U><<<grid, block, 0, stream>>>(                                  \
+        (const T*)x, x_sb, x_sy, (int)x_sx, (T*)state, s_sb, s_sy, (int)s_sx, bits, B, H, W, C, \
+        Wd, thr);                                                                              \
+  else                                                                                         \
+    detect_generic_kernel<T, U><<<grid, block, 0, stream>>>(                                   \
+        (const T*)x, x_sb, x_sc, x_sy, x_sx, (T*)state, s_sb, s_sc, s_sy, s_sx, bits, B, H, W, \
+        C, Wd, thr);
+  switch (update) {
+    case CB_UPDATE_NONE: CB_DET(CB_UPDATE_NONE) break;
+    case CB_UPDATE_CHANGED: CB_DET(CB_UPDATE_CHANGED) break;
+    case CB_UPDATE_ALL: CB_DET(CB_UPDATE_ALL) break;
+    default: return fail(2, "change_detect: bad update_mode %d", update);
+  }
+#undef CB_DET
+  CB_CHECK_LAUNCH("change_detect");
+  return 0;
+}
+
+}  // namespace cb

@@ -1,0 +1,151 @@
+"""Random-init model builders for the BASELINE configs (the callers either side of the hot path).
+
+* :func:`sceneLabelingBaseline` -- the 11-slot scene-labeling CNN whose topology is pinned by the
+  reference's ``sceneLabeling/modelLoader.py:9-10,47,72-78`` (three KxK convs with ReLU, two
+  2x2 max-pools, two trailing 1x1 convs); channel widths / 7x7 follow the authors' papers (the
+  weight file ``models/modelBaseline.net`` is not shipped, so weights are random-init).
+* :func:`sceneLabelingCBinfer` -- the CBinfer version following the ``experimentIdx`` recipes of
+  ``sceneLabeling/modelLoader.py:41-87``.
+* :func:`poseModel` -- OpenPose-style CPM (VGG-19 stem + T stages) with the layer table of
+  ``poseDetection/openPose/PoseModel.py:34-68``.
+"""
+import copy
+
+import torch
+import torch.nn as nn
+
+from . import CBConv2d, CBPoolMax2d, convert, convertPools
+
+
+def sceneLabelingBaseline(seed=0):
+    g = torch.random.get_rng_state()
+    torch.manual_seed(seed)
+    m = nn.Sequential(
+        nn.Conv2d(3, 16, 7, padding=3), nn.ReLU(), nn.MaxPool2d(2, 2),
+        nn.Conv2d(16, 64, 7, padding=3), nn.ReLU(), nn.MaxPool2d(2, 2),
+        nn.Conv2d(64, 256, 7, padding=3), nn.ReLU(),
+        nn.Conv2d(256, 64, 1), nn.ReLU(),
+        nn.Conv2d(64, 8, 1),
+    ).eval()
+    torch.random.set_rng_state(g)
+    return m
+
+
+def sceneLabelingCBinfer(baseline, experimentIdx=6, threshold=1e-1, convertAll=True,
+                         clonePoolOutput=True):
+    """CBinfer scene-labeling model sharing the baseline's parameters.
+
+    experimentIdx follows sceneLabeling/modelLoader.py:8-16:
+      <=3 : plain conversion;  4: + feedback loop;  5/6: + change-based pooling with index
+      propagation;  7: fine-grained convolution.
+    ``convertAll=True`` converts the two trailing 1x1 convs as well (BASELINE config 2: "all
+    conv+maxpool converted"); ``False`` keeps them dense as modelLoader.py:65 does.
+    """
+    m = convert(copy.deepcopy(baseline), threshold=threshold)
+    if not convertAll:
+        kids = list(m.named_children())
+        dense_tail = list(baseline.children())[8:11]
+        m = nn.Sequential()
+        for name, node in kids[:5]:
+            m.add_module(name, node)
+        for i, node in enumerate(dense_tail):
+            m.add_module(str(8 + i), copy.deepcopy(node))
+    convs = [mm for mm in m.modules() if type(mm) is CBConv2d]
+    if experimentIdx >= 3:
+        for c in convs:
+            c.copyInput = False
+    if experimentIdx in (4, 5, 6):
+        for c in convs:
+            c.feedbackLoop = True
+    if experimentIdx in (5, 6):
+        m = convertPools(m)
+        for p in m.modules():
+            if type(p) is CBPoolMax2d:
+                p.cloneOutput = clonePoolOutput
+    if experimentIdx == 7:
+        for c in convs:
+            c.finegrained = True
+    return m.eval()
+
+
+def calibrateThresholds(baseline, cbmodel, frame, factor=0.02):
+    """Fixed per-layer thresholds for throughput runs: factor * (max - min) of
+    the dense activation feeding each CB conv, measured on one frame."""
+    feeds = {}
+    hooks = []
+    convs_dense = [mm for mm in baseline.modules() if type(mm) is nn.Conv2d]
+    for i, c in enumerate(convs_dense):
+        hooks.append(c.register_forward_hook(
+            lambda mod, inp, out, i=i: feeds.__setitem__(i, float(inp[0].max() - inp[0].min()))))
+    with torch.no_grad():
+        baseline(frame)
+    for h in hooks:
+        h.remove()
+    cbs = [mm for mm in cbmodel.modules() if type(mm) is CBConv2d]
+    for i, c in enumerate(cbs):
+        c.threshold = factor * feeds[i]
+    return [c.threshold for c in cbs]
+
+
+# ---- OpenPose-style CPM (poseDetection/openPose/PoseModel.py:34-68) ---------------------------
+
+def _stage(cfg):
+    layers = []
+    for i, (cin, cout, k) in enumerate(cfg):
+        layers.append(nn.Conv2d(cin, cout, k, padding=k // 2))
+        if i != len(cfg) - 1:
+            layers.append(nn.ReLU(inplace=True))
+    return nn.Sequential(*layers)
+
+
+class PoseModel(nn.Module):
+    def __init__(self, T=6, seed=0):
+        super(PoseModel, self).__init__()
+        assert 1 <= T <= 6
+        self.T = T
+        g = torch.random.get_rng_state()
+        torch.manual_seed(seed)
+        vgg = [(3, 64), (64, 64), 'P', (64, 128), (128, 128), 'P', (128, 256), (256, 256),
+               (256, 256), (256, 256), 'P', (256, 512), (512, 512), (512, 256), (256, 128)]
+        layers = []
+        for v in vgg:
+            if v == 'P':
+                layers.append(nn.MaxPool2d(2, 2))
+            else:
+                layers += [nn.Conv2d(v[0], v[1], 3, padding=1), nn.ReLU(inplace=True)]
+        self.model0 = nn.Sequential(*layers)
+        for br, cout in ((1, 38), (2, 19)):
+            setattr(self, 'model1_%d' % br, _stage([(128, 128, 3), (128, 128, 3), (128, 128, 3),
+                                                    (128, 512, 1), (512, cout, 1)]))
+            for t in range(2, T + 1):
+                setattr(self, 'model%d_%d' % (t, br),
+                        _stage([(185, 128, 7)] + [(128, 128, 7)] * 4 + [(128, 128, 1), (128, cout, 1)]))
+        torch.random.set_rng_state(g)
+        self.eval()
+
+    def forward(self, x):
+        feat = self.model0(x)
+        tmp = feat
+        for t in range(1, self.T + 1):
+            L = getattr(self, 'model%d_1' % t)(tmp)
+            S = getattr(self, 'model%d_2' % t)(tmp)
+            if t != self.T:
+                tmp = torch.cat([L, S, feat], 1)
+        return L, S
+
+
+def poseModelCBinfer(pose, threshold=1e-1, feedbackLoop=True, pools=True):
+    """Convert every nn.Sequential block of a PoseModel (poseDetection/modelConverter.py:85-86
+    sets feedbackLoop on all CB layers)."""
+    m = copy.deepcopy(pose)
+    for name, child in list(m.named_children()):
+        if type(child) is nn.Sequential:
+            c = convert(child, threshold=threshold)
+            if pools:
+                c = convertPools(c)
+            setattr(m, name, c)
+    for mm in m.modules():
+        if type(mm) is CBConv2d:
+            mm.feedbackLoop = feedbackLoop
+            mm.copyInput = False
+    return m.eval()

@@ -1,0 +1,153 @@
+/*
+ * cbinfer_b200.h -- C ABI of libcbinfer_sm100.so, the B200 (sm_100a) backend behind the
+ * pycbinfer surface.  Plain pointers and sizes only; no torch types.  This is the boundary the
+ * reference crosses with cffi in pycbinfer/conv2d_cg.py:6-50 and pycbinfer/conv2d_fg.py:12-32;
+ * each entry point names the reference symbol(s) it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a non-zero code on failure; the message is
+ *     available from cb_last_error() (the reference launchers are `void` and unchecked,
+ *     cbconv2d_cg_backend.cu:83-99).
+ *   - `stream` is a cudaStream_t passed as void* (the reference launches on the legacy default
+ *     stream).  All work is asynchronous on that stream; nothing synchronises the host.
+ *   - launch geometry is the library's business: the reference's gridz..blockx arguments
+ *     (conv2d_cg.py:7,17,23,31,35) are gone.
+ *   - all memory is caller-owned, including workspaces (same ownership rule as the reference,
+ *     where python allocates changeMap / XMatrix / state, conv2d_cg.py:105,249).
+ *   - dtype codes: CB_F32 = 0, CB_F16 = 1, CB_BF16 = 2 (the reference selects between twin
+ *     libraries with identical symbols instead, conv2d_cg.py:73,109,252,302).
+ *   - tensors are described by a base pointer plus element strides (sb, sc, sy, sx) for the
+ *     batch, channel, row and column dimension, so both the reference's planar NCHW layout
+ *     (sc = H*W, sy = W, sx = 1) and the backend's native pixel-major layout (sc = 1,
+ *     sx = pitch, sy = W*pitch) are accepted.  "pixel-major" arguments (state of the fused
+ *     path) take a single `pitch` (elements per pixel, a multiple of 16 bytes / element size).
+ *   - batch: B independent images (video streams).  The reference is batch 1.
+ *   - pixel indices are int32, ascending, b*H*W + y*W + x  (reference: y*W+x, conv2d_cg.py:202).
+ *   - change bitmaps hold one bit per pixel, row-padded: word (b*H + y) * cb_bitmap_row_words(W)
+ *     + x/32, bit x%32.
+ */
+#ifndef CBINFER_B200_H
+#define CBINFER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CB_F32 0
+#define CB_F16 1
+#define CB_BF16 2
+
+/* how cb_change_detect maintains the previous-input state */
+#define CB_UPDATE_NONE 0     /* leave state untouched (updateInputState=false, no copy)        */
+#define CB_UPDATE_CHANGED 1  /* feedback loop: state[:,p] = in[:,p] at own-changed pixels only  */
+#define CB_UPDATE_ALL 2      /* state = in everywhere (the prevInput.copy_(input) of conv2d.py:236) */
+
+/* arithmetic of the contraction in cb_conv_update */
+#define CB_GEMM_SIMT_F32 0   /* fp32 FFMA on CUDA cores (exact-fp32 products)                   */
+#define CB_GEMM_TC 1         /* tcgen05: 1xTF32 for fp32 data, f16/bf16 for 16-bit data          */
+#define CB_GEMM_TC_3X 2      /* tcgen05: 3xTF32 split (fp32-accurate) for fp32 data              */
+
+/* ---- library ---------------------------------------------------------------------------- */
+int cb_version(void);
+const char* cb_last_error(void);
+/* number of SMs / compute capability of the current device */
+int cb_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- sizes ------------------------------------------------------------------------------ */
+int cb_bitmap_row_words(int W);                       /* ceil(W/32)                             */
+size_t cb_bitmap_words(int B, int H, int W);          /* B*H*ceil(W/32)                         */
+size_t cb_compact_ws_bytes(int B, int H, int W);      /* workspace of cb_dilate_compact         */
+int cb_channel_pitch(int dtype, int C);               /* C rounded up to 16 bytes               */
+size_t cb_packed_weight_bytes(int dtype, int gemm, int Cout, int Cin, int kH, int kW);
+
+/* ---- change detection ---------------------------------------------------------------------
+ * replaces: changeDetection (conv2d_cg.py:7-13 -> cbconv2d_cg_backend.cu:6-100, half: :10-108),
+ *           detection half only; the dilation lives in cb_dilate_compact.
+ * raw_bits[word] bit = OR_c ( |state - x| > thr )   strict '>', fp32 flush-to-zero, fp16/bf16:
+ * rounded difference vs rounded threshold, two one-sided tests (half.cu:58-63).
+ * The whole bitmap (incl. row padding bits = 0) is written; no pre-zeroing needed. */
+int cb_change_detect(void* stream, int dtype,
+                     const void* x, long long x_sb, long long x_sc, long long x_sy, long long x_sx,
+                     void* state, long long s_sb, long long s_sc, long long s_sy, long long s_sx,
+                     uint32_t* raw_bits, int B, int C, int H, int W, float threshold,
+                     int update_mode);
+
+/* ---- propagation + compaction -------------------------------------------------------------
+ * replaces: the scatter-dilate inside changeDetection_kernel (cbconv2d_cg_backend.cu:62-72),
+ *           changePropagation (conv2d_cg.py:15-19 -> cbconv2d_cg_backend.cu:101-136) and
+ *           changeIndexesExtr / torch.nonzero(...).int() (conv2d_cg.py:200-213) incl. its host
+ *           sync: the count stays on the device.
+ * Dilates raw_bits by (2*kHHalf+1)x(2*kWHalf+1) inside each image, then writes
+ *   dil_bits (optional, may be NULL; may NOT alias raw_bits), dil_map (optional int8 [B,H,W]),
+ *   idx[0..n) ascending, *count = n.   `ws` is cb_compact_ws_bytes() of zero-initialised
+ * (once, at allocation) device memory private to the calling stream; the kernel leaves it
+ * clean for the next call. */
+int cb_dilate_compact(void* stream, const uint32_t* raw_bits, uint32_t* dil_bits, int8_t* dil_map,
+                      int32_t* idx, int32_t* count, void* ws, int B, int H, int W, int kHHalf,
+                      int kWHalf);
+
+/* int8/bool map [B,H,W] (non-zero = set) -> bitmap.  Lets callers that hold a reference-style
+ * changeMap (conv2d_cg.py:105) use cb_dilate_compact as changePropagation / changeIndexesExtr. */
+int cb_map_to_bits(void* stream, const int8_t* map, uint32_t* bits, int B, int H, int W);
+
+/* ---- fused gather + contraction + bias/ReLU + scatter -------------------------------------
+ * replaces: genXMatrix (conv2d_cg.py:21-27 -> cbconv2d_cg_backend.cu:138-173),
+ *           matrixMult_python / cuBLAS (conv2d_cg.py:342-349), the transpose copy
+ *           (conv2d.py:247, conv2d_cg.py:305) and updateOutput (conv2d_cg.py:29-31 ->
+ *           cbconv2d_cg_backend.cu:175-197).  X and Y are never materialised.
+ * For j < *count: out[idx[j], co] = act( bias[co] + sum_{ky,kx,ci} W[co,ci,ky,kx] *
+ *                                        state[pixel idx[j] + (ky-kH/2, kx-kW/2), ci] )
+ * with zero outside the image and act = ReLU iff relu (v <= 0 -> 0, cg.cu:187).
+ * state / out are pixel-major with the given pitches; bias is fp32[Cout]; packed_w comes from
+ * cb_pack_weights with the same dtype/gemm/shape.  *count is read on the device. */
+int cb_pack_weights(void* stream, int dtype, int gemm, const void* weight /*[Cout,Cin,kH,kW]*/,
+                    void* packed, int Cout, int Cin, int kH, int kW);
+int cb_conv_update(void* stream, int dtype, int gemm, const void* state, int pitch_in,
+                   const int32_t* idx, const int32_t* count, const void* packed_w,
+                   const float* bias, void* out, int pitch_out, int B, int H, int W, int Cin,
+                   int Cout, int kH, int kW, int relu);
+
+/* ---- change-based 2x2/stride-2 max pooling ------------------------------------------------
+ * replaces: maxPool2d (conv2d_cg.py:33-37 -> cbconv2d_cg_backend.cu:199-240, half :207-250).
+ * For every changed input pixel idx[j] (j < *count) recompute the max of its 2x2 window over
+ * all channels (init -inf, window clipped to the input) into out[b, :, y/2, x/2].  Windows whose
+ * output coordinate falls outside [oH,oW) are skipped (the reference writes out of bounds there).
+ * dil_bits (optional) is the bitmap the indices were compacted from; when given, each window is
+ * recomputed once instead of up to four times. */
+int cb_maxpool2x2(void* stream, int dtype,
+                  const void* x, long long x_sb, long long x_sc, long long x_sy, long long x_sx,
+                  const int32_t* idx, const int32_t* count, const uint32_t* dil_bits,
+                  void* out, long long o_sb, long long o_sc, long long o_sy, long long o_sx,
+                  int B, int C, int H, int W, int oH, int oW);
+
+/* ---- staged (unfused) ops in the reference's planar layout --------------------------------
+ * 1:1 replacements used by the op-level wrappers and parity tests. n is a host count here,
+ * exactly as in the reference signatures. */
+/* genXMatrix: conv2d_cg.py:21-27 -> cbconv2d_cg_backend.cu:138-173 */
+int cb_gen_xmatrix(void* stream, int dtype, void* columns, const void* input, const int32_t* idx,
+                   int kW, int kH, int C, int W, int H, int n);
+/* matrixMult_python: conv2d_cg.py:342-349 (fp32 accumulate; bias dtype = data dtype) */
+int cb_matrix_mult(void* stream, int dtype, const void* X, const void* weight, const void* bias,
+                   void* Y, int n, int K, int Cout);
+/* updateOutput: conv2d_cg.py:29-31 -> cbconv2d_cg_backend.cu:175-197 (Yt is [Cout,n]) */
+int cb_update_output(void* stream, int dtype, const void* Yt, void* output, const int32_t* idx,
+                     int numOutputPixel, int n, int Cout, int relu);
+
+/* ---- fine-grained path (fp32) -------------------------------------------------------------
+ * replaces: changeDetectionFG (conv2d_fg.py:20-24 -> cbconv2d_fg_backend.cu:7-35),
+ *           torch.nonzero (conv2d_fg.py:82) and updateOutputFG (conv2d_fg.py:14-18 ->
+ *           cbconv2d_fg_backend.cu:37-79), fused: per value d = x - prev, if |d| > thr then
+ *           out[co, y-ky+kH/2, x-kx+kW/2] += W[co,ci,ky,kx]*d for all co,ky,kx (atomic adds);
+ *           afterwards prev = x (conv2d.py:175).  *count receives the number of changed values.
+ * Planar NCHW fp32 tensors, batch B. */
+int cb_fg_update(void* stream, const float* x, float* prev, const float* weight, float* out,
+                 int32_t* count, int B, int Cin, int Cout, int H, int W, int kH, int kW,
+                 float threshold);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CBINFER_B200_H */

@@ -1,0 +1,108 @@
+"""CPU: the C-ABI library loads and exports every symbol include/cbinfer_b200.h declares, the
+host-side size helpers agree with their definition, and the python surface mirrors the
+reference's (no GPU compute calls here)."""
+import os
+import re
+
+import pytest
+import torch
+import torch.nn as nn
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(REPO, "include", "cbinfer_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(cb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from cbinfer_b200 import _lib
+    syms = header_symbols()
+    assert len(syms) >= 18
+    assert sorted(_lib.SYMBOLS) == syms
+    for s in syms:
+        assert hasattr(_lib.C, s), s
+    assert _lib.C.cb_version() >= 100
+
+
+def test_size_helpers():
+    from cbinfer_b200._lib import C
+    assert C.cb_bitmap_row_words(640) == 20 and C.cb_bitmap_row_words(46) == 2
+    assert C.cb_bitmap_words(2, 480, 640) == 2 * 480 * 20
+    assert C.cb_channel_pitch(0, 3) == 4 and C.cb_channel_pitch(0, 185) == 188
+    assert C.cb_channel_pitch(1, 3) == 8 and C.cb_channel_pitch(2, 185) == 192
+    assert C.cb_compact_ws_bytes(1, 480, 640) >= 16 + 8 * ((9600 + 255) // 256)
+    # simt packing: fp32 [Kp][CoutP]
+    assert C.cb_packed_weight_bytes(0, 0, 16, 3, 7, 7) == 49 * 4 * 16 * 4
+    # tc3x packing: 2 planes x CoutPad(64) x KpPad(196->224) fp32
+    assert C.cb_packed_weight_bytes(0, 2, 16, 3, 7, 7) == 2 * 16 * 224 * 4
+    assert C.cb_packed_weight_bytes(2, 1, 256, 64, 7, 7) == 256 * 3136 * 2
+
+
+def test_no_cpu_path():
+    import cbinfer_b200 as cb
+    from cbinfer_b200._lib import CBinferError
+    m = cb.convert(nn.Sequential(nn.Conv2d(3, 4, 3, padding=1)))
+    with pytest.raises(CBinferError):
+        m(torch.zeros(1, 3, 8, 8))
+
+
+def test_convert_surface_matches_reference_semantics():
+    import cbinfer_b200 as cb
+    import pycbinfer
+    assert pycbinfer.CBConv2d is cb.CBConv2d
+    base = nn.Sequential(
+        nn.Conv2d(3, 8, 7, padding=3), nn.ReLU(), nn.MaxPool2d(2, 2), nn.Dropout(),
+        nn.Sequential(nn.Conv2d(8, 8, 3, padding=1), nn.ReLU(), nn.Conv2d(8, 4, 1)),
+        nn.Tanh())
+    m = cb.convert(base, threshold=0.25)
+    assert isinstance(m, nn.Sequential)
+    names = [n for n, _ in m.named_children()]
+    assert names == ["0", "2", "4", "5"]              # ReLU merged, Dropout removed, names kept
+    c0 = m[0]
+    assert type(c0) is cb.CBConv2d and c0.withReLU and c0.threshold == 0.25
+    assert c0.weight is base[0].weight and c0.bias is base[0].bias     # parameters are shared
+    inner = m[2]
+    assert type(inner[0]) is cb.CBConv2d and inner[0].withReLU and not inner[1].withReLU
+    assert inner[0].threshold == 0.25  # threshold is passed down the recursion (__init__.py:28)
+    assert not c0.feedbackLoop and c0.copyInput and not c0.finegrained and not c0.propChangeIndexes
+    assert "CBConv2d (th=0.25, 3->8, k=(7, 7), s=(1, 1), copyInput=True, pad=(3, 3), withReLU=True, propChgIdxs=False)" == repr(c0)
+    assert cb.getStateTensors(m)[0].numel() == 0
+    cb.clearMemory(m)
+    m2 = cb.convertPools(m)
+    assert type(m2[1]) is cb.CBPoolMax2d and m2[0].propChangeIndexes
+    assert repr(m2[1]) == "CBPoolMax2d (k=(2, 2), s=(2, 2), ceil_mode=False, propChgIdxs=False)"
+    # unsupported convs are rejected exactly like the reference (conv2d.py:91-93,104)
+    for bad in (nn.Conv2d(3, 4, 3), nn.Conv2d(3, 4, 3, padding=1, stride=2),
+                nn.Conv2d(4, 4, 3, padding=1, groups=2), nn.Conv2d(3, 4, 3, padding=1, bias=False)):
+        with pytest.raises(AssertionError):
+            cb.CBConv2d(bad, 0.1)
+
+
+def test_models_build():
+    from cbinfer_b200 import models
+    import cbinfer_b200 as cb
+    b = models.sceneLabelingBaseline()
+    c = models.sceneLabelingCBinfer(b, experimentIdx=6)
+    kinds = [type(m).__name__ for m in c.children()]
+    assert kinds == ["CBConv2d", "CBPoolMax2d", "CBConv2d", "CBPoolMax2d", "CBConv2d", "CBConv2d", "CBConv2d"]
+    assert all(m.feedbackLoop for m in c.modules() if type(m) is cb.CBConv2d)
+    c2 = models.sceneLabelingCBinfer(b, experimentIdx=6, convertAll=False)
+    assert [type(m).__name__ for m in c2.children()][-3:] == ["Conv2d", "ReLU", "Conv2d"]
+    p = models.PoseModel(T=2)
+    assert sum(1 for m in p.modules() if isinstance(m, nn.Conv2d)) == 36
+    pc = models.poseModelCBinfer(p)
+    assert sum(1 for m in pc.modules() if type(m) is cb.CBConv2d) == 36
+    assert sum(1 for m in pc.modules() if type(m) is cb.CBPoolMax2d) == 3
+
+
+def test_synthetic_video_change_rate():
+    from cbinfer_b200 import video
+    fr = video.sequence(2, 48, 64, 4, 0.05)
+    for t in range(1, 4):
+        rate = (fr[t] != fr[t - 1]).any(1).float().mean().item()
+        assert abs(rate - 0.05) < 0.01
+    fr = video.sequence(1, 48, 64, 3, 0.2, mode="iid")
+    assert 0.1 < (fr[1] != fr[0]).any(1).float().mean().item() < 0.3

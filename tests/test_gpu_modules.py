@@ -1,0 +1,308 @@
+"""GPU parity tests, module level: CBConv2d / CBPoolMax2d / converted models against the oracle's
+restatement of the reference flow (oracle.OracleCBConv2d / OracleCBPoolMax2d), against dense
+nn.Conv2d at threshold 0, and against the UNMODIFIED reference kernels (oracle/_ref, JIT-compiled
+from their compute_52/61 PTX) run on the same GPU."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from tests.util import ORC_DT, TORCH_DT, perturb, rand_tensor, ref_lib, to_np, to_val, vp
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _no_tf32():
+    # the dense arbiter must be true fp32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def _frames(shape, dt, n, frac, seed):
+    f = [rand_tensor(shape, dt, seed)]
+    for t in range(1, n):
+        f.append(perturb(f[-1], frac, seed + t))
+    return f
+
+
+def _rel(got, exp):
+    return float(np.abs(got - exp).max() / (np.abs(exp).max() + 1e-30))
+
+
+# ---------------------------------------------------------------------------------------------
+# CBConv2d vs the oracle flow, frame by frame
+# ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("dt,mode,tol", [("f32", "auto", 1e-4), ("f32", "simt", 2e-5),
+                                         ("bf16", "auto", 1e-2), ("f16", "auto", 2e-3)])
+@pytest.mark.parametrize("feedback", [False, True])
+@pytest.mark.parametrize("cfg", [(3, 16, 7, 20, 27), (16, 24, 3, 13, 18), (8, 8, 1, 9, 9)])
+def test_cbconv_sequence_vs_oracle(orc, dt, mode, tol, feedback, cfg):
+    import cbinfer_b200 as cb
+    Cin, Cout, k, H, W = cfg
+    torch.manual_seed(1)
+    conv = nn.Conv2d(Cin, Cout, k, padding=k // 2).cuda().to(TORCH_DT[dt])
+    m = cb.CBConv2d(conv, 0.3)
+    m.withReLU = True
+    m.feedbackLoop = feedback
+    m.saveChangeMap = True
+    m.gemmMode = mode
+    o = orc.OracleCBConv2d(to_np(conv.weight), to_np(conv.bias), 0.3, dtype=ORC_DT[dt],
+                           withReLU=True, feedbackLoop=feedback)
+    frames = _frames((1, Cin, H, W), dt, 5, 0.06, seed=Cin)
+    frames.insert(3, frames[2].clone())          # an unchanged frame: n == 0 must be a no-op
+    for t, f in enumerate(frames):
+        out = m(f)
+        exp = o.forward(to_np(f))
+        assert out is m.prevOutput                 # aliased, as in the reference (conv2d.py:259)
+        assert np.array_equal(m.changeMap.cpu().numpy().astype(np.uint8), o.changeMap), t
+        assert np.array_equal(to_np(m.prevInput), o.prevInput), t      # state is bit-exact
+        assert _rel(to_val(out), orc.from_bits(exp, ORC_DT[dt])) <= tol, t
+    assert int(m._scratch["count"].item()) > 0
+    m(frames[-1])
+    assert int(m._scratch["count"].item()) == 0
+
+
+def test_threshold_zero_equals_dense_conv():
+    """north star: with threshold 0, outputs must match dense nn.Conv2d."""
+    import cbinfer_b200 as cb
+    torch.manual_seed(2)
+    conv = nn.Conv2d(16, 32, 7, padding=3).cuda()
+    for fb in (False, True):
+        m = cb.CBConv2d(conv, 0.0)
+        m.feedbackLoop = fb
+        for f in _frames((2, 16, 24, 31), "f32", 4, 0.1, seed=5):
+            out = m(f)
+            ref = F.conv2d(f, conv.weight, conv.bias, padding=3)
+            assert _rel(to_val(out), to_val(ref)) <= 1e-4
+
+
+def test_tuple_protocol_pool_and_graph(orc):
+    """conv (propChangeIndexes) -> CBPoolMax2d -> conv, eager vs oracle chain, then the same
+    frames replayed through a CUDA graph."""
+    import cbinfer_b200 as cb
+    torch.manual_seed(3)
+    base = nn.Sequential(nn.Conv2d(3, 8, 7, padding=3), nn.ReLU(), nn.MaxPool2d(2, 2),
+                         nn.Conv2d(8, 12, 3, padding=1), nn.ReLU(), nn.Conv2d(12, 5, 1)).cuda().eval()
+    m = cb.convertPools(cb.convert(base, threshold=0.05))
+    for c in m.modules():
+        if type(c) is cb.CBConv2d:
+            c.feedbackLoop = True
+    o1 = orc.OracleCBConv2d(to_np(base[0].weight), to_np(base[0].bias), 0.05, withReLU=True,
+                            feedbackLoop=True, propChangeIndexes=True)
+    op = orc.OracleCBPoolMax2d()
+    o2 = orc.OracleCBConv2d(to_np(base[3].weight), to_np(base[3].bias), 0.05, withReLU=True,
+                            feedbackLoop=True)
+    o3 = orc.OracleCBConv2d(to_np(base[5].weight), to_np(base[5].bias), 0.05, feedbackLoop=True)
+    frames = _frames((1, 3, 22, 30), "f32", 6, 0.05, seed=8)
+    outs = []
+    for f in frames:
+        out = m(f)
+        exp = o3.forward(o2.forward(op.forward(o1.forward(to_np(f)))))
+        assert _rel(to_val(out), exp.astype(np.float64)) <= 2e-4
+        outs.append(out.clone())
+    r = m[0](frames[-1])
+    assert type(r) is tuple and r[0] == 'changeIndexes' and isinstance(r[2], cb.ChangeIndexes)
+    assert len(r[2]) == 0
+    # CUDA graph: reset, warm up on frame 0, capture one step, replay the rest
+    cb.clearMemory(m)
+    static_in = frames[0].clone()
+    m(static_in)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        m(static_in)                                  # warm-up on the capture stream
+    torch.cuda.current_stream().wait_stream(side)
+    with torch.cuda.graph(g):
+        static_out = m(static_in)
+    for t in range(1, len(frames)):
+        static_in.copy_(frames[t])
+        g.replay()
+        assert _rel(to_val(static_out), to_val(outs[t])) <= 1e-6
+
+
+def test_user_supplied_index_tensor(orc):
+    """reference-style callers hand in a plain int32 index tensor (conv2d.py:180-187)."""
+    import cbinfer_b200 as cb
+    x = rand_tensor((1, 6, 10, 12), "f32", 1)
+    pool = cb.CBPoolMax2d(nn.MaxPool2d(2, 2))
+    full = torch.arange(120, dtype=torch.int32, device="cuda")
+    y = pool(('changeIndexes', x, full))
+    assert torch.equal(y, F.max_pool2d(x, 2, 2))
+    x2 = x.clone()
+    x2[0, :, 4, 7] += 3.0
+    y2 = pool(('changeIndexes', x2, torch.tensor([4 * 12 + 7], dtype=torch.int32, device="cuda")))
+    assert torch.equal(y2, F.max_pool2d(x2, 2, 2))
+    assert y2.data_ptr() != pool.outputState.data_ptr()       # clone, conv2d.py:73
+
+
+def test_fine_grained_module(orc):
+    import cbinfer_b200 as cb
+    torch.manual_seed(4)
+    conv = nn.Conv2d(4, 6, 3, padding=1).cuda()
+    m = cb.CBConv2d(conv, 0.2)
+    m.finegrained = True
+    m.withReLU = True
+    o = orc.OracleCBConv2d(to_np(conv.weight), to_np(conv.bias), 0.2, withReLU=True, finegrained=True)
+    for f in _frames((1, 4, 11, 13), "f32", 4, 0.1, seed=2):
+        out = m(f)
+        exp = o.forward(to_np(f))
+        np.testing.assert_allclose(out.cpu().numpy(), exp, rtol=1e-4, atol=1e-4)
+
+
+def test_scene_model_small_vs_dense_and_oracle(orc):
+    """the whole scene-labeling CBinfer model (all convs + pools converted, feedback loop):
+    threshold 0 == dense model; threshold > 0 == oracle chain."""
+    import cbinfer_b200 as cb
+    from cbinfer_b200 import models, video
+    base = models.sceneLabelingBaseline().cuda()
+    frames = [f.cuda() for f in video.sequence(1, 48, 64, 4, 0.05)]
+    m0 = models.sceneLabelingCBinfer(base, experimentIdx=6, threshold=0.0)
+    for f in frames:
+        out = m0(f)
+        with torch.no_grad():
+            ref = base(f)
+        assert _rel(to_val(out), to_val(ref)) <= 2e-4
+    m = models.sceneLabelingCBinfer(base, experimentIdx=6, threshold=0.05)
+    cbs = [mm for mm in m.children()]
+    chain = []
+    for mm in cbs:
+        if type(mm) is cb.CBConv2d:
+            chain.append(orc.OracleCBConv2d(to_np(mm.weight), to_np(mm.bias), 0.05,
+                                            withReLU=mm.withReLU, feedbackLoop=True,
+                                            propChangeIndexes=mm.propChangeIndexes))
+        else:
+            chain.append(orc.OracleCBPoolMax2d())
+    for f in frames:
+        out = m(f)
+        e = to_np(f)
+        for o in chain:
+            e = o.forward(e)
+        assert _rel(to_val(out), e.astype(np.float64)) <= 5e-4
+
+
+@pytest.mark.parametrize("res", [(480, 640)])
+def test_full_size_properties(res):
+    """BASELINE config 2 size (640x480): size-independent properties instead of the slow oracle:
+    threshold 0 == dense; an unchanged frame yields zero changes everywhere and leaves the output
+    bit-identical; index lists are sorted, unique and match the bitmap popcount."""
+    import cbinfer_b200 as cb
+    from cbinfer_b200 import models, video
+    H, W = res
+    base = models.sceneLabelingBaseline().cuda()
+    frames = [f.cuda() for f in video.sequence(1, H, W, 3, 0.05)]
+    m = models.sceneLabelingCBinfer(base, experimentIdx=6, threshold=0.0)
+    for f in frames:
+        out = m(f)
+    with torch.no_grad():
+        ref = base(frames[-1])
+    assert _rel(to_val(out), to_val(ref)) <= 2e-4
+    convs = [mm for mm in m.modules() if type(mm) is cb.CBConv2d]
+    n1 = int(convs[0]._scratch["count"].item())
+    assert 0.05 * H * W <= n1 <= 0.08 * H * W          # 5 % block + 3-pixel dilation ring
+    idx = convs[0]._scratch["idx"][:n1]
+    assert bool((idx[1:] > idx[:-1]).all())
+    bits = convs[0]._scratch["dil_bits"].cpu().numpy().view(np.uint32)
+    assert int(np.unpackbits(bits.view(np.uint8)).sum()) == n1
+    before = out.clone()
+    out2 = m(frames[-1])
+    assert all(int(c._scratch["count"].item()) == 0 for c in convs)
+    assert torch.equal(out2, before)
+
+
+# ---------------------------------------------------------------------------------------------
+# the UNMODIFIED reference kernels on the same GPU (oracle/_ref, PTX JIT)
+# ---------------------------------------------------------------------------------------------
+
+def _ref_or_skip(name):
+    lib = ref_lib(name)
+    if lib is None:
+        pytest.skip("oracle/_ref/%s not built (reference checkout absent at build time)" % name)
+    return lib
+
+
+@pytest.mark.parametrize("half", [False, True])
+def test_reference_cuda_kernels_change_detection(half):
+    """bit-exact masks + feedback state vs cbconv2d_cg[_half]_backend.cu run on this GPU."""
+    from cbinfer_b200 import conv2d_cg as cg
+    lib = _ref_or_skip("cbconv2d_cg_half_backend" if half else "cbconv2d_cg_backend")
+    dt = "f16" if half else "f32"
+    for (C, H, W, k, thr) in ((16, 400, 300, 3, 0.1), (3, 97, 131, 7, 0.3), (64, 30, 40, 1, 0.5)):
+        prev = rand_tensor((1, C, H, W), dt, C)
+        x = perturb(prev, 0.05, C + 1, scale=0.7)
+        for update in (False, True):
+            st_ref = prev.clone()
+            cmap_ref = torch.zeros(H, W, dtype=torch.int8, device="cuda")
+            grid = (H * W - 1) // 128 + 1
+            lib.changeDetection(1, 1, grid, 1, 1, 128, vp(x), vp(st_ref), vp(cmap_ref), W, H, C,
+                                (k - 1) // 2, (k - 1) // 2, ctypes.c_float(thr), ctypes.c_bool(update))
+            torch.cuda.synchronize()
+            st = prev.clone()
+            cmap = cg.changeDetection(x, st, (k, k), thr, updateInputState=update)
+            assert torch.equal(cmap, cmap_ref)
+            assert torch.equal(st, st_ref)
+            idx = cg.changeIndexesExtr(cmap)
+            assert torch.equal(idx, torch.nonzero(cmap_ref.view(-1)).int().view(-1))
+
+
+def test_reference_cuda_kernels_gather_scatter_pool():
+    from cbinfer_b200 import conv2d_cg as cg
+    lib = _ref_or_skip("cbconv2d_cg_backend")
+    C, H, W, k, Cout = 8, 37, 53, 7, 12
+    x = rand_tensor((1, C, H, W), "f32", 1)
+    g = torch.Generator().manual_seed(2)
+    idx = torch.nonzero(torch.rand(H * W, generator=g) < 0.2).view(-1).int().cuda()
+    n = idx.numel()
+    # genXMatrix
+    X_ref = torch.zeros(n, C * k * k, device="cuda")
+    tz = 128 // (k * k)
+    lib.genXMatrix(1, 1, (n - 1) // tz + 1, k, tz, k, vp(X_ref), vp(x), vp(idx), k, k, C, W, H, n)
+    assert torch.equal(cg.genXMatrix(x, idx, (k, k)), X_ref)
+    # updateOutput
+    Yt = rand_tensor((Cout, n), "f32", 3)
+    po_ref = rand_tensor((1, Cout, H, W), "f32", 4)
+    po = po_ref.clone()
+    lib.updateOutput(1, 1, (n * Cout - 1) // 1024 + 1, 1, 1, 1024, vp(Yt), vp(po_ref), vp(idx),
+                     H * W, n, Cout, ctypes.c_bool(True))
+    cg.updateOutput(Yt, idx, po, withReLU=True)
+    assert torch.equal(po, po_ref)
+    # maxPool2d (even sizes: the reference kernel has no bounds guard for odd ones)
+    xe = rand_tensor((1, C, 36, 52), "f32", 5)
+    idx2 = torch.nonzero(torch.rand(36 * 52, generator=g) < 0.2).view(-1).int().cuda()
+    st_ref = torch.full((1, C, 18, 26), float("inf"), device="cuda")
+    st = st_ref.clone()
+    lib.maxPool2d((idx2.numel() - 1) // 64 + 1, 64, vp(xe), vp(st_ref), vp(idx2), idx2.numel(), C,
+                  36, 52, 18, 26, 2, 2)
+    cg.maxPool2d(xe, st, idx2)
+    torch.cuda.synchronize()
+    assert torch.equal(st, st_ref)
+
+
+def test_reference_cuda_fg_kernels():
+    from cbinfer_b200 import conv2d_fg as fg
+    lib = _ref_or_skip("cbconv2d_fg_backend")
+    Cin, Cout, H, W, k = 5, 7, 21, 26, 3
+    prev = rand_tensor((1, Cin, H, W), "f32", 1)
+    x = perturb(prev, 0.1, 2)
+    w = rand_tensor((Cout, Cin, k, k), "f32", 3, scale=0.3)
+    out_ref = rand_tensor((1, Cout, H, W), "f32", 4)
+    out = out_ref.clone()
+    diffs = torch.zeros_like(x)
+    cmap = torch.zeros(x.shape, dtype=torch.int8, device="cuda")
+    lib.changeDetectionFG(vp(x), vp(prev), vp(diffs), vp(cmap), x.numel(), ctypes.c_float(0.2))
+    coords = torch.nonzero(cmap.view(-1)).view(-1).contiguous()
+    nchg = coords.numel()
+    lib.updateOutputFG(1, 1, (nchg - 1) // 128 + 1, 1, 1, 128, vp(diffs), vp(w), vp(out_ref),
+                       vp(coords), Cout, Cin, H, W, k, k, nchg)
+    cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+    fg.cbconvFG(x, prev.clone(), out, w, 0.2, cnt)
+    torch.cuda.synchronize()
+    assert int(cnt.item()) == nchg
+    np.testing.assert_allclose(out.cpu().numpy(), out_ref.cpu().numpy(), rtol=1e-5, atol=1e-4)

@@ -1,0 +1,338 @@
+"""GPU parity tests, op level: every kernel of libcbinfer_sm100.so (called through the C ABI via
+the python wrappers) against the CPU oracle on the same seeded inputs.
+
+Bars: bit-exact for change masks, bitmaps, index lists, im2col copies, scatters and pooling;
+stated tolerances for the contraction.
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests.util import (ORC_DT, TORCH_DT, bits_to_map, perturb, rand_tensor, to_np, to_val)
+
+pytestmark = pytest.mark.gpu
+
+# tolerance of the fused contraction vs the fp64-accumulated oracle, relative to max|ref| of the
+# compared tensor: (gemm mode, dtype) -> rel
+CONV_TOL = {
+    ("simt", "f32"): 2e-5,     # fp32 FFMA, fp32 accumulation
+    ("tc3x", "f32"): 1e-4,     # 3xTF32 split: north-star bar "rel 1e-4 fp32"
+    ("tc", "f32"): 4e-3,       # single-pass TF32 (10-bit mantissa), opt-in fast mode
+    ("simt", "f16"): 2e-3, ("tc", "f16"): 2e-3,      # output rounding to fp16 dominates
+    ("simt", "bf16"): 1e-2, ("tc", "bf16"): 1e-2,    # north-star bar "1e-2 bf16"
+}
+
+
+@pytest.fixture(scope="module")
+def cbm():
+    import cbinfer_b200 as cb
+    from cbinfer_b200 import _lib, conv2d_cg, conv2d_fg
+    assert torch.cuda.is_available()
+    return dict(cb=cb, lib=_lib, cg=conv2d_cg, fg=conv2d_fg)
+
+
+def kat_input(seed=1234):
+    rs = np.random.RandomState(seed)
+    inp = rs.randn(1, 16, 400, 300).astype(np.float32)
+    prev = inp.copy()
+    for (c, y, x, d) in ((0, 0, 4, 1.00), (1, 6, 9, 0.05), (2, 10, 4, -11.00), (1, 6, 19, -0.05)):
+        prev[0, c, y, x] += np.float32(d)
+    return inp, prev, 0.1, (3, 3)
+
+
+# ---------------------------------------------------------------------------------------------
+# change detection + propagation + compaction
+# ---------------------------------------------------------------------------------------------
+
+def test_kat1_reference_gentestdata(cbm, orc, golden):
+    """conv2d_cg.py:84-97,136-142: the reference's own KAT -- 15 dilated pixels."""
+    cg = cbm["cg"]
+    inp, prev, thr, fs = kat_input(int(golden["kat1_seed"]))
+    x = torch.from_numpy(inp).cuda()
+    for layout in ("planar", "pixel"):
+        st = torch.from_numpy(prev).cuda()
+        xx = x
+        if layout == "pixel":
+            xx = x.contiguous(memory_format=torch.channels_last)
+            st = st.contiguous(memory_format=torch.channels_last)
+        cmap = cg.changeDetection(xx, st, fs, thr)
+        idx = cg.changeIndexesExtr(cmap)
+        assert idx.dtype == torch.int32
+        assert idx.cpu().tolist() == golden["kat1_map_idx"].tolist()
+        assert np.array_equal(cmap.cpu().numpy().astype(np.uint8),
+                              orc.changeDetection(inp, prev.copy(), fs, thr))
+        X = cg.genXMatrix(x, idx, fs)
+        assert np.array_equal(X.cpu().numpy(), golden["kat1_X"])
+
+
+def test_kat2_change_indexes(cbm):
+    """conv2d_cg.py:215-236."""
+    cm = torch.zeros(129, 254, dtype=torch.int8)
+    for (y, x) in ((3, 3), (7, 5), (5, 7), (7, 1), (1, 5), (24, 31)):
+        cm[y][x] = 1
+    idx = cbm["cg"].changeIndexesExtr(cm.cuda())
+    assert idx.cpu().tolist() == [259, 765, 1277, 1779, 1783, 6127]
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d"])
+def test_golden_twins(cbm, golden, tag):
+    """every staged op against the outputs of the reference's python twins."""
+    cg = cbm["cg"]
+    C, H, W, kH, kW, Cout, relu = [int(v) for v in golden[f"{tag}_params"]]
+    thr = float(golden[f"{tag}_thr"])
+    f0 = torch.from_numpy(golden[f"{tag}_f0"]).cuda()
+    f1 = torch.from_numpy(golden[f"{tag}_f1"]).cuda()
+    cmap = cg.changeDetection(f1, f0.clone(), (kH, kW), thr)
+    assert np.array_equal(cmap.cpu().numpy().astype(np.uint8), golden[f"{tag}_map"])
+    raw = cg.changeDetection(f1, f0.clone(), (1, 1), thr)
+    assert np.array_equal(raw.cpu().numpy().astype(np.uint8), golden[f"{tag}_raw"])
+    prop = cg.changePropagation(raw, (kH, kW))
+    assert np.array_equal(prop.cpu().numpy().astype(np.uint8), golden[f"{tag}_prop"])
+    idx = cg.changeIndexesExtr(cmap)
+    assert np.array_equal(idx.cpu().numpy(), golden[f"{tag}_idx"])
+    X = cg.genXMatrix(f1, idx, (kH, kW))
+    assert np.array_equal(X.cpu().numpy(), golden[f"{tag}_X"])
+    Y = cg.matrixMult(X, torch.from_numpy(golden[f"{tag}_w"]).cuda(),
+                      torch.from_numpy(golden[f"{tag}_b"]).cuda())
+    np.testing.assert_allclose(Y.cpu().numpy(), golden[f"{tag}_Y"], rtol=1e-5, atol=1e-5)
+    po = torch.from_numpy(golden[f"{tag}_prevOut"].copy()).cuda()
+    Yt = torch.from_numpy(np.ascontiguousarray(golden[f"{tag}_Y"].T)).cuda()
+    out = cg.updateOutput(Yt, idx, po, withReLU=bool(relu))
+    assert np.array_equal(out.cpu().numpy(), golden[f"{tag}_out"])
+
+
+DET_CASES = [  # B, C, H, W, kH, kW, thr
+    (1, 3, 15, 20, 3, 3, 0.4), (1, 16, 33, 65, 7, 7, 0.6), (2, 5, 9, 14, 5, 3, 0.5),
+    (1, 64, 12, 31, 1, 1, 0.3), (3, 8, 7, 96, 3, 7, 0.7), (1, 38, 10, 46, 7, 7, 0.5),
+    (1, 185, 6, 9, 7, 7, 0.9), (1, 4, 1, 1, 3, 3, 0.1), (1, 2, 40, 300, 9, 9, 0.8),
+]
+
+
+@pytest.mark.parametrize("dt", ["f32", "f16", "bf16"])
+@pytest.mark.parametrize("layout", ["planar", "pixel"])
+@pytest.mark.parametrize("case", DET_CASES)
+def test_detect_dilate_compact(cbm, orc, dt, layout, case):
+    """bit-exact mask, feedback-updated state and index list; planar = generic-stride kernel,
+    pixel = vectorised pixel-major kernel (incl. padded pitch for C % vec != 0)."""
+    cg, lib = cbm["cg"], cbm["lib"]
+    B, C, H, W, kH, kW, thr = case
+    prev = rand_tensor((B, C, H, W), dt, seed=sum(case[:4]) + 1)
+    x = perturb(prev, 0.08, seed=B * 7 + C, scale=1.0)
+    if layout == "pixel":
+        xv, _ = cg.pixel_major((B, C, H, W), TORCH_DT[dt], "cuda", 0)
+        xv.copy_(x)
+        sv, _ = cg.pixel_major((B, C, H, W), TORCH_DT[dt], "cuda", 0)
+        sv.copy_(prev)
+    else:
+        xv, sv = x.contiguous(), prev.clone().contiguous()
+    for update in (False, True):
+        st = sv.clone() if layout == "planar" else cg.pixel_major((B, C, H, W), TORCH_DT[dt], "cuda", 0)[0]
+        st.copy_(prev)
+        s = cg.alloc_scratch((B, H, W), "cuda", want_map=True)
+        cg.detect(xv, st, s["raw_bits"], thr, lib.UPDATE_CHANGED if update else lib.UPDATE_NONE)
+        cg.dilate_compact(s["raw_bits"], (B, H, W), (kH, kW), s["idx"], s["count"], s["ws"],
+                          dil_bits=s["dil_bits"], dil_map=s["dil_map"])
+        n = int(s["count"].item())
+        got_idx = s["idx"][:n].cpu().numpy()
+        exp_maps, exp_idx, exp_state = [], [], []
+        for b in range(B):
+            xb, pb = to_np(x[b:b + 1]), to_np(prev[b:b + 1])
+            m, raw = orc.changeDetection(xb, pb, (kH, kW), thr, updateInputState=update,
+                                         dtype=ORC_DT[dt], return_raw=True)
+            exp_maps.append(m)
+            exp_idx.append(orc.changeIndexesExtr(m) + b * H * W)
+            exp_state.append(pb)
+            assert np.array_equal(bits_to_map(s["raw_bits"], B, H, W)[b], raw)
+        assert np.array_equal(s["dil_map"].cpu().numpy().astype(np.uint8), np.stack(exp_maps))
+        assert np.array_equal(bits_to_map(s["dil_bits"], B, H, W), np.stack(exp_maps))
+        assert np.array_equal(got_idx, np.concatenate(exp_idx))
+        assert np.array_equal(to_np(st), np.concatenate(exp_state))           # feedback writes
+        # workspace self-cleans: a second call gives the same answer
+        cg.dilate_compact(s["raw_bits"], (B, H, W), (kH, kW), s["idx"], s["count"], s["ws"])
+        assert int(s["count"].item()) == n
+
+
+def test_detect_update_all_and_special_values(cbm, orc):
+    cg, lib = cbm["cg"], cbm["lib"]
+    x = torch.zeros(1, 1, 2, 4, device="cuda")
+    st = torch.tensor([[[[0.5, 1e-40, float("nan"), float("inf")],
+                         [-0.5, 0.6, -0.6, float("-inf")]]]], device="cuda")
+    for thr, expect in ((0.5, [[0, 0, 0, 1], [0, 1, 1, 1]]), (0.0, [[1, 0, 0, 1], [1, 1, 1, 1]])):
+        m = cg.changeDetection(x, st.clone(), (1, 1), thr)
+        assert m.cpu().tolist() == expect
+        assert orc.changeDetection(to_np(x), to_np(st), (1, 1), thr).tolist() == expect
+    # fresh state (+inf) marks everything; UPDATE_ALL copies the whole frame (conv2d.py:236)
+    xx = rand_tensor((2, 6, 5, 37), "f32", 3)
+    view, _ = cg.pixel_major(xx.shape, torch.float32, "cuda", float("inf"))
+    s = cg.alloc_scratch((2, 5, 37), "cuda")
+    cg.detect(xx, view, s["raw_bits"], 0.1, lib.UPDATE_ALL)
+    assert bits_to_map(s["raw_bits"], 2, 5, 37).all()
+    assert torch.equal(view, xx)
+
+
+def test_large_compaction_chained_scan(cbm):
+    """many tiles -> exercises the decoupled look-back; checksum + sortedness properties."""
+    cg = cbm["cg"]
+    B, H, W = 3, 1080, 1920
+    g = torch.Generator().manual_seed(9)
+    m = (torch.rand(B, H, W, generator=g) < 0.07).to(torch.int8).cuda()
+    ci = cg.changeIndexesExtr(m, lazy=True)
+    n = len(ci)
+    idx = ci.tensor()
+    ref = torch.nonzero(m.view(-1)).int().view(-1)
+    assert n == ref.numel() and torch.equal(idx, ref)
+    d = cg.changePropagation(m, (7, 7))
+    ref_d = torch.nn.functional.max_pool2d(m.float().unsqueeze(1), 7, 1, 3).squeeze(1).to(torch.int8)
+    assert torch.equal(d, ref_d)
+
+
+# ---------------------------------------------------------------------------------------------
+# fused gather + contraction + scatter
+# ---------------------------------------------------------------------------------------------
+
+CONV_CASES = [  # B, Cin, Cout, H, W, kH, kW, frac, relu
+    (1, 3, 16, 24, 40, 7, 7, 0.10, True),
+    (1, 16, 64, 20, 33, 7, 7, 0.15, True),
+    (2, 64, 256, 9, 12, 7, 7, 0.30, True),
+    (1, 256, 64, 10, 16, 1, 1, 0.40, True),
+    (1, 64, 8, 10, 16, 1, 1, 1.00, False),
+    (1, 185, 38, 8, 11, 7, 7, 0.50, False),
+    (1, 128, 19, 6, 7, 3, 3, 1.00, True),
+    (1, 5, 6, 9, 14, 5, 3, 0.60, True),
+    (1, 40, 130, 6, 5, 3, 3, 1.00, False),
+]
+
+
+def _oracle_conv(orc, state_np, idx_np, w_np, b_np, out_np, filt, relu, dtype, B, H, W):
+    """per-image reference: genXMatrix -> matrixMult (fp64 acc) -> updateOutput."""
+    for b in range(B):
+        sel = idx_np[(idx_np >= b * H * W) & (idx_np < (b + 1) * H * W)] - b * H * W
+        X = orc.genXMatrix(state_np[b:b + 1], sel.astype(np.int32), filt, dtype)
+        Y = orc.matrixMult(X, w_np, b_np, dtype)
+        ob = np.ascontiguousarray(out_np[b:b + 1])
+        orc.updateOutput(np.ascontiguousarray(Y.T), sel.astype(np.int32), ob, relu, dtype)
+        out_np[b:b + 1] = ob
+    return out_np
+
+
+@pytest.mark.parametrize("mode,dt", [("simt", "f32"), ("tc3x", "f32"), ("tc", "f32"),
+                                     ("tc", "bf16"), ("tc", "f16"), ("simt", "bf16")])
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_update(cbm, orc, mode, dt, case):
+    cg, lib, cb = cbm["cg"], cbm["lib"], cbm["cb"]
+    B, Cin, Cout, H, W, kH, kW, frac, relu = case
+    tdt = TORCH_DT[dt]
+    gemm = cb.CBConv2d.GEMM_MODES[mode]
+    state, sbuf = cg.pixel_major((B, Cin, H, W), tdt, "cuda", 0)
+    state.copy_(rand_tensor((B, Cin, H, W), dt, seed=Cin + H))
+    out, obuf = cg.pixel_major((B, Cout, H, W), tdt, "cuda", 0)
+    out.copy_(rand_tensor((B, Cout, H, W), dt, seed=Cout + W))
+    w = rand_tensor((Cout, Cin, kH, kW), dt, seed=11, scale=(Cin * kH * kW) ** -0.5)
+    bias = rand_tensor((Cout,), dt, seed=12)
+    g = torch.Generator().manual_seed(5)
+    sel = torch.nonzero(torch.rand(B * H * W, generator=g) < frac).view(-1).int().cuda()
+    ci = cg.ChangeIndexes.from_tensor(sel, (B, H, W))
+    out_before = to_np(out).copy()
+    packed = cg.pack_weights(w, gemm)
+    cg.conv_update(sbuf, ci, packed, bias.float().contiguous(), obuf, Cin, Cout, (kH, kW), relu, gemm)
+    torch.cuda.synchronize()
+    exp = _oracle_conv(orc, to_np(state), sel.cpu().numpy(), to_np(w), to_np(bias), out_before,
+                       (kH, kW), relu, ORC_DT[dt], B, H, W)
+    got_v, exp_v = to_val(out), orc.from_bits(exp, ORC_DT[dt])
+    # untouched pixels must be bit-identical; touched ones within tolerance
+    touched = np.zeros(B * H * W, bool)
+    touched[sel.cpu().numpy()] = True
+    tm = np.broadcast_to(touched.reshape(B, 1, H, W), got_v.shape)
+    assert np.array_equal(to_np(out)[~tm], exp[~tm])
+    if touched.any():
+        scale = np.abs(exp_v[tm]).max() + 1e-30
+        err = np.abs(got_v[tm] - exp_v[tm]).max() / scale
+        assert err <= CONV_TOL[(mode, dt)], (err, mode, dt)
+    # pad channels of the pixel-major buffer stay zero
+    assert float(obuf[..., Cout:].abs().sum()) == 0.0
+
+
+def test_conv_update_zero_changes_is_noop(cbm):
+    cg, lib = cbm["cg"], cbm["lib"]
+    state, sbuf = cg.pixel_major((1, 16, 8, 8), torch.float32, "cuda", 1.0)
+    out, obuf = cg.pixel_major((1, 32, 8, 8), torch.float32, "cuda", 7.0)
+    w = rand_tensor((32, 16, 3, 3), "f32", 1)
+    ci = cg.ChangeIndexes.from_tensor(torch.zeros(0, dtype=torch.int32, device="cuda"), (1, 8, 8))
+    for gemm in (lib.GEMM_SIMT_F32, lib.GEMM_TC, lib.GEMM_TC_3X):
+        cg.conv_update(sbuf, ci, cg.pack_weights(w, gemm), torch.zeros(32, device="cuda"), obuf,
+                       16, 32, (3, 3), True, gemm)
+    torch.cuda.synchronize()
+    assert float((out - 7.0).abs().max()) == 0.0
+
+
+# ---------------------------------------------------------------------------------------------
+# pooling
+# ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("dt", ["f32", "f16", "bf16"])
+@pytest.mark.parametrize("layout", ["planar", "pixel"])
+@pytest.mark.parametrize("shape,ceil", [((1, 16, 8, 10), False), ((2, 5, 9, 13), True),
+                                        ((1, 64, 7, 7), False), ((1, 3, 1, 2), True)])
+def test_maxpool(cbm, orc, dt, layout, shape, ceil):
+    cg = cbm["cg"]
+    B, C, H, W = shape
+    oH, oW = ((H - 1) // 2 + 1, (W - 1) // 2 + 1) if ceil else (H // 2, W // 2)
+    x0 = rand_tensor(shape, dt, 21)
+    if layout == "pixel":
+        xv, _ = cg.pixel_major(shape, TORCH_DT[dt], "cuda", 0)
+        xv.copy_(x0)
+        st, _ = cg.pixel_major((B, C, oH, oW), TORCH_DT[dt], "cuda", float("inf"))
+    else:
+        xv = x0
+        st = torch.full((B, C, oH, oW), float("inf"), dtype=TORCH_DT[dt], device="cuda")
+    g = torch.Generator().manual_seed(4)
+    m = (torch.rand(B, H, W, generator=g) < 0.3).to(torch.int8).cuda()
+    for with_bits in (False, True):
+        ci = cg.changeIndexesExtr(m, lazy=True)
+        if with_bits:
+            ci.bits = cg._map_to_bits(m)[0]
+        stc = st.clone() if layout == "planar" else cg.pixel_major((B, C, oH, oW), TORCH_DT[dt], "cuda", float("inf"))[0]
+        cg.maxPool2d(xv, stc, ci)
+        exp = []
+        for b in range(B):
+            eb = orc.inf_like((1, C, oH, oW), ORC_DT[dt])
+            sel = orc.changeIndexesExtr(m[b].cpu().numpy())
+            orc.maxPool2d(to_np(x0[b:b + 1]), eb, sel, dtype=ORC_DT[dt])
+            exp.append(eb)
+        assert np.array_equal(to_np(stc), np.concatenate(exp))
+
+
+# ---------------------------------------------------------------------------------------------
+# fine-grained path
+# ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("tag", ["fg1", "fg2"])
+def test_fg_golden(cbm, golden, tag):
+    """cbconvFG_test1 (conv2d_fg.py:98-150) data through the fused FG kernel vs the reference's
+    native conv2d_fg_cpu output; tolerance 1e-4 abs (atomics reorder fp32 sums)."""
+    fg = cbm["fg"]
+    out = torch.from_numpy(golden[f"{tag}_prevOut"].copy()).cuda()
+    prev = torch.from_numpy(golden[f"{tag}_prev"].copy()).cuda()
+    x = torch.from_numpy(golden[f"{tag}_in"]).cuda()
+    cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+    fg.cbconvFG(x, prev, out, torch.from_numpy(golden[f"{tag}_w"]).cuda(), float(golden[f"{tag}_thr"]), cnt)
+    np.testing.assert_allclose(out.cpu().numpy(), golden[f"{tag}_out"], rtol=1e-5, atol=1e-4)
+    assert torch.equal(prev, x)
+    d = np.abs(golden[f"{tag}_in"] - golden[f"{tag}_prev"])
+    assert int(cnt.item()) == int((d > float(golden[f"{tag}_thr"])).sum())
+
+
+def test_fg_random_vs_oracle(cbm, orc):
+    fg = cbm["fg"]
+    B, Cin, Cout, H, W, kH, kW = 2, 6, 10, 17, 23, 7, 3
+    prev = rand_tensor((B, Cin, H, W), "f32", 31)
+    x = perturb(prev, 0.1, 32)
+    w = rand_tensor((Cout, Cin, kH, kW), "f32", 33, scale=0.2)
+    out0 = rand_tensor((B, Cout, H, W), "f32", 34)
+    out = out0.clone()
+    p = prev.clone()
+    fg.cbconvFG(x, p, out, w, 0.25)
+    for b in range(B):
+        e = to_np(out0[b:b + 1])
+        orc.cbconvFG(to_np(x[b:b + 1]), to_np(prev[b:b + 1]), e, to_np(w), 0.25)
+        np.testing.assert_allclose(out[b:b + 1].cpu().numpy(), e, rtol=1e-5, atol=1e-4)
