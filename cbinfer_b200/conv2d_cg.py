@@ -46,6 +46,8 @@ class ChangeIndexes(object):
     def from_tensor(cls, idx, shape):
         idx = idx.to(torch.int32).contiguous()
         count = torch.full((1,), idx.numel(), dtype=torch.int32, device=idx.device)
+        if idx.numel() == 0:                  # keep a valid device pointer for the C ABI
+            idx = torch.zeros(1, dtype=torch.int32, device=idx.device)
         return cls(idx, count, shape)
 
     def tensor(self):
