@@ -105,7 +105,7 @@ int cb_dilate_compact(void* stream, const uint32_t* raw_bits, uint32_t* dil_bits
     CB_CHECK_LAUNCH("dilate_compact(memset)");
     return 0;
   }
-  const int ntiles = (int)((nwords + kCompactThreads - 1) / kCompactThreads);
+  const int ntiles = (int)((nwords + kCompactTile - 1) / kCompactTile);
   dilate_compact_kernel<<<ntiles, kCompactThreads, 0, s>>>(raw_bits, dil_bits, dil_map, idx, count,
                                                           ws, B, H, W, (W + 31) / 32, kHHalf,
                                                           kWHalf, nwords, ntiles);
@@ -180,10 +180,28 @@ int cb_maxpool2x2(void* stream, int dtype, const void* x, long long x_sb, long l
                   long long o_sy, long long o_sx, int B, int C, int H, int W, int oH, int oW) {
   CB_CHECK_ARG(x && idx && count && out, "maxpool2x2: null pointer");
   if (B == 0 || H == 0 || W == 0 || C == 0) return 0;
-  const unsigned grid = (unsigned)(sm_count() * 8);
-  CB_DISPATCH_DTYPE(dtype, (maxpool2x2_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
-                               (const T*)x, x_sb, x_sc, x_sy, x_sx, idx, count, dil_bits, (T*)out,
-                               o_sb, o_sc, o_sy, o_sx, C, H, W, oH, oW)));
+  const unsigned grid = (unsigned)(sm_count() * 16);
+  const size_t es = cb::esize(dtype);
+  const int vec = (int)(16 / es);
+  // pixel-major fast path: channel-contiguous, 16-byte aligned pixels on both sides.  Chunks that
+  // cover pad channels (pitch > C) are processed too: pads are zero on both sides by construction.
+  const bool vec_ok = x_sc == 1 && o_sc == 1 && (x_sx % vec) == 0 && (o_sx % vec) == 0 &&
+                      x_sx == o_sx && x_sx >= C && x_sx < (1 << 20) && ((x_sy * es) % 16) == 0 &&
+                      ((o_sy * es) % 16) == 0 && ((x_sb * es) % 16) == 0 && ((o_sb * es) % 16) == 0 &&
+                      ((uintptr_t)x % 16) == 0 && ((uintptr_t)out % 16) == 0 &&
+                      (x_sx == C || (C + vec - 1) / vec * vec == x_sx);
+  if (vec_ok) {
+    const int cpp = (int)(x_sx / vec);
+    int glog = 0;
+    while ((1 << glog) < cpp && glog < 5) ++glog;
+    CB_DISPATCH_DTYPE(dtype, (maxpool2x2_vec_kernel<T, VEC><<<grid, 256, 0, (cudaStream_t)stream>>>(
+                                 (const T*)x, x_sb, x_sy, (int)x_sx, idx, count, dil_bits, (T*)out,
+                                 o_sb, o_sy, (int)o_sx, cpp, glog, H, W, oH, oW)));
+  } else {
+    CB_DISPATCH_DTYPE(dtype, (maxpool2x2_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
+                                 (const T*)x, x_sb, x_sc, x_sy, x_sx, idx, count, dil_bits, (T*)out,
+                                 o_sb, o_sc, o_sy, o_sx, C, H, W, oH, oW)));
+  }
   CB_CHECK_LAUNCH("maxpool2x2");
   return 0;
 }

@@ -14,14 +14,16 @@
 
 namespace cb {
 
-constexpr int kCompactThreads = 256;           // words per tile
+constexpr int kCompactThreads = 512;
+constexpr int kCompactWPT = 2;                               // words per thread
+constexpr int kCompactTile = kCompactThreads * kCompactWPT;  // words per tile (32768 pixels)
 
 struct CompactHeader {                         // first 16 bytes of the workspace
-  unsigned ticket, done, epoch, pad;
+  unsigned reserved, done, epoch, pad;
 };
 
 __host__ __device__ inline size_t compact_ws_bytes(size_t nwords) {
-  const size_t tiles = (nwords + kCompactThreads - 1) / kCompactThreads;
+  const size_t tiles = (nwords + kCompactTile - 1) / kCompactTile;
   return sizeof(CompactHeader) + 8 * (tiles + 1);
 }
 
@@ -30,6 +32,30 @@ __device__ __forceinline__ unsigned long long pack_state(unsigned tag, unsigned 
   return ((unsigned long long)tag << 34) | ((unsigned long long)status << 32) | v;
 }
 
+// One dilated bitmap word: vertical OR of the raw rows in the window, then horizontal dilation
+// with funnel shifts across the neighbouring words.
+__device__ __forceinline__ unsigned dilated_word(const uint32_t* __restrict__ raw, long long r,
+                                                 int y, int j, int H, int W, int Wd, int kh,
+                                                 int kw) {
+  unsigned vp = 0, vc = 0, vn = 0;
+  const int y0 = max(0, y - kh), y1 = min(H - 1, y + kh);
+  const uint32_t* row = raw + (r - y + y0) * Wd + j;
+  for (int yy = y0; yy <= y1; ++yy, row += Wd) {
+    vc |= __ldg(row);
+    if (j > 0) vp |= __ldg(row - 1);
+    if (j + 1 < Wd) vn |= __ldg(row + 1);
+  }
+  unsigned d = vc;
+  for (int dx = 1; dx <= kw; ++dx) {
+    d |= (vc << dx) | (vp >> (32 - dx));       // source pixel dx to the left
+    d |= (vc >> dx) | (vn << (32 - dx));       // source pixel dx to the right
+  }
+  if (j == Wd - 1 && (W & 31)) d &= (1u << (W & 31)) - 1u;
+  return d;
+}
+
+// Tiles are taken in blockIdx order (blocks are dispatched in index order, so every predecessor of
+// a running tile is running or finished and the look-back cannot starve).
 __global__ void __launch_bounds__(kCompactThreads)
 dilate_compact_kernel(const uint32_t* __restrict__ raw, uint32_t* __restrict__ dil_bits,
                       int8_t* __restrict__ dil_map, int32_t* __restrict__ idx,
@@ -38,47 +64,33 @@ dilate_compact_kernel(const uint32_t* __restrict__ raw, uint32_t* __restrict__ d
   CompactHeader* hdr = reinterpret_cast<CompactHeader*>(ws);
   volatile unsigned long long* tstate =
       reinterpret_cast<volatile unsigned long long*>(reinterpret_cast<char*>(ws) + sizeof(CompactHeader));
-  __shared__ unsigned s_tile, s_epoch;
-  __shared__ int s_warp[kCompactThreads / 32];
+  constexpr int NW = kCompactThreads / 32;
+  __shared__ int s_warp[NW];
   __shared__ int s_base;
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  if (tid == 0) {
-    s_epoch = *reinterpret_cast<volatile unsigned*>(&hdr->epoch);
-    s_tile = atomicAdd(&hdr->ticket, 1u);      // ticket order == start order: look-back is safe
-  }
-  __syncthreads();
-  const int tile = (int)s_tile;
-  const unsigned tag = s_epoch % 0x3ffffffeu + 1u;
+  const int tile = blockIdx.x;
+  const unsigned epoch = *reinterpret_cast<volatile unsigned*>(&hdr->epoch);
+  const unsigned tag = epoch % 0x3ffffffeu + 1u;
 
-  // ---- dilated word --------------------------------------------------------------------
-  const long long w = (long long)tile * kCompactThreads + tid;
-  unsigned d = 0;
-  int j = 0, y = 0;
-  long long r = 0;
-  if (w < nwords) {
-    j = (int)(w % Wd);
-    r = w / Wd;
-    y = (int)(r % H);
-    unsigned vp = 0, vc = 0, vn = 0;
-    const int y0 = max(0, y - kh), y1 = min(H - 1, y + kh);
-    const uint32_t* row = raw + (r - y + y0) * Wd + j;
-    for (int yy = y0; yy <= y1; ++yy, row += Wd) {
-      vc |= __ldg(row);
-      if (j > 0) vp |= __ldg(row - 1);
-      if (j + 1 < Wd) vn |= __ldg(row + 1);
+  // ---- dilated words (consecutive words per thread keep the index order) ------------------
+  unsigned d[kCompactWPT];
+  int cnt = 0;
+  const long long w0 = (long long)tile * kCompactTile + (long long)tid * kCompactWPT;
+#pragma unroll
+  for (int i = 0; i < kCompactWPT; ++i) {
+    const long long w = w0 + i;
+    d[i] = 0;
+    if (w < nwords) {
+      const int j = (int)(w % Wd);
+      const long long r = w / Wd;
+      d[i] = dilated_word(raw, r, (int)(r % H), j, H, W, Wd, kh, kw);
+      if (dil_bits) dil_bits[w] = d[i];
     }
-    d = vc;
-    for (int dx = 1; dx <= kw; ++dx) {
-      d |= (vc << dx) | (vp >> (32 - dx));     // source pixel dx to the left
-      d |= (vc >> dx) | (vn << (32 - dx));     // source pixel dx to the right
-    }
-    if (j == Wd - 1 && (W & 31)) d &= (1u << (W & 31)) - 1u;
-    if (dil_bits) dil_bits[w] = d;
+    cnt += __popc(d[i]);
   }
 
   // ---- block scan of popcounts -----------------------------------------------------------
-  const int cnt = __popc(d);
   int incl = cnt;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -88,15 +100,15 @@ dilate_compact_kernel(const uint32_t* __restrict__ raw, uint32_t* __restrict__ d
   if (lane == 31) s_warp[wid] = incl;
   __syncthreads();
   if (wid == 0) {
-    int v = lane < kCompactThreads / 32 ? s_warp[lane] : 0;
+    int v = lane < NW ? s_warp[lane] : 0;
     int inc2 = v;
 #pragma unroll
-    for (int o = 1; o < kCompactThreads / 32; o <<= 1) {
+    for (int o = 1; o < NW; o <<= 1) {
       const int n = __shfl_up_sync(0xffffffffu, inc2, o);
       if (lane >= o) inc2 += n;
     }
-    if (lane < kCompactThreads / 32) s_warp[lane] = inc2 - v;   // exclusive warp offsets
-    const int total = __shfl_sync(0xffffffffu, inc2, kCompactThreads / 32 - 1);
+    if (lane < NW) s_warp[lane] = inc2 - v;                  // exclusive warp offsets
+    const int total = __shfl_sync(0xffffffffu, inc2, NW - 1);
 
     // ---- chained scan across tiles (decoupled look-back), warp 0 ----------------------------
     int exclusive = 0;
@@ -122,7 +134,6 @@ dilate_compact_kernel(const uint32_t* __restrict__ raw, uint32_t* __restrict__ d
       }
     }
     if (lane == 0) {
-      __threadfence();
       tstate[tile] = pack_state(tag, 2u, (unsigned)(exclusive + total));     // inclusive prefix
       s_base = exclusive;
       if (tile == ntiles - 1) *count = exclusive + total;
@@ -131,11 +142,15 @@ dilate_compact_kernel(const uint32_t* __restrict__ raw, uint32_t* __restrict__ d
   __syncthreads();
 
   // ---- expand set bits to ascending pixel indices ------------------------------------------
-  if (w < nwords) {
-    int o = s_base + s_warp[wid] + (incl - cnt);
-    const int b = (int)(r / H);
-    const int pix0 = (int)(((long long)b * H + y) * W + j * 32);
-    unsigned dd = d;
+  int o = s_base + s_warp[wid] + (incl - cnt);
+#pragma unroll
+  for (int i = 0; i < kCompactWPT; ++i) {
+    const long long w = w0 + i;
+    if (w >= nwords) break;
+    const int j = (int)(w % Wd);
+    const long long r = w / Wd;                              // r = b*H + y
+    const int pix0 = (int)(r * W + j * 32);
+    unsigned dd = d[i];
     while (dd) {
       const int bit = __ffs(dd) - 1;
       idx[o++] = pix0 + bit;
@@ -144,7 +159,7 @@ dilate_compact_kernel(const uint32_t* __restrict__ raw, uint32_t* __restrict__ d
     if (dil_map) {
       const int n = min(32, W - j * 32);
       int8_t* m = dil_map + pix0;
-      for (int i = 0; i < n; ++i) m[i] = (int8_t)((d >> i) & 1u);
+      for (int q = 0; q < n; ++q) m[q] = (int8_t)((d[i] >> q) & 1u);
     }
   }
 
@@ -153,10 +168,9 @@ dilate_compact_kernel(const uint32_t* __restrict__ raw, uint32_t* __restrict__ d
     __threadfence();
     const unsigned prev = atomicAdd(&hdr->done, 1u);
     if (prev == (unsigned)ntiles - 1u) {
-      hdr->ticket = 0;
       hdr->done = 0;
       __threadfence();
-      *reinterpret_cast<volatile unsigned*>(&hdr->epoch) = s_epoch + 1u;
+      *reinterpret_cast<volatile unsigned*>(&hdr->epoch) = epoch + 1u;
     }
   }
 }

@@ -9,14 +9,14 @@
 //   N : BN output channels
 //   K : kH*kW*Cp ordered (ky,kx,ci): every filter tap is a contiguous channel run of the
 //       pixel-major state, so one 16-byte chunk never straddles a tap.
-// Warp roles (192 threads):
-//   warps 0-3  gather producers: im2col rows of ONLY the changed receptive fields, 16-byte
+// Warp roles (320 threads):
+//   warps 0-7  gather producers: im2col rows of ONLY the changed receptive fields, 16-byte
 //              global loads -> 128B-swizzled K-major smem tile (the UMMA canonical layout);
 //              for fp32 data in 3xTF32 mode they also split every value into tf32 hi + lo.
 //              The same warps run the epilogue: tcgen05.ld accumulators from TMEM, + bias,
 //              ReLU, convert, scatter one contiguous channel run per pixel.
-//   warp 4     TMA producer for the (regular) weight tiles: cp.async.bulk.tensor.2d, SWIZZLE_128B.
-//   warp 5     MMA issuer: one elected thread issues tcgen05.mma (kind::tf32 / kind::f16) with
+//   warp 8     TMA producer for the (regular) weight tiles: cp.async.bulk.tensor.2d, SWIZZLE_128B.
+//   warp 9     MMA issuer: one elected thread issues tcgen05.mma (kind::tf32 / kind::f16) with
 //              the accumulator in TMEM; tcgen05.commit releases smem stages / signals the epilogue.
 // Stages are handed over with mbarriers (full/empty ring + tmem full/empty).
 #pragma once
@@ -28,8 +28,8 @@
 namespace cb {
 
 constexpr int UM_BM = 128;                     // rows per tile (UMMA M, cta_group::1)
-constexpr int UM_PRODUCERS = 128;              // gather / epilogue threads (warps 0-3)
-constexpr int UM_THREADS = 192;
+constexpr int UM_PRODUCERS = 256;              // gather / epilogue threads (warps 0-7)
+constexpr int UM_THREADS = UM_PRODUCERS + 64;  // + TMA warp + MMA warp
 constexpr int UM_ROW_BYTES = 128;              // K bytes per stage row = one swizzle-128B span
 
 // ---- PTX wrappers ----------------------------------------------------------------------------
@@ -158,10 +158,9 @@ struct UmmaCtrl {                              // lives after the stage buffers
 };
 static_assert(sizeof(UmmaCtrl) <= 2048, "ctrl block too large");
 
-template <typename T>
-__device__ __forceinline__ void store_chunk(uint8_t* a_hi, uint8_t* a_lo, uint32_t off, uint4 v,
-                                            bool split) {
-  if (split) {                                  // fp32 -> tf32 hi (exact) + lo (= v - hi, exact)
+template <bool SPLIT>
+__device__ __forceinline__ void store_chunk(uint8_t* a_hi, uint8_t* a_lo, uint32_t off, uint4 v) {
+  if (SPLIT) {                                  // fp32 -> tf32 hi (exact) + lo (= v - hi, exact)
     uint4 hi, lo;
     hi.x = v.x & 0xFFFFE000u; hi.y = v.y & 0xFFFFE000u; hi.z = v.z & 0xFFFFE000u; hi.w = v.w & 0xFFFFE000u;
     lo.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(hi.x));
@@ -175,6 +174,27 @@ __device__ __forceinline__ void store_chunk(uint8_t* a_hi, uint8_t* a_lo, uint32
   }
 }
 
+// Incremental (ky,kx,ci) decode of this thread's K position: advances by one stage (BK elements)
+// per call, in stage order, without integer divisions in the hot loop.
+struct KCursor {
+  int ci, kx, ky, k;
+  __device__ __forceinline__ void init(int k0, int Cp, int kW) {
+    k = k0;
+    const int tap = k0 / Cp;
+    ci = k0 - tap * Cp;
+    ky = tap / kW;
+    kx = tap - ky * kW;
+  }
+  __device__ __forceinline__ void advance(int bk, int Cp, int kW) {
+    k += bk;
+    ci += bk;
+    while (ci >= Cp) {
+      ci -= Cp;
+      if (++kx == kW) { kx = 0; ++ky; }
+    }
+  }
+};
+
 // packed weights: [NSPLIT][CoutPad][KpPad] elements of T (K-major); tensor map dims {KpPad, NSPLIT*CoutPad}
 template <typename T, bool SPLIT3, int BN>
 __global__ void __launch_bounds__(UM_THREADS)
@@ -183,6 +203,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
                  const float* __restrict__ bias, T* __restrict__ out, int Op, int H, int W,
                  int Cout, int CoutPad, int kH, int kW, int Kp, int relu) {
   using C = UmmaCfg<T, SPLIT3, BN>;
+  constexpr int RPT = UM_BM * 8 / UM_PRODUCERS;            // 16-byte chunks per thread per stage
+  constexpr int RSTEP = UM_PRODUCERS / 8;                  // row stride between a thread's chunks
   const int n = *count;
   const int mtiles = (n + UM_BM - 1) / UM_BM;
   const int ntiles = CoutPad / BN;
@@ -195,6 +217,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
   UmmaCtrl* ctrl = reinterpret_cast<UmmaCtrl*>(smem + C::STAGES * C::STAGE_BYTES);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int num_kb = (Kp + C::BK - 1) / C::BK;
+  constexpr int TMA_WARP = UM_PRODUCERS / 32, MMA_WARP = TMA_WARP + 1;
 
   if (tid == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
@@ -205,14 +228,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
     mbar_init(&ctrl->tmem_empty, UM_PRODUCERS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 5) {                                         // TMEM allocation (one warp)
+  if (warp == MMA_WARP) {                                  // TMEM allocation (one warp)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(&ctrl->tmem_base)),
                  "r"((uint32_t)C::TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (warp == 4 && lane == 0)
+  if (warp == TMA_WARP && lane == 0)
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&wmap)) : "memory");
   tc_fence_before();
   __syncthreads();
@@ -222,14 +245,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
   const int ph = (kH - 1) / 2, pw = (kW - 1) / 2;
   const int P = H * W;
 
-  if (warp < 4) {
+  if (warp < TMA_WARP) {
     // =============================== gather producers + epilogue ============================
     uint32_t stage = 0, phase = 0, acc_phase = 0;
     const int c = tid & 7;                                  // my 16-byte chunk column
-    const int r0 = tid >> 3;                                // my rows: r0 + 16*it
+    const int r0 = tid >> 3;                                // my rows: r0 + RSTEP*it
+    uint32_t soff[RPT];                                     // swizzled smem offsets of my chunks
+#pragma unroll
+    for (int it = 0; it < RPT; ++it) {
+      const int r = r0 + RSTEP * it;
+      soff[it] = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
+    }
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int mt = tile / ntiles, nt = tile - mt * ntiles;
-      {                                                     // row table of this tile
+      if (tid < UM_BM) {                                    // row table of this tile
         const int j = mt * UM_BM + tid;
         int pix = -1, yx = 0;
         if (j < n) {
@@ -241,45 +270,64 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
         ctrl->pix[tid] = pix;
         ctrl->yx[tid] = yx;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");       // producers only
-      for (int kb = 0; kb < num_kb; ++kb) {
+      asm volatile("bar.sync 1, %0;" ::"n"(UM_PRODUCERS) : "memory");   // producers only
+      int rpix[RPT], ryx[RPT];
+#pragma unroll
+      for (int it = 0; it < RPT; ++it) {
+        rpix[it] = ctrl->pix[r0 + RSTEP * it];
+        ryx[it] = ctrl->yx[r0 + RSTEP * it];
+      }
+      KCursor cur;
+      cur.init(c * C::VEC, Cp, kW);
+      // issue the 16-byte global loads of one stage into registers (zero outside image / K)
+      auto load_stage = [&](uint4(&v)[RPT]) {
+        const int dy = cur.ky - ph, dx = cur.kx - pw;
+        const bool kvalid = cur.k < Kp;
+        const long long koff = ((long long)dy * W + dx) * Cp + cur.ci;
+#pragma unroll
+        for (int it = 0; it < RPT; ++it) {
+          const int iy = (ryx[it] >> 16) + dy, ix = (ryx[it] & 0xffff) + dx;
+          v[it] = make_uint4(0u, 0u, 0u, 0u);
+          if (kvalid && rpix[it] >= 0 && iy >= 0 && iy < H && ix >= 0 && ix < W)
+            v[it] = ldg16(state + (long long)rpix[it] * Cp + koff);
+        }
+        cur.advance(C::BK, Cp, kW);
+      };
+      auto store_stage = [&](const uint4(&v)[RPT]) {
         mbar_wait(&ctrl->empty[stage], phase ^ 1u);
         uint8_t* a_hi = smem + stage * C::STAGE_BYTES;
         uint8_t* a_lo = a_hi + C::A_BYTES;                  // only used when SPLIT3
-        const int k = kb * C::BK + c * C::VEC;
-        const bool kvalid = k < Kp;
-        const int tap = k / Cp, ci = k - tap * Cp;
-        const int ky = tap / kW, kx = tap - ky * kW;
-        const int dy = ky - ph, dx = kx - pw;
-        const long long koff = ((long long)dy * W + dx) * Cp + ci;
-        uint4 v[8];
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int r = r0 + 16 * it;
-          const int pix = ctrl->pix[r], yx = ctrl->yx[r];
-          const int iy = (yx >> 16) + dy, ix = (yx & 0xffff) + dx;
-          v[it] = make_uint4(0u, 0u, 0u, 0u);
-          if (kvalid && pix >= 0 && iy >= 0 && iy < H && ix >= 0 && ix < W)
-            v[it] = ld16(state + (long long)pix * Cp + koff);
-        }
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int r = r0 + 16 * it;
-          const uint32_t off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
-          store_chunk<T>(a_hi, a_lo, off, v[it], SPLIT3);
-        }
+        for (int it = 0; it < RPT; ++it) store_chunk<SPLIT3>(a_hi, a_lo, soff[it], v[it]);
         fence_proxy_async_smem();                            // generic writes -> async proxy (UMMA)
         mbar_arrive(&ctrl->full[stage]);
         if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+      };
+      // two register buffers: the loads of stage kb+2 are in flight while stage kb is stored
+      uint4 va[RPT], vb[RPT];
+      load_stage(va);
+      if (num_kb > 1) load_stage(vb);
+      for (int kb = 0; kb < num_kb; kb += 2) {
+        store_stage(va);
+        if (kb + 2 < num_kb) load_stage(va);
+        if (kb + 1 < num_kb) {
+          store_stage(vb);
+          if (kb + 3 < num_kb) load_stage(vb);
+        }
       }
       // ---- epilogue: TMEM -> registers -> bias / ReLU -> scatter -------------------------
       mbar_wait(&ctrl->tmem_full, acc_phase);
       tc_fence_after();
-      const int pix = ctrl->pix[tid];                       // TMEM lane == tile row == tid
-      const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+      const int q = warp & 3;                                // TMEM lane quarter of this warp
+      const int row = q * 32 + lane;
+      const int pix = ctrl->pix[row];
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
       T* orow = out + (long long)(pix < 0 ? 0 : pix) * Op;
+      constexpr int NGROUP = UM_PRODUCERS / 128;             // warps sharing a lane quarter
+      constexpr int COLS = (BN / NGROUP) < 16 ? 16 : (BN / NGROUP);
+      const int cbeg = (warp >> 2) * COLS;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 16) {
+      for (int c0 = cbeg; c0 < cbeg + COLS && c0 < BN; c0 += 16) {
         uint32_t acc[16];
         tmem_ld16(trow + (uint32_t)c0, acc);
         tmem_ld_wait();
@@ -318,9 +366,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
       tc_fence_before();
       mbar_arrive(&ctrl->tmem_empty);
       acc_phase ^= 1u;
-      asm volatile("bar.sync 1, 128;" ::: "memory");       // row table is rewritten next tile
+      asm volatile("bar.sync 1, %0;" ::"n"(UM_PRODUCERS) : "memory");   // row table reused next tile
     }
-  } else if (warp == 4) {
+  } else if (warp == TMA_WARP) {
     // =============================== TMA producer: weight tiles ==============================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
@@ -378,7 +426,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == MMA_WARP) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                  "r"((uint32_t)C::TMEM_COLS)

@@ -26,11 +26,14 @@ __device__ __forceinline__ uint4 merge_tail(uint4 xv, const uint4& sv, int tail)
 }
 
 // x: pixel-major, pitch xp (elements); state: pixel-major, pitch sp.  Rows may be strided (sy).
-template <typename T, int VEC, int UPDATE>
+// U chunk-iterations are batched: all 2*U 16-byte loads of a batch are issued before the first
+// ballot, so every lane keeps 2*U loads in flight (the ballots would otherwise serialise them).
+template <typename T, int VEC, int UPDATE, int U>
 __global__ void __launch_bounds__(256)
 detect_vec_kernel(const T* __restrict__ x, long long x_sb, long long x_sy, int xp,
                   T* __restrict__ st, long long s_sb, long long s_sy, int sp,
-                  uint32_t* __restrict__ bits, int B, int H, int W, int C, int Wd, T thr) {
+                  uint32_t* __restrict__ bits, int B, int H, int W, int C, int Wd, T thr,
+                  unsigned cpv_magic) {
   const int lane = threadIdx.x & 31;
   const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (warp >= (long long)B * H * Wd) return;
@@ -45,26 +48,41 @@ detect_vec_kernel(const T* __restrict__ x, long long x_sb, long long x_sy, int x
   const int cpv = (C + VEC - 1) / VEC;       // 16-byte chunks per pixel that hold real channels
   const int tail = C % VEC;                  // valid elements of the last chunk (0 = all)
   const int nq = npx * cpv;
+  // q / cpv without a divide: exact for q*cpv < 2^32 (q <= 32*cpv here)
+  auto pixel_of = [&](int q) { return cpv == 1 ? q : (int)__umulhi((unsigned)q, cpv_magic); };
 
   bool mychg = false;                        // flag of pixel `lane`
   const int plo = lane * cpv, phi = plo + cpv;
-  for (int q0 = 0; q0 < nq; q0 += 32) {
-    const int q = q0 + lane;
-    bool f = false;
-    if (q < nq) {
-      const int px = q / cpv, cc = q - px * cpv;
-      uint4 xv = ldg16(xb + (long long)px * xp + cc * VEC);
-      T* sptr = sb + (long long)px * sp + cc * VEC;
-      const uint4 sv = ld16(sptr);
-      if (tail && cc == cpv - 1) xv = merge_tail<T, VEC>(xv, sv, tail);
-      f = Chunk<T>::changed(sv, xv, thr);
-      if (UPDATE == CB_UPDATE_ALL) st16(sptr, xv);
+  for (int q0 = 0; q0 < nq; q0 += 32 * U) {
+    uint4 xv[U], sv[U];
+    T* sptr[U];
+    bool valid[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int q = q0 + u * 32 + lane;
+      valid[u] = q < nq;
+      const int px = pixel_of(q), cc = q - px * cpv;
+      sptr[u] = sb + (long long)px * sp + cc * VEC;
+      if (valid[u]) {
+        xv[u] = ldg16(xb + (long long)px * xp + cc * VEC);
+        sv[u] = ld16(sptr[u]);
+        if (tail && cc == cpv - 1) xv[u] = merge_tail<T, VEC>(xv[u], sv[u], tail);
+      }
     }
-    const unsigned bal = __ballot_sync(0xffffffffu, f);
-    const int lo = max(plo, q0) - q0, hi = min(phi, q0 + 32) - q0;
-    if (hi > lo) {
-      const unsigned m = (hi - lo >= 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
-      mychg |= (bal & m) != 0u;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      bool f = false;
+      if (valid[u]) {
+        f = Chunk<T>::changed(sv[u], xv[u], thr);
+        if (UPDATE == CB_UPDATE_ALL) st16(sptr[u], xv[u]);
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, f);
+      const int qb = q0 + u * 32;
+      const int lo = max(plo, qb) - qb, hi = min(phi, qb + 32) - qb;
+      if (hi > lo) {
+        const unsigned m = (hi - lo >= 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
+        mychg |= (bal & m) != 0u;
+      }
     }
   }
   const unsigned word = __ballot_sync(0xffffffffu, mychg);
@@ -72,15 +90,48 @@ detect_vec_kernel(const T* __restrict__ x, long long x_sb, long long x_sy, int x
 
   if (UPDATE == CB_UPDATE_CHANGED && word) {  // feedback: accept the new value at changed pixels
     for (int q = lane; q < nq; q += 32) {
-      const int px = q / cpv, cc = q - px * cpv;
+      const int px = pixel_of(q), cc = q - px * cpv;
       if ((word >> px) & 1u) {
         uint4 xv = ldg16(xb + (long long)px * xp + cc * VEC);
-        T* sptr = sb + (long long)px * sp + cc * VEC;
-        if (tail && cc == cpv - 1) xv = merge_tail<T, VEC>(xv, ld16(sptr), tail);
-        st16(sptr, xv);
+        T* sp2 = sb + (long long)px * sp + cc * VEC;
+        if (tail && cc == cpv - 1) xv = merge_tail<T, VEC>(xv, ld16(sp2), tail);
+        st16(sp2, xv);
       }
     }
   }
+}
+
+// Generic x (any strides, e.g. the user's planar NCHW frame) against a pixel-major state whose
+// pixel is exactly one 16-byte chunk (C <= 4 fp32 / C <= 8 half): lane = pixel, the state is one
+// vector load/store per pixel and x is read plane by plane (coalesced across lanes).
+template <typename T, int VEC, int UPDATE>
+__global__ void __launch_bounds__(256)
+detect_narrow_kernel(const T* __restrict__ x, long long x_sb, long long x_sc, long long x_sy,
+                     long long x_sx, T* __restrict__ st, long long s_sb, long long s_sy,
+                     uint32_t* __restrict__ bits, int B, int H, int W, int C, int Wd, T thr) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (warp >= (long long)B * H * Wd) return;
+  const int j = (int)(warp % Wd);
+  const long long r = warp / Wd;
+  const int y = (int)(r % H);
+  const int b = (int)(r / H);
+  const int xx = j * 32 + lane;
+  bool f = false;
+  if (xx < W) {
+    const T* xp = x + b * x_sb + y * x_sy + xx * x_sx;
+    T* sp = st + b * s_sb + y * s_sy + (long long)xx * VEC;
+    uint4 sv = ld16(sp);
+    uint4 nv = sv;                             // pad lanes keep the state's (zero) value
+    T* ne = reinterpret_cast<T*>(&nv);
+#pragma unroll
+    for (int c = 0; c < VEC; ++c)
+      if (c < C) ne[c] = xp[c * x_sc];
+    f = Chunk<T>::changed(sv, nv, thr);
+    if (UPDATE == CB_UPDATE_ALL || (UPDATE == CB_UPDATE_CHANGED && f)) st16(sp, nv);
+  }
+  const unsigned word = __ballot_sync(0xffffffffu, f);
+  if (lane == 0) bits[warp] = word;
 }
 
 template <typename T, int UPDATE>
@@ -139,16 +190,30 @@ int launch_detect(cudaStream_t stream, const void* x, long long x_sb, long long 
                       ((x_sb * es) % 16) == 0 && ((s_sb * es) % 16) == 0 &&
                       ((uintptr_t)x % 16) == 0 && ((uintptr_t)state % 16) == 0 &&
                       x_sx < (1ll << 30) && s_sx < (1ll << 30);
+  const bool narrow_ok = !vec_ok && s_sc == 1 && s_sx == VEC && C <= VEC &&
+                         ((s_sy * es) % 16) == 0 && ((s_sb * es) % 16) == 0 &&
+                         ((uintptr_t)state % 16) == 0;
+  const int cpv = (C + VEC - 1) / VEC;
+  const unsigned magic = cpv > 1 ? (unsigned)((0x100000000ull + cpv - 1) / cpv) : 0u;
   dim3 grid((unsigned)blocks), block(wpb * 32);
-#define CB_DET(U)                                                                              \
-  if (vec_ok)                                                                                  \
-    detect_vec_kernel<T, VEC, U><<<grid, block, 0, stream>>>(                                  \
-        (const T*)x, x_sb, x_sy, (int)x_sx, (T*)state, s_sb, s_sy, (int)s_sx, bits, B, H, W, C, \
-        Wd, thr);                                                                              \
-  else                                                                                         \
-    detect_generic_kernel<T, U><<<grid, block, 0, stream>>>(                                   \
+#define CB_DET(U_)                                                                             \
+  if (vec_ok) {                                                                                \
+    if (cpv >= 4)                                                                              \
+      detect_vec_kernel<T, VEC, U_, 4><<<grid, block, 0, stream>>>(                            \
+          (const T*)x, x_sb, x_sy, (int)x_sx, (T*)state, s_sb, s_sy, (int)s_sx, bits, B, H, W, \
+          C, Wd, thr, magic);                                                                  \
+    else                                                                                       \
+      detect_vec_kernel<T, VEC, U_, 2><<<grid, block, 0, stream>>>(                            \
+          (const T*)x, x_sb, x_sy, (int)x_sx, (T*)state, s_sb, s_sy, (int)s_sx, bits, B, H, W, \
+          C, Wd, thr, magic);                                                                  \
+  } else if (narrow_ok) {                                                                      \
+    detect_narrow_kernel<T, VEC, U_><<<grid, block, 0, stream>>>(                              \
+        (const T*)x, x_sb, x_sc, x_sy, x_sx, (T*)state, s_sb, s_sy, bits, B, H, W, C, Wd, thr); \
+  } else {                                                                                     \
+    detect_generic_kernel<T, U_><<<grid, block, 0, stream>>>(                                  \
         (const T*)x, x_sb, x_sc, x_sy, x_sx, (T*)state, s_sb, s_sc, s_sy, s_sx, bits, B, H, W, \
-        C, Wd, thr);
+        C, Wd, thr);                                                                           \
+  }
   switch (update) {
     case CB_UPDATE_NONE: CB_DET(CB_UPDATE_NONE) break;
     case CB_UPDATE_CHANGED: CB_DET(CB_UPDATE_CHANGED) break;

@@ -73,4 +73,69 @@ maxpool2x2_kernel(const T* __restrict__ x, long long x_sb, long long x_sc, long 
   }
 }
 
+// Pixel-major fast path: a group of G lanes (G = power of two >= chunks per pixel, <= 32) owns one
+// changed pixel, so a warp works on 32/G list entries at once with 16-byte loads/stores; the four
+// window pixels are 4 independent vector loads per lane.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+maxpool2x2_vec_kernel(const T* __restrict__ x, long long x_sb, long long x_sy, int xp,
+                      const int32_t* __restrict__ idx, const int32_t* __restrict__ count,
+                      const uint32_t* __restrict__ bits, T* __restrict__ out, long long o_sb,
+                      long long o_sy, int op, int cpp, int glog, int H, int W, int oH, int oW) {
+  const int n = *count;
+  const int lane = threadIdx.x & 31;
+  const int G = 1 << glog, ppw = 32 >> glog;                // lanes per pixel, pixels per warp
+  const int sub = lane >> glog, gl = lane & (G - 1);
+  const int P = H * W, Wd = (W + 31) >> 5;
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long j0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * ppw;
+       j0 < n; j0 += nwarps * ppw) {
+    const long long j = j0 + sub;
+    if (j >= n) continue;
+    const int pix = __ldg(idx + j);
+    const int b = pix / P, p = pix - b * P;
+    const int y = p / W, xx = p - y * W;
+    const int yo = y >> 1, xo = xx >> 1;
+    if (yo >= oH || xo >= oW) continue;
+    if (bits) {                                // first changed pixel of the window owns it
+      const long long r = (long long)b * H + y;
+      bool owner = true;
+      if (xx & 1) owner = !bit_at(bits, r, Wd, xx - 1);
+      if (owner && (y & 1)) {
+        const int xe = xx & ~1;
+        owner = !bit_at(bits, r - 1, Wd, xe) && !(xe + 1 < W && bit_at(bits, r - 1, Wd, xe + 1));
+      }
+      if (!owner) continue;
+    }
+    const int y0 = yo * 2, x0 = xo * 2;
+    const bool hy = y0 + 1 < H, hx = x0 + 1 < W;
+    const T* base = x + b * x_sb + y0 * x_sy + (long long)x0 * xp;
+    T* o = out + b * o_sb + yo * o_sy + (long long)xo * op;
+    for (int cc = gl; cc < cpp; cc += G) {
+      const T* q = base + cc * VEC;
+      uint4 v00 = ldg16(q), v01 = v00, v10 = v00, v11 = v00;
+      if (hx) v01 = ldg16(q + xp);
+      if (hy) {
+        v10 = ldg16(q + x_sy);
+        v11 = hx ? ldg16(q + x_sy + xp) : v10;
+      }
+      uint4 res;
+      const T* e00 = reinterpret_cast<const T*>(&v00);
+      const T* e01 = reinterpret_cast<const T*>(&v01);
+      const T* e10 = reinterpret_cast<const T*>(&v10);
+      const T* e11 = reinterpret_cast<const T*>(&v11);
+      T* er = reinterpret_cast<T*>(&res);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        T v = max_keep(neg_inf<T>(), e00[e]);
+        v = max_keep(v, e01[e]);
+        v = max_keep(v, e10[e]);
+        v = max_keep(v, e11[e]);
+        er[e] = v;
+      }
+      st16(o + cc * VEC, res);
+    }
+  }
+}
+
 }  // namespace cb
