@@ -140,6 +140,8 @@ class CBConv2d(nn.Module):
         self.prevOutput = self.weight.data.new_empty(0)
         self._inBuf = None        # pixel-major storage behind prevInput / prevOutput
         self._outBuf = None
+        self._loView = None       # fp32 only: tf32 remainder plane of prevInput (3xTF32 operand)
+        self._loBuf = None
         self._scratch = None      # bitmaps, index list, count, compaction workspace
         self._packed = None       # (key, packed weights, fp32 bias)
         self.changeMap = None
@@ -203,6 +205,8 @@ class CBConv2d(nn.Module):
 
         if self.prevInput.size() != input.size() or self.prevInput.dtype != dt or self._inBuf is None:
             self.prevInput, self._inBuf = cg.pixel_major(input.shape, dt, dev, _INF)   # :192-194
+            self._loView, self._loBuf = (cg.pixel_major(input.shape, dt, dev, 0)
+                                         if dt == torch.float32 else (None, None))
             self._scratch = None
         outpSize = (B, self.out_channels, H, W)
         if tuple(self.prevOutput.size()) != outpSize or self.prevOutput.dtype != dt or self._outBuf is None:
@@ -222,7 +226,8 @@ class CBConv2d(nn.Module):
             # copy is part of the detection pass; copyInput=False (alias the input as state) is
             # honoured as a copy -- the state always owns its memory.
             cg.detect(input, self.prevInput, s["raw_bits"], self.threshold,
-                      _lib.UPDATE_CHANGED if self.feedbackLoop else _lib.UPDATE_ALL)
+                      _lib.UPDATE_CHANGED if self.feedbackLoop else _lib.UPDATE_ALL,
+                      state_lo=self._loView)
             dil_map = s.get("dil_map") if self.saveChangeMap else None
             cg.dilate_compact(s["raw_bits"], (B, H, W), self.kernel_size, s["idx"], s["count"],
                               s["ws"], dil_bits=s["dil_bits"], dil_map=dil_map)
@@ -235,11 +240,14 @@ class CBConv2d(nn.Module):
                 changeIndexes = ChangeIndexes.from_tensor(changeIndexes.detach(), (B, H, W))
             if not self.feedbackLoop:
                 self.prevInput.copy_(input)                                            # :234-236
+                if self._loView is not None:
+                    self._loView.copy_(cg.tf32_lo(input))
             # (with feedbackLoop the reference never refreshes prevInput here either, :220,234)
 
         gemm, packed, bias32 = self._weights(dt, dev)
         cg.conv_update(self._inBuf, changeIndexes, packed, bias32, self._outBuf, self.in_channels,
-                       self.out_channels, self.kernel_size, self.withReLU, gemm)      # :242-251
+                       self.out_channels, self.kernel_size, self.withReLU, gemm,
+                       lo_buf=self._loBuf)                                             # :242-251
 
         if self.propChangeIndexes:
             return 'changeIndexes', self.prevOutput, changeIndexes

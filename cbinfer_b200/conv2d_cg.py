@@ -88,14 +88,18 @@ class ChangeIndexes(object):
 # fused-path primitives (native pixel-major layout, batch-capable, no host sync)
 # ---------------------------------------------------------------------------------------------
 
-def detect(x, state, raw_bits, threshold, update_mode):
-    """cb_change_detect: raw (un-dilated) change bitmap of x vs state; updates state."""
+def detect(x, state, raw_bits, threshold, update_mode, state_lo=None):
+    """cb_change_detect: raw (un-dilated) change bitmap of x vs state; updates state (and, when
+    given, the tf32 remainder plane `state_lo`, a tensor with the strides of `state`)."""
     require_cuda(x, state, raw_bits)
     B, Cc, H, W = x.shape
     assert state.shape == x.shape and state.dtype == x.dtype
+    if state_lo is not None:
+        assert state_lo.stride() == state.stride() and state_lo.dtype == state.dtype
     check(C.cb_change_detect(stream_ptr(x.device), dtype_code(x), x.data_ptr(), *_strides4(x),
-                             state.data_ptr(), *_strides4(state), raw_bits.data_ptr(),
-                             B, Cc, H, W, float(threshold), int(update_mode)))
+                             state.data_ptr(), *_strides4(state),
+                             state_lo.data_ptr() if state_lo is not None else None,
+                             raw_bits.data_ptr(), B, Cc, H, W, float(threshold), int(update_mode)))
 
 
 def dilate_compact(raw_bits, shape, filtSize, idx, count, ws, dil_bits=None, dil_map=None):
@@ -138,12 +142,23 @@ def pack_weights(weight, gemm):
     return packed
 
 
-def conv_update(state_buf, changes, packed_w, bias_f32, out_buf, Cin, Cout, filtSize, relu, gemm):
-    """cb_conv_update on pixel-major buffers [B,H,W,pitch]."""
+def tf32_lo(x):
+    """v - trunc_tf32(v): the remainder plane the 3xTF32 contraction consumes (exact in fp32)."""
+    hi = (x.contiguous().view(torch.int32) & -8192).view(torch.float32)
+    return x - hi
+
+
+def conv_update(state_buf, changes, packed_w, bias_f32, out_buf, Cin, Cout, filtSize, relu, gemm,
+                lo_buf=None):
+    """cb_conv_update on pixel-major buffers [B,H,W,pitch]; lo_buf = tf32 remainder plane of
+    state_buf (needed for GEMM_TC_3X on fp32; computed on the fly when not supplied)."""
     B, H, W, Cp = state_buf.shape
     assert out_buf.shape[:3] == state_buf.shape[:3]
+    if gemm == _lib.GEMM_TC_3X and state_buf.dtype == torch.float32 and lo_buf is None:
+        lo_buf = tf32_lo(state_buf)
     check(C.cb_conv_update(stream_ptr(state_buf.device), dtype_code(state_buf), gemm,
-                           state_buf.data_ptr(), Cp, changes.buffer.data_ptr(),
+                           state_buf.data_ptr(), lo_buf.data_ptr() if lo_buf is not None else None,
+                           Cp, changes.buffer.data_ptr(),
                            changes.count.data_ptr(), packed_w.data_ptr(), bias_f32.data_ptr(),
                            out_buf.data_ptr(), out_buf.shape[3], B, H, W, Cin, Cout,
                            filtSize[0], filtSize[1], int(bool(relu))))

@@ -80,12 +80,12 @@ int cb_channel_pitch(int dtype, int C) {
 
 int cb_change_detect(void* stream, int dtype, const void* x, long long x_sb, long long x_sc,
                      long long x_sy, long long x_sx, void* state, long long s_sb, long long s_sc,
-                     long long s_sy, long long s_sx, uint32_t* raw_bits, int B, int C, int H, int W,
-                     float threshold, int update_mode) {
+                     long long s_sy, long long s_sx, void* state_lo, uint32_t* raw_bits, int B, int C,
+                     int H, int W, float threshold, int update_mode) {
   CB_CHECK_ARG(x && state && raw_bits, "change_detect: null pointer");
   CB_CHECK_ARG(B >= 0 && C > 0 && H >= 0 && W >= 0, "change_detect: bad shape");
   CB_DISPATCH_DTYPE(dtype, return (launch_detect<T, VEC>((cudaStream_t)stream, x, x_sb, x_sc, x_sy,
-                                                        x_sx, state, s_sb, s_sc, s_sy, s_sx,
+                                                        x_sx, state, s_sb, s_sc, s_sy, s_sx, state_lo,
                                                         raw_bits, B, C, H, W, threshold,
                                                         update_mode)));
   return 0;
@@ -149,8 +149,8 @@ int cb_pack_weights(void* stream, int dtype, int gemm, const void* weight, void*
   return cb::umma_pack_weights(s, dtype, gemm, weight, packed, Cout, Cin, Cp, kH, kW);
 }
 
-int cb_conv_update(void* stream, int dtype, int gemm, const void* state, int pitch_in,
-                   const int32_t* idx, const int32_t* count, const void* packed_w,
+int cb_conv_update(void* stream, int dtype, int gemm, const void* state, const void* state_lo,
+                   int pitch_in, const int32_t* idx, const int32_t* count, const void* packed_w,
                    const float* bias, void* out, int pitch_out, int B, int H, int W, int Cin,
                    int Cout, int kH, int kW, int relu) {
   CB_CHECK_ARG(state && idx && count && packed_w && bias && out, "conv_update: null pointer");
@@ -170,7 +170,7 @@ int cb_conv_update(void* stream, int dtype, int gemm, const void* state, int pit
     CB_CHECK_LAUNCH("conv_update(simt)");
     return 0;
   }
-  return cb::umma_conv_update(s, dtype, gemm, state, pitch_in, idx, count, packed_w, bias, out,
+  return cb::umma_conv_update(s, dtype, gemm, state, state_lo, pitch_in, idx, count, packed_w, bias, out,
                               pitch_out, B, H, W, Cin, Cout, kH, kW, relu);
 }
 

@@ -11,8 +11,10 @@
 //       pixel-major state, so one 16-byte chunk never straddles a tap.
 // Warp roles (320 threads):
 //   warps 0-7  gather producers: im2col rows of ONLY the changed receptive fields, 16-byte
-//              global loads -> 128B-swizzled K-major smem tile (the UMMA canonical layout);
-//              for fp32 data in 3xTF32 mode they also split every value into tf32 hi + lo.
+//              cp.async copies global -> 128B-swizzled K-major smem tile (the UMMA canonical
+//              layout), zero-filled outside the image.  In 3xTF32 mode the tf32 "hi" operand is
+//              the raw fp32 state (the tensor core ignores the low 13 mantissa bits) and the
+//              "lo" operand is the remainder plane cb_change_detect maintains.
 //              The same warps run the epilogue: tcgen05.ld accumulators from TMEM, + bias,
 //              ReLU, convert, scatter one contiguous channel run per pixel.
 //   warp 8     TMA producer for the (regular) weight tiles: cp.async.bulk.tensor.2d, SWIZZLE_128B.
@@ -67,6 +69,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       else if (now - t0 > 4000000000ll) __trap();      // ~2 s at 2 GHz
     }
   }
+}
+// 16-byte async copy global -> shared (LDGSTS); src_bytes = 0 zero-fills (out-of-image taps)
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes)
+               : "memory");
+}
+// arrive on `bar` once all cp.async issued so far by this thread have landed (counts as one of
+// the barrier's expected arrivals)
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -158,22 +170,6 @@ struct UmmaCtrl {                              // lives after the stage buffers
 };
 static_assert(sizeof(UmmaCtrl) <= 2048, "ctrl block too large");
 
-template <bool SPLIT>
-__device__ __forceinline__ void store_chunk(uint8_t* a_hi, uint8_t* a_lo, uint32_t off, uint4 v) {
-  if (SPLIT) {                                  // fp32 -> tf32 hi (exact) + lo (= v - hi, exact)
-    uint4 hi, lo;
-    hi.x = v.x & 0xFFFFE000u; hi.y = v.y & 0xFFFFE000u; hi.z = v.z & 0xFFFFE000u; hi.w = v.w & 0xFFFFE000u;
-    lo.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(hi.x));
-    lo.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(hi.y));
-    lo.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(hi.z));
-    lo.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(hi.w));
-    *reinterpret_cast<uint4*>(a_hi + off) = hi;
-    *reinterpret_cast<uint4*>(a_lo + off) = lo;
-  } else {
-    *reinterpret_cast<uint4*>(a_hi + off) = v;
-  }
-}
-
 // Incremental (ky,kx,ci) decode of this thread's K position: advances by one stage (BK elements)
 // per call, in stage order, without integer divisions in the hot loop.
 struct KCursor {
@@ -198,8 +194,8 @@ struct KCursor {
 // packed weights: [NSPLIT][CoutPad][KpPad] elements of T (K-major); tensor map dims {KpPad, NSPLIT*CoutPad}
 template <typename T, bool SPLIT3, int BN>
 __global__ void __launch_bounds__(UM_THREADS)
-conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__ state, int Cp,
-                 const int32_t* __restrict__ idx, const int32_t* __restrict__ count,
+conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__ state,
+                 const T* __restrict__ state_lo, int Cp, const int32_t* __restrict__ idx, const int32_t* __restrict__ count,
                  const float* __restrict__ bias, T* __restrict__ out, int Op, int H, int W,
                  int Cout, int CoutPad, int kH, int kW, int Kp, int relu) {
   using C = UmmaCfg<T, SPLIT3, BN>;
@@ -271,49 +267,38 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
         ctrl->yx[tid] = yx;
       }
       asm volatile("bar.sync 1, %0;" ::"n"(UM_PRODUCERS) : "memory");   // producers only
-      int rpix[RPT], ryx[RPT];
+      // per-row source pointers (pixel base) and coordinates of my RPT rows
+      const T* rbase[RPT];
+      int ry[RPT], rx[RPT];
 #pragma unroll
       for (int it = 0; it < RPT; ++it) {
-        rpix[it] = ctrl->pix[r0 + RSTEP * it];
-        ryx[it] = ctrl->yx[r0 + RSTEP * it];
+        const int pix = ctrl->pix[r0 + RSTEP * it], yx = ctrl->yx[r0 + RSTEP * it];
+        rbase[it] = state + (long long)(pix < 0 ? 0 : pix) * Cp;
+        ry[it] = pix < 0 ? -0x40000000 : (yx >> 16);        // invalid rows fail every bounds test
+        rx[it] = yx & 0xffff;
       }
+      const long long lo_delta = SPLIT3 ? (state_lo - state) : 0;
       KCursor cur;
       cur.init(c * C::VEC, Cp, kW);
-      // issue the 16-byte global loads of one stage into registers (zero outside image / K)
-      auto load_stage = [&](uint4(&v)[RPT]) {
+      // Gather = async 16-byte copies straight into the swizzled UMMA tile (zero-filled outside
+      // the image / beyond K); no register staging, so up to STAGES stages of loads are in flight.
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&ctrl->empty[stage], phase ^ 1u);
+        const uint32_t a_hi = smem_u32(smem + stage * C::STAGE_BYTES);
         const int dy = cur.ky - ph, dx = cur.kx - pw;
         const bool kvalid = cur.k < Kp;
         const long long koff = ((long long)dy * W + dx) * Cp + cur.ci;
 #pragma unroll
         for (int it = 0; it < RPT; ++it) {
-          const int iy = (ryx[it] >> 16) + dy, ix = (ryx[it] & 0xffff) + dx;
-          v[it] = make_uint4(0u, 0u, 0u, 0u);
-          if (kvalid && rpix[it] >= 0 && iy >= 0 && iy < H && ix >= 0 && ix < W)
-            v[it] = ldg16(state + (long long)rpix[it] * Cp + koff);
+          const bool ok = kvalid && (unsigned)(ry[it] + dy) < (unsigned)H &&
+                          (unsigned)(rx[it] + dx) < (unsigned)W;
+          const T* src = ok ? rbase[it] + koff : state;
+          cp_async16(a_hi + soff[it], src, ok ? 16u : 0u);
+          if (SPLIT3) cp_async16(a_hi + C::A_BYTES + soff[it], src + lo_delta, ok ? 16u : 0u);
         }
+        cp_async_arrive_noinc(&ctrl->full[stage]);
         cur.advance(C::BK, Cp, kW);
-      };
-      auto store_stage = [&](const uint4(&v)[RPT]) {
-        mbar_wait(&ctrl->empty[stage], phase ^ 1u);
-        uint8_t* a_hi = smem + stage * C::STAGE_BYTES;
-        uint8_t* a_lo = a_hi + C::A_BYTES;                  // only used when SPLIT3
-#pragma unroll
-        for (int it = 0; it < RPT; ++it) store_chunk<SPLIT3>(a_hi, a_lo, soff[it], v[it]);
-        fence_proxy_async_smem();                            // generic writes -> async proxy (UMMA)
-        mbar_arrive(&ctrl->full[stage]);
         if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
-      };
-      // two register buffers: the loads of stage kb+2 are in flight while stage kb is stored
-      uint4 va[RPT], vb[RPT];
-      load_stage(va);
-      if (num_kb > 1) load_stage(vb);
-      for (int kb = 0; kb < num_kb; kb += 2) {
-        store_stage(va);
-        if (kb + 2 < num_kb) load_stage(va);
-        if (kb + 1 < num_kb) {
-          store_stage(vb);
-          if (kb + 3 < num_kb) load_stage(vb);
-        }
       }
       // ---- epilogue: TMEM -> registers -> bias / ReLU -> scatter -------------------------
       mbar_wait(&ctrl->tmem_full, acc_phase);
@@ -398,6 +383,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
         tc_fence_after();
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&ctrl->full[stage], phase);
+          fence_proxy_async_smem();                          // cp.async writes -> async proxy (UMMA)
           tc_fence_after();
           const uint32_t a_hi = smem_u32(smem + stage * C::STAGE_BYTES);
           const uint32_t a_lo = a_hi + C::A_BYTES;
@@ -523,7 +509,8 @@ inline PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
 }
 
 template <typename T, bool SPLIT3, int BN>
-int launch_conv_umma(cudaStream_t s, int dtype, const void* state, int Cp, const int32_t* idx,
+int launch_conv_umma(cudaStream_t s, int dtype, const void* state, const void* state_lo, int Cp,
+                     const int32_t* idx,
                      const int32_t* count, const void* packed, const float* bias, void* out,
                      int Op, int B, int H, int W, int Cout, int CoutPad, int kH, int kW, int relu) {
   using C = UmmaCfg<T, SPLIT3, BN>;
@@ -557,7 +544,8 @@ int launch_conv_umma(cudaStream_t s, int dtype, const void* state, int Cp, const
   long long grid = (long long)sm_count() * 2;
   if (grid > max_tiles) grid = max_tiles;
   if (grid < 1) grid = 1;
-  kern<<<(unsigned)grid, UM_THREADS, C::SMEM_BYTES, s>>>(map, (const T*)state, Cp, idx, count, bias,
+  kern<<<(unsigned)grid, UM_THREADS, C::SMEM_BYTES, s>>>(map, (const T*)state, (const T*)state_lo, Cp,
+                                                        idx, count, bias,
                                                         (T*)out, Op, H, W, Cout, CoutPad, kH, kW,
                                                         Kp, relu);
   CB_CHECK_LAUNCH("conv_update(umma)");
@@ -565,26 +553,27 @@ int launch_conv_umma(cudaStream_t s, int dtype, const void* state, int Cp, const
 }
 
 template <typename T, bool SPLIT3>
-int dispatch_bn(int bn, cudaStream_t s, int dtype, const void* state, int Cp, const int32_t* idx,
+int dispatch_bn(int bn, cudaStream_t s, int dtype, const void* state, const void* state_lo, int Cp,
+                const int32_t* idx,
                 const int32_t* count, const void* packed, const float* bias, void* out, int Op,
                 int B, int H, int W, int Cout, int CoutPad, int kH, int kW, int relu) {
 #define CB_BN(N)                                                                              \
   case N:                                                                                     \
-    return launch_conv_umma<T, SPLIT3, N>(s, dtype, state, Cp, idx, count, packed, bias, out, \
+    return launch_conv_umma<T, SPLIT3, N>(s, dtype, state, state_lo, Cp, idx, count, packed, bias, out, \
                                           Op, B, H, W, Cout, CoutPad, kH, kW, relu);
   switch (bn) {
     CB_BN(16) CB_BN(32) CB_BN(64)
     case 128:
       if (!SPLIT3)
-        return launch_conv_umma<T, false, 128>(s, dtype, state, Cp, idx, count, packed, bias, out,
+        return launch_conv_umma<T, false, 128>(s, dtype, state, state_lo, Cp, idx, count, packed, bias, out,
                                                Op, B, H, W, Cout, CoutPad, kH, kW, relu);
     default: return fail(2, "conv_update: unsupported N tile %d", bn);
   }
 #undef CB_BN
 }
 
-inline int umma_conv_update(cudaStream_t s, int dtype, int gemm, const void* state, int Cp,
-                            const int32_t* idx, const int32_t* count, const void* packed,
+inline int umma_conv_update(cudaStream_t s, int dtype, int gemm, const void* state,
+                            const void* state_lo, int Cp, const int32_t* idx, const int32_t* count, const void* packed,
                             const float* bias, void* out, int Op, int B, int H, int W, int Cin,
                             int Cout, int kH, int kW, int relu) {
   (void)Cin;
@@ -594,17 +583,19 @@ inline int umma_conv_update(cudaStream_t s, int dtype, int gemm, const void* sta
                "conv_update: state must be 16-byte and packed weights 128-byte aligned");
   const int bn = umma_bn(gemm, Cout), CoutPad = umma_cout_pad(gemm, Cout);
   const bool split3 = gemm == CB_GEMM_TC_3X && dtype == CB_F32;
+  CB_CHECK_ARG(!split3 || (state_lo && ((uintptr_t)state_lo % 16) == 0),
+               "conv_update: CB_GEMM_TC_3X needs the 16-byte aligned tf32 remainder plane (state_lo)");
   switch (dtype) {
     case CB_F32:
-      return split3 ? dispatch_bn<float, true>(bn, s, dtype, state, Cp, idx, count, packed, bias,
+      return split3 ? dispatch_bn<float, true>(bn, s, dtype, state, state_lo, Cp, idx, count, packed, bias,
                                                out, Op, B, H, W, Cout, CoutPad, kH, kW, relu)
-                    : dispatch_bn<float, false>(bn, s, dtype, state, Cp, idx, count, packed, bias,
+                    : dispatch_bn<float, false>(bn, s, dtype, state, state_lo, Cp, idx, count, packed, bias,
                                                 out, Op, B, H, W, Cout, CoutPad, kH, kW, relu);
     case CB_F16:
-      return dispatch_bn<__half, false>(bn, s, dtype, state, Cp, idx, count, packed, bias, out, Op,
+      return dispatch_bn<__half, false>(bn, s, dtype, state, state_lo, Cp, idx, count, packed, bias, out, Op,
                                         B, H, W, Cout, CoutPad, kH, kW, relu);
     case CB_BF16:
-      return dispatch_bn<__nv_bfloat16, false>(bn, s, dtype, state, Cp, idx, count, packed, bias,
+      return dispatch_bn<__nv_bfloat16, false>(bn, s, dtype, state, state_lo, Cp, idx, count, packed, bias,
                                                out, Op, B, H, W, Cout, CoutPad, kH, kW, relu);
     default: return fail(2, "conv_update: bad dtype %d", dtype);
   }

@@ -3,12 +3,13 @@
 // Replaces the detection half of changeDetection[_1x1]_kernel
 // (reference pycbinfer/cbconv2d_cg_backend.cu:6-81, half: cbconv2d_cg_half_backend.cu:10-88).
 //
-// One warp owns 32 consecutive pixels of one image row (= one bitmap word).
-//   * vector path (pixel-major x and state): the warp streams the 32 pixels' channels as
-//     16-byte chunks, fully coalesced; per-chunk flags are folded to per-pixel flags with
-//     __ballot_sync + bit-range masks, then one ballot builds the bitmap word.
-//   * generic path (any strides, e.g. the user's planar NCHW frame): lane = pixel, loop over
-//     channels (coalesced across lanes for planar inputs).
+// One bitmap word = 32 consecutive pixels of one image row.
+//   * vector path (pixel-major x and state): WPW warps share one word; each streams its slice of
+//     the 32 pixels' channels as 16-byte chunks, fully coalesced, with 2*U loads in flight per
+//     lane; per-chunk flags are folded to per-pixel flags with __ballot_sync + bit-range masks and
+//     OR-ed across the word's warps through shared memory.
+//   * narrow path (any x strides, state pixel = one 16-byte chunk, e.g. the RGB input frame).
+//   * generic path (any strides on both sides).
 // HBM-bound: algorithmic bytes = 2*C*P*s read (+ P/8 bitmap, + feedback writes).
 #pragma once
 #include "cb_common.cuh"
@@ -25,77 +26,121 @@ __device__ __forceinline__ uint4 merge_tail(uint4 xv, const uint4& sv, int tail)
   return xv;
 }
 
+// tf32 split plane for the 3xTF32 contraction: lo = v - trunc_tf32(v) (exact in fp32).  The conv
+// kernel feeds the raw fp32 state as the "hi" operand (the tensor core ignores the 13 low mantissa
+// bits) and this plane as the "lo" operand, so the split is paid once per accepted pixel here
+// instead of once per gathered filter tap there.  lo_off = element offset state -> lo plane (0: off).
+__device__ __forceinline__ unsigned tf32_lo(unsigned v) {
+  return __float_as_uint(__uint_as_float(v) - __uint_as_float(v & 0xFFFFE000u));
+}
+template <typename T>
+__device__ __forceinline__ void store_state(T* sptr, const uint4& v, long long lo_off) {
+  st16(sptr, v);
+  if (sizeof(T) == 4 && lo_off != 0)
+    st16(sptr + lo_off, make_uint4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w)));
+}
+__device__ __forceinline__ void store_state_scalar(float* sptr, float v, long long lo_off) {
+  *sptr = v;
+  if (lo_off != 0) sptr[lo_off] = __uint_as_float(tf32_lo(__float_as_uint(v)));
+}
+template <typename T>
+__device__ __forceinline__ void store_state_scalar(T* sptr, T v, long long) { *sptr = v; }
+
+constexpr int kDetWarps = 8;                   // warps per block
+
 // x: pixel-major, pitch xp (elements); state: pixel-major, pitch sp.  Rows may be strided (sy).
 // U chunk-iterations are batched: all 2*U 16-byte loads of a batch are issued before the first
 // ballot, so every lane keeps 2*U loads in flight (the ballots would otherwise serialise them).
+// wlog = log2(warps per word): a block of 8 warps covers 8 >> wlog words.
 template <typename T, int VEC, int UPDATE, int U>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kDetWarps * 32)
 detect_vec_kernel(const T* __restrict__ x, long long x_sb, long long x_sy, int xp,
-                  T* __restrict__ st, long long s_sb, long long s_sy, int sp,
+                  T* __restrict__ st, long long s_sb, long long s_sy, int sp, long long lo_off,
                   uint32_t* __restrict__ bits, int B, int H, int W, int C, int Wd, T thr,
-                  unsigned cpv_magic) {
-  const int lane = threadIdx.x & 31;
-  const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (warp >= (long long)B * H * Wd) return;
-  const int j = (int)(warp % Wd);
-  const long long r = warp / Wd;
-  const int y = (int)(r % H);
-  const int b = (int)(r / H);
-  const int x0 = j * 32;
-  const int npx = min(32, W - x0);
-  const T* xb = x + b * x_sb + y * x_sy + (long long)x0 * xp;
-  T* sb = st + b * s_sb + y * s_sy + (long long)x0 * sp;
+                  unsigned cpv_magic, int wlog) {
+  __shared__ unsigned s_word[kDetWarps];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int wpw = 1 << wlog;
+  const int part = wid & (wpw - 1), slot = wid >> wlog;
+  const long long word = (long long)blockIdx.x * (kDetWarps >> wlog) + slot;
+  const bool active = word < (long long)B * H * Wd;
+  if (wlog > 0) {
+    if (threadIdx.x < kDetWarps) s_word[threadIdx.x] = 0u;
+    __syncthreads();
+  } else if (!active) {
+    return;
+  }
   const int cpv = (C + VEC - 1) / VEC;       // 16-byte chunks per pixel that hold real channels
   const int tail = C % VEC;                  // valid elements of the last chunk (0 = all)
-  const int nq = npx * cpv;
   // q / cpv without a divide: exact for q*cpv < 2^32 (q <= 32*cpv here)
   auto pixel_of = [&](int q) { return cpv == 1 ? q : (int)__umulhi((unsigned)q, cpv_magic); };
+  const T* xb = nullptr;
+  T* sb = nullptr;
+  int nq = 0;
+  unsigned wordbits = 0;
+  if (active) {
+    const int j = (int)(word % Wd);
+    const long long r = word / Wd;
+    const int y = (int)(r % H);
+    const int b = (int)(r / H);
+    const int x0 = j * 32;
+    const int npx = min(32, W - x0);
+    xb = x + b * x_sb + y * x_sy + (long long)x0 * xp;
+    sb = st + b * s_sb + y * s_sy + (long long)x0 * sp;
+    nq = npx * cpv;
 
-  bool mychg = false;                        // flag of pixel `lane`
-  const int plo = lane * cpv, phi = plo + cpv;
-  for (int q0 = 0; q0 < nq; q0 += 32 * U) {
-    uint4 xv[U], sv[U];
-    T* sptr[U];
-    bool valid[U];
+    bool mychg = false;                      // flag of pixel `lane` (this warp's slice only)
+    const int plo = lane * cpv, phi = plo + cpv;
+    for (int q0 = part * 32 * U; q0 < nq; q0 += wpw * 32 * U) {
+      uint4 xv[U], sv[U];
+      T* sptr[U];
+      bool valid[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int q = q0 + u * 32 + lane;
-      valid[u] = q < nq;
-      const int px = pixel_of(q), cc = q - px * cpv;
-      sptr[u] = sb + (long long)px * sp + cc * VEC;
-      if (valid[u]) {
-        xv[u] = ldg16(xb + (long long)px * xp + cc * VEC);
-        sv[u] = ld16(sptr[u]);
-        if (tail && cc == cpv - 1) xv[u] = merge_tail<T, VEC>(xv[u], sv[u], tail);
+      for (int u = 0; u < U; ++u) {
+        const int q = q0 + u * 32 + lane;
+        valid[u] = q < nq;
+        const int px = pixel_of(q), cc = q - px * cpv;
+        sptr[u] = sb + (long long)px * sp + cc * VEC;
+        if (valid[u]) {
+          xv[u] = ldg16(xb + (long long)px * xp + cc * VEC);
+          sv[u] = ld16(sptr[u]);
+          if (tail && cc == cpv - 1) xv[u] = merge_tail<T, VEC>(xv[u], sv[u], tail);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        bool f = false;
+        if (valid[u]) {
+          f = Chunk<T>::changed(sv[u], xv[u], thr);
+          if (UPDATE == CB_UPDATE_ALL) store_state<T>(sptr[u], xv[u], lo_off);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, f);
+        const int qb = q0 + u * 32;
+        const int lo = max(plo, qb) - qb, hi = min(phi, qb + 32) - qb;
+        if (hi > lo) {
+          const unsigned m = (hi - lo >= 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
+          mychg |= (bal & m) != 0u;
+        }
       }
     }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      bool f = false;
-      if (valid[u]) {
-        f = Chunk<T>::changed(sv[u], xv[u], thr);
-        if (UPDATE == CB_UPDATE_ALL) st16(sptr[u], xv[u]);
-      }
-      const unsigned bal = __ballot_sync(0xffffffffu, f);
-      const int qb = q0 + u * 32;
-      const int lo = max(plo, qb) - qb, hi = min(phi, qb + 32) - qb;
-      if (hi > lo) {
-        const unsigned m = (hi - lo >= 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
-        mychg |= (bal & m) != 0u;
-      }
-    }
+    wordbits = __ballot_sync(0xffffffffu, mychg);
   }
-  const unsigned word = __ballot_sync(0xffffffffu, mychg);
-  if (lane == 0) bits[warp] = word;
+  if (wlog > 0) {                              // OR the partial words of the warps sharing a word
+    if (active && lane == 0 && wordbits) atomicOr(&s_word[slot], wordbits);
+    __syncthreads();
+    wordbits = s_word[slot];
+    if (!active) return;
+  }
+  if (part == 0 && lane == 0) bits[word] = wordbits;
 
-  if (UPDATE == CB_UPDATE_CHANGED && word) {  // feedback: accept the new value at changed pixels
-    for (int q = lane; q < nq; q += 32) {
+  if (UPDATE == CB_UPDATE_CHANGED && wordbits) {  // feedback: accept the new value at changed pixels
+    for (int q = part * 32 + lane; q < nq; q += wpw * 32) {
       const int px = pixel_of(q), cc = q - px * cpv;
-      if ((word >> px) & 1u) {
+      if ((wordbits >> px) & 1u) {
         uint4 xv = ldg16(xb + (long long)px * xp + cc * VEC);
         T* sp2 = sb + (long long)px * sp + cc * VEC;
         if (tail && cc == cpv - 1) xv = merge_tail<T, VEC>(xv, ld16(sp2), tail);
-        st16(sp2, xv);
+        store_state<T>(sp2, xv, lo_off);
       }
     }
   }
@@ -108,7 +153,8 @@ template <typename T, int VEC, int UPDATE>
 __global__ void __launch_bounds__(256)
 detect_narrow_kernel(const T* __restrict__ x, long long x_sb, long long x_sc, long long x_sy,
                      long long x_sx, T* __restrict__ st, long long s_sb, long long s_sy,
-                     uint32_t* __restrict__ bits, int B, int H, int W, int C, int Wd, T thr) {
+                     long long lo_off, uint32_t* __restrict__ bits, int B, int H, int W, int C,
+                     int Wd, T thr) {
   const int lane = threadIdx.x & 31;
   const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (warp >= (long long)B * H * Wd) return;
@@ -128,7 +174,7 @@ detect_narrow_kernel(const T* __restrict__ x, long long x_sb, long long x_sc, lo
     for (int c = 0; c < VEC; ++c)
       if (c < C) ne[c] = xp[c * x_sc];
     f = Chunk<T>::changed(sv, nv, thr);
-    if (UPDATE == CB_UPDATE_ALL || (UPDATE == CB_UPDATE_CHANGED && f)) st16(sp, nv);
+    if (UPDATE == CB_UPDATE_ALL || (UPDATE == CB_UPDATE_CHANGED && f)) store_state<T>(sp, nv, lo_off);
   }
   const unsigned word = __ballot_sync(0xffffffffu, f);
   if (lane == 0) bits[warp] = word;
@@ -138,8 +184,8 @@ template <typename T, int UPDATE>
 __global__ void __launch_bounds__(256)
 detect_generic_kernel(const T* __restrict__ x, long long x_sb, long long x_sc, long long x_sy,
                       long long x_sx, T* __restrict__ st, long long s_sb, long long s_sc,
-                      long long s_sy, long long s_sx, uint32_t* __restrict__ bits, int B, int H,
-                      int W, int C, int Wd, T thr) {
+                      long long s_sy, long long s_sx, long long lo_off,
+                      uint32_t* __restrict__ bits, int B, int H, int W, int C, int Wd, T thr) {
   const int lane = threadIdx.x & 31;
   const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (warp >= (long long)B * H * Wd) return;
@@ -156,10 +202,10 @@ detect_generic_kernel(const T* __restrict__ x, long long x_sb, long long x_sc, l
       const T xv = xp[c * x_sc];
       const T sv = sp[c * s_sc];
       f |= value_changed(sv, xv, thr);
-      if (UPDATE == CB_UPDATE_ALL) sp[c * s_sc] = xv;
+      if (UPDATE == CB_UPDATE_ALL) store_state_scalar(sp + c * s_sc, xv, lo_off);
     }
     if (UPDATE == CB_UPDATE_CHANGED && f)
-      for (int c = 0; c < C; ++c) sp[c * s_sc] = xp[c * x_sc];
+      for (int c = 0; c < C; ++c) store_state_scalar(sp + c * s_sc, xp[c * x_sc], lo_off);
   }
   const unsigned word = __ballot_sync(0xffffffffu, f);
   if (lane == 0) bits[warp] = word;
@@ -175,16 +221,19 @@ template <> __host__ __device__ inline __nv_bfloat16 thr_cast<__nv_bfloat16>(flo
 template <typename T, int VEC>
 int launch_detect(cudaStream_t stream, const void* x, long long x_sb, long long x_sc,
                   long long x_sy, long long x_sx, void* state, long long s_sb, long long s_sc,
-                  long long s_sy, long long s_sx, uint32_t* bits, int B, int C, int H, int W,
-                  float threshold, int update) {
+                  long long s_sy, long long s_sx, void* state_lo, uint32_t* bits, int B, int C,
+                  int H, int W, float threshold, int update) {
   const int Wd = (W + 31) / 32;
-  const long long warps = (long long)B * H * Wd;
-  if (warps == 0) return 0;
-  const int wpb = 8;
-  const long long blocks = (warps + wpb - 1) / wpb;
-  CB_CHECK_ARG(blocks < (1ll << 31), "change_detect: image too large");
+  const long long words = (long long)B * H * Wd;
+  if (words == 0) return 0;
   const T thr = thr_cast<T>(threshold);
   const size_t es = sizeof(T);
+  long long lo_off = 0;
+  if (state_lo) {
+    CB_CHECK_ARG(sizeof(T) == 4, "change_detect: the tf32 lo plane exists for fp32 only");
+    lo_off = (long long)((const T*)state_lo - (const T*)state);
+    CB_CHECK_ARG(lo_off != 0 && ((uintptr_t)state_lo % 16) == 0, "change_detect: bad lo plane");
+  }
   const bool vec_ok = x_sc == 1 && s_sc == 1 && (x_sx % VEC) == 0 && (s_sx % VEC) == 0 &&
                       x_sx >= C && s_sx >= C && ((x_sy * es) % 16) == 0 && ((s_sy * es) % 16) == 0 &&
                       ((x_sb * es) % 16) == 0 && ((s_sb * es) % 16) == 0 &&
@@ -195,24 +244,31 @@ int launch_detect(cudaStream_t stream, const void* x, long long x_sb, long long 
                          ((uintptr_t)state % 16) == 0;
   const int cpv = (C + VEC - 1) / VEC;
   const unsigned magic = cpv > 1 ? (unsigned)((0x100000000ull + cpv - 1) / cpv) : 0u;
-  dim3 grid((unsigned)blocks), block(wpb * 32);
+  // warps per word: keep >= 2 load batches (of U*32 chunks) per warp, at most one block per word
+  int wlog = 0;
+  while (wlog < 3 && (32 * cpv) / (1 << (wlog + 1)) >= 2 * 4 * 32) ++wlog;
+  const long long vec_blocks = (words + (kDetWarps >> wlog) - 1) / (kDetWarps >> wlog);
+  const long long blocks = vec_ok ? vec_blocks : (words + 7) / 8;
+  CB_CHECK_ARG(blocks < (1ll << 31), "change_detect: image too large");
+  dim3 grid((unsigned)blocks), block(256);
 #define CB_DET(U_)                                                                             \
   if (vec_ok) {                                                                                \
     if (cpv >= 4)                                                                              \
       detect_vec_kernel<T, VEC, U_, 4><<<grid, block, 0, stream>>>(                            \
-          (const T*)x, x_sb, x_sy, (int)x_sx, (T*)state, s_sb, s_sy, (int)s_sx, bits, B, H, W, \
-          C, Wd, thr, magic);                                                                  \
+          (const T*)x, x_sb, x_sy, (int)x_sx, (T*)state, s_sb, s_sy, (int)s_sx, lo_off, bits,  \
+          B, H, W, C, Wd, thr, magic, wlog);                                                   \
     else                                                                                       \
       detect_vec_kernel<T, VEC, U_, 2><<<grid, block, 0, stream>>>(                            \
-          (const T*)x, x_sb, x_sy, (int)x_sx, (T*)state, s_sb, s_sy, (int)s_sx, bits, B, H, W, \
-          C, Wd, thr, magic);                                                                  \
+          (const T*)x, x_sb, x_sy, (int)x_sx, (T*)state, s_sb, s_sy, (int)s_sx, lo_off, bits,  \
+          B, H, W, C, Wd, thr, magic, wlog);                                                   \
   } else if (narrow_ok) {                                                                      \
     detect_narrow_kernel<T, VEC, U_><<<grid, block, 0, stream>>>(                              \
-        (const T*)x, x_sb, x_sc, x_sy, x_sx, (T*)state, s_sb, s_sy, bits, B, H, W, C, Wd, thr); \
+        (const T*)x, x_sb, x_sc, x_sy, x_sx, (T*)state, s_sb, s_sy, lo_off, bits, B, H, W, C,  \
+        Wd, thr);                                                                              \
   } else {                                                                                     \
     detect_generic_kernel<T, U_><<<grid, block, 0, stream>>>(                                  \
-        (const T*)x, x_sb, x_sc, x_sy, x_sx, (T*)state, s_sb, s_sc, s_sy, s_sx, bits, B, H, W, \
-        C, Wd, thr);                                                                           \
+        (const T*)x, x_sb, x_sc, x_sy, x_sx, (T*)state, s_sb, s_sc, s_sy, s_sx, lo_off, bits,  \
+        B, H, W, C, Wd, thr);                                                                  \
   }
   switch (update) {
     case CB_UPDATE_NONE: CB_DET(CB_UPDATE_NONE) break;

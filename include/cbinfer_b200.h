@@ -68,12 +68,15 @@ size_t cb_packed_weight_bytes(int dtype, int gemm, int Cout, int Cin, int kH, in
  *           detection half only; the dilation lives in cb_dilate_compact.
  * raw_bits[word] bit = OR_c ( |state - x| > thr )   strict '>', fp32 flush-to-zero, fp16/bf16:
  * rounded difference vs rounded threshold, two one-sided tests (half.cu:58-63).
- * The whole bitmap (incl. row padding bits = 0) is written; no pre-zeroing needed. */
+ * The whole bitmap (incl. row padding bits = 0) is written; no pre-zeroing needed.
+ * state_lo (optional, fp32 only, same strides as state): wherever the state is written, the tf32
+ * remainder  v - trunc_tf32(v)  is written to this plane; cb_conv_update(CB_GEMM_TC_3X) consumes
+ * it, so the hi/lo split is paid once per accepted pixel instead of once per gathered tap. */
 int cb_change_detect(void* stream, int dtype,
                      const void* x, long long x_sb, long long x_sc, long long x_sy, long long x_sx,
                      void* state, long long s_sb, long long s_sc, long long s_sy, long long s_sx,
-                     uint32_t* raw_bits, int B, int C, int H, int W, float threshold,
-                     int update_mode);
+                     void* state_lo, uint32_t* raw_bits, int B, int C, int H, int W,
+                     float threshold, int update_mode);
 
 /* ---- propagation + compaction -------------------------------------------------------------
  * replaces: the scatter-dilate inside changeDetection_kernel (cbconv2d_cg_backend.cu:62-72),
@@ -102,11 +105,13 @@ int cb_map_to_bits(void* stream, const int8_t* map, uint32_t* bits, int B, int H
  *                                        state[pixel idx[j] + (ky-kH/2, kx-kW/2), ci] )
  * with zero outside the image and act = ReLU iff relu (v <= 0 -> 0, cg.cu:187).
  * state / out are pixel-major with the given pitches; bias is fp32[Cout]; packed_w comes from
- * cb_pack_weights with the same dtype/gemm/shape.  *count is read on the device. */
+ * cb_pack_weights with the same dtype/gemm/shape.  *count is read on the device.
+ * state_lo: the tf32 remainder plane maintained by cb_change_detect; required for
+ * CB_GEMM_TC_3X on fp32 data, ignored (may be NULL) otherwise. */
 int cb_pack_weights(void* stream, int dtype, int gemm, const void* weight /*[Cout,Cin,kH,kW]*/,
                     void* packed, int Cout, int Cin, int kH, int kW);
-int cb_conv_update(void* stream, int dtype, int gemm, const void* state, int pitch_in,
-                   const int32_t* idx, const int32_t* count, const void* packed_w,
+int cb_conv_update(void* stream, int dtype, int gemm, const void* state, const void* state_lo,
+                   int pitch_in, const int32_t* idx, const int32_t* count, const void* packed_w,
                    const float* bias, void* out, int pitch_out, int B, int H, int W, int Cin,
                    int Cout, int kH, int kW, int relu);
 

@@ -168,6 +168,26 @@ def test_detect_update_all_and_special_values(cbm, orc):
     cg.detect(xx, view, s["raw_bits"], 0.1, lib.UPDATE_ALL)
     assert bits_to_map(s["raw_bits"], 2, 5, 37).all()
     assert torch.equal(view, xx)
+    # tf32 remainder plane: written wherever the state is written, lo = v - trunc_tf32(v), exact
+    for shape, layout in (((2, 6, 5, 37), "pixel"), ((1, 3, 9, 40), "narrow"), ((1, 5, 7, 33), "planar")):
+        x0, x1 = rand_tensor(shape, "f32", 5), None
+        x1 = perturb(x0, 0.2, 6)
+        if layout == "planar":
+            st, lo = x0.clone(), torch.zeros_like(x0)
+            xin = x1
+        else:
+            st, _ = cg.pixel_major(shape, torch.float32, "cuda", 0)
+            lo, _ = cg.pixel_major(shape, torch.float32, "cuda", 0)
+            st.copy_(x0)
+            xin = x1 if layout == "narrow" else cg.pixel_major(shape, torch.float32, "cuda", 0)[0].copy_(x1)
+        lo.copy_(cg.tf32_lo(x0))
+        s = cg.alloc_scratch((shape[0], shape[2], shape[3]), "cuda")
+        cg.detect(xin, st, s["raw_bits"], 0.3, lib.UPDATE_CHANGED, state_lo=lo)
+        assert torch.equal(lo, cg.tf32_lo(st.contiguous()))
+        hi = (st.contiguous().view(torch.int32) & -8192).view(torch.float32)
+        assert torch.equal(hi + lo.contiguous(), st.contiguous())
+        cg.detect(xin, st, s["raw_bits"], 0.3, lib.UPDATE_ALL, state_lo=lo)
+        assert torch.equal(st.contiguous(), x1) and torch.equal(lo.contiguous(), cg.tf32_lo(x1))
 
 
 def test_large_compaction_chained_scan(cbm):

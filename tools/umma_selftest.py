@@ -59,6 +59,24 @@ def main():
             match = [(c, float((src[c] - col).abs().max())) for c in range(Cin)]
             best = min(match, key=lambda t: t[1])
             print("one-hot k=%2d -> output matches input channel %2d (err %.2e)" % (kprobe, best[0], best[1]))
+    # how does kind::tf32 convert fp32 operands?  v = 1 + 2^-11 + 2^-12: truncation -> 1.0,
+    # round-to-nearest -> 1 + 2^-10.  The 3xTF32 path assumes truncation (hi = raw fp32 state).
+    Cin, Cout, H, W = 32, 16, 8, 16
+    w = torch.zeros(Cout, Cin, 1, 1, device="cuda")
+    w[0, 0] = 1.0
+    state, sbuf = cg.pixel_major((1, Cin, H, W), torch.float32, "cuda", 0)
+    v = 1.0 + 2.0 ** -11 + 2.0 ** -12
+    state.fill_(v)
+    out, obuf = cg.pixel_major((1, Cout, H, W), torch.float32, "cuda", 0)
+    sel = torch.arange(H * W, dtype=torch.int32, device="cuda")
+    ci = cg.ChangeIndexes.from_tensor(sel, (1, H, W))
+    cg.conv_update(sbuf, ci, cg.pack_weights(w, _lib.GEMM_TC), torch.zeros(Cout, device="cuda"), obuf,
+                   Cin, Cout, (1, 1), False, _lib.GEMM_TC)
+    torch.cuda.synchronize()
+    r = float(out[0, 0, 0, 0])
+    print("tf32 operand conversion probe: in %.10f -> out %.10f  (%s)" %
+          (v, r, "TRUNCATION" if r == 1.0 else "ROUNDING" if r == 1.0 + 2.0 ** -10 else "??"))
+    bad |= r != 1.0
     print("SELFTEST", "FAILED" if bad else "PASSED")
 
 
