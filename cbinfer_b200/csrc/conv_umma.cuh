@@ -156,8 +156,11 @@ struct UmmaCfg {
   static constexpr int A_BYTES = UM_BM * UM_ROW_BYTES;       // 16 KB
   static constexpr int B_BYTES = BN * UM_ROW_BYTES;
   static constexpr int STAGE_BYTES = NSPLIT * (A_BYTES + B_BYTES);
-  static constexpr int STAGES = (96 * 1024 / STAGE_BYTES) < 2 ? 2
-                                : (96 * 1024 / STAGE_BYTES) > 6 ? 6 : (96 * 1024 / STAGE_BYTES);
+  // two CTAs per SM (<= ~100 KB each) unless a stage is so large that only one CTA fits
+  static constexpr int CTAS_PER_SM = STAGE_BYTES > 48 * 1024 ? 1 : 2;
+  static constexpr int BUDGET = CTAS_PER_SM == 1 ? 200 * 1024 : 98 * 1024;
+  static constexpr int STAGES = (BUDGET / STAGE_BYTES) < 2 ? 2
+                                : (BUDGET / STAGE_BYTES) > 8 ? 8 : (BUDGET / STAGE_BYTES);
   static constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 2048 /*ctrl*/;
 };
@@ -448,7 +451,7 @@ __global__ void pack_weights_umma_kernel(const T* __restrict__ w, T* __restrict_
 }
 
 inline int umma_bn(int gemm, int Cout) {
-  const int maxbn = gemm == CB_GEMM_TC_3X ? 64 : 128;
+  const int maxbn = 256;
   int bn = 16;
   while (bn < Cout && bn < maxbn) bn <<= 1;
   return bn;
@@ -541,7 +544,7 @@ int launch_conv_umma(cudaStream_t s, int dtype, const void* state, const void* s
     attr_dev = dev;
   }
   const long long max_tiles = (((long long)B * H * W + UM_BM - 1) / UM_BM) * (CoutPad / BN);
-  long long grid = (long long)sm_count() * 2;
+  long long grid = (long long)sm_count() * C::CTAS_PER_SM;
   if (grid > max_tiles) grid = max_tiles;
   if (grid < 1) grid = 1;
   kern<<<(unsigned)grid, UM_THREADS, C::SMEM_BYTES, s>>>(map, (const T*)state, (const T*)state_lo, Cp,
@@ -562,11 +565,7 @@ int dispatch_bn(int bn, cudaStream_t s, int dtype, const void* state, const void
     return launch_conv_umma<T, SPLIT3, N>(s, dtype, state, state_lo, Cp, idx, count, packed, bias, out, \
                                           Op, B, H, W, Cout, CoutPad, kH, kW, relu);
   switch (bn) {
-    CB_BN(16) CB_BN(32) CB_BN(64)
-    case 128:
-      if (!SPLIT3)
-        return launch_conv_umma<T, false, 128>(s, dtype, state, state_lo, Cp, idx, count, packed, bias, out,
-                                               Op, B, H, W, Cout, CoutPad, kH, kW, relu);
+    CB_BN(16) CB_BN(32) CB_BN(64) CB_BN(128) CB_BN(256)
     default: return fail(2, "conv_update: unsupported N tile %d", bn);
   }
 #undef CB_BN
