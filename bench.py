@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16", "f16"])
     ap.add_argument("--gemm", default="auto", choices=["auto", "simt", "tc", "tc3x"])
     ap.add_argument("--threshold-factor", type=float, default=0.02)
+    ap.add_argument("--dense-scan", action="store_true",
+                    help="re-scan every layer's whole input like the reference (default: candidate detection)")
     ap.add_argument("--no-extras", action="store_true", help="skip dense/latency/kernel/cpu legs")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     return ap.parse_args()
@@ -203,7 +205,8 @@ def workload_config(args, streams):
                         "%dx%d video, %.0f%% %s change per frame" % (args.width, args.height, args.rate * 100, args.mode),
             "streams_per_gpu": streams, "height": args.height, "width": args.width,
             "change_rate": args.rate, "change_mode": args.mode, "threshold_factor": args.threshold_factor,
-            "gemm": args.gemm, "parallelism": "independent video streams sharded per GPU, no collective"}
+            "gemm": args.gemm, "detection": "dense re-scan per layer" if args.dense_scan else
+            "dense scan on the input frame, candidate detection on CB-fed layers", "parallelism": "independent video streams sharded per GPU, no collective"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -235,7 +238,7 @@ def main():
     # ---- model + synthetic video (each rank: its own streams, seeds offset by rank) ----------
     base = models.sceneLabelingBaseline().to(dev).to(tdt)
     model = models.sceneLabelingCBinfer(base, experimentIdx=6, threshold=0.1, convertAll=True,
-                                        clonePoolOutput=False)
+                                        clonePoolOutput=False, candidateDetect=not args.dense_scan)
     for m in model.modules():
         if type(m) is cb.CBConv2d:
             m.gemmMode = args.gemm
@@ -262,7 +265,9 @@ def main():
     torch.cuda.current_stream().wait_stream(side)
     with torch.cuda.graph(graph), torch.no_grad():
         static_out = model(static_in)
-    my_launches_per_step = 5 * 3 + 2          # per CBConv2d: detect, dilate+compact, conv; per pool: 1
+    # my kernels per step: per CBConv2d detect + dilate/compact + conv; per pool 1 (+1 pooled
+    # compaction when it hands candidates on)
+    my_launches_per_step = 5 * 3 + 2 + (0 if args.dense_scan else 2)
 
     def step(t):
         static_in.copy_(frames[t])
@@ -388,7 +393,8 @@ def kernel_roofline(args, model, frames, dev, tdt):
     es = 4 if args.dtype == "f32" else 2
     rec = {}
     cur = {"layer": None}
-    orig = {n: getattr(cg, n) for n in ("detect", "dilate_compact", "conv_update", "maxPool2d")}
+    orig = {n: getattr(cg, n) for n in ("detect", "detect_sparse", "dilate_compact", "pool_compact",
+                                        "conv_update", "maxPool2d")}
 
     def timed(name):
         fn = orig[name]
@@ -431,7 +437,9 @@ def kernel_roofline(args, model, frames, dev, tdt):
             P = B * Hh * Ww
             n = int(m._scratch["count"].item())
             k2 = m.kernel_size[0] * m.kernel_size[1]
-            if kname == "detect":
+            if kname == "detect_sparse":
+                row.update(bound="hbm")
+            elif kname == "detect":
                 by = 2 * Cin * P * es + P // 8
                 row.update(bound="hbm", bytes=by, achieved=by / (us * 1e-6) / 1e9, peak=hbm, unit="GB/s")
             elif kname == "dilate_compact":
@@ -504,7 +512,7 @@ def single_stream_latency(args, base, dev, tdt):
     import cbinfer_b200 as cb
     from cbinfer_b200 import models, video
     model = models.sceneLabelingCBinfer(base, experimentIdx=6, threshold=0.1, convertAll=True,
-                                        clonePoolOutput=False)
+                                        clonePoolOutput=False, candidateDetect=not args.dense_scan)
     for m in model.modules():
         if type(m) is cb.CBConv2d:
             m.gemmMode = args.gemm

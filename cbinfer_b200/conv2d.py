@@ -46,6 +46,7 @@ class CBPoolMax2d(nn.Module):
         self.kernel_size = ks
         self.ceil_mode = m.ceil_mode
         self.propChangeIndexes = False
+        self.propPooledIndexes = False  # extension: hand pooled-resolution change candidates on
         self.cloneOutput = True   # reference returns outputState.clone() (conv2d.py:73)
         self.register_buffer('outputState', torch.empty(0))
         self._stateBuf = None
@@ -54,6 +55,7 @@ class CBPoolMax2d(nn.Module):
     def clearMemory(self):
         self.outputState = self.outputState.new_empty(0)
         self._stateBuf = None
+        self._scratch = None
 
     def getStateTensors(self):
         return [self.outputState] if hasattr(self, 'outputState') else []
@@ -78,10 +80,22 @@ class CBPoolMax2d(nn.Module):
             # (conv2d.py:53-62); deciding that needs a host sync, so the state is allocated up front.
             self.outputState, self._stateBuf = cg.pixel_major((B, nc, oh, ow), input.dtype,
                                                               input.device, _INF)
+            self._scratch = None
         cg.maxPool2d(input, self.outputState, changeIndexes, self.kernel_size, self.stride)
 
         output = self.outputState.clone() if self.cloneOutput else self.outputState
+        if getattr(self, 'propPooledIndexes', False) and changeIndexes.bits is not None:
+            # extension (no reference counterpart): change candidates at the pooled resolution for
+            # a downstream CBConv2d with candidateDetect=True
+            if self._scratch is None:
+                self._scratch = cg.alloc_scratch((B, oh, ow), input.device)
+            s = self._scratch
+            cg.pool_compact(changeIndexes.bits, (B, h, w), (B, oh, ow), s["idx"], s["count"], s["ws"],
+                            out_bits=s["dil_bits"])
+            return 'changeIndexes', output, ChangeIndexes(s["idx"], s["count"], (B, oh, ow),
+                                                          bits=s["dil_bits"])
         if self.propChangeIndexes:
+            # reference behaviour: the *input-resolution* indices are forwarded (conv2d.py:75-76)
             return 'changeIndexes', output, changeIndexes
         else:
             return output
@@ -132,6 +146,9 @@ class CBConv2d(nn.Module):
         self.copyInput = True
         self.feedbackLoop = False
         self.gemmMode = 'auto'
+        # extension: treat indices received from upstream as *candidates* for the thresholded
+        # detection instead of as the final change set (exact, see cb_change_detect_sparse)
+        self.candidateDetect = False
 
     # ---- state ---------------------------------------------------------------------------
     def clearMemory(self):
@@ -144,6 +161,8 @@ class CBConv2d(nn.Module):
         self._loBuf = None
         self._scratch = None      # bitmaps, index list, count, compaction workspace
         self._packed = None       # (key, packed weights, fp32 bias)
+        self._fresh = True        # state holds +inf: the next detection must be a full scan
+        self._lastThr = None
         self.changeMap = None
         if hasattr(self, 'compStats'):
             self.compStats = None
@@ -208,6 +227,7 @@ class CBConv2d(nn.Module):
             self._loView, self._loBuf = (cg.pixel_major(input.shape, dt, dev, 0)
                                          if dt == torch.float32 else (None, None))
             self._scratch = None
+            self._fresh = True
         outpSize = (B, self.out_channels, H, W)
         if tuple(self.prevOutput.size()) != outpSize or self.prevOutput.dtype != dt or self._outBuf is None:
             self.prevOutput, self._outBuf = cg.pixel_major(outpSize, dt, dev, _INF)    # :195-199
@@ -220,14 +240,29 @@ class CBConv2d(nn.Module):
         if self.gatherComputationStats:
             self._gatherStats(input)
 
+        candidates = None
+        if changeIndexes is not None and getattr(self, 'candidateDetect', False):
+            candidates, changeIndexes = changeIndexes, None
+            if not isinstance(candidates, ChangeIndexes):
+                candidates = ChangeIndexes.from_tensor(candidates.detach(), (B, H, W))
+            if self._fresh or self._lastThr is None or self.threshold < self._lastThr \
+                    or tuple(candidates.shape) != (B, H, W):
+                candidates = None          # exactness conditions not met: full scan
+
         if changeIndexes is None:
             # reference: detect (feedback updates prevInput at changed pixels, :222-224), nonzero
             # (:232), then prevInput.copy_(input) when not in feedback mode (:234-238).  Here the
             # copy is part of the detection pass; copyInput=False (alias the input as state) is
             # honoured as a copy -- the state always owns its memory.
-            cg.detect(input, self.prevInput, s["raw_bits"], self.threshold,
-                      _lib.UPDATE_CHANGED if self.feedbackLoop else _lib.UPDATE_ALL,
-                      state_lo=self._loView)
+            mode = _lib.UPDATE_CHANGED if self.feedbackLoop else _lib.UPDATE_ALL
+            if candidates is not None:
+                cg.detect_sparse(input, self.prevInput, s["raw_bits"], self.threshold, mode,
+                                 candidates, state_lo=self._loView)
+            else:
+                cg.detect(input, self.prevInput, s["raw_bits"], self.threshold, mode,
+                          state_lo=self._loView)
+            self._fresh = False
+            self._lastThr = self.threshold
             dil_map = s.get("dil_map") if self.saveChangeMap else None
             cg.dilate_compact(s["raw_bits"], (B, H, W), self.kernel_size, s["idx"], s["count"],
                               s["ws"], dil_bits=s["dil_bits"], dil_map=dil_map)
@@ -302,6 +337,7 @@ class CBConv2d(nn.Module):
     def _setDefaultValues(self):
         for name, val in (('saveChangeMap', False), ('propChangeIndexes', False),
                           ('gatherComputationStats', False), ('finegrained', False),
-                          ('copyInput', True), ('feedbackLoop', False), ('gemmMode', 'auto')):
+                          ('copyInput', True), ('feedbackLoop', False), ('gemmMode', 'auto'),
+                          ('candidateDetect', False)):
             if not(hasattr(self, name)):
                 setattr(self, name, val)

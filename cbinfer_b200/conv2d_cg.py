@@ -102,6 +102,31 @@ def detect(x, state, raw_bits, threshold, update_mode, state_lo=None):
                              raw_bits.data_ptr(), B, Cc, H, W, float(threshold), int(update_mode)))
 
 
+def detect_sparse(x, state, raw_bits, threshold, update_mode, candidates, state_lo=None):
+    """cb_change_detect_sparse: the detection test at the candidate pixels only (see the header
+    for the exactness conditions).  `candidates` is a :class:`ChangeIndexes` at x's resolution."""
+    require_cuda(x, state, raw_bits)
+    B, Cc, H, W = x.shape
+    assert state.shape == x.shape and state.dtype == x.dtype
+    assert tuple(candidates.shape) == (B, H, W)
+    check(C.cb_change_detect_sparse(stream_ptr(x.device), dtype_code(x), x.data_ptr(), *_strides4(x),
+                                    state.data_ptr(), *_strides4(state),
+                                    state_lo.data_ptr() if state_lo is not None else None,
+                                    candidates.buffer.data_ptr(), candidates.count.data_ptr(),
+                                    raw_bits.data_ptr(), B, Cc, H, W, float(threshold),
+                                    int(update_mode)))
+
+
+def pool_compact(in_bits, in_shape, out_shape, idx, count, ws, out_bits=None):
+    """cb_pool_compact: change candidates at the 2x2-pooled resolution from an input bitmap."""
+    B, H, W = in_shape
+    B2, oH, oW = out_shape
+    assert B == B2
+    check(C.cb_pool_compact(stream_ptr(in_bits.device), in_bits.data_ptr(),
+                            out_bits.data_ptr() if out_bits is not None else None,
+                            idx.data_ptr(), count.data_ptr(), ws.data_ptr(), B, H, W, oH, oW))
+
+
 def dilate_compact(raw_bits, shape, filtSize, idx, count, ws, dil_bits=None, dil_map=None):
     """cb_dilate_compact: dilation by the filter footprint + ordered compaction."""
     B, H, W = shape

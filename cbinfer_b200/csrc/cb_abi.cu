@@ -105,11 +105,47 @@ int cb_dilate_compact(void* stream, const uint32_t* raw_bits, uint32_t* dil_bits
     CB_CHECK_LAUNCH("dilate_compact(memset)");
     return 0;
   }
+  CB_CHECK_ARG(nwords < (1ll << 31), "dilate_compact: bitmap too large");
   const int ntiles = (int)((nwords + kCompactTile - 1) / kCompactTile);
   dilate_compact_kernel<<<ntiles, kCompactThreads, 0, s>>>(raw_bits, dil_bits, dil_map, idx, count,
                                                           ws, B, H, W, (W + 31) / 32, kHHalf,
-                                                          kWHalf, nwords, ntiles);
+                                                          kWHalf, (int)nwords, ntiles, 0, 0);
   CB_CHECK_LAUNCH("dilate_compact");
+  return 0;
+}
+
+int cb_pool_compact(void* stream, const uint32_t* in_bits, uint32_t* out_bits, int32_t* idx,
+                    int32_t* count, void* ws, int B, int H, int W, int oH, int oW) {
+  CB_CHECK_ARG(in_bits && idx && count && ws, "pool_compact: null pointer");
+  CB_CHECK_ARG(in_bits != out_bits, "pool_compact: out_bits must not alias in_bits");
+  const long long nwords = (long long)cb_bitmap_words(B, oH, oW);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (nwords == 0 || H == 0) {
+    cudaMemsetAsync(count, 0, sizeof(int32_t), s);
+    CB_CHECK_LAUNCH("pool_compact(memset)");
+    return 0;
+  }
+  CB_CHECK_ARG(nwords < (1ll << 31), "pool_compact: bitmap too large");
+  const int ntiles = (int)((nwords + kCompactTile - 1) / kCompactTile);
+  dilate_compact_kernel<<<ntiles, kCompactThreads, 0, s>>>(in_bits, out_bits, nullptr, idx, count, ws,
+                                                          B, oH, oW, (oW + 31) / 32, 0, 0,
+                                                          (int)nwords, ntiles, H, (W + 31) / 32);
+  CB_CHECK_LAUNCH("pool_compact");
+  return 0;
+}
+
+int cb_change_detect_sparse(void* stream, int dtype, const void* x, long long x_sb, long long x_sc,
+                            long long x_sy, long long x_sx, void* state, long long s_sb,
+                            long long s_sc, long long s_sy, long long s_sx, void* state_lo,
+                            const int32_t* candidates, const int32_t* n_candidates,
+                            uint32_t* raw_bits, int B, int C, int H, int W, float threshold,
+                            int update_mode) {
+  CB_CHECK_ARG(x && state && raw_bits && candidates && n_candidates, "change_detect_sparse: null pointer");
+  CB_CHECK_ARG(B >= 0 && C > 0 && H >= 0 && W >= 0, "change_detect_sparse: bad shape");
+  CB_DISPATCH_DTYPE(dtype, return (launch_detect_sparse<T, VEC>(
+                               (cudaStream_t)stream, x, x_sb, x_sc, x_sy, x_sx, state, s_sb, s_sc,
+                               s_sy, s_sx, state_lo, candidates, n_candidates, raw_bits, B, C, H, W,
+                               threshold, update_mode)));
   return 0;
 }
 

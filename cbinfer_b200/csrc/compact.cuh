@@ -54,13 +54,41 @@ __device__ __forceinline__ unsigned dilated_word(const uint32_t* __restrict__ ra
   return d;
 }
 
+// Word j of row (b, yo) of the 2x2/stride-2 pooled view of a bitmap with Hin x Win pixels:
+// bit xo = OR of the four input bits of window (yo, xo).  Used to hand pooled-resolution change
+// candidates from a CBPoolMax2d to the next layer.
+__device__ __forceinline__ unsigned compress_pairs(unsigned v) {
+  unsigned t = (v | (v >> 1)) & 0x55555555u;
+  t = (t | (t >> 1)) & 0x33333333u;
+  t = (t | (t >> 2)) & 0x0f0f0f0fu;
+  t = (t | (t >> 4)) & 0x00ff00ffu;
+  t = (t | (t >> 8)) & 0x0000ffffu;
+  return t;
+}
+__device__ __forceinline__ unsigned pooled_word(const uint32_t* __restrict__ raw, int b, int yo,
+                                                int j, int Hin, int Wdin, int oW) {
+  unsigned v0 = 0, v1 = 0;
+  for (int dy = 0; dy < 2; ++dy) {
+    const int y = 2 * yo + dy;
+    if (y < Hin) {
+      const uint32_t* row = raw + ((long long)b * Hin + y) * Wdin;
+      if (2 * j < Wdin) v0 |= __ldg(row + 2 * j);
+      if (2 * j + 1 < Wdin) v1 |= __ldg(row + 2 * j + 1);
+    }
+  }
+  unsigned d = compress_pairs(v0) | (compress_pairs(v1) << 16);
+  const int rem = oW - j * 32;
+  if (rem < 32) d &= (1u << rem) - 1u;
+  return d;
+}
+
 // Tiles are taken in blockIdx order (blocks are dispatched in index order, so every predecessor of
 // a running tile is running or finished and the look-back cannot starve).
 __global__ void __launch_bounds__(kCompactThreads)
 dilate_compact_kernel(const uint32_t* __restrict__ raw, uint32_t* __restrict__ dil_bits,
                       int8_t* __restrict__ dil_map, int32_t* __restrict__ idx,
                       int32_t* __restrict__ count, void* ws, int B, int H, int W, int Wd, int kh,
-                      int kw, long long nwords, int ntiles) {
+                      int kw, int nwords, int ntiles, int pool_hin, int pool_wdin) {
   CompactHeader* hdr = reinterpret_cast<CompactHeader*>(ws);
   volatile unsigned long long* tstate =
       reinterpret_cast<volatile unsigned long long*>(reinterpret_cast<char*>(ws) + sizeof(CompactHeader));
@@ -76,15 +104,17 @@ dilate_compact_kernel(const uint32_t* __restrict__ raw, uint32_t* __restrict__ d
   // ---- dilated words (consecutive words per thread keep the index order) ------------------
   unsigned d[kCompactWPT];
   int cnt = 0;
-  const long long w0 = (long long)tile * kCompactTile + (long long)tid * kCompactWPT;
+  const int w0 = tile * kCompactTile + tid * kCompactWPT;    // 32-bit index math: nwords < 2^31
 #pragma unroll
   for (int i = 0; i < kCompactWPT; ++i) {
-    const long long w = w0 + i;
+    const int w = w0 + i;
     d[i] = 0;
     if (w < nwords) {
-      const int j = (int)(w % Wd);
-      const long long r = w / Wd;
-      d[i] = dilated_word(raw, r, (int)(r % H), j, H, W, Wd, kh, kw);
+      const int j = w % Wd;
+      const int r = w / Wd;
+      const int y = r % H;
+      d[i] = pool_hin ? pooled_word(raw, r / H, y, j, pool_hin, pool_wdin, W)
+                      : dilated_word(raw, r, y, j, H, W, Wd, kh, kw);
       if (dil_bits) dil_bits[w] = d[i];
     }
     cnt += __popc(d[i]);
@@ -145,11 +175,11 @@ dilate_compact_kernel(const uint32_t* __restrict__ raw, uint32_t* __restrict__ d
   int o = s_base + s_warp[wid] + (incl - cnt);
 #pragma unroll
   for (int i = 0; i < kCompactWPT; ++i) {
-    const long long w = w0 + i;
+    const int w = w0 + i;
     if (w >= nwords) break;
-    const int j = (int)(w % Wd);
-    const long long r = w / Wd;                              // r = b*H + y
-    const int pix0 = (int)(r * W + j * 32);
+    const int j = w % Wd;
+    const int r = w / Wd;                                    // r = b*H + y
+    const int pix0 = r * W + j * 32;
     unsigned dd = d[i];
     while (dd) {
       const int bit = __ffs(dd) - 1;

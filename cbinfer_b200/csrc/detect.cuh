@@ -281,4 +281,144 @@ int launch_detect(cudaStream_t stream, const void* x, long long x_sb, long long 
   return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Candidate ("sparse") detection: the same per-pixel test, evaluated only at the pixels an
+// upstream change-based layer reports as rewritten.  Exact w.r.t. the dense scan as long as x is
+// unchanged everywhere else, the threshold was not lowered and the state is not fresh (the module
+// checks this): an untouched pixel was either accepted last frame (state == x, difference 0) or
+// is as far below the threshold as it was.  Replaces the O(C*P) scan with O(C*n_candidates).
+// A group of 1 << glog lanes owns one candidate (16-byte chunks, pixel-major); set bits are
+// OR-ed into the pre-zeroed bitmap.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int VEC, int UPDATE>
+__global__ void __launch_bounds__(256)
+detect_sparse_vec_kernel(const T* __restrict__ x, long long x_sb, long long x_sy, int xp,
+                         T* __restrict__ st, long long s_sb, long long s_sy, int sp,
+                         long long lo_off, const int32_t* __restrict__ cand,
+                         const int32_t* __restrict__ ncand, uint32_t* __restrict__ bits, int H,
+                         int W, int C, int Wd, T thr, int glog) {
+  const int n = *ncand;
+  const int lane = threadIdx.x & 31;
+  const int G = 1 << glog, ppw = 32 >> glog;
+  const int sub = lane >> glog, gl = lane & (G - 1);
+  const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (sub * G);
+  const int P = H * W;
+  const int cpv = (C + VEC - 1) / VEC, tail = C % VEC;
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long j0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * ppw;
+       j0 < n; j0 += nwarps * ppw) {
+    const long long j = j0 + sub;
+    const bool have = j < n;
+    int b = 0, y = 0, xx = 0;
+    if (have) {
+      const int pix = __ldg(cand + j);
+      b = pix / P;
+      const int p = pix - b * P;
+      y = p / W;
+      xx = p - y * W;
+    }
+    const T* xb = x + b * x_sb + y * x_sy + (long long)xx * xp;
+    T* sb = st + b * s_sb + y * s_sy + (long long)xx * sp;
+    bool f = false;
+    if (have) {
+      for (int cc = gl; cc < cpv; cc += G) {
+        uint4 xv = ldg16(xb + cc * VEC);
+        const uint4 sv = ld16(sb + cc * VEC);
+        if (tail && cc == cpv - 1) xv = merge_tail<T, VEC>(xv, sv, tail);
+        f |= Chunk<T>::changed(sv, xv, thr);
+        if (UPDATE == CB_UPDATE_ALL) store_state<T>(sb + cc * VEC, xv, lo_off);
+      }
+    }
+    const bool chg = (__ballot_sync(0xffffffffu, f) & gmask) != 0u;   // any lane of my group
+    if (have && chg) {
+      if (gl == 0) atomicOr(bits + ((long long)b * H + y) * Wd + (xx >> 5), 1u << (xx & 31));
+      if (UPDATE == CB_UPDATE_CHANGED) {
+        for (int cc = gl; cc < cpv; cc += G) {
+          uint4 xv = ldg16(xb + cc * VEC);
+          if (tail && cc == cpv - 1) xv = merge_tail<T, VEC>(xv, ld16(sb + cc * VEC), tail);
+          store_state<T>(sb + cc * VEC, xv, lo_off);
+        }
+      }
+    }
+  }
+}
+
+template <typename T, int UPDATE>
+__global__ void __launch_bounds__(256)
+detect_sparse_generic_kernel(const T* __restrict__ x, long long x_sb, long long x_sc,
+                             long long x_sy, long long x_sx, T* __restrict__ st, long long s_sb,
+                             long long s_sc, long long s_sy, long long s_sx, long long lo_off,
+                             const int32_t* __restrict__ cand, const int32_t* __restrict__ ncand,
+                             uint32_t* __restrict__ bits, int H, int W, int C, int Wd, T thr) {
+  const int n = *ncand;
+  const int P = H * W;
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n;
+       j += (long long)gridDim.x * blockDim.x) {
+    const int pix = __ldg(cand + j);
+    const int b = pix / P, p = pix - b * P;
+    const int y = p / W, xx = p - y * W;
+    const T* xp = x + b * x_sb + y * x_sy + xx * x_sx;
+    T* sp = st + b * s_sb + y * s_sy + xx * s_sx;
+    bool f = false;
+    for (int c = 0; c < C; ++c) {
+      const T xv = xp[c * x_sc];
+      f |= value_changed(sp[c * s_sc], xv, thr);
+      if (UPDATE == CB_UPDATE_ALL) store_state_scalar(sp + c * s_sc, xv, lo_off);
+    }
+    if (f) {
+      atomicOr(bits + ((long long)b * H + y) * Wd + (xx >> 5), 1u << (xx & 31));
+      if (UPDATE == CB_UPDATE_CHANGED)
+        for (int c = 0; c < C; ++c) store_state_scalar(sp + c * s_sc, xp[c * x_sc], lo_off);
+    }
+  }
+}
+
+template <typename T, int VEC>
+int launch_detect_sparse(cudaStream_t stream, const void* x, long long x_sb, long long x_sc,
+                         long long x_sy, long long x_sx, void* state, long long s_sb,
+                         long long s_sc, long long s_sy, long long s_sx, void* state_lo,
+                         const int32_t* cand, const int32_t* ncand, uint32_t* bits, int B, int C,
+                         int H, int W, float threshold, int update) {
+  const int Wd = (W + 31) / 32;
+  const long long words = (long long)B * H * Wd;
+  if (words == 0) return 0;
+  if (cudaMemsetAsync(bits, 0, (size_t)words * 4, stream) != cudaSuccess)
+    return fail(3, "change_detect_sparse: memset failed");
+  const T thr = thr_cast<T>(threshold);
+  const size_t es = sizeof(T);
+  long long lo_off = 0;
+  if (state_lo) {
+    CB_CHECK_ARG(sizeof(T) == 4, "change_detect_sparse: the tf32 lo plane exists for fp32 only");
+    lo_off = (long long)((const T*)state_lo - (const T*)state);
+  }
+  const bool vec_ok = x_sc == 1 && s_sc == 1 && (x_sx % VEC) == 0 && (s_sx % VEC) == 0 &&
+                      x_sx >= C && s_sx >= C && ((x_sy * es) % 16) == 0 && ((s_sy * es) % 16) == 0 &&
+                      ((x_sb * es) % 16) == 0 && ((s_sb * es) % 16) == 0 &&
+                      ((uintptr_t)x % 16) == 0 && ((uintptr_t)state % 16) == 0 &&
+                      x_sx < (1ll << 30) && s_sx < (1ll << 30);
+  const unsigned grid = (unsigned)(sm_count() * 16);
+  const int cpv = (C + VEC - 1) / VEC;
+  int glog = 0;
+  while ((1 << glog) < cpv && glog < 5) ++glog;
+#define CB_DETS(U_)                                                                              \
+  if (vec_ok)                                                                                    \
+    detect_sparse_vec_kernel<T, VEC, U_><<<grid, 256, 0, stream>>>(                              \
+        (const T*)x, x_sb, x_sy, (int)x_sx, (T*)state, s_sb, s_sy, (int)s_sx, lo_off, cand,      \
+        ncand, bits, H, W, C, Wd, thr, glog);                                                    \
+  else                                                                                           \
+    detect_sparse_generic_kernel<T, U_><<<grid, 256, 0, stream>>>(                               \
+        (const T*)x, x_sb, x_sc, x_sy, x_sx, (T*)state, s_sb, s_sc, s_sy, s_sx, lo_off, cand,    \
+        ncand, bits, H, W, C, Wd, thr);
+  switch (update) {
+    case CB_UPDATE_NONE: CB_DETS(CB_UPDATE_NONE) break;
+    case CB_UPDATE_CHANGED: CB_DETS(CB_UPDATE_CHANGED) break;
+    case CB_UPDATE_ALL: CB_DETS(CB_UPDATE_ALL) break;
+    default: return fail(2, "change_detect_sparse: bad update_mode %d", update);
+  }
+#undef CB_DETS
+  CB_CHECK_LAUNCH("change_detect_sparse");
+  return 0;
+}
+
 }  // namespace cb

@@ -31,8 +31,27 @@ def sceneLabelingBaseline(seed=0):
     return m
 
 
+def enableCandidateDetection(m):
+    """B200 extension (no reference counterpart): inside every nn.Sequential, let each CB layer
+    hand its change set to a directly following CB layer as detection *candidates*, so that layer
+    thresholds only the pixels that were just rewritten instead of re-scanning its whole input.
+    Results are identical to the dense scan (tests/test_gpu_modules.py)."""
+    import torch.nn as nn
+    for seq in [mm for mm in m.modules() if type(mm) is nn.Sequential]:
+        kids = list(seq.children())
+        for a, b in zip(kids[:-1], kids[1:]):
+            if type(b) is CBConv2d and not b.finegrained:
+                if type(a) is CBConv2d and not a.finegrained:
+                    a.propChangeIndexes = True
+                    b.candidateDetect = True
+                elif type(a) is CBPoolMax2d:
+                    a.propPooledIndexes = True
+                    b.candidateDetect = True
+    return m
+
+
 def sceneLabelingCBinfer(baseline, experimentIdx=6, threshold=1e-1, convertAll=True,
-                         clonePoolOutput=True):
+                         clonePoolOutput=True, candidateDetect=False):
     """CBinfer scene-labeling model sharing the baseline's parameters.
 
     experimentIdx follows sceneLabeling/modelLoader.py:8-16:
@@ -65,6 +84,8 @@ def sceneLabelingCBinfer(baseline, experimentIdx=6, threshold=1e-1, convertAll=T
     if experimentIdx == 7:
         for c in convs:
             c.finegrained = True
+    if candidateDetect:
+        enableCandidateDetection(m)
     return m.eval()
 
 

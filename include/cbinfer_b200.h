@@ -92,6 +92,28 @@ int cb_dilate_compact(void* stream, const uint32_t* raw_bits, uint32_t* dil_bits
                       int32_t* idx, int32_t* count, void* ws, int B, int H, int W, int kHHalf,
                       int kWHalf);
 
+/* ---- candidate ("sparse") detection ---------------------------------------------------------
+ * Same per-pixel test and state maintenance as cb_change_detect, evaluated only at the
+ * `*n_candidates` pixels listed in `candidates` (indices b*H*W + y*W + x, any order); raw_bits is
+ * cleared and the bits of the changed candidates are set.  No reference counterpart: the reference
+ * re-scans every layer's whole input (conv2d.py:222-224).  Equal to the dense scan whenever x is
+ * untouched outside the candidate set, the threshold was not lowered since the previous frame and
+ * the state is not fresh -- conditions the calling module checks (see CBConv2d.candidateDetect). */
+int cb_change_detect_sparse(void* stream, int dtype,
+                            const void* x, long long x_sb, long long x_sc, long long x_sy, long long x_sx,
+                            void* state, long long s_sb, long long s_sc, long long s_sy, long long s_sx,
+                            void* state_lo, const int32_t* candidates, const int32_t* n_candidates,
+                            uint32_t* raw_bits, int B, int C, int H, int W, float threshold,
+                            int update_mode);
+
+/* 2x2/stride-2 pooled view of a change bitmap, compacted: out bit (yo,xo) = OR of the input bits
+ * of window (yo,xo); writes out_bits (optional), idx[0..n) ascending at pooled resolution
+ * [B,oH,oW] and *count.  Hands change candidates across a CBPoolMax2d (the reference forwards the
+ * input-resolution indices unchanged, conv2d.py:75-76, which no consumer can use).
+ * ws: cb_compact_ws_bytes(B,oH,oW), same rules as cb_dilate_compact. */
+int cb_pool_compact(void* stream, const uint32_t* in_bits, uint32_t* out_bits, int32_t* idx,
+                    int32_t* count, void* ws, int B, int H, int W, int oH, int oW);
+
 /* int8/bool map [B,H,W] (non-zero = set) -> bitmap.  Lets callers that hold a reference-style
  * changeMap (conv2d_cg.py:105) use cb_dilate_compact as changePropagation / changeIndexesExtr. */
 int cb_map_to_bits(void* stream, const int8_t* map, uint32_t* bits, int B, int H, int W);

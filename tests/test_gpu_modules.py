@@ -188,6 +188,80 @@ def test_scene_model_small_vs_dense_and_oracle(orc):
         assert _rel(to_val(out), e.astype(np.float64)) <= 5e-4
 
 
+@pytest.mark.parametrize("feedback", [True, False])
+@pytest.mark.parametrize("dt", ["f32", "bf16"])
+def test_candidate_detection_equals_dense_scan(feedback, dt):
+    """B200 extension: thresholding only the pixels the upstream CB layer rewrote gives exactly
+    the change maps, index lists, states and outputs of the reference's full re-scan."""
+    import cbinfer_b200 as cb
+    from cbinfer_b200 import models, video
+    base = models.sceneLabelingBaseline().cuda().to(TORCH_DT[dt])
+    frames = [f.cuda().to(TORCH_DT[dt]) for f in video.sequence(2, 50, 78, 7, 0.08)]
+    frames.insert(4, frames[3].clone())
+    ms = []
+    for cand in (False, True):
+        m = models.sceneLabelingCBinfer(base, experimentIdx=6, threshold=0.03, candidateDetect=cand)
+        for c in m.modules():
+            if type(c) is cb.CBConv2d:
+                c.feedbackLoop = feedback
+                c.saveChangeMap = True
+        ms.append(m)
+    for t, f in enumerate(frames):
+        outs = [m(f) for m in ms]
+        if t == 5:      # raising a threshold keeps the candidate path exact, lowering falls back
+            for m in ms:
+                m[3].threshold *= 2.0
+                m[6].threshold *= 0.5
+        assert torch.equal(outs[0], outs[1]), t
+        for a, b in zip(ms[0].children(), ms[1].children()):
+            if type(a) is cb.CBConv2d:
+                assert torch.equal(a.changeMap, b.changeMap), t
+                assert torch.equal(a.prevInput, b.prevInput), t
+                na, nb = int(a._scratch["count"].item()), int(b._scratch["count"].item())
+                assert na == nb and torch.equal(a._scratch["idx"][:na], b._scratch["idx"][:nb]), t
+            else:
+                assert torch.equal(a.outputState, b.outputState), t
+
+
+def test_pool_compact_and_sparse_detect_ops():
+    from cbinfer_b200 import _lib, conv2d_cg as cg
+    g = torch.Generator().manual_seed(3)
+    for (B, H, W, ceil) in ((2, 9, 70, True), (1, 8, 64, False), (3, 5, 33, False), (1, 1, 1, True)):
+        oH, oW = ((H - 1) // 2 + 1, (W - 1) // 2 + 1) if ceil else (H // 2, W // 2)
+        m = (torch.rand(B, H, W, generator=g) < 0.15).to(torch.int8).cuda()
+        bits, _ = cg._map_to_bits(m)
+        s = cg.alloc_scratch((B, max(oH, 1), max(oW, 1)), "cuda")
+        cg.pool_compact(bits, (B, H, W), (B, oH, oW), s["idx"], s["count"], s["ws"], out_bits=s["dil_bits"])
+        pm = torch.nn.functional.max_pool2d(m.float().unsqueeze(1), 2, 2, ceil_mode=ceil).squeeze(1)
+        ref = torch.nonzero(pm.reshape(-1)).view(-1).int()
+        n = int(s["count"].item())
+        assert n == ref.numel() and torch.equal(s["idx"][:n], ref)
+    # sparse detect == dense detect when the candidates cover every difference
+    for dt in ("f32", "f16"):
+        shape = (2, 40, 13, 37)
+        prev = rand_tensor(shape, dt, 1)
+        x = perturb(prev, 0.1, 2)
+        diff = (x != prev).any(1)
+        extra = torch.rand(diff.shape, generator=g).cuda() < 0.05
+        cand = cg.changeIndexesExtr((diff | extra).to(torch.int8), lazy=True)
+        for layout in ("planar", "pixel"):
+            for mode in (_lib.UPDATE_CHANGED, _lib.UPDATE_ALL, _lib.UPDATE_NONE):
+                res = []
+                for sparse in (False, True):
+                    if layout == "pixel":
+                        st = cg.pixel_major(shape, TORCH_DT[dt], "cuda", 0)[0].copy_(prev)
+                        xin = cg.pixel_major(shape, TORCH_DT[dt], "cuda", 0)[0].copy_(x)
+                    else:
+                        st, xin = prev.clone(), x
+                    sc = cg.alloc_scratch((2, 13, 37), "cuda")
+                    if sparse:
+                        cg.detect_sparse(xin, st, sc["raw_bits"], 0.4, mode, cand)
+                    else:
+                        cg.detect(xin, st, sc["raw_bits"], 0.4, mode)
+                    res.append((sc["raw_bits"].clone(), st.contiguous().clone()))
+                assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+
+
 @pytest.mark.parametrize("res", [(480, 640)])
 def test_full_size_properties(res):
     """BASELINE config 2 size (640x480): size-independent properties instead of the slow oracle:
