@@ -210,8 +210,9 @@ def test_candidate_detection_equals_dense_scan(feedback, dt):
         outs = [m(f) for m in ms]
         if t == 5:      # raising a threshold keeps the candidate path exact, lowering falls back
             for m in ms:
-                m[3].threshold *= 2.0
-                m[6].threshold *= 0.5
+                kids = dict(m.named_children())
+                kids['3'].threshold *= 2.0
+                kids['6'].threshold *= 0.5
         assert torch.equal(outs[0], outs[1]), t
         for a, b in zip(ms[0].children(), ms[1].children()):
             if type(a) is cb.CBConv2d:
