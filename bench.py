@@ -32,7 +32,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--streams", type=int, default=8, help="video streams per GPU (batch)")
+    ap.add_argument("--streams", type=int, default=8, help="video streams per GPU")
+    ap.add_argument("--groups", type=int, default=2,
+                    help="independent stream groups per GPU run as parallel branches of one CUDA graph "
+                         "(each group = streams/groups videos batched through its own model replica)")
     ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--width", type=int, default=640)
     ap.add_argument("--rate", type=float, default=0.05, help="fraction of pixels changed per frame")
@@ -203,7 +206,7 @@ def run_reference(args):
 def workload_config(args, streams):
     return {"workload": "sceneLabeling CBinfer CNN (5 CBConv2d + 2 CBPoolMax2d, feedback loop) on synthetic "
                         "%dx%d video, %.0f%% %s change per frame" % (args.width, args.height, args.rate * 100, args.mode),
-            "streams_per_gpu": streams, "height": args.height, "width": args.width,
+            "streams_per_gpu": streams, "stream_groups": getattr(args, "groups", 1), "height": args.height, "width": args.width,
             "change_rate": args.rate, "change_mode": args.mode, "threshold_factor": args.threshold_factor,
             "gemm": args.gemm, "detection": "dense re-scan per layer" if args.dense_scan else
             "dense scan on the input frame, candidate detection on CB-fed layers", "parallelism": "independent video streams sharded per GPU, no collective"}
@@ -236,38 +239,63 @@ def main():
     torch.backends.cudnn.benchmark = True
 
     # ---- model + synthetic video (each rank: its own streams, seeds offset by rank) ----------
+    G = max(1, min(args.groups, S))
+    assert S % G == 0, "--streams must be a multiple of --groups"
+    Sg = S // G
     base = models.sceneLabelingBaseline().to(dev).to(tdt)
-    model = models.sceneLabelingCBinfer(base, experimentIdx=6, threshold=0.1, convertAll=True,
-                                        clonePoolOutput=False, candidateDetect=not args.dense_scan)
-    for m in model.modules():
-        if type(m) is cb.CBConv2d:
-            m.gemmMode = args.gemm
+
+    def make_model():
+        mdl = models.sceneLabelingCBinfer(base, experimentIdx=6, threshold=0.1, convertAll=True,
+                                          clonePoolOutput=False, candidateDetect=not args.dense_scan)
+        for m in mdl.modules():
+            if type(m) is cb.CBConv2d:
+                m.gemmMode = args.gemm
+        return mdl
+
+    model = make_model()                      # eager / e2e / kernel-table model (all S streams)
+    replicas = [make_model() for _ in range(G)]
     nframes = K + Wm + 2
     frames_cpu = video.sequence(S, H, W, nframes, args.rate, args.mode, seed=rank)
     thresholds = models.calibrateThresholds(base, model, frames_cpu[0].to(dev).to(tdt),
                                             factor=args.threshold_factor)
+    for r in replicas:
+        for c, th in zip([m for m in r.modules() if type(m) is cb.CBConv2d], thresholds):
+            c.threshold = th
     pinned = [f.to(tdt).pin_memory() for f in frames_cpu]
     frames = [f.to(dev, non_blocking=True) for f in pinned]
     torch.cuda.synchronize()
 
-    # ---- warm-up + CUDA graph of one step ---------------------------------------------------------
+    # ---- warm-up + ONE CUDA graph of one step: G independent branches (stream groups) ------------
     static_in = frames[0].clone()
+    ins = [static_in[g * Sg:(g + 1) * Sg] for g in range(G)]
     with torch.no_grad():
-        model(static_in)                      # first frame: everything changed
+        for r, x in zip(replicas, ins):
+            r(x)                              # first frame: everything changed
         static_in.copy_(frames[1])
-        model(static_in)
+        for r, x in zip(replicas, ins):
+            r(x)
     torch.cuda.synchronize()
     graph = torch.cuda.CUDAGraph()
+    branches = [torch.cuda.Stream() for _ in range(G)]
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side), torch.no_grad():
-        model(static_in)
+        for r, x in zip(replicas, ins):
+            r(x)
     torch.cuda.current_stream().wait_stream(side)
+    outs = [None] * G
     with torch.cuda.graph(graph), torch.no_grad():
-        static_out = model(static_in)
-    # my kernels per step: per CBConv2d detect + dilate/compact + conv; per pool 1 (+1 pooled
-    # compaction when it hands candidates on)
-    my_launches_per_step = 5 * 3 + 2 + (0 if args.dense_scan else 2)
+        main = torch.cuda.current_stream()
+        for g in range(G):
+            branches[g].wait_stream(main)
+            with torch.cuda.stream(branches[g]):
+                outs[g] = replicas[g](ins[g])
+        for g in range(G):
+            main.wait_stream(branches[g])
+    static_out = outs[0]
+    # my kernels per step and group: per CBConv2d detect + dilate/compact + conv; per pool 1 (+1
+    # pooled compaction when it hands candidates on)
+    my_launches_per_step = G * (5 * 3 + 2 + (0 if args.dense_scan else 2))
 
     def step(t):
         static_in.copy_(frames[t])
@@ -300,11 +328,17 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         elapsed_ms = float(tt.item())
     fps = world * S * K / (elapsed_ms * 1e-3)
-    counts = [int(m._scratch["count"].item()) for m in model.modules() if type(m) is cb.CBConv2d]
-    state_mb = sum(t.numel() * t.element_size() for t in cb.getStateTensors(model)) / 1e6
+    counts = [sum(int(m._scratch["count"].item()) for m in ms)
+              for ms in zip(*[[m for m in r.modules() if type(m) is cb.CBConv2d] for r in replicas])]
+    state_mb = sum(t.numel() * t.element_size() for r in replicas for t in cb.getStateTensors(r)) / 1e6
 
     # ---- e2e: host frames -> H2D -> model -> D2H logits, every step ----------------------------
-    out_host = torch.empty(static_out.shape, dtype=static_out.dtype).pin_memory()
+    for r in replicas:
+        cb.clearMemory(r)
+    del graph
+    with torch.no_grad():
+        probe = model(frames[0])
+    out_host = torch.empty(probe.shape, dtype=probe.dtype).pin_memory()
     cb.clearMemory(model)        # fresh sequence through the public call (not the graph)
     h2d = pinned[0].numel() * pinned[0].element_size()
     d2h = out_host.numel() * out_host.element_size()

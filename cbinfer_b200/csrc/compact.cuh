@@ -17,6 +17,7 @@ namespace cb {
 constexpr int kCompactThreads = 512;
 constexpr int kCompactWPT = 2;                               // words per thread
 constexpr int kCompactTile = kCompactThreads * kCompactWPT;  // words per tile (32768 pixels)
+constexpr int kCompactWin = 6144;                            // staged raw window (words, 24 KB)
 
 struct CompactHeader {                         // first 16 bytes of the workspace
   unsigned reserved, done, epoch, pad;
@@ -34,16 +35,18 @@ __device__ __forceinline__ unsigned long long pack_state(unsigned tag, unsigned 
 
 // One dilated bitmap word: vertical OR of the raw rows in the window, then horizontal dilation
 // with funnel shifts across the neighbouring words.
-__device__ __forceinline__ unsigned dilated_word(const uint32_t* __restrict__ raw, long long r,
+// `win` holds raw words [win0, win0 + len) of the flat bitmap (staged in shared memory when the
+// window fits, else the global bitmap itself with win0 = 0).
+__device__ __forceinline__ unsigned dilated_word(const uint32_t* __restrict__ win, int win0, int r,
                                                  int y, int j, int H, int W, int Wd, int kh,
                                                  int kw) {
   unsigned vp = 0, vc = 0, vn = 0;
   const int y0 = max(0, y - kh), y1 = min(H - 1, y + kh);
-  const uint32_t* row = raw + (r - y + y0) * Wd + j;
+  const uint32_t* row = win + ((r - y + y0) * Wd + j - win0);
   for (int yy = y0; yy <= y1; ++yy, row += Wd) {
-    vc |= __ldg(row);
-    if (j > 0) vp |= __ldg(row - 1);
-    if (j + 1 < Wd) vn |= __ldg(row + 1);
+    vc |= row[0];
+    if (j > 0) vp |= row[-1];
+    if (j + 1 < Wd) vn |= row[1];
   }
   unsigned d = vc;
   for (int dx = 1; dx <= kw; ++dx) {
@@ -95,11 +98,27 @@ dilate_compact_kernel(const uint32_t* __restrict__ raw, uint32_t* __restrict__ d
   constexpr int NW = kCompactThreads / 32;
   __shared__ int s_warp[NW];
   __shared__ int s_base;
+  __shared__ uint32_t s_win[kCompactWin];
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int tile = blockIdx.x;
   const unsigned epoch = *reinterpret_cast<volatile unsigned*>(&hdr->epoch);
   const unsigned tag = epoch % 0x3ffffffeu + 1u;
+
+  // ---- stage the raw words this tile can touch (tile +- kh rows +- 1 word): one round of
+  //      independent coalesced loads instead of (2kh+1) dependent ones per word ----------------
+  const uint32_t* win = raw;
+  int win0 = 0;
+  if (!pool_hin) {
+    const int lo = max(0, tile * kCompactTile - kh * Wd - 1);
+    const int hi = min(nwords, (tile + 1) * kCompactTile + kh * Wd + 1);
+    if (hi - lo <= kCompactWin) {
+      for (int i = tid; i < hi - lo; i += kCompactThreads) s_win[i] = __ldg(raw + lo + i);
+      win = s_win;
+      win0 = lo;
+      __syncthreads();
+    }
+  }
 
   // ---- dilated words (consecutive words per thread keep the index order) ------------------
   unsigned d[kCompactWPT];
@@ -114,7 +133,7 @@ dilate_compact_kernel(const uint32_t* __restrict__ raw, uint32_t* __restrict__ d
       const int r = w / Wd;
       const int y = r % H;
       d[i] = pool_hin ? pooled_word(raw, r / H, y, j, pool_hin, pool_wdin, W)
-                      : dilated_word(raw, r, y, j, H, W, Wd, kh, kw);
+                      : dilated_word(win, win0, r, y, j, H, W, Wd, kh, kw);
       if (dil_bits) dil_bits[w] = d[i];
     }
     cnt += __popc(d[i]);

@@ -162,7 +162,9 @@ struct UmmaCfg {
   static constexpr int STAGES = (BUDGET / STAGE_BYTES) < 2 ? 2
                                 : (BUDGET / STAGE_BYTES) > 8 ? 8 : (BUDGET / STAGE_BYTES);
   static constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 2048 /*ctrl*/;
+  static constexpr int TABLE_MAX = 1024;        // chunk-offset table entries (8 KB)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 2048 /*ctrl*/ +
+                                    TABLE_MAX * 8;
 };
 
 struct UmmaCtrl {                              // lives after the stage buffers
@@ -217,6 +219,24 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int num_kb = (Kp + C::BK - 1) / C::BK;
   constexpr int TMA_WARP = UM_PRODUCERS / 32, MMA_WARP = TMA_WARP + 1;
+  const int ph = (kH - 1) / 2, pw = (kW - 1) / 2;
+  // Per 16-byte K chunk q (k = q*VEC): element offset of its filter tap relative to the pixel and
+  // the tap's (dy,dx); built once per CTA so the gather loop has no divisions.
+  int2* ktab = reinterpret_cast<int2*>(reinterpret_cast<uint8_t*>(ctrl) + 2048);
+  const bool use_table = num_kb * 8 <= C::TABLE_MAX;
+  if (use_table) {
+    for (int q = tid; q < num_kb * 8; q += UM_THREADS) {
+      const int k = q * C::VEC;
+      int2 e = make_int2(0, (int)0x80008000u);             // k beyond K: dy = dx = -32768 (invalid)
+      if (k < Kp) {
+        const int tap = k / Cp, ci = k - tap * Cp;
+        const int ky = tap / kW, kx = tap - ky * kW;
+        e.x = ((ky - ph) * W + (kx - pw)) * Cp + ci;
+        e.y = (int)(((unsigned)(ky - ph) << 16) | ((unsigned)(kx - pw) & 0xffffu));
+      }
+      ktab[q] = e;
+    }
+  }
 
   if (tid == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
@@ -240,8 +260,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctrl->tmem_base;
-
-  const int ph = (kH - 1) / 2, pw = (kW - 1) / 2;
   const int P = H * W;
 
   if (warp < TMA_WARP) {
@@ -288,9 +306,22 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&ctrl->empty[stage], phase ^ 1u);
         const uint32_t a_hi = smem_u32(smem + stage * C::STAGE_BYTES);
-        const int dy = cur.ky - ph, dx = cur.kx - pw;
-        const bool kvalid = cur.k < Kp;
-        const long long koff = ((long long)dy * W + dx) * Cp + cur.ci;
+        int dy, dx;
+        long long koff;
+        bool kvalid;
+        if (use_table) {
+          const int2 e = ktab[kb * 8 + c];
+          koff = e.x;
+          dy = e.y >> 16;
+          dx = (int)(short)(e.y & 0xffff);
+          kvalid = true;                                     // invalid chunks fail the bounds test
+        } else {
+          dy = cur.ky - ph;
+          dx = cur.kx - pw;
+          kvalid = cur.k < Kp;
+          koff = ((long long)dy * W + dx) * Cp + cur.ci;
+          cur.advance(C::BK, Cp, kW);
+        }
 #pragma unroll
         for (int it = 0; it < RPT; ++it) {
           const bool ok = kvalid && (unsigned)(ry[it] + dy) < (unsigned)H &&
@@ -300,7 +331,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
           if (SPLIT3) cp_async16(a_hi + C::A_BYTES + soff[it], src + lo_delta, ok ? 16u : 0u);
         }
         cp_async_arrive_noinc(&ctrl->full[stage]);
-        cur.advance(C::BK, Cp, kW);
         if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
       }
       // ---- epilogue: TMEM -> registers -> bias / ReLU -> scatter -------------------------
@@ -577,7 +607,7 @@ inline int umma_conv_update(cudaStream_t s, int dtype, int gemm, const void* sta
                             int Cout, int kH, int kW, int relu) {
   (void)Cin;
   CB_CHECK_ARG(gemm == CB_GEMM_TC || gemm == CB_GEMM_TC_3X, "conv_update: bad gemm mode %d", gemm);
-  CB_CHECK_ARG(H < 65536 && W < 65536, "conv_update: H, W must be < 65536");
+  CB_CHECK_ARG(H < 32768 && W < 32768, "conv_update: H, W must be < 32768");
   CB_CHECK_ARG(((uintptr_t)state % 16) == 0 && ((uintptr_t)packed % 128) == 0,
                "conv_update: state must be 16-byte and packed weights 128-byte aligned");
   const int bn = umma_bn(gemm, Cout), CoutPad = umma_cout_pad(gemm, Cout);
