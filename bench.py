@@ -33,7 +33,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streams", type=int, default=8, help="video streams per GPU")
-    ap.add_argument("--groups", type=int, default=2,
+    ap.add_argument("--groups", type=int, default=1,
                     help="independent stream groups per GPU run as parallel branches of one CUDA graph "
                          "(each group = streams/groups videos batched through its own model replica)")
     ap.add_argument("--height", type=int, default=480)
@@ -223,7 +223,7 @@ def main():
     import torch
     import torch.distributed as dist
     import cbinfer_b200 as cb
-    from cbinfer_b200 import models, video, conv2d_cg as cg
+    from cbinfer_b200 import models, video, streams, conv2d_cg as cg
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -255,7 +255,8 @@ def main():
     model = make_model()                      # eager / e2e / kernel-table model (all S streams)
     replicas = [make_model() for _ in range(G)]
     nframes = K + Wm + 2
-    frames_cpu = video.sequence(S, H, W, nframes, args.rate, args.mode, seed=rank)
+    my_streams = streams.shard_streams(S * world, world, rank)      # global stream ids of this rank
+    frames_cpu = video.sequence(S, H, W, nframes, args.rate, args.mode, seed=my_streams[0])
     thresholds = models.calibrateThresholds(base, model, frames_cpu[0].to(dev).to(tdt),
                                             factor=args.threshold_factor)
     for r in replicas:
@@ -322,12 +323,8 @@ def main():
     e1.record()
     barrier()
     clocks = sampler.stop()
-    elapsed_ms = e0.elapsed_time(e1)
-    if world > 1:
-        tt = torch.tensor([elapsed_ms], device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(tt.item())
-    fps = world * S * K / (elapsed_ms * 1e-3)
+    # whole-job rate: frames of all ranks / slowest rank's device time
+    fps, elapsed_ms = streams.whole_job_rate(S * K, e0.elapsed_time(e1), dev)
     counts = [sum(int(m._scratch["count"].item()) for m in ms)
               for ms in zip(*[[m for m in r.modules() if type(m) is cb.CBConv2d] for r in replicas])]
     state_mb = sum(t.numel() * t.element_size() for r in replicas for t in cb.getStateTensors(r)) / 1e6
@@ -357,12 +354,7 @@ def main():
         e2e_step(i)
     e1.record()
     barrier()
-    e2e_ms = e0.elapsed_time(e1)
-    if world > 1:
-        tt = torch.tensor([e2e_ms], device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_ms = float(tt.item())
-    e2e_fps = world * S * K / (e2e_ms * 1e-3)
+    e2e_fps, e2e_ms = streams.whole_job_rate(S * K, e0.elapsed_time(e1), dev)
 
     result = {
         "metric": "frames/s", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
