@@ -51,10 +51,10 @@ def _load():
         "cb_packed_weight_bytes": (sz, [i32] * 6),
         "cb_change_detect": (i32, [vp, i32, vp, i64, i64, i64, i64, vp, i64, i64, i64, i64, vp, vp,
                                    i32, i32, i32, i32, f32, i32]),
-        "cb_dilate_compact": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32]),
+        "cb_dilate_compact": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32]),
         "cb_map_to_bits": (i32, [vp, vp, vp, i32, i32, i32]),
         "cb_change_detect_sparse": (i32, [vp, i32, vp, i64, i64, i64, i64, vp, i64, i64, i64, i64, vp,
-                                          vp, vp, vp, i32, i32, i32, i32, f32, i32]),
+                                          vp, vp, vp, i32, i32, i32, i32, f32, i32, i32]),
         "cb_pool_compact": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32]),
         "cb_pack_weights": (i32, [vp, i32, i32, vp, vp, i32, i32, i32, i32]),
         "cb_conv_update": (i32, [vp, i32, i32, vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32,

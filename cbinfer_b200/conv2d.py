@@ -255,17 +255,23 @@ class CBConv2d(nn.Module):
             # copy is part of the detection pass; copyInput=False (alias the input as state) is
             # honoured as a copy -- the state always owns its memory.
             mode = _lib.UPDATE_CHANGED if self.feedbackLoop else _lib.UPDATE_ALL
+            sparse_next = bool(getattr(self, 'candidateDetect', False))
             if candidates is not None:
                 cg.detect_sparse(input, self.prevInput, s["raw_bits"], self.threshold, mode,
-                                 candidates, state_lo=self._loView)
+                                 candidates, state_lo=self._loView,
+                                 bits_are_clear=s.get("raw_clear", False))
             else:
                 cg.detect(input, self.prevInput, s["raw_bits"], self.threshold, mode,
                           state_lo=self._loView)
             self._fresh = False
             self._lastThr = self.threshold
             dil_map = s.get("dil_map") if self.saveChangeMap else None
+            # a layer on the candidate path lets the compaction zero the raw bitmap once it has
+            # been consumed, so the next frame's candidate detection needs no memset
             cg.dilate_compact(s["raw_bits"], (B, H, W), self.kernel_size, s["idx"], s["count"],
-                              s["ws"], dil_bits=s["dil_bits"], dil_map=dil_map)
+                              s["ws"], dil_bits=s["dil_bits"], dil_map=dil_map,
+                              clear_raw=sparse_next)
+            s["raw_clear"] = sparse_next
             if self.saveChangeMap:
                 self.changeMap = dil_map[0] if B == 1 else dil_map
             changeIndexes = ChangeIndexes(s["idx"], s["count"], (B, H, W), bits=s["dil_bits"])

@@ -102,7 +102,8 @@ def detect(x, state, raw_bits, threshold, update_mode, state_lo=None):
                              raw_bits.data_ptr(), B, Cc, H, W, float(threshold), int(update_mode)))
 
 
-def detect_sparse(x, state, raw_bits, threshold, update_mode, candidates, state_lo=None):
+def detect_sparse(x, state, raw_bits, threshold, update_mode, candidates, state_lo=None,
+                  bits_are_clear=False):
     """cb_change_detect_sparse: the detection test at the candidate pixels only (see the header
     for the exactness conditions).  `candidates` is a :class:`ChangeIndexes` at x's resolution."""
     require_cuda(x, state, raw_bits)
@@ -114,7 +115,7 @@ def detect_sparse(x, state, raw_bits, threshold, update_mode, candidates, state_
                                     state_lo.data_ptr() if state_lo is not None else None,
                                     candidates.buffer.data_ptr(), candidates.count.data_ptr(),
                                     raw_bits.data_ptr(), B, Cc, H, W, float(threshold),
-                                    int(update_mode)))
+                                    int(update_mode), int(bool(bits_are_clear))))
 
 
 def pool_compact(in_bits, in_shape, out_shape, idx, count, ws, out_bits=None):
@@ -127,14 +128,15 @@ def pool_compact(in_bits, in_shape, out_shape, idx, count, ws, out_bits=None):
                             idx.data_ptr(), count.data_ptr(), ws.data_ptr(), B, H, W, oH, oW))
 
 
-def dilate_compact(raw_bits, shape, filtSize, idx, count, ws, dil_bits=None, dil_map=None):
+def dilate_compact(raw_bits, shape, filtSize, idx, count, ws, dil_bits=None, dil_map=None,
+                   clear_raw=False):
     """cb_dilate_compact: dilation by the filter footprint + ordered compaction."""
     B, H, W = shape
     check(C.cb_dilate_compact(stream_ptr(raw_bits.device), raw_bits.data_ptr(),
                               dil_bits.data_ptr() if dil_bits is not None else None,
                               dil_map.data_ptr() if dil_map is not None else None,
                               idx.data_ptr(), count.data_ptr(), ws.data_ptr(), B, H, W,
-                              (filtSize[0] - 1) // 2, (filtSize[1] - 1) // 2))
+                              (filtSize[0] - 1) // 2, (filtSize[1] - 1) // 2, int(bool(clear_raw))))
 
 
 def alloc_scratch(shape, device, want_map=False):

@@ -93,7 +93,7 @@ int cb_change_detect(void* stream, int dtype, const void* x, long long x_sb, lon
 
 int cb_dilate_compact(void* stream, const uint32_t* raw_bits, uint32_t* dil_bits, int8_t* dil_map,
                       int32_t* idx, int32_t* count, void* ws, int B, int H, int W, int kHHalf,
-                      int kWHalf) {
+                      int kWHalf, int clear_raw) {
   CB_CHECK_ARG(raw_bits && idx && count && ws, "dilate_compact: null pointer");
   CB_CHECK_ARG(raw_bits != dil_bits, "dilate_compact: dil_bits must not alias raw_bits");
   CB_CHECK_ARG(kHHalf >= 0 && kWHalf >= 0 && kWHalf <= 31, "dilate_compact: kWHalf must be <= 31");
@@ -109,7 +109,8 @@ int cb_dilate_compact(void* stream, const uint32_t* raw_bits, uint32_t* dil_bits
   const int ntiles = (int)((nwords + kCompactTile - 1) / kCompactTile);
   dilate_compact_kernel<<<ntiles, kCompactThreads, 0, s>>>(raw_bits, dil_bits, dil_map, idx, count,
                                                           ws, B, H, W, (W + 31) / 32, kHHalf,
-                                                          kWHalf, (int)nwords, ntiles, 0, 0);
+                                                          kWHalf, (int)nwords, ntiles, 0, 0,
+                                                          clear_raw ? const_cast<uint32_t*>(raw_bits) : nullptr);
   CB_CHECK_LAUNCH("dilate_compact");
   return 0;
 }
@@ -129,7 +130,7 @@ int cb_pool_compact(void* stream, const uint32_t* in_bits, uint32_t* out_bits, i
   const int ntiles = (int)((nwords + kCompactTile - 1) / kCompactTile);
   dilate_compact_kernel<<<ntiles, kCompactThreads, 0, s>>>(in_bits, out_bits, nullptr, idx, count, ws,
                                                           B, oH, oW, (oW + 31) / 32, 0, 0,
-                                                          (int)nwords, ntiles, H, (W + 31) / 32);
+                                                          (int)nwords, ntiles, H, (W + 31) / 32, nullptr);
   CB_CHECK_LAUNCH("pool_compact");
   return 0;
 }
@@ -139,13 +140,13 @@ int cb_change_detect_sparse(void* stream, int dtype, const void* x, long long x_
                             long long s_sc, long long s_sy, long long s_sx, void* state_lo,
                             const int32_t* candidates, const int32_t* n_candidates,
                             uint32_t* raw_bits, int B, int C, int H, int W, float threshold,
-                            int update_mode) {
+                            int update_mode, int bits_are_clear) {
   CB_CHECK_ARG(x && state && raw_bits && candidates && n_candidates, "change_detect_sparse: null pointer");
   CB_CHECK_ARG(B >= 0 && C > 0 && H >= 0 && W >= 0, "change_detect_sparse: bad shape");
   CB_DISPATCH_DTYPE(dtype, return (launch_detect_sparse<T, VEC>(
                                (cudaStream_t)stream, x, x_sb, x_sc, x_sy, x_sx, state, s_sb, s_sc,
                                s_sy, s_sx, state_lo, candidates, n_candidates, raw_bits, B, C, H, W,
-                               threshold, update_mode)));
+                               threshold, update_mode, bits_are_clear)));
   return 0;
 }
 

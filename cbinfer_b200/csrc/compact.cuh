@@ -91,7 +91,8 @@ __global__ void __launch_bounds__(kCompactThreads)
 dilate_compact_kernel(const uint32_t* __restrict__ raw, uint32_t* __restrict__ dil_bits,
                       int8_t* __restrict__ dil_map, int32_t* __restrict__ idx,
                       int32_t* __restrict__ count, void* ws, int B, int H, int W, int Wd, int kh,
-                      int kw, int nwords, int ntiles, int pool_hin, int pool_wdin) {
+                      int kw, int nwords, int ntiles, int pool_hin, int pool_wdin,
+                      uint32_t* __restrict__ clear_bits) {
   CompactHeader* hdr = reinterpret_cast<CompactHeader*>(ws);
   volatile unsigned long long* tstate =
       reinterpret_cast<volatile unsigned long long*>(reinterpret_cast<char*>(ws) + sizeof(CompactHeader));
@@ -213,14 +214,23 @@ dilate_compact_kernel(const uint32_t* __restrict__ raw, uint32_t* __restrict__ d
   }
 
   // ---- leave the workspace clean for the next launch ---------------------------------------
+  __shared__ unsigned s_last;
   if (tid == 0) {
     __threadfence();
     const unsigned prev = atomicAdd(&hdr->done, 1u);
-    if (prev == (unsigned)ntiles - 1u) {
+    s_last = prev == (unsigned)ntiles - 1u;
+    if (s_last) {
       hdr->done = 0;
       __threadfence();
       *reinterpret_cast<volatile unsigned*>(&hdr->epoch) = epoch + 1u;
     }
+  }
+  // The last tile to finish (every tile has read its raw window by then) may zero the raw
+  // bitmap, so next frame's candidate detection can OR bits into it without a memset launch.
+  if (clear_bits) {
+    __syncthreads();
+    if (s_last)
+      for (int i = tid; i < nwords; i += kCompactThreads) clear_bits[i] = 0u;
   }
 }
 

@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(UM_THREADS)
 conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__ state,
                  const T* __restrict__ state_lo, int Cp, const int32_t* __restrict__ idx, const int32_t* __restrict__ count,
                  const float* __restrict__ bias, T* __restrict__ out, int Op, int H, int W,
-                 int Cout, int CoutPad, int kH, int kW, int Kp, int relu) {
+                 int Cout, int CoutPad, int kH, int kW, int Kp, int relu, int sel_lo, int sel_hi) {
   using C = UmmaCfg<T, SPLIT3, BN>;
   constexpr int RPT = UM_BM * 8 / UM_PRODUCERS;            // 16-byte chunks per thread per stage
   constexpr int RSTEP = UM_PRODUCERS / 8;                  // row stride between a thread's chunks
@@ -210,6 +210,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
   const int mtiles = (n + UM_BM - 1) / UM_BM;
   const int ntiles = CoutPad / BN;
   const int total_tiles = mtiles * ntiles;
+  // sel window: two tilings of the same layer may be launched back to back; the change count
+  // (known only on the device) decides which one does the work
+  if (mtiles < sel_lo || mtiles >= sel_hi) return;
   if ((int)blockIdx.x >= total_tiles) return;             // uniform: before any barrier / alloc
 
   extern __shared__ uint8_t smem_raw[];
@@ -545,7 +548,8 @@ template <typename T, bool SPLIT3, int BN>
 int launch_conv_umma(cudaStream_t s, int dtype, const void* state, const void* state_lo, int Cp,
                      const int32_t* idx,
                      const int32_t* count, const void* packed, const float* bias, void* out,
-                     int Op, int B, int H, int W, int Cout, int CoutPad, int kH, int kW, int relu) {
+                     int Op, int B, int H, int W, int Cout, int CoutPad, int kH, int kW, int relu,
+                     int sel_lo, int sel_hi) {
   using C = UmmaCfg<T, SPLIT3, BN>;
   const int Kp = kH * kW * Cp;
   const int KpPad = umma_kp_pad(dtype, Cp, kH, kW);
@@ -580,7 +584,7 @@ int launch_conv_umma(cudaStream_t s, int dtype, const void* state, const void* s
   kern<<<(unsigned)grid, UM_THREADS, C::SMEM_BYTES, s>>>(map, (const T*)state, (const T*)state_lo, Cp,
                                                         idx, count, bias,
                                                         (T*)out, Op, H, W, Cout, CoutPad, kH, kW,
-                                                        Kp, relu);
+                                                        Kp, relu, sel_lo, sel_hi);
   CB_CHECK_LAUNCH("conv_update(umma)");
   return 0;
 }
@@ -589,11 +593,13 @@ template <typename T, bool SPLIT3>
 int dispatch_bn(int bn, cudaStream_t s, int dtype, const void* state, const void* state_lo, int Cp,
                 const int32_t* idx,
                 const int32_t* count, const void* packed, const float* bias, void* out, int Op,
-                int B, int H, int W, int Cout, int CoutPad, int kH, int kW, int relu) {
+                int B, int H, int W, int Cout, int CoutPad, int kH, int kW, int relu, int sel_lo,
+                int sel_hi) {
 #define CB_BN(N)                                                                              \
   case N:                                                                                     \
     return launch_conv_umma<T, SPLIT3, N>(s, dtype, state, state_lo, Cp, idx, count, packed, bias, out, \
-                                          Op, B, H, W, Cout, CoutPad, kH, kW, relu);
+                                          Op, B, H, W, Cout, CoutPad, kH, kW, relu, sel_lo,   \
+                                          sel_hi);
   switch (bn) {
     CB_BN(16) CB_BN(32) CB_BN(64) CB_BN(128) CB_BN(256)
     default: return fail(2, "conv_update: unsupported N tile %d", bn);
@@ -614,20 +620,43 @@ inline int umma_conv_update(cudaStream_t s, int dtype, int gemm, const void* sta
   const bool split3 = gemm == CB_GEMM_TC_3X && dtype == CB_F32;
   CB_CHECK_ARG(!split3 || (state_lo && ((uintptr_t)state_lo % 16) == 0),
                "conv_update: CB_GEMM_TC_3X needs the 16-byte aligned tf32 remainder plane (state_lo)");
-  switch (dtype) {
-    case CB_F32:
-      return split3 ? dispatch_bn<float, true>(bn, s, dtype, state, state_lo, Cp, idx, count, packed, bias,
-                                               out, Op, B, H, W, Cout, CoutPad, kH, kW, relu)
-                    : dispatch_bn<float, false>(bn, s, dtype, state, state_lo, Cp, idx, count, packed, bias,
-                                                out, Op, B, H, W, Cout, CoutPad, kH, kW, relu);
-    case CB_F16:
-      return dispatch_bn<__half, false>(bn, s, dtype, state, state_lo, Cp, idx, count, packed, bias, out, Op,
-                                        B, H, W, Cout, CoutPad, kH, kW, relu);
-    case CB_BF16:
-      return dispatch_bn<__nv_bfloat16, false>(bn, s, dtype, state, state_lo, Cp, idx, count, packed, bias,
-                                               out, Op, B, H, W, Cout, CoutPad, kH, kW, relu);
-    default: return fail(2, "conv_update: bad dtype %d", dtype);
+  // Tiling policy.  Large N tiles minimise the im2col re-gather (the kernel is L2-bound on big
+  // layers) but give few CTAs when few pixels changed; the count is only known on the device, so
+  // when a small change set is plausible (expected tiles at 10 % change < half the SMs) a second,
+  // finer tiling is launched as well and each kernel checks the count to see whether it is its turn.
+  auto run = [&](int tile_n, int lo, int hi) -> int {
+    switch (dtype) {
+      case CB_F32:
+        return split3 ? dispatch_bn<float, true>(tile_n, s, dtype, state, state_lo, Cp, idx, count,
+                                                 packed, bias, out, Op, B, H, W, Cout, CoutPad, kH,
+                                                 kW, relu, lo, hi)
+                      : dispatch_bn<float, false>(tile_n, s, dtype, state, state_lo, Cp, idx, count,
+                                                  packed, bias, out, Op, B, H, W, Cout, CoutPad,
+                                                  kH, kW, relu, lo, hi);
+      case CB_F16:
+        return dispatch_bn<__half, false>(tile_n, s, dtype, state, state_lo, Cp, idx, count, packed,
+                                          bias, out, Op, B, H, W, Cout, CoutPad, kH, kW, relu, lo, hi);
+      case CB_BF16:
+        return dispatch_bn<__nv_bfloat16, false>(tile_n, s, dtype, state, state_lo, Cp, idx, count,
+                                                 packed, bias, out, Op, B, H, W, Cout, CoutPad, kH,
+                                                 kW, relu, lo, hi);
+      default: return fail(2, "conv_update: bad dtype %d", dtype);
+    }
+  };
+  const long long P = (long long)B * H * W;
+  const int sms = sm_count();
+  const long long exp_tiles = (P / 10 / UM_BM + 1) * (CoutPad / bn);
+  int bn_small = bn / 4;
+  if (bn_small < 16) bn_small = 16;
+  if (bn_small < bn && exp_tiles < sms / 2) {
+    // switch point: the coarse tiling takes over once it alone fills ~2/3 of the SMs
+    int m_switch = (2 * sms / 3) / (CoutPad / bn);
+    if (m_switch < 1) m_switch = 1;
+    const int rc = run(bn_small, 0, m_switch);
+    if (rc) return rc;
+    return run(bn, m_switch, 0x7fffffff);
   }
+  return run(bn, 0, 0x7fffffff);
 }
 
 }  // namespace cb

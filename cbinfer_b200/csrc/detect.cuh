@@ -379,11 +379,11 @@ int launch_detect_sparse(cudaStream_t stream, const void* x, long long x_sb, lon
                          long long x_sy, long long x_sx, void* state, long long s_sb,
                          long long s_sc, long long s_sy, long long s_sx, void* state_lo,
                          const int32_t* cand, const int32_t* ncand, uint32_t* bits, int B, int C,
-                         int H, int W, float threshold, int update) {
+                         int H, int W, float threshold, int update, int bits_are_clear) {
   const int Wd = (W + 31) / 32;
   const long long words = (long long)B * H * Wd;
   if (words == 0) return 0;
-  if (cudaMemsetAsync(bits, 0, (size_t)words * 4, stream) != cudaSuccess)
+  if (!bits_are_clear && cudaMemsetAsync(bits, 0, (size_t)words * 4, stream) != cudaSuccess)
     return fail(3, "change_detect_sparse: memset failed");
   const T thr = thr_cast<T>(threshold);
   const size_t es = sizeof(T);

@@ -87,10 +87,11 @@ int cb_change_detect(void* stream, int dtype,
  *   dil_bits (optional, may be NULL; may NOT alias raw_bits), dil_map (optional int8 [B,H,W]),
  *   idx[0..n) ascending, *count = n.   `ws` is cb_compact_ws_bytes() of zero-initialised
  * (once, at allocation) device memory private to the calling stream; the kernel leaves it
- * clean for the next call. */
+ * clean for the next call.  clear_raw != 0: raw_bits is zeroed once every tile has consumed it, so
+ * a following cb_change_detect_sparse(bits_are_clear = 1) needs no memset. */
 int cb_dilate_compact(void* stream, const uint32_t* raw_bits, uint32_t* dil_bits, int8_t* dil_map,
                       int32_t* idx, int32_t* count, void* ws, int B, int H, int W, int kHHalf,
-                      int kWHalf);
+                      int kWHalf, int clear_raw);
 
 /* ---- candidate ("sparse") detection ---------------------------------------------------------
  * Same per-pixel test and state maintenance as cb_change_detect, evaluated only at the
@@ -104,7 +105,7 @@ int cb_change_detect_sparse(void* stream, int dtype,
                             void* state, long long s_sb, long long s_sc, long long s_sy, long long s_sx,
                             void* state_lo, const int32_t* candidates, const int32_t* n_candidates,
                             uint32_t* raw_bits, int B, int C, int H, int W, float threshold,
-                            int update_mode);
+                            int update_mode, int bits_are_clear);
 
 /* 2x2/stride-2 pooled view of a change bitmap, compacted: out bit (yo,xo) = OR of the input bits
  * of window (yo,xo); writes out_bits (optional), idx[0..n) ascending at pooled resolution
