@@ -53,7 +53,9 @@ def main():
     counts = {n: int(m._scratch["count"].item()) for n, m in model.named_children() if type(m) is cb.CBConv2d}
     total = 0.0
     rows = []
-    for layer, name, a, k in calls:
+    # reverse order: a producer's repetitions (e.g. a second feedback detection finds no change)
+    # must not wipe the inputs of its consumers before those are timed
+    for layer, name, a, k in reversed(calls):
         k = dict(k)
         if name == "dilate_compact":
             k["clear_raw"] = False          # keep the input intact across repetitions
