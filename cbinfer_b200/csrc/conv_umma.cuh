@@ -146,7 +146,9 @@ __host__ __device__ inline uint32_t umma_idesc(int fmt, int N) {
 }
 
 // ---- configuration -----------------------------------------------------------------------------
-template <typename T, bool SPLIT3, int BN>
+// DEEP: one CTA per SM with as many stages as fit (used when few tiles exist: latency, not
+// occupancy, is then the limiter).
+template <typename T, bool SPLIT3, int BN, bool DEEP = false>
 struct UmmaCfg {
   static constexpr int ES = sizeof(T);
   static constexpr int VEC = 16 / ES;                        // elements per 16-byte chunk
@@ -157,7 +159,7 @@ struct UmmaCfg {
   static constexpr int B_BYTES = BN * UM_ROW_BYTES;
   static constexpr int STAGE_BYTES = NSPLIT * (A_BYTES + B_BYTES);
   // two CTAs per SM (<= ~100 KB each) unless a stage is so large that only one CTA fits
-  static constexpr int CTAS_PER_SM = STAGE_BYTES > 48 * 1024 ? 1 : 2;
+  static constexpr int CTAS_PER_SM = (DEEP || STAGE_BYTES > 48 * 1024) ? 1 : 2;
   static constexpr int BUDGET = CTAS_PER_SM == 1 ? 200 * 1024 : 98 * 1024;
   static constexpr int STAGES = (BUDGET / STAGE_BYTES) < 2 ? 2
                                 : (BUDGET / STAGE_BYTES) > 8 ? 8 : (BUDGET / STAGE_BYTES);
@@ -197,13 +199,13 @@ struct KCursor {
 };
 
 // packed weights: [NSPLIT][CoutPad][KpPad] elements of T (K-major); tensor map dims {KpPad, NSPLIT*CoutPad}
-template <typename T, bool SPLIT3, int BN>
+template <typename T, bool SPLIT3, int BN, bool DEEP>
 __global__ void __launch_bounds__(UM_THREADS)
 conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__ state,
                  const T* __restrict__ state_lo, int Cp, const int32_t* __restrict__ idx, const int32_t* __restrict__ count,
                  const float* __restrict__ bias, T* __restrict__ out, int Op, int H, int W,
                  int Cout, int CoutPad, int kH, int kW, int Kp, int relu, int sel_lo, int sel_hi) {
-  using C = UmmaCfg<T, SPLIT3, BN>;
+  using C = UmmaCfg<T, SPLIT3, BN, DEEP>;
   constexpr int RPT = UM_BM * 8 / UM_PRODUCERS;            // 16-byte chunks per thread per stage
   constexpr int RSTEP = UM_PRODUCERS / 8;                  // row stride between a thread's chunks
   const int n = *count;
@@ -544,13 +546,13 @@ inline PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
   return fn;
 }
 
-template <typename T, bool SPLIT3, int BN>
+template <typename T, bool SPLIT3, int BN, bool DEEP>
 int launch_conv_umma(cudaStream_t s, int dtype, const void* state, const void* state_lo, int Cp,
                      const int32_t* idx,
                      const int32_t* count, const void* packed, const float* bias, void* out,
                      int Op, int B, int H, int W, int Cout, int CoutPad, int kH, int kW, int relu,
                      int sel_lo, int sel_hi) {
-  using C = UmmaCfg<T, SPLIT3, BN>;
+  using C = UmmaCfg<T, SPLIT3, BN, DEEP>;
   const int Kp = kH * kW * Cp;
   const int KpPad = umma_kp_pad(dtype, Cp, kH, kW);
   auto enc = tensor_map_encoder();
@@ -567,7 +569,7 @@ int launch_conv_umma(cudaStream_t s, int dtype, const void* state, const void* s
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(3, "conv_update: cuTensorMapEncodeTiled failed (%d)", (int)r);
-  auto kern = conv_umma_kernel<T, SPLIT3, BN>;
+  auto kern = conv_umma_kernel<T, SPLIT3, BN, DEEP>;
   static thread_local int attr_dev = -1;
   int dev = 0;
   cudaGetDevice(&dev);
@@ -589,7 +591,7 @@ int launch_conv_umma(cudaStream_t s, int dtype, const void* state, const void* s
   return 0;
 }
 
-template <typename T, bool SPLIT3>
+template <typename T, bool SPLIT3, bool DEEP>
 int dispatch_bn(int bn, cudaStream_t s, int dtype, const void* state, const void* state_lo, int Cp,
                 const int32_t* idx,
                 const int32_t* count, const void* packed, const float* bias, void* out, int Op,
@@ -597,9 +599,15 @@ int dispatch_bn(int bn, cudaStream_t s, int dtype, const void* state, const void
                 int sel_hi) {
 #define CB_BN(N)                                                                              \
   case N:                                                                                     \
-    return launch_conv_umma<T, SPLIT3, N>(s, dtype, state, state_lo, Cp, idx, count, packed, bias, out, \
+    return launch_conv_umma<T, SPLIT3, N, DEEP>(s, dtype, state, state_lo, Cp, idx, count, packed, bias, out, \
                                           Op, B, H, W, Cout, CoutPad, kH, kW, relu, sel_lo,   \
                                           sel_hi);
+  if (DEEP) {                                  // the deep variant only exists for N tiles <= 64
+    switch (bn) {
+      CB_BN(16) CB_BN(32) CB_BN(64)
+      default: return fail(2, "conv_update: unsupported deep N tile %d", bn);
+    }
+  }
   switch (bn) {
     CB_BN(16) CB_BN(32) CB_BN(64) CB_BN(128) CB_BN(256)
     default: return fail(2, "conv_update: unsupported N tile %d", bn);
@@ -624,20 +632,21 @@ inline int umma_conv_update(cudaStream_t s, int dtype, int gemm, const void* sta
   // layers) but give few CTAs when few pixels changed; the count is only known on the device, so
   // when a small change set is plausible (expected tiles at 10 % change < half the SMs) a second,
   // finer tiling is launched as well and each kernel checks the count to see whether it is its turn.
-  auto run = [&](int tile_n, int lo, int hi) -> int {
+  auto run_t = [&](auto deep_tag, int tile_n, int lo, int hi) -> int {
+    constexpr bool DP = decltype(deep_tag)::value;
     switch (dtype) {
       case CB_F32:
-        return split3 ? dispatch_bn<float, true>(tile_n, s, dtype, state, state_lo, Cp, idx, count,
+        return split3 ? dispatch_bn<float, true, DP>(tile_n, s, dtype, state, state_lo, Cp, idx, count,
                                                  packed, bias, out, Op, B, H, W, Cout, CoutPad, kH,
                                                  kW, relu, lo, hi)
-                      : dispatch_bn<float, false>(tile_n, s, dtype, state, state_lo, Cp, idx, count,
+                      : dispatch_bn<float, false, DP>(tile_n, s, dtype, state, state_lo, Cp, idx, count,
                                                   packed, bias, out, Op, B, H, W, Cout, CoutPad,
                                                   kH, kW, relu, lo, hi);
       case CB_F16:
-        return dispatch_bn<__half, false>(tile_n, s, dtype, state, state_lo, Cp, idx, count, packed,
+        return dispatch_bn<__half, false, DP>(tile_n, s, dtype, state, state_lo, Cp, idx, count, packed,
                                           bias, out, Op, B, H, W, Cout, CoutPad, kH, kW, relu, lo, hi);
       case CB_BF16:
-        return dispatch_bn<__nv_bfloat16, false>(tile_n, s, dtype, state, state_lo, Cp, idx, count,
+        return dispatch_bn<__nv_bfloat16, false, DP>(tile_n, s, dtype, state, state_lo, Cp, idx, count,
                                                  packed, bias, out, Op, B, H, W, Cout, CoutPad, kH,
                                                  kW, relu, lo, hi);
       default: return fail(2, "conv_update: bad dtype %d", dtype);
@@ -646,17 +655,19 @@ inline int umma_conv_update(cudaStream_t s, int dtype, int gemm, const void* sta
   const long long P = (long long)B * H * W;
   const int sms = sm_count();
   const long long exp_tiles = (P / 10 / UM_BM + 1) * (CoutPad / bn);
-  int bn_small = bn / 4;
-  if (bn_small < 16) bn_small = 16;
-  if (bn_small < bn && exp_tiles < sms / 2) {
+  if (exp_tiles < sms / 2) {
+    // small-change regime: fewer tiles than SMs, so run ONE CTA per SM with a deep stage ring
+    // (latency-bound otherwise) and, for wide layers, a 4x finer N tiling to spread the work
+    int bn_small = bn > 64 ? (bn / 4 < 64 ? 64 : bn / 4) : bn;
+    if (bn_small > 64) bn_small = 64;
     // switch point: the coarse tiling takes over once it alone fills ~2/3 of the SMs
     int m_switch = (2 * sms / 3) / (CoutPad / bn);
     if (m_switch < 1) m_switch = 1;
-    const int rc = run(bn_small, 0, m_switch);
+    const int rc = run_t(std::true_type{}, bn_small, 0, m_switch);
     if (rc) return rc;
-    return run(bn, m_switch, 0x7fffffff);
+    return run_t(std::false_type{}, bn, m_switch, 0x7fffffff);
   }
-  return run(bn, 0, 0x7fffffff);
+  return run_t(std::false_type{}, bn, 0, 0x7fffffff);
 }
 
 }  // namespace cb
