@@ -13,8 +13,8 @@
 //   warps 0-7  gather producers: im2col rows of ONLY the changed receptive fields, 16-byte
 //              cp.async copies global -> 128B-swizzled K-major smem tile (the UMMA canonical
 //              layout), zero-filled outside the image.  In 3xTF32 mode the tf32 "hi" operand is
-//              the landed raw fp32 tile (the tensor core ignores the low 13 mantissa bits) and
-//              each thread derives the "lo" remainder tile from the chunks it copied itself.
+//              the raw fp32 state (the tensor core ignores the low 13 mantissa bits) and the
+//              "lo" operand is the remainder plane cb_change_detect maintains.
 //              The same warps run the epilogue: tcgen05.ld accumulators from TMEM, + bias,
 //              ReLU, convert, scatter one contiguous channel run per pixel.
 //   warp 8     TMA producer for the (regular) weight tiles: cp.async.bulk.tensor.2d, SWIZZLE_128B.
@@ -303,11 +303,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
         ry[it] = pix < 0 ? -0x40000000 : (yx >> 16);        // invalid rows fail every bounds test
         rx[it] = yx & 0xffff;
       }
+      const long long lo_delta = SPLIT3 ? (state_lo - state) : 0;
       KCursor cur;
       cur.init(c * C::VEC, Cp, kW);
       // Gather = async 16-byte copies straight into the swizzled UMMA tile (zero-filled outside
-      // the image / beyond K); no register staging, so several stages of loads are in flight.
-      auto issue_stage = [&](int kb) {
+      // the image / beyond K); no register staging, so up to STAGES stages of loads are in flight.
+      for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&ctrl->empty[stage], phase ^ 1u);
         const uint32_t a_hi = smem_u32(smem + stage * C::STAGE_BYTES);
         int dy, dx;
@@ -330,47 +331,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
         for (int it = 0; it < RPT; ++it) {
           const bool ok = kvalid && (unsigned)(ry[it] + dy) < (unsigned)H &&
                           (unsigned)(rx[it] + dx) < (unsigned)W;
-          cp_async16(a_hi + soff[it], ok ? rbase[it] + koff : state, ok ? 16u : 0u);
+          const T* src = ok ? rbase[it] + koff : state;
+          cp_async16(a_hi + soff[it], src, ok ? 16u : 0u);
+          if (SPLIT3) cp_async16(a_hi + C::A_BYTES + soff[it], src + lo_delta, ok ? 16u : 0u);
         }
-      };
-      if (!SPLIT3) {
-        for (int kb = 0; kb < num_kb; ++kb) {
-          issue_stage(kb);
-          cp_async_arrive_noinc(&ctrl->full[stage]);         // arrives when my copies have landed
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
-        }
-      } else {
-        // 3xTF32: the tensor core ignores the 13 low mantissa bits, so the landed fp32 tile IS the
-        // tf32 "hi" operand; each thread derives the "lo" remainder of the chunks it copied itself
-        // (smem -> registers -> smem, no cross-thread hazard) once its copy group has landed.  The
-        // im2col gather therefore moves every state value through L2 once, not twice.
-        constexpr int D = C::STAGES - 1;                     // stages of copies kept in flight
-        uint32_t cstage = stage;                             // stage being converted
-        for (int kb = 0; kb < num_kb + D; ++kb) {
-          if (kb < num_kb) {
-            issue_stage(kb);
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
-          }
-          if (kb >= D) {
-            if (kb < num_kb) asm volatile("cp.async.wait_group %0;" ::"n"(D) : "memory");
-            else asm volatile("cp.async.wait_group 0;" ::: "memory");
-            uint8_t* a_hi = smem + cstage * C::STAGE_BYTES;
-#pragma unroll
-            for (int it = 0; it < RPT; ++it) {
-              const uint4 v = *reinterpret_cast<const uint4*>(a_hi + soff[it]);
-              uint4 lo;
-              lo.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(v.x & 0xFFFFE000u));
-              lo.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(v.y & 0xFFFFE000u));
-              lo.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(v.z & 0xFFFFE000u));
-              lo.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(v.w & 0xFFFFE000u));
-              *reinterpret_cast<uint4*>(a_hi + C::A_BYTES + soff[it]) = lo;
-            }
-            fence_proxy_async_smem();                        // generic writes -> async proxy (UMMA)
-            mbar_arrive(&ctrl->full[cstage]);
-            if (++cstage == C::STAGES) cstage = 0;
-          }
-        }
+        cp_async_arrive_noinc(&ctrl->full[stage]);
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
       }
       // ---- epilogue: TMEM -> registers -> bias / ReLU -> scatter -------------------------
       mbar_wait(&ctrl->tmem_full, acc_phase);
@@ -660,7 +626,8 @@ inline int umma_conv_update(cudaStream_t s, int dtype, int gemm, const void* sta
                "conv_update: state must be 16-byte and packed weights 128-byte aligned");
   const int bn = umma_bn(gemm, Cout), CoutPad = umma_cout_pad(gemm, Cout);
   const bool split3 = gemm == CB_GEMM_TC_3X && dtype == CB_F32;
-  (void)state_lo;   // accepted for ABI stability: the remainder is derived in shared memory
+  CB_CHECK_ARG(!split3 || (state_lo && ((uintptr_t)state_lo % 16) == 0),
+               "conv_update: CB_GEMM_TC_3X needs the 16-byte aligned tf32 remainder plane (state_lo)");
   // Tiling policy.  Large N tiles minimise the im2col re-gather (the kernel is L2-bound on big
   // layers) but give few CTAs when few pixels changed; the count is only known on the device, so
   // when a small change set is plausible (expected tiles at 10 % change < half the SMs) a second,
