@@ -224,7 +224,8 @@ class CBConv2d(nn.Module):
 
         if self.prevInput.size() != input.size() or self.prevInput.dtype != dt or self._inBuf is None:
             self.prevInput, self._inBuf = cg.pixel_major(input.shape, dt, dev, _INF)   # :192-194
-            self._loView, self._loBuf = None, None   # (remainder plane: no longer needed)
+            self._loView, self._loBuf = (cg.pixel_major(input.shape, dt, dev, 0)
+                                         if dt == torch.float32 else (None, None))
             self._scratch = None
             self._fresh = True
         outpSize = (B, self.out_channels, H, W)

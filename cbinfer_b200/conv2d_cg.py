@@ -177,10 +177,12 @@ def tf32_lo(x):
 
 def conv_update(state_buf, changes, packed_w, bias_f32, out_buf, Cin, Cout, filtSize, relu, gemm,
                 lo_buf=None):
-    """cb_conv_update on pixel-major buffers [B,H,W,pitch].  lo_buf (optional tf32 remainder
-    plane) is accepted for ABI stability; the kernel derives the remainder in shared memory."""
+    """cb_conv_update on pixel-major buffers [B,H,W,pitch]; lo_buf = tf32 remainder plane of
+    state_buf (needed for GEMM_TC_3X on fp32; computed on the fly when not supplied)."""
     B, H, W, Cp = state_buf.shape
     assert out_buf.shape[:3] == state_buf.shape[:3]
+    if gemm == _lib.GEMM_TC_3X and state_buf.dtype == torch.float32 and lo_buf is None:
+        lo_buf = tf32_lo(state_buf)
     check(C.cb_conv_update(stream_ptr(state_buf.device), dtype_code(state_buf), gemm,
                            state_buf.data_ptr(), lo_buf.data_ptr() if lo_buf is not None else None,
                            Cp, changes.buffer.data_ptr(),

@@ -9,13 +9,12 @@
 //   N : BN output channels
 //   K : kH*kW*Cp ordered (ky,kx,ci): every filter tap is a contiguous channel run of the
 //       pixel-major state, so one 16-byte chunk never straddles a tap.
-// Warp roles (448 threads):
+// Warp roles (320 threads):
 //   warps 0-7  gather producers: im2col rows of ONLY the changed receptive fields, 16-byte
 //              cp.async copies global -> 128B-swizzled K-major smem tile (the UMMA canonical
-//              layout), zero-filled outside the image.
-//   warps 10-13 (3xTF32 only) converters: the landed raw fp32 tile is the tf32 "hi" operand (the
-//              tensor core ignores the low 13 mantissa bits); they derive the "lo" remainder tile
-//              in shared memory, so the gather moves each value through L2 once.
+//              layout), zero-filled outside the image.  In 3xTF32 mode the tf32 "hi" operand is
+//              the raw fp32 state (the tensor core ignores the low 13 mantissa bits) and the
+//              "lo" operand is the remainder plane cb_change_detect maintains.
 //              The same warps run the epilogue: tcgen05.ld accumulators from TMEM, + bias,
 //              ReLU, convert, scatter one contiguous channel run per pixel.
 //   warp 8     TMA producer for the (regular) weight tiles: cp.async.bulk.tensor.2d, SWIZZLE_128B.
@@ -32,8 +31,7 @@ namespace cb {
 
 constexpr int UM_BM = 128;                     // rows per tile (UMMA M, cta_group::1)
 constexpr int UM_PRODUCERS = 256;              // gather / epilogue threads (warps 0-7)
-constexpr int UM_CONVERTERS = 128;             // 3xTF32 only: warps deriving the tf32 "lo" tile
-constexpr int UM_THREADS = UM_PRODUCERS + 64 + UM_CONVERTERS;  // + TMA warp + MMA warp + converters
+constexpr int UM_THREADS = UM_PRODUCERS + 64;  // + TMA warp + MMA warp
 constexpr int UM_ROW_BYTES = 128;              // K bytes per stage row = one swizzle-128B span
 
 // ---- PTX wrappers ----------------------------------------------------------------------------
@@ -172,7 +170,7 @@ struct UmmaCfg {
 };
 
 struct UmmaCtrl {                              // lives after the stage buffers
-  uint64_t full[8], empty[8], raw[8], tmem_full, tmem_empty;
+  uint64_t full[8], empty[8], tmem_full, tmem_empty;
   uint32_t tmem_base, pad;
   int pix[UM_BM];
   int yx[UM_BM];
@@ -232,7 +230,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
   int2* ktab = reinterpret_cast<int2*>(reinterpret_cast<uint8_t*>(ctrl) + 2048);
   const bool use_table = num_kb * 8 <= C::TABLE_MAX;
   if (use_table) {
-    for (int q = tid; q < num_kb * 8; q += (int)blockDim.x) {
+    for (int q = tid; q < num_kb * 8; q += UM_THREADS) {
       const int k = q * C::VEC;
       int2 e = make_int2(0, (int)0x80008000u);             // k beyond K: dy = dx = -32768 (invalid)
       if (k < Kp) {
@@ -247,10 +245,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
 
   if (tid == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
-      // full: gather complete (+ TMA weights).  3xTF32: the gather lands on `raw`, the converter
-      // warps turn it into hi + lo tiles and are the ones arriving on `full`.
-      mbar_init(&ctrl->full[s], (SPLIT3 ? UM_CONVERTERS : UM_PRODUCERS) + 1);
-      mbar_init(&ctrl->raw[s], UM_PRODUCERS);
+      mbar_init(&ctrl->full[s], UM_PRODUCERS + 1);
       mbar_init(&ctrl->empty[s], 1);
     }
     mbar_init(&ctrl->tmem_full, 1);
@@ -308,6 +303,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
         ry[it] = pix < 0 ? -0x40000000 : (yx >> 16);        // invalid rows fail every bounds test
         rx[it] = yx & 0xffff;
       }
+      const long long lo_delta = SPLIT3 ? (state_lo - state) : 0;
       KCursor cur;
       cur.init(c * C::VEC, Cp, kW);
       // Gather = async 16-byte copies straight into the swizzled UMMA tile (zero-filled outside
@@ -335,10 +331,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
         for (int it = 0; it < RPT; ++it) {
           const bool ok = kvalid && (unsigned)(ry[it] + dy) < (unsigned)H &&
                           (unsigned)(rx[it] + dx) < (unsigned)W;
-          cp_async16(a_hi + soff[it], ok ? rbase[it] + koff : state, ok ? 16u : 0u);
+          const T* src = ok ? rbase[it] + koff : state;
+          cp_async16(a_hi + soff[it], src, ok ? 16u : 0u);
+          if (SPLIT3) cp_async16(a_hi + C::A_BYTES + soff[it], src + lo_delta, ok ? 16u : 0u);
         }
-        // arrives once my copies of this stage have landed (fully asynchronous)
-        cp_async_arrive_noinc(SPLIT3 ? &ctrl->raw[stage] : &ctrl->full[stage]);
+        cp_async_arrive_noinc(&ctrl->full[stage]);
         if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
       }
       // ---- epilogue: TMEM -> registers -> bias / ReLU -> scatter -------------------------
@@ -393,36 +390,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
       mbar_arrive(&ctrl->tmem_empty);
       acc_phase ^= 1u;
       asm volatile("bar.sync 1, %0;" ::"n"(UM_PRODUCERS) : "memory");   // row table reused next tile
-    }
-  } else if (warp > MMA_WARP) {
-    // =============================== 3xTF32 converters ======================================
-    // The tensor core ignores the 13 low mantissa bits of fp32 operands, so the landed raw tile IS
-    // the tf32 "hi" operand; these warps derive the "lo" remainder tile (v - trunc_tf32(v), exact)
-    // in shared memory.  The im2col gather thus moves each state value through L2 once, and the
-    // gather warps never wait for data.
-    if (SPLIT3) {
-      const int ct = tid - (MMA_WARP + 1) * 32;             // 0..127
-      uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&ctrl->raw[stage], phase);
-          uint8_t* a_hi = smem + stage * C::STAGE_BYTES;
-#pragma unroll
-          for (int i = 0; i < UM_BM * 8 / UM_CONVERTERS; ++i) {
-            const uint32_t off = (uint32_t)((i * UM_CONVERTERS + ct) * 16);   // layout-agnostic
-            const uint4 v = *reinterpret_cast<const uint4*>(a_hi + off);
-            uint4 lo;
-            lo.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(v.x & 0xFFFFE000u));
-            lo.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(v.y & 0xFFFFE000u));
-            lo.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(v.z & 0xFFFFE000u));
-            lo.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(v.w & 0xFFFFE000u));
-            *reinterpret_cast<uint4*>(a_hi + C::A_BYTES + off) = lo;
-          }
-          fence_proxy_async_smem();                          // generic writes -> async proxy (UMMA)
-          mbar_arrive(&ctrl->full[stage]);
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
-        }
-      }
     }
   } else if (warp == TMA_WARP) {
     // =============================== TMA producer: weight tiles ==============================
@@ -616,7 +583,7 @@ int launch_conv_umma(cudaStream_t s, int dtype, const void* state, const void* s
   long long grid = (long long)sm_count() * C::CTAS_PER_SM;
   if (grid > max_tiles) grid = max_tiles;
   if (grid < 1) grid = 1;
-  kern<<<(unsigned)grid, SPLIT3 ? UM_THREADS : UM_THREADS - UM_CONVERTERS, C::SMEM_BYTES, s>>>(map, (const T*)state, (const T*)state_lo, Cp,
+  kern<<<(unsigned)grid, UM_THREADS, C::SMEM_BYTES, s>>>(map, (const T*)state, (const T*)state_lo, Cp,
                                                         idx, count, bias,
                                                         (T*)out, Op, H, W, Cout, CoutPad, kH, kW,
                                                         Kp, relu, sel_lo, sel_hi);
@@ -659,7 +626,8 @@ inline int umma_conv_update(cudaStream_t s, int dtype, int gemm, const void* sta
                "conv_update: state must be 16-byte and packed weights 128-byte aligned");
   const int bn = umma_bn(gemm, Cout), CoutPad = umma_cout_pad(gemm, Cout);
   const bool split3 = gemm == CB_GEMM_TC_3X && dtype == CB_F32;
-  (void)state_lo;   // accepted for ABI stability: the remainder tile is derived in shared memory
+  CB_CHECK_ARG(!split3 || (state_lo && ((uintptr_t)state_lo % 16) == 0),
+               "conv_update: CB_GEMM_TC_3X needs the 16-byte aligned tf32 remainder plane (state_lo)");
   // Tiling policy.  Large N tiles minimise the im2col re-gather (the kernel is L2-bound on big
   // layers) but give few CTAs when few pixels changed; the count is only known on the device, so
   // when a small change set is plausible (expected tiles at 10 % change < half the SMs) a second,
