@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--rate", type=float, default=0.05, help="fraction of pixels changed per frame")
     ap.add_argument("--mode", default="block", choices=["block", "iid"])
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16", "f16"])
-    ap.add_argument("--gemm", default="auto", choices=["auto", "simt", "tc", "tc3x"])
+    ap.add_argument("--gemm", default="auto", choices=["auto", "simt", "tc", "tc3x", "bf16x3"])
     ap.add_argument("--threshold-factor", type=float, default=0.02)
     ap.add_argument("--dense-scan", action="store_true",
                     help="re-scan every layer's whole input like the reference (default: candidate detection)")
@@ -480,7 +480,7 @@ def kernel_roofline(args, model, frames, dev, tdt):
             elif kname == "conv_update":
                 fl = 2.0 * n * Cin * k2 * m.out_channels
                 by = min(n * k2, P) * Cin * es + m.out_channels * Cin * k2 * es + 4 * n + n * m.out_channels * es
-                pk = bf16 / 2 if args.dtype == "f32" else bf16
+                pk = bf16 / 2 if (args.dtype == "f32" and args.gemm in ("tc", "tc3x")) else bf16
                 row.update(bound="tensor", flops=fl, bytes=by, achieved=fl / (us * 1e-6) / 1e12, peak=pk,
                            unit="TFLOP/s", n=n, hbm_gbs=by / (us * 1e-6) / 1e9)
         else:

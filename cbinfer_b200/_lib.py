@@ -14,7 +14,8 @@ from . import build as _build
 
 F32, F16, BF16 = 0, 1, 2
 UPDATE_NONE, UPDATE_CHANGED, UPDATE_ALL = 0, 1, 2
-GEMM_SIMT_F32, GEMM_TC, GEMM_TC_3X = 0, 1, 2
+GEMM_SIMT_F32, GEMM_TC, GEMM_TC_3X, GEMM_TC_BF16X3 = 0, 1, 2, 3
+AUX_NONE, AUX_TF32_LO, AUX_BF16_PAIR = 0, 1, 2
 
 _DTYPES = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
 
@@ -49,12 +50,12 @@ def _load():
         "cb_compact_ws_bytes": (sz, [i32, i32, i32]),
         "cb_channel_pitch": (i32, [i32, i32]),
         "cb_packed_weight_bytes": (sz, [i32] * 6),
-        "cb_change_detect": (i32, [vp, i32, vp, i64, i64, i64, i64, vp, i64, i64, i64, i64, vp, vp,
-                                   i32, i32, i32, i32, f32, i32]),
+        "cb_change_detect": (i32, [vp, i32, vp, i64, i64, i64, i64, vp, i64, i64, i64, i64, i32, vp, vp,
+                                   vp, i32, i32, i32, i32, f32, i32]),
         "cb_dilate_compact": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32]),
         "cb_map_to_bits": (i32, [vp, vp, vp, i32, i32, i32]),
-        "cb_change_detect_sparse": (i32, [vp, i32, vp, i64, i64, i64, i64, vp, i64, i64, i64, i64, vp,
-                                          vp, vp, vp, i32, i32, i32, i32, f32, i32, i32]),
+        "cb_change_detect_sparse": (i32, [vp, i32, vp, i64, i64, i64, i64, vp, i64, i64, i64, i64, i32,
+                                          vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, i32, i32]),
         "cb_pool_compact": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32]),
         "cb_pack_weights": (i32, [vp, i32, i32, vp, vp, i32, i32, i32, i32]),
         "cb_conv_update": (i32, [vp, i32, i32, vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32,

@@ -108,9 +108,11 @@ class CBPoolMax2d(nn.Module):
 
 
 class CBConv2d(nn.Module):
-    #: contraction arithmetic per dtype (see include/cbinfer_b200.h): fp32 data defaults to the
-    #: fp32-accurate 3xTF32 tensor-core split, 16-bit data to kind::f16 with fp32 accumulation.
-    GEMM_MODES = {'simt': _lib.GEMM_SIMT_F32, 'tc': _lib.GEMM_TC, 'tc3x': _lib.GEMM_TC_3X}
+    #: contraction arithmetic (see include/cbinfer_b200.h).  gemmMode 'auto': fp32 data -> 3xBF16
+    #: split on the tensor cores (max rel. error ~2e-5, bar 1e-4), 16-bit data -> kind::f16 with
+    #: fp32 accumulation.  'tc3x' = 3xTF32 (~2e-6), 'tc' = single-pass TF32, 'simt' = fp32 FFMA.
+    GEMM_MODES = {'simt': _lib.GEMM_SIMT_F32, 'tc': _lib.GEMM_TC, 'tc3x': _lib.GEMM_TC_3X,
+                  'bf16x3': _lib.GEMM_TC_BF16X3}
 
     def __init__(self, m, threshold):
         super(CBConv2d, self).__init__()
@@ -157,8 +159,7 @@ class CBConv2d(nn.Module):
         self.prevOutput = self.weight.data.new_empty(0)
         self._inBuf = None        # pixel-major storage behind prevInput / prevOutput
         self._outBuf = None
-        self._loView = None       # fp32 only: tf32 remainder plane of prevInput (3xTF32 operand)
-        self._loBuf = None
+        self._auxPlanes = None    # fp32 only: operand planes of prevInput for the 3x modes
         self._scratch = None      # bitmaps, index list, count, compaction workspace
         self._packed = None       # (key, packed weights, fp32 bias)
         self._fresh = True        # state holds +inf: the next detection must be a full scan
@@ -178,11 +179,30 @@ class CBConv2d(nn.Module):
     def _gemm(self, dtype):
         mode = getattr(self, 'gemmMode', 'auto')
         if mode == 'auto':
-            return _lib.GEMM_TC_3X if dtype == torch.float32 else _lib.GEMM_TC
+            return _lib.GEMM_TC_BF16X3 if dtype == torch.float32 else _lib.GEMM_TC
         g = self.GEMM_MODES[mode]
-        if g == _lib.GEMM_TC_3X and dtype != torch.float32:
+        if g in (_lib.GEMM_TC_3X, _lib.GEMM_TC_BF16X3) and dtype != torch.float32:
             g = _lib.GEMM_TC
         return g
+
+    def _aux(self, gemm):
+        """Auxiliary operand planes of prevInput for the 3x modes (kept in step by the detection
+        kernel); (re)built from prevInput when the mode changes or after a plain copy."""
+        want = {_lib.GEMM_TC_3X: 'tf32', _lib.GEMM_TC_BF16X3: 'bf16'}.get(gemm) \
+            if self.prevInput.dtype == torch.float32 else None
+        if want is None:
+            self._auxPlanes = None
+        elif self._auxPlanes is None or self._auxPlanes[0] != want:
+            if want == 'tf32':
+                view, buf = cg.pixel_major(self.prevInput.shape, torch.float32, self.prevInput.device, 0)
+                fin = torch.isfinite(self.prevInput)
+                view.copy_(torch.where(fin, cg.tf32_lo(torch.where(fin, self.prevInput, 0)), 0))
+                self._auxPlanes = ('tf32', view, buf)
+            else:
+                hi, lo = cg.bf16_planes(torch.nan_to_num(self._inBuf, posinf=0.0, neginf=0.0),
+                                        self.in_channels)
+                self._auxPlanes = ('bf16', hi, lo)
+        return self._auxPlanes
 
     def _weights(self, dtype, device):
         gemm = self._gemm(dtype)
@@ -224,8 +244,7 @@ class CBConv2d(nn.Module):
 
         if self.prevInput.size() != input.size() or self.prevInput.dtype != dt or self._inBuf is None:
             self.prevInput, self._inBuf = cg.pixel_major(input.shape, dt, dev, _INF)   # :192-194
-            self._loView, self._loBuf = (cg.pixel_major(input.shape, dt, dev, 0)
-                                         if dt == torch.float32 else (None, None))
+            self._auxPlanes = None
             self._scratch = None
             self._fresh = True
         outpSize = (B, self.out_channels, H, W)
@@ -239,6 +258,10 @@ class CBConv2d(nn.Module):
 
         if self.gatherComputationStats:
             self._gatherStats(input)
+
+        gemm, packed, bias32 = self._weights(dt, dev)
+        aux = self._aux(gemm)
+        aux_arg = None if aux is None else (aux[:2] if aux[0] == 'tf32' else aux)
 
         candidates = None
         if changeIndexes is not None and getattr(self, 'candidateDetect', False):
@@ -258,11 +281,10 @@ class CBConv2d(nn.Module):
             sparse_next = bool(getattr(self, 'candidateDetect', False))
             if candidates is not None:
                 cg.detect_sparse(input, self.prevInput, s["raw_bits"], self.threshold, mode,
-                                 candidates, state_lo=self._loView,
+                                 candidates, aux=aux_arg,
                                  bits_are_clear=s.get("raw_clear", False))
             else:
-                cg.detect(input, self.prevInput, s["raw_bits"], self.threshold, mode,
-                          state_lo=self._loView)
+                cg.detect(input, self.prevInput, s["raw_bits"], self.threshold, mode, aux=aux_arg)
             self._fresh = False
             self._lastThr = self.threshold
             dil_map = s.get("dil_map") if self.saveChangeMap else None
@@ -281,14 +303,14 @@ class CBConv2d(nn.Module):
                 changeIndexes = ChangeIndexes.from_tensor(changeIndexes.detach(), (B, H, W))
             if not self.feedbackLoop:
                 self.prevInput.copy_(input)                                            # :234-236
-                if self._loView is not None:
-                    self._loView.copy_(cg.tf32_lo(input))
+                self._auxPlanes = None
+                aux = self._aux(gemm)
             # (with feedbackLoop the reference never refreshes prevInput here either, :220,234)
 
-        gemm, packed, bias32 = self._weights(dt, dev)
         cg.conv_update(self._inBuf, changeIndexes, packed, bias32, self._outBuf, self.in_channels,
                        self.out_channels, self.kernel_size, self.withReLU, gemm,
-                       lo_buf=self._loBuf)                                             # :242-251
+                       lo_buf=aux[2] if aux is not None and aux[0] == 'tf32' else None,
+                       planes16=aux[1:] if aux is not None and aux[0] == 'bf16' else None)  # :242-251
 
         if self.propChangeIndexes:
             return 'changeIndexes', self.prevOutput, changeIndexes

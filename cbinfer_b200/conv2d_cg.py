@@ -88,21 +88,30 @@ class ChangeIndexes(object):
 # fused-path primitives (native pixel-major layout, batch-capable, no host sync)
 # ---------------------------------------------------------------------------------------------
 
-def detect(x, state, raw_bits, threshold, update_mode, state_lo=None):
-    """cb_change_detect: raw (un-dilated) change bitmap of x vs state; updates state (and, when
-    given, the tf32 remainder plane `state_lo`, a tensor with the strides of `state`)."""
+def _aux_args(aux, state):
+    """aux: None | ('tf32', lo_view) | ('bf16', hi16_buf, lo16_buf) -> (mode, hi_ptr, lo_ptr)."""
+    if aux is None:
+        return _lib.AUX_NONE, None, None
+    if aux[0] == 'tf32':
+        assert aux[1].stride() == state.stride() and aux[1].dtype == state.dtype
+        return _lib.AUX_TF32_LO, None, aux[1].data_ptr()
+    assert aux[0] == 'bf16' and aux[1].dtype == torch.bfloat16 and aux[2].dtype == torch.bfloat16
+    return _lib.AUX_BF16_PAIR, aux[1].data_ptr(), aux[2].data_ptr()
+
+
+def detect(x, state, raw_bits, threshold, update_mode, aux=None):
+    """cb_change_detect: raw (un-dilated) change bitmap of x vs state; updates state and, when
+    given, the auxiliary operand planes `aux` (see _aux_args)."""
     require_cuda(x, state, raw_bits)
     B, Cc, H, W = x.shape
     assert state.shape == x.shape and state.dtype == x.dtype
-    if state_lo is not None:
-        assert state_lo.stride() == state.stride() and state_lo.dtype == state.dtype
+    mode, hi, lo = _aux_args(aux, state)
     check(C.cb_change_detect(stream_ptr(x.device), dtype_code(x), x.data_ptr(), *_strides4(x),
-                             state.data_ptr(), *_strides4(state),
-                             state_lo.data_ptr() if state_lo is not None else None,
+                             state.data_ptr(), *_strides4(state), mode, hi, lo,
                              raw_bits.data_ptr(), B, Cc, H, W, float(threshold), int(update_mode)))
 
 
-def detect_sparse(x, state, raw_bits, threshold, update_mode, candidates, state_lo=None,
+def detect_sparse(x, state, raw_bits, threshold, update_mode, candidates, aux=None,
                   bits_are_clear=False):
     """cb_change_detect_sparse: the detection test at the candidate pixels only (see the header
     for the exactness conditions).  `candidates` is a :class:`ChangeIndexes` at x's resolution."""
@@ -110,9 +119,9 @@ def detect_sparse(x, state, raw_bits, threshold, update_mode, candidates, state_
     B, Cc, H, W = x.shape
     assert state.shape == x.shape and state.dtype == x.dtype
     assert tuple(candidates.shape) == (B, H, W)
+    mode, hi, lo = _aux_args(aux, state)
     check(C.cb_change_detect_sparse(stream_ptr(x.device), dtype_code(x), x.data_ptr(), *_strides4(x),
-                                    state.data_ptr(), *_strides4(state),
-                                    state_lo.data_ptr() if state_lo is not None else None,
+                                    state.data_ptr(), *_strides4(state), mode, hi, lo,
                                     candidates.buffer.data_ptr(), candidates.count.data_ptr(),
                                     raw_bits.data_ptr(), B, Cc, H, W, float(threshold),
                                     int(update_mode), int(bool(bits_are_clear))))
@@ -175,17 +184,43 @@ def tf32_lo(x):
     return x - hi
 
 
+def bf16_pair(x):
+    """(bf16(v), bf16(v - bf16(v))): the operand planes of the 3xBF16 contraction."""
+    hi = x.to(torch.bfloat16)
+    return hi, (x - hi.float()).to(torch.bfloat16)
+
+
+def bf16_planes(state_buf, C_):
+    """pixel-major bf16 hi/lo planes [B,H,W,pitch16] of a pixel-major fp32 buffer."""
+    B, H, W, _ = state_buf.shape
+    p16 = (C_ + 7) // 8 * 8
+    hi = torch.zeros(B, H, W, p16, dtype=torch.bfloat16, device=state_buf.device)
+    lo = torch.zeros_like(hi)
+    h, l = bf16_pair(state_buf[..., :C_])
+    hi[..., :C_] = h
+    lo[..., :C_] = l
+    return hi, lo
+
+
 def conv_update(state_buf, changes, packed_w, bias_f32, out_buf, Cin, Cout, filtSize, relu, gemm,
-                lo_buf=None):
-    """cb_conv_update on pixel-major buffers [B,H,W,pitch]; lo_buf = tf32 remainder plane of
-    state_buf (needed for GEMM_TC_3X on fp32; computed on the fly when not supplied)."""
+                lo_buf=None, planes16=None):
+    """cb_conv_update on pixel-major buffers [B,H,W,pitch].  GEMM_TC_3X (fp32) consumes the tf32
+    remainder plane `lo_buf`, GEMM_TC_BF16X3 the bf16 hi/lo planes `planes16`; both are derived
+    on the fly when the caller does not maintain them (cb_change_detect can)."""
     B, H, W, Cp = state_buf.shape
     assert out_buf.shape[:3] == state_buf.shape[:3]
-    if gemm == _lib.GEMM_TC_3X and state_buf.dtype == torch.float32 and lo_buf is None:
-        lo_buf = tf32_lo(state_buf)
+    src, src_lo, pitch = state_buf, lo_buf, Cp
+    if gemm == _lib.GEMM_TC_BF16X3:
+        assert state_buf.dtype == torch.float32
+        if planes16 is None:
+            planes16 = bf16_planes(state_buf, Cin)
+        src, src_lo = planes16
+        pitch = src.shape[3]
+    elif gemm == _lib.GEMM_TC_3X and state_buf.dtype == torch.float32 and lo_buf is None:
+        src_lo = tf32_lo(state_buf)
     check(C.cb_conv_update(stream_ptr(state_buf.device), dtype_code(state_buf), gemm,
-                           state_buf.data_ptr(), lo_buf.data_ptr() if lo_buf is not None else None,
-                           Cp, changes.buffer.data_ptr(),
+                           src.data_ptr(), src_lo.data_ptr() if src_lo is not None else None,
+                           pitch, changes.buffer.data_ptr(),
                            changes.count.data_ptr(), packed_w.data_ptr(), bias_f32.data_ptr(),
                            out_buf.data_ptr(), out_buf.shape[3], B, H, W, Cin, Cout,
                            filtSize[0], filtSize[1], int(bool(relu))))

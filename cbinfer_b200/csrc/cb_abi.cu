@@ -80,13 +80,14 @@ int cb_channel_pitch(int dtype, int C) {
 
 int cb_change_detect(void* stream, int dtype, const void* x, long long x_sb, long long x_sc,
                      long long x_sy, long long x_sx, void* state, long long s_sb, long long s_sc,
-                     long long s_sy, long long s_sx, void* state_lo, uint32_t* raw_bits, int B, int C,
-                     int H, int W, float threshold, int update_mode) {
+                     long long s_sy, long long s_sx, int aux_mode, void* aux_hi, void* aux_lo,
+                     uint32_t* raw_bits, int B, int C, int H, int W, float threshold,
+                     int update_mode) {
   CB_CHECK_ARG(x && state && raw_bits, "change_detect: null pointer");
   CB_CHECK_ARG(B >= 0 && C > 0 && H >= 0 && W >= 0, "change_detect: bad shape");
   CB_DISPATCH_DTYPE(dtype, return (launch_detect<T, VEC>((cudaStream_t)stream, x, x_sb, x_sc, x_sy,
-                                                        x_sx, state, s_sb, s_sc, s_sy, s_sx, state_lo,
-                                                        raw_bits, B, C, H, W, threshold,
+                                                        x_sx, state, s_sb, s_sc, s_sy, s_sx, aux_mode,
+                                                        aux_hi, aux_lo, raw_bits, B, C, H, W, threshold,
                                                         update_mode)));
   return 0;
 }
@@ -137,15 +138,16 @@ int cb_pool_compact(void* stream, const uint32_t* in_bits, uint32_t* out_bits, i
 
 int cb_change_detect_sparse(void* stream, int dtype, const void* x, long long x_sb, long long x_sc,
                             long long x_sy, long long x_sx, void* state, long long s_sb,
-                            long long s_sc, long long s_sy, long long s_sx, void* state_lo,
-                            const int32_t* candidates, const int32_t* n_candidates,
+                            long long s_sc, long long s_sy, long long s_sx, int aux_mode,
+                            void* aux_hi, void* aux_lo, const int32_t* candidates, const int32_t* n_candidates,
                             uint32_t* raw_bits, int B, int C, int H, int W, float threshold,
                             int update_mode, int bits_are_clear) {
   CB_CHECK_ARG(x && state && raw_bits && candidates && n_candidates, "change_detect_sparse: null pointer");
   CB_CHECK_ARG(B >= 0 && C > 0 && H >= 0 && W >= 0, "change_detect_sparse: bad shape");
   CB_DISPATCH_DTYPE(dtype, return (launch_detect_sparse<T, VEC>(
                                (cudaStream_t)stream, x, x_sb, x_sc, x_sy, x_sx, state, s_sb, s_sc,
-                               s_sy, s_sx, state_lo, candidates, n_candidates, raw_bits, B, C, H, W,
+                               s_sy, s_sx, aux_mode, aux_hi, aux_lo, candidates, n_candidates, raw_bits,
+                               B, C, H, W,
                                threshold, update_mode, bits_are_clear)));
   return 0;
 }
@@ -162,7 +164,7 @@ int cb_map_to_bits(void* stream, const int8_t* map, uint32_t* bits, int B, int H
 }
 
 size_t cb_packed_weight_bytes(int dtype, int gemm, int Cout, int Cin, int kH, int kW) {
-  const int Cp = cb_channel_pitch(dtype, Cin);
+  const int Cp = gemm == CB_GEMM_TC_BF16X3 ? (Cin + 7) / 8 * 8 : cb_channel_pitch(dtype, Cin);
   if (gemm == CB_GEMM_SIMT_F32) {
     const int CoutP = (Cout + 3) / 4 * 4;
     return (size_t)kH * kW * Cp * CoutP * sizeof(float);
@@ -173,7 +175,7 @@ size_t cb_packed_weight_bytes(int dtype, int gemm, int Cout, int Cin, int kH, in
 int cb_pack_weights(void* stream, int dtype, int gemm, const void* weight, void* packed, int Cout,
                     int Cin, int kH, int kW) {
   CB_CHECK_ARG(weight && packed, "pack_weights: null pointer");
-  const int Cp = cb_channel_pitch(dtype, Cin);
+  const int Cp = gemm == CB_GEMM_TC_BF16X3 ? (Cin + 7) / 8 * 8 : cb_channel_pitch(dtype, Cin);
   cudaStream_t s = (cudaStream_t)stream;
   if (gemm == CB_GEMM_SIMT_F32) {
     const int CoutP = (Cout + 3) / 4 * 4;
@@ -191,8 +193,9 @@ int cb_conv_update(void* stream, int dtype, int gemm, const void* state, const v
                    const float* bias, void* out, int pitch_out, int B, int H, int W, int Cin,
                    int Cout, int kH, int kW, int relu) {
   CB_CHECK_ARG(state && idx && count && packed_w && bias && out, "conv_update: null pointer");
-  CB_CHECK_ARG(pitch_in == cb_channel_pitch(dtype, Cin), "conv_update: pitch_in %d != channel pitch %d",
-               pitch_in, cb_channel_pitch(dtype, Cin));
+  const int want_pitch = gemm == CB_GEMM_TC_BF16X3 ? (Cin + 7) / 8 * 8 : cb_channel_pitch(dtype, Cin);
+  CB_CHECK_ARG(pitch_in == want_pitch, "conv_update: pitch_in %d != channel pitch %d", pitch_in,
+               want_pitch);
   CB_CHECK_ARG(pitch_out >= Cout, "conv_update: pitch_out < Cout");
   CB_CHECK_ARG((kH & 1) && (kW & 1), "conv_update: even kernel sizes unsupported (padding==k//2)");
   CB_CHECK_ARG((long long)B * H * W < (1ll << 31), "conv_update: more than 2^31 pixels");

@@ -199,11 +199,13 @@ struct KCursor {
 };
 
 // packed weights: [NSPLIT][CoutPad][KpPad] elements of T (K-major); tensor map dims {KpPad, NSPLIT*CoutPad}
-template <typename T, bool SPLIT3, int BN, bool DEEP>
+// T = operand element type in the state planes / shared memory, TO = element type of `out`
+// (TO != T only for 3xBF16: bf16 hi/lo operand planes of an fp32 layer).
+template <typename T, typename TO, bool SPLIT3, int BN, bool DEEP>
 __global__ void __launch_bounds__(UM_THREADS)
 conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__ state,
                  const T* __restrict__ state_lo, int Cp, const int32_t* __restrict__ idx, const int32_t* __restrict__ count,
-                 const float* __restrict__ bias, T* __restrict__ out, int Op, int H, int W,
+                 const float* __restrict__ bias, TO* __restrict__ out, int Op, int H, int W,
                  int Cout, int CoutPad, int kH, int kW, int Kp, int relu, int sel_lo, int sel_hi) {
   using C = UmmaCfg<T, SPLIT3, BN, DEEP>;
   constexpr int RPT = UM_BM * 8 / UM_PRODUCERS;            // 16-byte chunks per thread per stage
@@ -345,7 +347,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
       const int row = q * 32 + lane;
       const int pix = ctrl->pix[row];
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-      T* orow = out + (long long)(pix < 0 ? 0 : pix) * Op;
+      TO* orow = out + (long long)(pix < 0 ? 0 : pix) * Op;
+      constexpr int OVEC = 16 / (int)sizeof(TO);
       constexpr int NGROUP = UM_PRODUCERS / 128;             // warps sharing a lane quarter
       constexpr int COLS = (BN / NGROUP) < 16 ? 16 : (BN / NGROUP);
       const int cbeg = (warp >> 2) * COLS;
@@ -364,8 +367,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
             if (relu && t <= 0.f) t = 0.f;
             f[i] = t;
           }
-          if (co0 + 16 <= Cout && (Op % C::VEC) == 0) {      // full, 16-byte aligned run
-            if (sizeof(T) == 4) {
+          if (co0 + 16 <= Cout && (Op % OVEC) == 0) {        // full, 16-byte aligned run
+            if (sizeof(TO) == 4) {
 #pragma unroll
               for (int i = 0; i < 16; i += 4)
                 *reinterpret_cast<float4*>(reinterpret_cast<float*>(orow) + co0 + i) =
@@ -373,16 +376,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
             } else {
 #pragma unroll
               for (int i = 0; i < 16; i += 8) {
-                T h[8];
+                TO h[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) h[e] = from_float<T>(f[i + e]);
+                for (int e = 0; e < 8; ++e) h[e] = from_float<TO>(f[i + e]);
                 *reinterpret_cast<uint4*>(orow + co0 + i) = *reinterpret_cast<uint4*>(h);
               }
             }
           } else {
 #pragma unroll
             for (int i = 0; i < 16; ++i)
-              if (co0 + i < Cout) orow[co0 + i] = from_float<T>(f[i]);
+              if (co0 + i < Cout) orow[co0 + i] = from_float<TO>(f[i]);
           }
         }
       }
@@ -461,8 +464,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
 // ---- weight packing ----------------------------------------------------------------------------
 // weight [Cout][Cin][kH][kW] (T) -> packed [NSPLIT][CoutPad][KpPad] (T), k = (ky*kW+kx)*Cp + ci.
 // fp32 + SPLIT3: plane 0 = tf32-truncated hi, plane 1 = lo = w - hi (exact).
-template <typename T>
-__global__ void pack_weights_umma_kernel(const T* __restrict__ w, T* __restrict__ packed, int Cout,
+// split: 0 none, 1 = tf32 hi (truncated) + lo, 2 = bf16 hi (rounded) + lo
+template <typename T, typename TP>
+__global__ void pack_weights_umma_kernel(const T* __restrict__ w, TP* __restrict__ packed, int Cout,
                                          int Cin, int kH, int kW, int Cp, int CoutPad, int KpPad,
                                          int split3) {
   const long long plane = (long long)CoutPad * KpPad;
@@ -472,15 +476,19 @@ __global__ void pack_weights_umma_kernel(const T* __restrict__ w, T* __restrict_
     const int co = (int)(i / KpPad);
     const int tap = k / Cp, ci = k - tap * Cp;
     const int ky = tap / kW, kx = tap - ky * kW;
-    T v = from_float<T>(0.f);
-    if (co < Cout && ci < Cin && tap < kH * kW) v = w[(((long long)co * Cin + ci) * kH + ky) * kW + kx];
-    if (split3) {
-      const float f = to_float(v);
+    float f = 0.f;
+    if (co < Cout && ci < Cin && tap < kH * kW)
+      f = to_float(w[(((long long)co * Cin + ci) * kH + ky) * kW + kx]);
+    if (split3 == 1) {
       const float hi = __uint_as_float(__float_as_uint(f) & 0xFFFFE000u);
-      packed[i] = from_float<T>(hi);
-      packed[plane + i] = from_float<T>(f - hi);
+      packed[i] = from_float<TP>(hi);
+      packed[plane + i] = from_float<TP>(f - hi);
+    } else if (split3 == 2) {
+      const TP hi = from_float<TP>(f);
+      packed[i] = hi;
+      packed[plane + i] = from_float<TP>(f - to_float(hi));
     } else {
-      packed[i] = v;
+      packed[i] = from_float<TP>(f);     // exact: TP == T
     }
   }
 }
@@ -495,35 +503,53 @@ inline int umma_cout_pad(int gemm, int Cout) {
   const int bn = umma_bn(gemm, Cout);
   return (Cout + bn - 1) / bn * bn;
 }
-inline int umma_kp_pad(int dtype, int Cp, int kH, int kW) {
-  const int bk = UM_ROW_BYTES / esize(dtype);
+inline int umma_kp_pad_es(int es, int Cp, int kH, int kW) {
+  const int bk = UM_ROW_BYTES / es;
   return (kH * kW * Cp + bk - 1) / bk * bk;
 }
+// operand element size of a (dtype, gemm) pair: 3xBF16 feeds bf16 planes of fp32 data
+inline int umma_operand_es(int dtype, int gemm) {
+  return gemm == CB_GEMM_TC_BF16X3 ? 2 : esize(dtype);
+}
+inline int umma_kp_pad(int dtype, int Cp, int kH, int kW) {
+  return umma_kp_pad_es(esize(dtype), Cp, kH, kW);
+}
 
+inline bool umma_is_split(int dtype, int gemm) {
+  return dtype == CB_F32 && (gemm == CB_GEMM_TC_3X || gemm == CB_GEMM_TC_BF16X3);
+}
 inline size_t umma_packed_bytes(int dtype, int gemm, int Cout, int Cp, int kH, int kW) {
-  const int nsplit = (gemm == CB_GEMM_TC_3X && dtype == CB_F32) ? 2 : 1;
-  return (size_t)nsplit * umma_cout_pad(gemm, Cout) * umma_kp_pad(dtype, Cp, kH, kW) * esize(dtype);
+  const int nsplit = umma_is_split(dtype, gemm) ? 2 : 1;
+  const int es = umma_operand_es(dtype, gemm);
+  return (size_t)nsplit * umma_cout_pad(gemm, Cout) * umma_kp_pad_es(es, Cp, kH, kW) * es;
 }
 
 inline int umma_pack_weights(cudaStream_t s, int dtype, int gemm, const void* weight, void* packed,
                              int Cout, int Cin, int Cp, int kH, int kW) {
-  CB_CHECK_ARG(gemm == CB_GEMM_TC || gemm == CB_GEMM_TC_3X, "pack_weights: bad gemm mode %d", gemm);
-  const int split3 = (gemm == CB_GEMM_TC_3X && dtype == CB_F32) ? 1 : 0;
-  const int CoutPad = umma_cout_pad(gemm, Cout), KpPad = umma_kp_pad(dtype, Cp, kH, kW);
+  CB_CHECK_ARG(gemm == CB_GEMM_TC || gemm == CB_GEMM_TC_3X || gemm == CB_GEMM_TC_BF16X3,
+               "pack_weights: bad gemm mode %d", gemm);
+  CB_CHECK_ARG(gemm != CB_GEMM_TC_BF16X3 || dtype == CB_F32, "pack_weights: 3xBF16 is for fp32 data");
+  const int es = umma_operand_es(dtype, gemm);
+  const int CoutPad = umma_cout_pad(gemm, Cout), KpPad = umma_kp_pad_es(es, Cp, kH, kW);
   const long long plane = (long long)CoutPad * KpPad;
   long long blocks = (plane + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   switch (dtype) {
     case CB_F32:
-      pack_weights_umma_kernel<float><<<(unsigned)blocks, 256, 0, s>>>(
-          (const float*)weight, (float*)packed, Cout, Cin, kH, kW, Cp, CoutPad, KpPad, split3);
+      if (gemm == CB_GEMM_TC_BF16X3)
+        pack_weights_umma_kernel<float, __nv_bfloat16><<<(unsigned)blocks, 256, 0, s>>>(
+            (const float*)weight, (__nv_bfloat16*)packed, Cout, Cin, kH, kW, Cp, CoutPad, KpPad, 2);
+      else
+        pack_weights_umma_kernel<float, float><<<(unsigned)blocks, 256, 0, s>>>(
+            (const float*)weight, (float*)packed, Cout, Cin, kH, kW, Cp, CoutPad, KpPad,
+            gemm == CB_GEMM_TC_3X ? 1 : 0);
       break;
     case CB_F16:
-      pack_weights_umma_kernel<__half><<<(unsigned)blocks, 256, 0, s>>>(
+      pack_weights_umma_kernel<__half, __half><<<(unsigned)blocks, 256, 0, s>>>(
           (const __half*)weight, (__half*)packed, Cout, Cin, kH, kW, Cp, CoutPad, KpPad, 0);
       break;
     case CB_BF16:
-      pack_weights_umma_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, s>>>(
+      pack_weights_umma_kernel<__nv_bfloat16, __nv_bfloat16><<<(unsigned)blocks, 256, 0, s>>>(
           (const __nv_bfloat16*)weight, (__nv_bfloat16*)packed, Cout, Cin, kH, kW, Cp, CoutPad,
           KpPad, 0);
       break;
@@ -546,7 +572,7 @@ inline PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
   return fn;
 }
 
-template <typename T, bool SPLIT3, int BN, bool DEEP>
+template <typename T, typename TO, bool SPLIT3, int BN, bool DEEP>
 int launch_conv_umma(cudaStream_t s, int dtype, const void* state, const void* state_lo, int Cp,
                      const int32_t* idx,
                      const int32_t* count, const void* packed, const float* bias, void* out,
@@ -554,7 +580,8 @@ int launch_conv_umma(cudaStream_t s, int dtype, const void* state, const void* s
                      int sel_lo, int sel_hi) {
   using C = UmmaCfg<T, SPLIT3, BN, DEEP>;
   const int Kp = kH * kW * Cp;
-  const int KpPad = umma_kp_pad(dtype, Cp, kH, kW);
+  const int KpPad = umma_kp_pad_es((int)sizeof(T), Cp, kH, kW);
+  (void)dtype;
   auto enc = tensor_map_encoder();
   if (!enc) return fail(3, "conv_update: cuTensorMapEncodeTiled unavailable");
   alignas(64) CUtensorMap map;
@@ -562,14 +589,14 @@ int launch_conv_umma(cudaStream_t s, int dtype, const void* state, const void* s
   const cuuint64_t gstr[1] = {(cuuint64_t)KpPad * sizeof(T)};
   const cuuint32_t box[2] = {(cuuint32_t)C::BK, (cuuint32_t)BN};
   const cuuint32_t estr[2] = {1, 1};
-  const CUtensorMapDataType dt = dtype == CB_F32   ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
-                                 : dtype == CB_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
-                                                   : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUtensorMapDataType dt = sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                 : std::is_same<T, __half>::value ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                                                  : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   const CUresult r = enc(&map, dt, 2, const_cast<void*>(packed), gdim, gstr, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(3, "conv_update: cuTensorMapEncodeTiled failed (%d)", (int)r);
-  auto kern = conv_umma_kernel<T, SPLIT3, BN, DEEP>;
+  auto kern = conv_umma_kernel<T, TO, SPLIT3, BN, DEEP>;
   static thread_local int attr_dev = -1;
   int dev = 0;
   cudaGetDevice(&dev);
@@ -585,13 +612,13 @@ int launch_conv_umma(cudaStream_t s, int dtype, const void* state, const void* s
   if (grid < 1) grid = 1;
   kern<<<(unsigned)grid, UM_THREADS, C::SMEM_BYTES, s>>>(map, (const T*)state, (const T*)state_lo, Cp,
                                                         idx, count, bias,
-                                                        (T*)out, Op, H, W, Cout, CoutPad, kH, kW,
+                                                        (TO*)out, Op, H, W, Cout, CoutPad, kH, kW,
                                                         Kp, relu, sel_lo, sel_hi);
   CB_CHECK_LAUNCH("conv_update(umma)");
   return 0;
 }
 
-template <typename T, bool SPLIT3, bool DEEP>
+template <typename T, typename TO, bool SPLIT3, bool DEEP>
 int dispatch_bn(int bn, cudaStream_t s, int dtype, const void* state, const void* state_lo, int Cp,
                 const int32_t* idx,
                 const int32_t* count, const void* packed, const float* bias, void* out, int Op,
@@ -599,7 +626,7 @@ int dispatch_bn(int bn, cudaStream_t s, int dtype, const void* state, const void
                 int sel_hi) {
 #define CB_BN(N)                                                                              \
   case N:                                                                                     \
-    return launch_conv_umma<T, SPLIT3, N, DEEP>(s, dtype, state, state_lo, Cp, idx, count, packed, bias, out, \
+    return launch_conv_umma<T, TO, SPLIT3, N, DEEP>(s, dtype, state, state_lo, Cp, idx, count, packed, bias, out, \
                                           Op, B, H, W, Cout, CoutPad, kH, kW, relu, sel_lo,   \
                                           sel_hi);
   if (DEEP) {                                  // the deep variant only exists for N tiles <= 64
@@ -620,33 +647,40 @@ inline int umma_conv_update(cudaStream_t s, int dtype, int gemm, const void* sta
                             const float* bias, void* out, int Op, int B, int H, int W, int Cin,
                             int Cout, int kH, int kW, int relu) {
   (void)Cin;
-  CB_CHECK_ARG(gemm == CB_GEMM_TC || gemm == CB_GEMM_TC_3X, "conv_update: bad gemm mode %d", gemm);
+  CB_CHECK_ARG(gemm == CB_GEMM_TC || gemm == CB_GEMM_TC_3X || gemm == CB_GEMM_TC_BF16X3,
+               "conv_update: bad gemm mode %d", gemm);
+  CB_CHECK_ARG(gemm != CB_GEMM_TC_BF16X3 || dtype == CB_F32, "conv_update: 3xBF16 is for fp32 data");
   CB_CHECK_ARG(H < 32768 && W < 32768, "conv_update: H, W must be < 32768");
   CB_CHECK_ARG(((uintptr_t)state % 16) == 0 && ((uintptr_t)packed % 128) == 0,
                "conv_update: state must be 16-byte and packed weights 128-byte aligned");
   const int bn = umma_bn(gemm, Cout), CoutPad = umma_cout_pad(gemm, Cout);
   const bool split3 = gemm == CB_GEMM_TC_3X && dtype == CB_F32;
-  CB_CHECK_ARG(!split3 || (state_lo && ((uintptr_t)state_lo % 16) == 0),
-               "conv_update: CB_GEMM_TC_3X needs the 16-byte aligned tf32 remainder plane (state_lo)");
+  const bool bf16x3 = gemm == CB_GEMM_TC_BF16X3;
+  CB_CHECK_ARG(!(split3 || bf16x3) || (state_lo && ((uintptr_t)state_lo % 16) == 0),
+               "conv_update: the 3x modes need their 16-byte aligned lo operand plane (state_lo)");
   // Tiling policy.  Large N tiles minimise the im2col re-gather (the kernel is L2-bound on big
   // layers) but give few CTAs when few pixels changed; the count is only known on the device, so
   // when a small change set is plausible (expected tiles at 10 % change < half the SMs) a second,
   // finer tiling is launched as well and each kernel checks the count to see whether it is its turn.
   auto run_t = [&](auto deep_tag, int tile_n, int lo, int hi) -> int {
     constexpr bool DP = decltype(deep_tag)::value;
+    if (bf16x3)
+      return dispatch_bn<__nv_bfloat16, float, true, DP>(tile_n, s, dtype, state, state_lo, Cp, idx,
+                                                         count, packed, bias, out, Op, B, H, W,
+                                                         Cout, CoutPad, kH, kW, relu, lo, hi);
     switch (dtype) {
       case CB_F32:
-        return split3 ? dispatch_bn<float, true, DP>(tile_n, s, dtype, state, state_lo, Cp, idx, count,
+        return split3 ? dispatch_bn<float, float, true, DP>(tile_n, s, dtype, state, state_lo, Cp, idx, count,
                                                  packed, bias, out, Op, B, H, W, Cout, CoutPad, kH,
                                                  kW, relu, lo, hi)
-                      : dispatch_bn<float, false, DP>(tile_n, s, dtype, state, state_lo, Cp, idx, count,
+                      : dispatch_bn<float, float, false, DP>(tile_n, s, dtype, state, state_lo, Cp, idx, count,
                                                   packed, bias, out, Op, B, H, W, Cout, CoutPad,
                                                   kH, kW, relu, lo, hi);
       case CB_F16:
-        return dispatch_bn<__half, false, DP>(tile_n, s, dtype, state, state_lo, Cp, idx, count, packed,
+        return dispatch_bn<__half, __half, false, DP>(tile_n, s, dtype, state, state_lo, Cp, idx, count, packed,
                                           bias, out, Op, B, H, W, Cout, CoutPad, kH, kW, relu, lo, hi);
       case CB_BF16:
-        return dispatch_bn<__nv_bfloat16, false, DP>(tile_n, s, dtype, state, state_lo, Cp, idx, count,
+        return dispatch_bn<__nv_bfloat16, __nv_bfloat16, false, DP>(tile_n, s, dtype, state, state_lo, Cp, idx, count,
                                                  packed, bias, out, Op, B, H, W, Cout, CoutPad, kH,
                                                  kW, relu, lo, hi);
       default: return fail(2, "conv_update: bad dtype %d", dtype);

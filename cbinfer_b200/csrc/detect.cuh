@@ -26,25 +26,61 @@ __device__ __forceinline__ uint4 merge_tail(uint4 xv, const uint4& sv, int tail)
   return xv;
 }
 
-// tf32 split plane for the 3xTF32 contraction: lo = v - trunc_tf32(v) (exact in fp32).  The conv
-// kernel feeds the raw fp32 state as the "hi" operand (the tensor core ignores the 13 low mantissa
-// bits) and this plane as the "lo" operand, so the split is paid once per accepted pixel here
-// instead of once per gathered filter tap there.  lo_off = element offset state -> lo plane (0: off).
+// Auxiliary operand planes kept in step with the state (written wherever the state is written), so
+// the contraction's operand split is paid once per accepted pixel instead of once per gathered tap:
+//   mode 1: fp32 plane  lo = v - trunc_tf32(v)            (3xTF32: the raw state is the "hi" operand,
+//           the tensor core ignores the 13 low mantissa bits)
+//   mode 2: two bf16 planes  hi = bf16(v), lo = bf16(v - hi)   (3xBF16: ~16 mantissa bits at twice
+//           the tensor rate and half the bytes of 3xTF32), pixel-major with their own pitch.
+struct AuxPlanes {
+  int mode;
+  int pitch16;               // mode 2: bf16 elements per pixel (multiple of 8)
+  long long lo_off;          // mode 1: element offset state -> lo plane (same strides as the state)
+  __nv_bfloat16* hi16;       // mode 2
+  __nv_bfloat16* lo16;
+};
+
 __device__ __forceinline__ unsigned tf32_lo(unsigned v) {
   return __float_as_uint(__uint_as_float(v) - __uint_as_float(v & 0xFFFFE000u));
 }
+__device__ __forceinline__ void bf16_split(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+// pix = global pixel index, ch0 = first channel of this 16-byte chunk
 template <typename T>
-__device__ __forceinline__ void store_state(T* sptr, const uint4& v, long long lo_off) {
+__device__ __forceinline__ void store_state(T* sptr, const uint4& v, const AuxPlanes& aux,
+                                            long long pix, int ch0) {
   st16(sptr, v);
-  if (sizeof(T) == 4 && lo_off != 0)
-    st16(sptr + lo_off, make_uint4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w)));
+  if (sizeof(T) == 4 && aux.mode == 1) {
+    st16(sptr + aux.lo_off, make_uint4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w)));
+  } else if (sizeof(T) == 4 && aux.mode == 2) {
+    __nv_bfloat16 h[4], l[4];
+    bf16_split(__uint_as_float(v.x), h[0], l[0]);
+    bf16_split(__uint_as_float(v.y), h[1], l[1]);
+    bf16_split(__uint_as_float(v.z), h[2], l[2]);
+    bf16_split(__uint_as_float(v.w), h[3], l[3]);
+    const long long o = pix * aux.pitch16 + ch0;
+    *reinterpret_cast<uint2*>(aux.hi16 + o) = *reinterpret_cast<uint2*>(h);
+    *reinterpret_cast<uint2*>(aux.lo16 + o) = *reinterpret_cast<uint2*>(l);
+  }
 }
-__device__ __forceinline__ void store_state_scalar(float* sptr, float v, long long lo_off) {
+__device__ __forceinline__ void store_state_scalar(float* sptr, float v, const AuxPlanes& aux,
+                                                   long long pix, int ch) {
   *sptr = v;
-  if (lo_off != 0) sptr[lo_off] = __uint_as_float(tf32_lo(__float_as_uint(v)));
+  if (aux.mode == 1) {
+    sptr[aux.lo_off] = __uint_as_float(tf32_lo(__float_as_uint(v)));
+  } else if (aux.mode == 2) {
+    __nv_bfloat16 h, l;
+    bf16_split(v, h, l);
+    aux.hi16[pix * aux.pitch16 + ch] = h;
+    aux.lo16[pix * aux.pitch16 + ch] = l;
+  }
 }
 template <typename T>
-__device__ __forceinline__ void store_state_scalar(T* sptr, T v, long long) { *sptr = v; }
+__device__ __forceinline__ void store_state_scalar(T* sptr, T v, const AuxPlanes&, long long, int) {
+  *sptr = v;
+}
 
 constexpr int kDetWarps = 8;                   // warps per block
 
@@ -55,7 +91,7 @@ constexpr int kDetWarps = 8;                   // warps per block
 template <typename T, int VEC, int UPDATE, int U>
 __global__ void __launch_bounds__(kDetWarps * 32)
 detect_vec_kernel(const T* __restrict__ x, long long x_sb, long long x_sy, int xp,
-                  T* __restrict__ st, long long s_sb, long long s_sy, int sp, long long lo_off,
+                  T* __restrict__ st, long long s_sb, long long s_sy, int sp, AuxPlanes aux,
                   uint32_t* __restrict__ bits, int B, int H, int W, int C, int Wd, T thr,
                   unsigned cpv_magic, int wlog) {
   __shared__ unsigned s_word[kDetWarps];
@@ -77,6 +113,7 @@ detect_vec_kernel(const T* __restrict__ x, long long x_sb, long long x_sy, int x
   const T* xb = nullptr;
   T* sb = nullptr;
   int nq = 0;
+  long long pixbase = 0;
   unsigned wordbits = 0;
   if (active) {
     const int j = (int)(word % Wd);
@@ -88,18 +125,22 @@ detect_vec_kernel(const T* __restrict__ x, long long x_sb, long long x_sy, int x
     xb = x + b * x_sb + y * x_sy + (long long)x0 * xp;
     sb = st + b * s_sb + y * s_sy + (long long)x0 * sp;
     nq = npx * cpv;
+    pixbase = ((long long)b * H + y) * W + x0;
 
     bool mychg = false;                      // flag of pixel `lane` (this warp's slice only)
     const int plo = lane * cpv, phi = plo + cpv;
     for (int q0 = part * 32 * U; q0 < nq; q0 += wpw * 32 * U) {
       uint4 xv[U], sv[U];
       T* sptr[U];
+      int pxs[U], ccs[U];
       bool valid[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int q = q0 + u * 32 + lane;
         valid[u] = q < nq;
         const int px = pixel_of(q), cc = q - px * cpv;
+        pxs[u] = px;
+        ccs[u] = cc;
         sptr[u] = sb + (long long)px * sp + cc * VEC;
         if (valid[u]) {
           xv[u] = ldg16(xb + (long long)px * xp + cc * VEC);
@@ -112,7 +153,7 @@ detect_vec_kernel(const T* __restrict__ x, long long x_sb, long long x_sy, int x
         bool f = false;
         if (valid[u]) {
           f = Chunk<T>::changed(sv[u], xv[u], thr);
-          if (UPDATE == CB_UPDATE_ALL) store_state<T>(sptr[u], xv[u], lo_off);
+          if (UPDATE == CB_UPDATE_ALL) store_state<T>(sptr[u], xv[u], aux, pixbase + pxs[u], ccs[u] * VEC);
         }
         const unsigned bal = __ballot_sync(0xffffffffu, f);
         const int qb = q0 + u * 32;
@@ -140,7 +181,7 @@ detect_vec_kernel(const T* __restrict__ x, long long x_sb, long long x_sy, int x
         uint4 xv = ldg16(xb + (long long)px * xp + cc * VEC);
         T* sp2 = sb + (long long)px * sp + cc * VEC;
         if (tail && cc == cpv - 1) xv = merge_tail<T, VEC>(xv, ld16(sp2), tail);
-        store_state<T>(sp2, xv, lo_off);
+        store_state<T>(sp2, xv, aux, pixbase + px, cc * VEC);
       }
     }
   }
@@ -153,7 +194,7 @@ template <typename T, int VEC, int UPDATE>
 __global__ void __launch_bounds__(256)
 detect_narrow_kernel(const T* __restrict__ x, long long x_sb, long long x_sc, long long x_sy,
                      long long x_sx, T* __restrict__ st, long long s_sb, long long s_sy,
-                     long long lo_off, uint32_t* __restrict__ bits, int B, int H, int W, int C,
+                     AuxPlanes aux, uint32_t* __restrict__ bits, int B, int H, int W, int C,
                      int Wd, T thr) {
   const int lane = threadIdx.x & 31;
   const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -174,7 +215,8 @@ detect_narrow_kernel(const T* __restrict__ x, long long x_sb, long long x_sc, lo
     for (int c = 0; c < VEC; ++c)
       if (c < C) ne[c] = xp[c * x_sc];
     f = Chunk<T>::changed(sv, nv, thr);
-    if (UPDATE == CB_UPDATE_ALL || (UPDATE == CB_UPDATE_CHANGED && f)) store_state<T>(sp, nv, lo_off);
+    if (UPDATE == CB_UPDATE_ALL || (UPDATE == CB_UPDATE_CHANGED && f))
+      store_state<T>(sp, nv, aux, ((long long)b * H + y) * W + xx, 0);
   }
   const unsigned word = __ballot_sync(0xffffffffu, f);
   if (lane == 0) bits[warp] = word;
@@ -184,7 +226,7 @@ template <typename T, int UPDATE>
 __global__ void __launch_bounds__(256)
 detect_generic_kernel(const T* __restrict__ x, long long x_sb, long long x_sc, long long x_sy,
                       long long x_sx, T* __restrict__ st, long long s_sb, long long s_sc,
-                      long long s_sy, long long s_sx, long long lo_off,
+                      long long s_sy, long long s_sx, AuxPlanes aux,
                       uint32_t* __restrict__ bits, int B, int H, int W, int C, int Wd, T thr) {
   const int lane = threadIdx.x & 31;
   const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -197,15 +239,16 @@ detect_generic_kernel(const T* __restrict__ x, long long x_sb, long long x_sc, l
   bool f = false;
   const T* xp = x + b * x_sb + y * x_sy + xx * x_sx;
   T* sp = st + b * s_sb + y * s_sy + xx * s_sx;
+  const long long gpix = ((long long)b * H + y) * W + xx;
   if (xx < W) {
     for (int c = 0; c < C; ++c) {
       const T xv = xp[c * x_sc];
       const T sv = sp[c * s_sc];
       f |= value_changed(sv, xv, thr);
-      if (UPDATE == CB_UPDATE_ALL) store_state_scalar(sp + c * s_sc, xv, lo_off);
+      if (UPDATE == CB_UPDATE_ALL) store_state_scalar(sp + c * s_sc, xv, aux, gpix, c);
     }
     if (UPDATE == CB_UPDATE_CHANGED && f)
-      for (int c = 0; c < C; ++c) store_state_scalar(sp + c * s_sc, xp[c * x_sc], lo_off);
+      for (int c = 0; c < C; ++c) store_state_scalar(sp + c * s_sc, xp[c * x_sc], aux, gpix, c);
   }
   const unsigned word = __ballot_sync(0xffffffffu, f);
   if (lane == 0) bits[warp] = word;
@@ -218,22 +261,41 @@ template <> __host__ __device__ inline __nv_bfloat16 thr_cast<__nv_bfloat16>(flo
   return __float2bfloat16_rn(t);
 }
 
+
+template <typename T>
+inline int make_aux(AuxPlanes& aux, int aux_mode, void* aux_hi, void* aux_lo, const void* state,
+                    int C) {
+  aux = AuxPlanes{0, 0, 0, nullptr, nullptr};
+  if (aux_mode == 0) return 0;
+  CB_CHECK_ARG(sizeof(T) == 4, "change_detect: auxiliary operand planes exist for fp32 data only");
+  if (aux_mode == 1) {
+    CB_CHECK_ARG(aux_lo && ((uintptr_t)aux_lo % 16) == 0, "change_detect: bad tf32 remainder plane");
+    aux.mode = 1;
+    aux.lo_off = (long long)((const T*)aux_lo - (const T*)state);
+    return 0;
+  }
+  CB_CHECK_ARG(aux_mode == 2, "change_detect: bad aux_mode %d", aux_mode);
+  CB_CHECK_ARG(aux_hi && aux_lo && ((uintptr_t)aux_hi % 16) == 0 && ((uintptr_t)aux_lo % 16) == 0,
+               "change_detect: bad bf16 operand planes");
+  aux.mode = 2;
+  aux.pitch16 = (C + 7) / 8 * 8;
+  aux.hi16 = (__nv_bfloat16*)aux_hi;
+  aux.lo16 = (__nv_bfloat16*)aux_lo;
+  return 0;
+}
+
 template <typename T, int VEC>
 int launch_detect(cudaStream_t stream, const void* x, long long x_sb, long long x_sc,
                   long long x_sy, long long x_sx, void* state, long long s_sb, long long s_sc,
-                  long long s_sy, long long s_sx, void* state_lo, uint32_t* bits, int B, int C,
-                  int H, int W, float threshold, int update) {
+                  long long s_sy, long long s_sx, int aux_mode, void* aux_hi, void* aux_lo,
+                  uint32_t* bits, int B, int C, int H, int W, float threshold, int update) {
   const int Wd = (W + 31) / 32;
   const long long words = (long long)B * H * Wd;
   if (words == 0) return 0;
   const T thr = thr_cast<T>(threshold);
   const size_t es = sizeof(T);
-  long long lo_off = 0;
-  if (state_lo) {
-    CB_CHECK_ARG(sizeof(T) == 4, "change_detect: the tf32 lo plane exists for fp32 only");
-    lo_off = (long long)((const T*)state_lo - (const T*)state);
-    CB_CHECK_ARG(lo_off != 0 && ((uintptr_t)state_lo % 16) == 0, "change_detect: bad lo plane");
-  }
+  AuxPlanes aux;
+  if (int rc = make_aux<T>(aux, aux_mode, aux_hi, aux_lo, state, C)) return rc;
   const bool vec_ok = x_sc == 1 && s_sc == 1 && (x_sx % VEC) == 0 && (s_sx % VEC) == 0 &&
                       x_sx >= C && s_sx >= C && ((x_sy * es) % 16) == 0 && ((s_sy * es) % 16) == 0 &&
                       ((x_sb * es) % 16) == 0 && ((s_sb * es) % 16) == 0 &&
@@ -255,19 +317,19 @@ int launch_detect(cudaStream_t stream, const void* x, long long x_sb, long long 
   if (vec_ok) {                                                                                \
     if (cpv >= 4)                                                                              \
       detect_vec_kernel<T, VEC, U_, 4><<<grid, block, 0, stream>>>(                            \
-          (const T*)x, x_sb, x_sy, (int)x_sx, (T*)state, s_sb, s_sy, (int)s_sx, lo_off, bits,  \
+          (const T*)x, x_sb, x_sy, (int)x_sx, (T*)state, s_sb, s_sy, (int)s_sx, aux, bits,  \
           B, H, W, C, Wd, thr, magic, wlog);                                                   \
     else                                                                                       \
       detect_vec_kernel<T, VEC, U_, 2><<<grid, block, 0, stream>>>(                            \
-          (const T*)x, x_sb, x_sy, (int)x_sx, (T*)state, s_sb, s_sy, (int)s_sx, lo_off, bits,  \
+          (const T*)x, x_sb, x_sy, (int)x_sx, (T*)state, s_sb, s_sy, (int)s_sx, aux, bits,  \
           B, H, W, C, Wd, thr, magic, wlog);                                                   \
   } else if (narrow_ok) {                                                                      \
     detect_narrow_kernel<T, VEC, U_><<<grid, block, 0, stream>>>(                              \
-        (const T*)x, x_sb, x_sc, x_sy, x_sx, (T*)state, s_sb, s_sy, lo_off, bits, B, H, W, C,  \
+        (const T*)x, x_sb, x_sc, x_sy, x_sx, (T*)state, s_sb, s_sy, aux, bits, B, H, W, C,  \
         Wd, thr);                                                                              \
   } else {                                                                                     \
     detect_generic_kernel<T, U_><<<grid, block, 0, stream>>>(                                  \
-        (const T*)x, x_sb, x_sc, x_sy, x_sx, (T*)state, s_sb, s_sc, s_sy, s_sx, lo_off, bits,  \
+        (const T*)x, x_sb, x_sc, x_sy, x_sx, (T*)state, s_sb, s_sc, s_sy, s_sx, aux, bits,  \
         B, H, W, C, Wd, thr);                                                                  \
   }
   switch (update) {
@@ -295,7 +357,7 @@ template <typename T, int VEC, int UPDATE>
 __global__ void __launch_bounds__(256)
 detect_sparse_vec_kernel(const T* __restrict__ x, long long x_sb, long long x_sy, int xp,
                          T* __restrict__ st, long long s_sb, long long s_sy, int sp,
-                         long long lo_off, const int32_t* __restrict__ cand,
+                         AuxPlanes aux, const int32_t* __restrict__ cand,
                          const int32_t* __restrict__ ncand, uint32_t* __restrict__ bits, int H,
                          int W, int C, int Wd, T thr, int glog) {
   const int n = *ncand;
@@ -310,9 +372,10 @@ detect_sparse_vec_kernel(const T* __restrict__ x, long long x_sb, long long x_sy
        j0 < n; j0 += nwarps * ppw) {
     const long long j = j0 + sub;
     const bool have = j < n;
-    int b = 0, y = 0, xx = 0;
+    int b = 0, y = 0, xx = 0, gpix = 0;
     if (have) {
       const int pix = __ldg(cand + j);
+      gpix = pix;
       b = pix / P;
       const int p = pix - b * P;
       y = p / W;
@@ -327,7 +390,7 @@ detect_sparse_vec_kernel(const T* __restrict__ x, long long x_sb, long long x_sy
         const uint4 sv = ld16(sb + cc * VEC);
         if (tail && cc == cpv - 1) xv = merge_tail<T, VEC>(xv, sv, tail);
         f |= Chunk<T>::changed(sv, xv, thr);
-        if (UPDATE == CB_UPDATE_ALL) store_state<T>(sb + cc * VEC, xv, lo_off);
+        if (UPDATE == CB_UPDATE_ALL) store_state<T>(sb + cc * VEC, xv, aux, gpix, cc * VEC);
       }
     }
     const bool chg = (__ballot_sync(0xffffffffu, f) & gmask) != 0u;   // any lane of my group
@@ -337,7 +400,7 @@ detect_sparse_vec_kernel(const T* __restrict__ x, long long x_sb, long long x_sy
         for (int cc = gl; cc < cpv; cc += G) {
           uint4 xv = ldg16(xb + cc * VEC);
           if (tail && cc == cpv - 1) xv = merge_tail<T, VEC>(xv, ld16(sb + cc * VEC), tail);
-          store_state<T>(sb + cc * VEC, xv, lo_off);
+          store_state<T>(sb + cc * VEC, xv, aux, gpix, cc * VEC);
         }
       }
     }
@@ -348,7 +411,7 @@ template <typename T, int UPDATE>
 __global__ void __launch_bounds__(256)
 detect_sparse_generic_kernel(const T* __restrict__ x, long long x_sb, long long x_sc,
                              long long x_sy, long long x_sx, T* __restrict__ st, long long s_sb,
-                             long long s_sc, long long s_sy, long long s_sx, long long lo_off,
+                             long long s_sc, long long s_sy, long long s_sx, AuxPlanes aux,
                              const int32_t* __restrict__ cand, const int32_t* __restrict__ ncand,
                              uint32_t* __restrict__ bits, int H, int W, int C, int Wd, T thr) {
   const int n = *ncand;
@@ -364,12 +427,12 @@ detect_sparse_generic_kernel(const T* __restrict__ x, long long x_sb, long long 
     for (int c = 0; c < C; ++c) {
       const T xv = xp[c * x_sc];
       f |= value_changed(sp[c * s_sc], xv, thr);
-      if (UPDATE == CB_UPDATE_ALL) store_state_scalar(sp + c * s_sc, xv, lo_off);
+      if (UPDATE == CB_UPDATE_ALL) store_state_scalar(sp + c * s_sc, xv, aux, (long long)pix, c);
     }
     if (f) {
       atomicOr(bits + ((long long)b * H + y) * Wd + (xx >> 5), 1u << (xx & 31));
       if (UPDATE == CB_UPDATE_CHANGED)
-        for (int c = 0; c < C; ++c) store_state_scalar(sp + c * s_sc, xp[c * x_sc], lo_off);
+        for (int c = 0; c < C; ++c) store_state_scalar(sp + c * s_sc, xp[c * x_sc], aux, (long long)pix, c);
     }
   }
 }
@@ -377,8 +440,8 @@ detect_sparse_generic_kernel(const T* __restrict__ x, long long x_sb, long long 
 template <typename T, int VEC>
 int launch_detect_sparse(cudaStream_t stream, const void* x, long long x_sb, long long x_sc,
                          long long x_sy, long long x_sx, void* state, long long s_sb,
-                         long long s_sc, long long s_sy, long long s_sx, void* state_lo,
-                         const int32_t* cand, const int32_t* ncand, uint32_t* bits, int B, int C,
+                         long long s_sc, long long s_sy, long long s_sx, int aux_mode,
+                         void* aux_hi, void* aux_lo, const int32_t* cand, const int32_t* ncand, uint32_t* bits, int B, int C,
                          int H, int W, float threshold, int update, int bits_are_clear) {
   const int Wd = (W + 31) / 32;
   const long long words = (long long)B * H * Wd;
@@ -387,11 +450,8 @@ int launch_detect_sparse(cudaStream_t stream, const void* x, long long x_sb, lon
     return fail(3, "change_detect_sparse: memset failed");
   const T thr = thr_cast<T>(threshold);
   const size_t es = sizeof(T);
-  long long lo_off = 0;
-  if (state_lo) {
-    CB_CHECK_ARG(sizeof(T) == 4, "change_detect_sparse: the tf32 lo plane exists for fp32 only");
-    lo_off = (long long)((const T*)state_lo - (const T*)state);
-  }
+  AuxPlanes aux;
+  if (int rc = make_aux<T>(aux, aux_mode, aux_hi, aux_lo, state, C)) return rc;
   const bool vec_ok = x_sc == 1 && s_sc == 1 && (x_sx % VEC) == 0 && (s_sx % VEC) == 0 &&
                       x_sx >= C && s_sx >= C && ((x_sy * es) % 16) == 0 && ((s_sy * es) % 16) == 0 &&
                       ((x_sb * es) % 16) == 0 && ((s_sb * es) % 16) == 0 &&
@@ -404,11 +464,11 @@ int launch_detect_sparse(cudaStream_t stream, const void* x, long long x_sb, lon
 #define CB_DETS(U_)                                                                              \
   if (vec_ok)                                                                                    \
     detect_sparse_vec_kernel<T, VEC, U_><<<grid, 256, 0, stream>>>(                              \
-        (const T*)x, x_sb, x_sy, (int)x_sx, (T*)state, s_sb, s_sy, (int)s_sx, lo_off, cand,      \
+        (const T*)x, x_sb, x_sy, (int)x_sx, (T*)state, s_sb, s_sy, (int)s_sx, aux, cand,      \
         ncand, bits, H, W, C, Wd, thr, glog);                                                    \
   else                                                                                           \
     detect_sparse_generic_kernel<T, U_><<<grid, 256, 0, stream>>>(                               \
-        (const T*)x, x_sb, x_sc, x_sy, x_sx, (T*)state, s_sb, s_sc, s_sy, s_sx, lo_off, cand,    \
+        (const T*)x, x_sb, x_sc, x_sy, x_sx, (T*)state, s_sb, s_sc, s_sy, s_sx, aux, cand,    \
         ncand, bits, H, W, C, Wd, thr);
   switch (update) {
     case CB_UPDATE_NONE: CB_DETS(CB_UPDATE_NONE) break;

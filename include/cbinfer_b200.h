@@ -48,7 +48,15 @@ extern "C" {
 /* arithmetic of the contraction in cb_conv_update */
 #define CB_GEMM_SIMT_F32 0   /* fp32 FFMA on CUDA cores (exact-fp32 products)                   */
 #define CB_GEMM_TC 1         /* tcgen05: 1xTF32 for fp32 data, f16/bf16 for 16-bit data          */
-#define CB_GEMM_TC_3X 2      /* tcgen05: 3xTF32 split (fp32-accurate) for fp32 data              */
+#define CB_GEMM_TC_3X 2      /* tcgen05: 3xTF32 split (fp32-accurate, ~2e-6) for fp32 data       */
+#define CB_GEMM_TC_BF16X3 3  /* tcgen05: 3xBF16 split of fp32 data (hi/lo bf16 pairs, ~2e-5) at
+                                twice the tensor rate and half the bytes of 3xTF32                */
+
+/* auxiliary operand planes cb_change_detect keeps in step with an fp32 state */
+#define CB_AUX_NONE 0
+#define CB_AUX_TF32_LO 1     /* aux_lo: fp32 plane v - trunc_tf32(v), same strides as the state    */
+#define CB_AUX_BF16_PAIR 2   /* aux_hi / aux_lo: bf16 planes bf16(v), bf16(v - hi); pixel-major,
+                                pitch = C rounded up to 8                                          */
 
 /* ---- library ---------------------------------------------------------------------------- */
 int cb_version(void);
@@ -69,14 +77,14 @@ size_t cb_packed_weight_bytes(int dtype, int gemm, int Cout, int Cin, int kH, in
  * raw_bits[word] bit = OR_c ( |state - x| > thr )   strict '>', fp32 flush-to-zero, fp16/bf16:
  * rounded difference vs rounded threshold, two one-sided tests (half.cu:58-63).
  * The whole bitmap (incl. row padding bits = 0) is written; no pre-zeroing needed.
- * state_lo (optional, fp32 only, same strides as state): wherever the state is written, the tf32
- * remainder  v - trunc_tf32(v)  is written to this plane; cb_conv_update(CB_GEMM_TC_3X) consumes
- * it, so the hi/lo split is paid once per accepted pixel instead of once per gathered tap. */
+ * aux_mode / aux_hi / aux_lo (fp32 only): auxiliary operand planes written wherever the state is
+ * written (CB_AUX_*), consumed by cb_conv_update, so the operand split of the 3x modes is paid
+ * once per accepted pixel instead of once per gathered filter tap. */
 int cb_change_detect(void* stream, int dtype,
                      const void* x, long long x_sb, long long x_sc, long long x_sy, long long x_sx,
                      void* state, long long s_sb, long long s_sc, long long s_sy, long long s_sx,
-                     void* state_lo, uint32_t* raw_bits, int B, int C, int H, int W,
-                     float threshold, int update_mode);
+                     int aux_mode, void* aux_hi, void* aux_lo, uint32_t* raw_bits, int B, int C,
+                     int H, int W, float threshold, int update_mode);
 
 /* ---- propagation + compaction -------------------------------------------------------------
  * replaces: the scatter-dilate inside changeDetection_kernel (cbconv2d_cg_backend.cu:62-72),
@@ -103,7 +111,8 @@ int cb_dilate_compact(void* stream, const uint32_t* raw_bits, uint32_t* dil_bits
 int cb_change_detect_sparse(void* stream, int dtype,
                             const void* x, long long x_sb, long long x_sc, long long x_sy, long long x_sx,
                             void* state, long long s_sb, long long s_sc, long long s_sy, long long s_sx,
-                            void* state_lo, const int32_t* candidates, const int32_t* n_candidates,
+                            int aux_mode, void* aux_hi, void* aux_lo,
+                            const int32_t* candidates, const int32_t* n_candidates,
                             uint32_t* raw_bits, int B, int C, int H, int W, float threshold,
                             int update_mode, int bits_are_clear);
 
@@ -129,8 +138,9 @@ int cb_map_to_bits(void* stream, const int8_t* map, uint32_t* bits, int B, int H
  * with zero outside the image and act = ReLU iff relu (v <= 0 -> 0, cg.cu:187).
  * state / out are pixel-major with the given pitches; bias is fp32[Cout]; packed_w comes from
  * cb_pack_weights with the same dtype/gemm/shape.  *count is read on the device.
- * state_lo: the tf32 remainder plane maintained by cb_change_detect; required for
- * CB_GEMM_TC_3X on fp32 data, ignored (may be NULL) otherwise. */
+ * Operands per mode: CB_GEMM_SIMT_F32 / CB_GEMM_TC: `state` only.  CB_GEMM_TC_3X (fp32): `state`
+ * plus `state_lo` = the CB_AUX_TF32_LO plane.  CB_GEMM_TC_BF16X3 (fp32 output): `state` and
+ * `state_lo` are the CB_AUX_BF16_PAIR planes (hi, lo) and pitch_in is their pitch. */
 int cb_pack_weights(void* stream, int dtype, int gemm, const void* weight /*[Cout,Cin,kH,kW]*/,
                     void* packed, int Cout, int Cin, int kH, int kW);
 int cb_conv_update(void* stream, int dtype, int gemm, const void* state, const void* state_lo,

@@ -38,7 +38,7 @@ def _rel(got, exp):
 # CBConv2d vs the oracle flow, frame by frame
 # ---------------------------------------------------------------------------------------------
 
-@pytest.mark.parametrize("dt,mode,tol", [("f32", "auto", 1e-4), ("f32", "simt", 2e-5),
+@pytest.mark.parametrize("dt,mode,tol", [("f32", "auto", 1e-4), ("f32", "tc3x", 1e-4), ("f32", "simt", 2e-5),
                                          ("bf16", "auto", 1e-2), ("f16", "auto", 2e-3)])
 @pytest.mark.parametrize("feedback", [False, True])
 @pytest.mark.parametrize("cfg", [(3, 16, 7, 20, 27), (16, 24, 3, 13, 18), (8, 8, 1, 9, 9)])

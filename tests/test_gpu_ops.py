@@ -16,7 +16,8 @@ pytestmark = pytest.mark.gpu
 # compared tensor: (gemm mode, dtype) -> rel
 CONV_TOL = {
     ("simt", "f32"): 2e-5,     # fp32 FFMA, fp32 accumulation
-    ("tc3x", "f32"): 1e-4,     # 3xTF32 split: north-star bar "rel 1e-4 fp32"
+    ("tc3x", "f32"): 1e-4,     # 3xTF32 split: north-star bar "rel 1e-4 fp32" (measured ~2e-6)
+    ("bf16x3", "f32"): 1e-4,   # 3xBF16 split (the fp32 default): same bar (measured ~2e-5)
     ("tc", "f32"): 4e-3,       # single-pass TF32 (10-bit mantissa), opt-in fast mode
     ("simt", "f16"): 2e-3, ("tc", "f16"): 2e-3,      # output rounding to fp16 dominates
     ("simt", "bf16"): 1e-2, ("tc", "bf16"): 1e-2,    # north-star bar "1e-2 bf16"
@@ -182,12 +183,25 @@ def test_detect_update_all_and_special_values(cbm, orc):
             xin = x1 if layout == "narrow" else cg.pixel_major(shape, torch.float32, "cuda", 0)[0].copy_(x1)
         lo.copy_(cg.tf32_lo(x0))
         s = cg.alloc_scratch((shape[0], shape[2], shape[3]), "cuda")
-        cg.detect(xin, st, s["raw_bits"], 0.3, lib.UPDATE_CHANGED, state_lo=lo)
+        p16 = (shape[1] + 7) // 8 * 8
+        h16 = torch.zeros(shape[0], shape[2], shape[3], p16, dtype=torch.bfloat16, device="cuda")
+        l16 = torch.zeros_like(h16)
+        eh, el = cg.bf16_pair(x0.permute(0, 2, 3, 1))
+        h16[..., :shape[1]], l16[..., :shape[1]] = eh, el
+        st2 = st.clone() if layout == "planar" else cg.pixel_major(shape, torch.float32, "cuda", 0)[0].copy_(st)
+        cg.detect(xin, st, s["raw_bits"], 0.3, lib.UPDATE_CHANGED, aux=('tf32', lo))
         assert torch.equal(lo, cg.tf32_lo(st.contiguous()))
         hi = (st.contiguous().view(torch.int32) & -8192).view(torch.float32)
         assert torch.equal(hi + lo.contiguous(), st.contiguous())
-        cg.detect(xin, st, s["raw_bits"], 0.3, lib.UPDATE_ALL, state_lo=lo)
+        cg.detect(xin, st2, s["raw_bits"], 0.3, lib.UPDATE_CHANGED, aux=('bf16', h16, l16))
+        eh, el = cg.bf16_pair(st2.permute(0, 2, 3, 1))
+        assert torch.equal(h16[..., :shape[1]], eh) and torch.equal(l16[..., :shape[1]], el)
+        assert float(h16[..., shape[1]:].abs().sum()) == 0.0
+        cg.detect(xin, st, s["raw_bits"], 0.3, lib.UPDATE_ALL, aux=('tf32', lo))
         assert torch.equal(st.contiguous(), x1) and torch.equal(lo.contiguous(), cg.tf32_lo(x1))
+        cg.detect(xin, st2, s["raw_bits"], 0.3, lib.UPDATE_ALL, aux=('bf16', h16, l16))
+        eh, el = cg.bf16_pair(x1.permute(0, 2, 3, 1))
+        assert torch.equal(h16[..., :shape[1]], eh) and torch.equal(l16[..., :shape[1]], el)
 
 
 def test_large_compaction_chained_scan(cbm):
@@ -235,7 +249,7 @@ def _oracle_conv(orc, state_np, idx_np, w_np, b_np, out_np, filt, relu, dtype, B
     return out_np
 
 
-@pytest.mark.parametrize("mode,dt", [("simt", "f32"), ("tc3x", "f32"), ("tc", "f32"),
+@pytest.mark.parametrize("mode,dt", [("simt", "f32"), ("tc3x", "f32"), ("bf16x3", "f32"), ("tc", "f32"),
                                      ("tc", "bf16"), ("tc", "f16"), ("simt", "bf16")])
 @pytest.mark.parametrize("case", CONV_CASES)
 def test_conv_update(cbm, orc, mode, dt, case):
@@ -278,7 +292,7 @@ def test_conv_update_zero_changes_is_noop(cbm):
     out, obuf = cg.pixel_major((1, 32, 8, 8), torch.float32, "cuda", 7.0)
     w = rand_tensor((32, 16, 3, 3), "f32", 1)
     ci = cg.ChangeIndexes.from_tensor(torch.zeros(0, dtype=torch.int32, device="cuda"), (1, 8, 8))
-    for gemm in (lib.GEMM_SIMT_F32, lib.GEMM_TC, lib.GEMM_TC_3X):
+    for gemm in (lib.GEMM_SIMT_F32, lib.GEMM_TC, lib.GEMM_TC_3X, lib.GEMM_TC_BF16X3):
         cg.conv_update(sbuf, ci, cg.pack_weights(w, gemm), torch.zeros(32, device="cuda"), obuf,
                        16, 32, (3, 3), True, gemm)
     torch.cuda.synchronize()

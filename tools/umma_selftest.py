@@ -33,7 +33,7 @@ def main():
     shapes = [(1, 16, 16, 8, 16, 1), (1, 32, 64, 8, 16, 1), (1, 16, 64, 12, 20, 3), (1, 3, 16, 20, 30, 7),
               (2, 64, 256, 9, 12, 7), (1, 256, 64, 10, 16, 1)]
     bad = False
-    for dt, modes in ((torch.float32, ("tc", "tc3x")), (torch.bfloat16, ("tc",)), (torch.float16, ("tc",))):
+    for dt, modes in ((torch.float32, ("tc", "tc3x", "bf16x3")), (torch.bfloat16, ("tc",)), (torch.float16, ("tc",))):
         for (B, Cin, Cout, H, W, k) in shapes:
             ref, _, _ = run("simt", dt, B, Cin, Cout, H, W, k)
             for mode in modes:
