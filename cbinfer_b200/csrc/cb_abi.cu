@@ -1,6 +1,7 @@
 // cb_abi.cu -- extern "C" entry points of libcbinfer_sm100.so (see include/cbinfer_b200.h).
 // sm_100a only: no other architecture, no CPU path, no dispatch to other backends.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "cb_common.cuh"
@@ -33,6 +34,15 @@ int sm_count() {
     cached_dev = dev;
   }
   return cached > 0 ? cached : 148;
+}
+
+bool pdl_enabled() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("CBINFER_PDL");
+    cached = (e && e[0] == '0') ? 0 : 1;
+  }
+  return cached != 0;
 }
 
 static inline unsigned grid_for(long long total, int threads, int per_sm = 8) {
@@ -108,7 +118,7 @@ int cb_dilate_compact(void* stream, const uint32_t* raw_bits, uint32_t* dil_bits
   }
   CB_CHECK_ARG(nwords < (1ll << 31), "dilate_compact: bitmap too large");
   const int ntiles = (int)((nwords + kCompactTile - 1) / kCompactTile);
-  dilate_compact_kernel<<<ntiles, kCompactThreads, 0, s>>>(raw_bits, dil_bits, dil_map, idx, count,
+  cb::launch_pdl(dilate_compact_kernel, ntiles, kCompactThreads, 0, s, raw_bits, dil_bits, dil_map, idx, count,
                                                           ws, B, H, W, (W + 31) / 32, kHHalf,
                                                           kWHalf, (int)nwords, ntiles, 0, 0,
                                                           clear_raw ? const_cast<uint32_t*>(raw_bits) : nullptr);
@@ -129,7 +139,7 @@ int cb_pool_compact(void* stream, const uint32_t* in_bits, uint32_t* out_bits, i
   }
   CB_CHECK_ARG(nwords < (1ll << 31), "pool_compact: bitmap too large");
   const int ntiles = (int)((nwords + kCompactTile - 1) / kCompactTile);
-  dilate_compact_kernel<<<ntiles, kCompactThreads, 0, s>>>(in_bits, out_bits, nullptr, idx, count, ws,
+  cb::launch_pdl(dilate_compact_kernel, ntiles, kCompactThreads, 0, s, in_bits, out_bits, nullptr, idx, count, ws,
                                                           B, oH, oW, (oW + 31) / 32, 0, 0,
                                                           (int)nwords, ntiles, H, (W + 31) / 32, nullptr);
   CB_CHECK_LAUNCH("pool_compact");
@@ -157,7 +167,7 @@ int cb_map_to_bits(void* stream, const int8_t* map, uint32_t* bits, int B, int H
   const long long nwords = (long long)cb_bitmap_words(B, H, W);
   if (nwords == 0) return 0;
   const long long blocks = (nwords + 7) / 8;
-  map_to_bits_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(map, bits, H, W,
+  cb::launch_pdl(map_to_bits_kernel, (unsigned)blocks, 256, 0, (cudaStream_t)stream, map, bits, H, W,
                                                                         (W + 31) / 32, nwords);
   CB_CHECK_LAUNCH("map_to_bits");
   return 0;
@@ -180,7 +190,7 @@ int cb_pack_weights(void* stream, int dtype, int gemm, const void* weight, void*
   if (gemm == CB_GEMM_SIMT_F32) {
     const int CoutP = (Cout + 3) / 4 * 4;
     const long long total = (long long)kH * kW * Cp * CoutP;
-    CB_DISPATCH_DTYPE(dtype, (pack_weights_simt_kernel<T><<<grid_for(total, 256), 256, 0, s>>>(
+    CB_DISPATCH_DTYPE(dtype, (cb::launch_pdl(pack_weights_simt_kernel<T>, grid_for(total, 256), 256, 0, s, 
                                  (const T*)weight, (float*)packed, Cout, Cin, kH, kW, Cp, CoutP)));
     CB_CHECK_LAUNCH("pack_weights");
     return 0;
@@ -204,7 +214,7 @@ int cb_conv_update(void* stream, int dtype, int gemm, const void* state, const v
   if (gemm == CB_GEMM_SIMT_F32) {
     const int CoutP = (Cout + 3) / 4 * 4;
     const unsigned grid = (unsigned)(sm_count() * 4);
-    CB_DISPATCH_DTYPE(dtype, (conv_simt_kernel<T><<<grid, SM_THREADS, 0, s>>>(
+    CB_DISPATCH_DTYPE(dtype, (cb::launch_pdl(conv_simt_kernel<T>, grid, SM_THREADS, 0, s, 
                                  (const T*)state, pitch_in, idx, count, (const float*)packed_w, bias,
                                  (T*)out, pitch_out, H, W, Cout, CoutP, kH, kW, relu)));
     CB_CHECK_LAUNCH("conv_update(simt)");
@@ -234,11 +244,11 @@ int cb_maxpool2x2(void* stream, int dtype, const void* x, long long x_sb, long l
     const int cpp = (int)(x_sx / vec);
     int glog = 0;
     while ((1 << glog) < cpp && glog < 5) ++glog;
-    CB_DISPATCH_DTYPE(dtype, (maxpool2x2_vec_kernel<T, VEC><<<grid, 256, 0, (cudaStream_t)stream>>>(
+    CB_DISPATCH_DTYPE(dtype, (cb::launch_pdl(maxpool2x2_vec_kernel<T, VEC>, grid, 256, 0, (cudaStream_t)stream, 
                                  (const T*)x, x_sb, x_sy, (int)x_sx, idx, count, dil_bits, (T*)out,
                                  o_sb, o_sy, (int)o_sx, cpp, glog, H, W, oH, oW)));
   } else {
-    CB_DISPATCH_DTYPE(dtype, (maxpool2x2_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
+    CB_DISPATCH_DTYPE(dtype, (cb::launch_pdl(maxpool2x2_kernel<T>, grid, 256, 0, (cudaStream_t)stream, 
                                  (const T*)x, x_sb, x_sc, x_sy, x_sx, idx, count, dil_bits, (T*)out,
                                  o_sb, o_sc, o_sy, o_sx, C, H, W, oH, oW)));
   }
@@ -251,7 +261,7 @@ int cb_gen_xmatrix(void* stream, int dtype, void* columns, const void* input, co
   if (n <= 0) return 0;
   CB_CHECK_ARG(columns && input && idx, "gen_xmatrix: null pointer");
   const long long total = (long long)n * C * kH * kW;
-  CB_DISPATCH_DTYPE(dtype, (gen_xmatrix_kernel<T><<<grid_for(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(
+  CB_DISPATCH_DTYPE(dtype, (cb::launch_pdl(gen_xmatrix_kernel<T>, grid_for(total, 256, 16), 256, 0, (cudaStream_t)stream, 
                                (T*)columns, (const T*)input, idx, kW, kH, C, W, H, n)));
   CB_CHECK_LAUNCH("gen_xmatrix");
   return 0;
@@ -263,7 +273,7 @@ int cb_matrix_mult(void* stream, int dtype, const void* X, const void* weight, c
   CB_CHECK_ARG(X && weight && bias && Y, "matrix_mult: null pointer");
   dim3 grid((Cout + 31) / 32, (n + 31) / 32);
   CB_CHECK_ARG(grid.y < 65536, "matrix_mult: n too large for the staged op");
-  CB_DISPATCH_DTYPE(dtype, (matrix_mult_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
+  CB_DISPATCH_DTYPE(dtype, (cb::launch_pdl(matrix_mult_kernel<T>, grid, 256, 0, (cudaStream_t)stream, 
                                (const T*)X, (const T*)weight, (const T*)bias, (T*)Y, n, K, Cout)));
   CB_CHECK_LAUNCH("matrix_mult");
   return 0;
@@ -274,7 +284,7 @@ int cb_update_output(void* stream, int dtype, const void* Yt, void* output, cons
   if (n <= 0) return 0;
   CB_CHECK_ARG(Yt && output && idx, "update_output: null pointer");
   const long long total = (long long)n * Cout;
-  CB_DISPATCH_DTYPE(dtype, (update_output_kernel<T><<<grid_for(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(
+  CB_DISPATCH_DTYPE(dtype, (cb::launch_pdl(update_output_kernel<T>, grid_for(total, 256, 16), 256, 0, (cudaStream_t)stream, 
                                (const T*)Yt, (T*)output, idx, numOutputPixel, n, Cout, relu)));
   CB_CHECK_LAUNCH("update_output");
   return 0;
@@ -288,7 +298,7 @@ int cb_fg_update(void* stream, const float* x, float* prev, const float* weight,
   cudaMemsetAsync(count, 0, sizeof(int32_t), s);
   const long long total = (long long)B * Cin * H * W;
   if (total == 0) return 0;
-  fg_update_kernel<<<grid_for((total + 31) / 32 * 32, 256, 8), 256, 0, s>>>(x, prev, weight, out, count, B, Cin,
+  cb::launch_pdl(fg_update_kernel, grid_for((total + 31) / 32 * 32, 256, 8), 256, 0, s, x, prev, weight, out, count, B, Cin,
                                                              Cout, H, W, kH, kW, threshold);
   CB_CHECK_LAUNCH("fg_update");
   return 0;

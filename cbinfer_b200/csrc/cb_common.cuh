@@ -26,6 +26,33 @@ int fail(int code, const char* fmt, ...);
   } while (0)
 
 int sm_count();
+bool pdl_enabled();
+
+// Programmatic dependent launch: every kernel of this library starts with pdl_prologue() --
+// "my dependents may be scheduled" + "wait until the grids I depend on have completed and their
+// writes are visible" -- and is launched with programmatic stream serialisation, so the next
+// kernel of the stream is already resident when its predecessor drains (no launch gap between the
+// ~20 dependent kernels of a frame; also inside CUDA graphs).  CBINFER_PDL=0 turns it off.
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                       Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 // ---- dtype traits --------------------------------------------------------------------------
 template <int DT> struct DType;

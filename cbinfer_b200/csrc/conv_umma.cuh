@@ -207,6 +207,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
                  const T* __restrict__ state_lo, int Cp, const int32_t* __restrict__ idx, const int32_t* __restrict__ count,
                  const float* __restrict__ bias, TO* __restrict__ out, int Op, int H, int W,
                  int Cout, int CoutPad, int kH, int kW, int Kp, int relu, int sel_lo, int sel_hi) {
+  pdl_prologue();
   using C = UmmaCfg<T, SPLIT3, BN, DEEP>;
   constexpr int RPT = UM_BM * 8 / UM_PRODUCERS;            // 16-byte chunks per thread per stage
   constexpr int RSTEP = UM_PRODUCERS / 8;                  // row stride between a thread's chunks
@@ -469,6 +470,7 @@ template <typename T, typename TP>
 __global__ void pack_weights_umma_kernel(const T* __restrict__ w, TP* __restrict__ packed, int Cout,
                                          int Cin, int kH, int kW, int Cp, int CoutPad, int KpPad,
                                          int split3) {
+  pdl_prologue();
   const long long plane = (long long)CoutPad * KpPad;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < plane;
        i += (long long)gridDim.x * blockDim.x) {
@@ -537,19 +539,19 @@ inline int umma_pack_weights(cudaStream_t s, int dtype, int gemm, const void* we
   switch (dtype) {
     case CB_F32:
       if (gemm == CB_GEMM_TC_BF16X3)
-        pack_weights_umma_kernel<float, __nv_bfloat16><<<(unsigned)blocks, 256, 0, s>>>(
+        cb::launch_pdl(pack_weights_umma_kernel<float, __nv_bfloat16>, (unsigned)blocks, 256, 0, s, 
             (const float*)weight, (__nv_bfloat16*)packed, Cout, Cin, kH, kW, Cp, CoutPad, KpPad, 2);
       else
-        pack_weights_umma_kernel<float, float><<<(unsigned)blocks, 256, 0, s>>>(
+        cb::launch_pdl(pack_weights_umma_kernel<float, float>, (unsigned)blocks, 256, 0, s, 
             (const float*)weight, (float*)packed, Cout, Cin, kH, kW, Cp, CoutPad, KpPad,
             gemm == CB_GEMM_TC_3X ? 1 : 0);
       break;
     case CB_F16:
-      pack_weights_umma_kernel<__half, __half><<<(unsigned)blocks, 256, 0, s>>>(
+      cb::launch_pdl(pack_weights_umma_kernel<__half, __half>, (unsigned)blocks, 256, 0, s, 
           (const __half*)weight, (__half*)packed, Cout, Cin, kH, kW, Cp, CoutPad, KpPad, 0);
       break;
     case CB_BF16:
-      pack_weights_umma_kernel<__nv_bfloat16, __nv_bfloat16><<<(unsigned)blocks, 256, 0, s>>>(
+      cb::launch_pdl(pack_weights_umma_kernel<__nv_bfloat16, __nv_bfloat16>, (unsigned)blocks, 256, 0, s, 
           (const __nv_bfloat16*)weight, (__nv_bfloat16*)packed, Cout, Cin, kH, kW, Cp, CoutPad,
           KpPad, 0);
       break;
@@ -610,7 +612,7 @@ int launch_conv_umma(cudaStream_t s, int dtype, const void* state, const void* s
   long long grid = (long long)sm_count() * C::CTAS_PER_SM;
   if (grid > max_tiles) grid = max_tiles;
   if (grid < 1) grid = 1;
-  kern<<<(unsigned)grid, UM_THREADS, C::SMEM_BYTES, s>>>(map, (const T*)state, (const T*)state_lo, Cp,
+  cb::launch_pdl(kern, (unsigned)grid, UM_THREADS, C::SMEM_BYTES, s, map, (const T*)state, (const T*)state_lo, Cp,
                                                         idx, count, bias,
                                                         (TO*)out, Op, H, W, Cout, CoutPad, kH, kW,
                                                         Kp, relu, sel_lo, sel_hi);

@@ -94,6 +94,7 @@ detect_vec_kernel(const T* __restrict__ x, long long x_sb, long long x_sy, int x
                   T* __restrict__ st, long long s_sb, long long s_sy, int sp, AuxPlanes aux,
                   uint32_t* __restrict__ bits, int B, int H, int W, int C, int Wd, T thr,
                   unsigned cpv_magic, int wlog) {
+  pdl_prologue();
   __shared__ unsigned s_word[kDetWarps];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int wpw = 1 << wlog;
@@ -196,6 +197,7 @@ detect_narrow_kernel(const T* __restrict__ x, long long x_sb, long long x_sc, lo
                      long long x_sx, T* __restrict__ st, long long s_sb, long long s_sy,
                      AuxPlanes aux, uint32_t* __restrict__ bits, int B, int H, int W, int C,
                      int Wd, T thr) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (warp >= (long long)B * H * Wd) return;
@@ -228,6 +230,7 @@ detect_generic_kernel(const T* __restrict__ x, long long x_sb, long long x_sc, l
                       long long x_sx, T* __restrict__ st, long long s_sb, long long s_sc,
                       long long s_sy, long long s_sx, AuxPlanes aux,
                       uint32_t* __restrict__ bits, int B, int H, int W, int C, int Wd, T thr) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (warp >= (long long)B * H * Wd) return;
@@ -316,19 +319,19 @@ int launch_detect(cudaStream_t stream, const void* x, long long x_sb, long long 
 #define CB_DET(U_)                                                                             \
   if (vec_ok) {                                                                                \
     if (cpv >= 4)                                                                              \
-      detect_vec_kernel<T, VEC, U_, 4><<<grid, block, 0, stream>>>(                            \
+      cb::launch_pdl(detect_vec_kernel<T, VEC, U_, 4>, grid, block, 0, stream,                             \
           (const T*)x, x_sb, x_sy, (int)x_sx, (T*)state, s_sb, s_sy, (int)s_sx, aux, bits,  \
           B, H, W, C, Wd, thr, magic, wlog);                                                   \
     else                                                                                       \
-      detect_vec_kernel<T, VEC, U_, 2><<<grid, block, 0, stream>>>(                            \
+      cb::launch_pdl(detect_vec_kernel<T, VEC, U_, 2>, grid, block, 0, stream,                             \
           (const T*)x, x_sb, x_sy, (int)x_sx, (T*)state, s_sb, s_sy, (int)s_sx, aux, bits,  \
           B, H, W, C, Wd, thr, magic, wlog);                                                   \
   } else if (narrow_ok) {                                                                      \
-    detect_narrow_kernel<T, VEC, U_><<<grid, block, 0, stream>>>(                              \
+    cb::launch_pdl(detect_narrow_kernel<T, VEC, U_>, grid, block, 0, stream,                               \
         (const T*)x, x_sb, x_sc, x_sy, x_sx, (T*)state, s_sb, s_sy, aux, bits, B, H, W, C,  \
         Wd, thr);                                                                              \
   } else {                                                                                     \
-    detect_generic_kernel<T, U_><<<grid, block, 0, stream>>>(                                  \
+    cb::launch_pdl(detect_generic_kernel<T, U_>, grid, block, 0, stream,                                   \
         (const T*)x, x_sb, x_sc, x_sy, x_sx, (T*)state, s_sb, s_sc, s_sy, s_sx, aux, bits,  \
         B, H, W, C, Wd, thr);                                                                  \
   }
@@ -360,6 +363,7 @@ detect_sparse_vec_kernel(const T* __restrict__ x, long long x_sb, long long x_sy
                          AuxPlanes aux, const int32_t* __restrict__ cand,
                          const int32_t* __restrict__ ncand, uint32_t* __restrict__ bits, int H,
                          int W, int C, int Wd, T thr, int glog) {
+  pdl_prologue();
   const int n = *ncand;
   const int lane = threadIdx.x & 31;
   const int G = 1 << glog, ppw = 32 >> glog;
@@ -414,6 +418,7 @@ detect_sparse_generic_kernel(const T* __restrict__ x, long long x_sb, long long 
                              long long s_sc, long long s_sy, long long s_sx, AuxPlanes aux,
                              const int32_t* __restrict__ cand, const int32_t* __restrict__ ncand,
                              uint32_t* __restrict__ bits, int H, int W, int C, int Wd, T thr) {
+  pdl_prologue();
   const int n = *ncand;
   const int P = H * W;
   for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n;
@@ -463,11 +468,11 @@ int launch_detect_sparse(cudaStream_t stream, const void* x, long long x_sb, lon
   while ((1 << glog) < cpv && glog < 5) ++glog;
 #define CB_DETS(U_)                                                                              \
   if (vec_ok)                                                                                    \
-    detect_sparse_vec_kernel<T, VEC, U_><<<grid, 256, 0, stream>>>(                              \
+    cb::launch_pdl(detect_sparse_vec_kernel<T, VEC, U_>, grid, 256, 0, stream,                               \
         (const T*)x, x_sb, x_sy, (int)x_sx, (T*)state, s_sb, s_sy, (int)s_sx, aux, cand,      \
         ncand, bits, H, W, C, Wd, thr, glog);                                                    \
   else                                                                                           \
-    detect_sparse_generic_kernel<T, U_><<<grid, 256, 0, stream>>>(                               \
+    cb::launch_pdl(detect_sparse_generic_kernel<T, U_>, grid, 256, 0, stream,                                \
         (const T*)x, x_sb, x_sc, x_sy, x_sx, (T*)state, s_sb, s_sc, s_sy, s_sx, aux, cand,    \
         ncand, bits, H, W, C, Wd, thr);
   switch (update) {

@@ -15,6 +15,7 @@ __global__ void __launch_bounds__(256)
 fg_update_kernel(const float* __restrict__ x, float* __restrict__ prev,
                  const float* __restrict__ w, float* __restrict__ out, int32_t* __restrict__ count,
                  int B, int Cin, int Cout, int H, int W, int kH, int kW, float thr) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const long long total = (long long)B * Cin * H * W;
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
