@@ -296,7 +296,9 @@ def main():
     static_out = outs[0]
     # my kernels per step and group: per CBConv2d detect + dilate/compact + conv; per pool 1 (+1
     # pooled compaction when it hands candidates on)
-    my_launches_per_step = G * (5 * 3 + 2 + (0 if args.dense_scan else 2))
+    # dense scan: 5 x (detect, compact, conv) + 2 pools = 17; candidate path: the two pools also run
+    # the next conv's detection (15 launches)
+    my_launches_per_step = G * (17 if args.dense_scan else 15)
 
     def step(t):
         static_in.copy_(frames[t])
@@ -426,7 +428,7 @@ def kernel_roofline(args, model, frames, dev, tdt):
     rec = {}
     cur = {"layer": None}
     orig = {n: getattr(cg, n) for n in ("detect", "detect_sparse", "dilate_compact", "pool_compact",
-                                        "conv_update", "maxPool2d")}
+                                        "conv_update", "maxPool2d", "maxPool2d_detect")}
 
     def timed(name):
         fn = orig[name]

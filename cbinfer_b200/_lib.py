@@ -23,7 +23,7 @@ _DTYPES = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
 SYMBOLS = [
     "cb_version", "cb_last_error", "cb_device_info", "cb_bitmap_row_words", "cb_bitmap_words",
     "cb_compact_ws_bytes", "cb_channel_pitch", "cb_packed_weight_bytes", "cb_change_detect",
-    "cb_dilate_compact", "cb_map_to_bits", "cb_change_detect_sparse", "cb_pool_compact", "cb_pack_weights", "cb_conv_update", "cb_maxpool2x2",
+    "cb_dilate_compact", "cb_map_to_bits", "cb_change_detect_sparse", "cb_pool_compact", "cb_maxpool2x2_detect", "cb_pack_weights", "cb_conv_update", "cb_maxpool2x2",
     "cb_gen_xmatrix", "cb_matrix_mult", "cb_update_output", "cb_fg_update",
 ]
 
@@ -62,6 +62,9 @@ def _load():
                                  i32, i32, i32, i32, i32]),
         "cb_maxpool2x2": (i32, [vp, i32, vp, i64, i64, i64, i64, vp, vp, vp, vp, i64, i64, i64,
                                 i64, i32, i32, i32, i32, i32, i32]),
+        "cb_maxpool2x2_detect": (i32, [vp, i32, vp, i64, i64, i32, vp, vp, vp, vp, i64, i64, i32,
+                                       i32, i32, i32, i32, i32, i32, vp, i64, i64, i32, i32, vp, vp,
+                                       vp, f32, i32]),
         "cb_gen_xmatrix": (i32, [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, i32]),
         "cb_matrix_mult": (i32, [vp, i32, vp, vp, vp, vp, i32, i32, i32]),
         "cb_update_output": (i32, [vp, i32, vp, vp, vp, i32, i32, i32, i32]),

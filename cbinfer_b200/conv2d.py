@@ -28,6 +28,15 @@ from .conv2d_fg import cbconvFG
 _INF = float("inf")
 
 
+class DetectionDone(object):
+    """Marker in the index slot of the ('changeIndexes', x, idx) tuple: the upstream CBPoolMax2d
+    already ran this layer's change detection (fused into its pooling kernel); the layer's raw
+    bitmap, state and operand planes are up to date."""
+
+    def __init__(self, owner):
+        self.owner = owner
+
+
 def _parse_input(inp):
     """tensor, or ('changeIndexes', tensor, indices) from an upstream CB layer (conv2d.py:180-187)."""
     if type(inp) == tuple:
@@ -47,6 +56,7 @@ class CBPoolMax2d(nn.Module):
         self.ceil_mode = m.ceil_mode
         self.propChangeIndexes = False
         self.propPooledIndexes = False  # extension: hand pooled-resolution change candidates on
+        self._fusedNext = []            # extension: [downstream CBConv2d] whose detection is fused in
         self.cloneOutput = True   # reference returns outputState.clone() (conv2d.py:73)
         self.register_buffer('outputState', torch.empty(0))
         self._stateBuf = None
@@ -81,6 +91,16 @@ class CBPoolMax2d(nn.Module):
             self.outputState, self._stateBuf = cg.pixel_major((B, nc, oh, ow), input.dtype,
                                                               input.device, _INF)
             self._scratch = None
+        nxt = self._fusedNext[0] if getattr(self, '_fusedNext', None) else None
+        tgt = None
+        if nxt is not None and changeIndexes.bits is not None and input.stride(1) == 1:
+            tgt = nxt._fusedDetectTarget(tuple(self.outputState.shape), input.dtype, input.device)
+        if tgt is not None:
+            # pooling + the next layer's detection in one kernel (cb_maxpool2x2_detect)
+            cg.maxPool2d_detect(input, self.outputState, changeIndexes, tgt['state'], tgt['raw_bits'],
+                                tgt['threshold'], tgt['mode'], aux=tgt['aux'])
+            output = self.outputState.clone() if self.cloneOutput else self.outputState
+            return 'changeIndexes', output, DetectionDone(nxt)
         cg.maxPool2d(input, self.outputState, changeIndexes, self.kernel_size, self.stride)
 
         output = self.outputState.clone() if self.cloneOutput else self.outputState
@@ -204,6 +224,24 @@ class CBConv2d(nn.Module):
                 self._auxPlanes = ('bf16', hi, lo)
         return self._auxPlanes
 
+    def _fusedDetectTarget(self, shape, dtype, device):
+        """What an upstream CBPoolMax2d needs to run this layer's detection inside its own kernel,
+        or None when the exactness conditions of candidate detection do not hold (fresh state,
+        lowered threshold, different shape) or the layer is not on the candidate path."""
+        if not getattr(self, 'candidateDetect', False) or self.finegrained or self._fresh \
+                or self._inBuf is None or tuple(self.prevInput.shape) != tuple(shape) \
+                or self.prevInput.dtype != dtype or self._lastThr is None \
+                or self.threshold < self._lastThr or self._scratch is None \
+                or not self._scratch.get("raw_clear", False):
+            return None
+        gemm, _, _ = self._weights(dtype, device)
+        aux = self._aux(gemm)
+        self._lastThr = self.threshold
+        return dict(state=self.prevInput, raw_bits=self._scratch["raw_bits"],
+                    threshold=self.threshold,
+                    mode=_lib.UPDATE_CHANGED if self.feedbackLoop else _lib.UPDATE_ALL,
+                    aux=None if aux is None else (aux[:2] if aux[0] == 'tf32' else aux))
+
     def _weights(self, dtype, device):
         gemm = self._gemm(dtype)
         key = (self.weight.data_ptr(), self.weight._version, self.bias.data_ptr(),
@@ -264,6 +302,10 @@ class CBConv2d(nn.Module):
         aux_arg = None if aux is None else (aux[:2] if aux[0] == 'tf32' else aux)
 
         candidates = None
+        detected = isinstance(changeIndexes, DetectionDone)
+        if detected:
+            assert changeIndexes.owner is self
+            changeIndexes = None
         if changeIndexes is not None and getattr(self, 'candidateDetect', False):
             candidates, changeIndexes = changeIndexes, None
             if not isinstance(candidates, ChangeIndexes):
@@ -279,7 +321,9 @@ class CBConv2d(nn.Module):
             # honoured as a copy -- the state always owns its memory.
             mode = _lib.UPDATE_CHANGED if self.feedbackLoop else _lib.UPDATE_ALL
             sparse_next = bool(getattr(self, 'candidateDetect', False))
-            if candidates is not None:
+            if detected:
+                pass                     # the upstream pool kernel already did it
+            elif candidates is not None:
                 cg.detect_sparse(input, self.prevInput, s["raw_bits"], self.threshold, mode,
                                  candidates, aux=aux_arg,
                                  bits_are_clear=s.get("raw_clear", False))

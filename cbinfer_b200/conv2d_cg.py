@@ -361,3 +361,25 @@ def maxPool2d(input, outputState, changeIndexes, kernelSize=(2, 2), stride=(2, 2
                           bits.data_ptr() if bits is not None else None,
                           outputState.data_ptr(), *_strides4(outputState), B, Cc, H, W, oH, oW))
     return outputState
+
+
+def maxPool2d_detect(input, outputState, changeIndexes, next_state, next_raw_bits, threshold,
+                     update_mode, aux=None):
+    """cb_maxpool2x2_detect: change-based pooling fused with the next layer's detection (pixel-major
+    tensors only; `changeIndexes.bits` required; `next_raw_bits` must be clear)."""
+    require_cuda(input, outputState, next_state)
+    B, Cc, H, W = input.shape
+    oH, oW = outputState.size(-2), outputState.size(-1)
+    assert changeIndexes.bits is not None and next_state.shape == outputState.shape
+    for t in (input, outputState, next_state):
+        assert t.stride(1) == 1, "pixel-major tensors only"
+    mode, hi, lo = _aux_args(aux, next_state)
+    check(C.cb_maxpool2x2_detect(stream_ptr(input.device), dtype_code(input), input.data_ptr(),
+                                 input.stride(0), input.stride(2), input.stride(3),
+                                 changeIndexes.buffer.data_ptr(), changeIndexes.count.data_ptr(),
+                                 changeIndexes.bits.data_ptr(), outputState.data_ptr(),
+                                 outputState.stride(0), outputState.stride(2), outputState.stride(3),
+                                 B, Cc, H, W, oH, oW, next_state.data_ptr(), next_state.stride(0),
+                                 next_state.stride(2), next_state.stride(3), mode, hi, lo,
+                                 next_raw_bits.data_ptr(), float(threshold), int(update_mode)))
+    return outputState

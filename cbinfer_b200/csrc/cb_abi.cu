@@ -256,6 +256,48 @@ int cb_maxpool2x2(void* stream, int dtype, const void* x, long long x_sb, long l
   return 0;
 }
 
+int cb_maxpool2x2_detect(void* stream, int dtype, const void* x, long long x_sb, long long x_sy,
+                         int x_pitch, const int32_t* idx, const int32_t* count,
+                         const uint32_t* dil_bits, void* out, long long o_sb, long long o_sy,
+                         int o_pitch, int B, int C, int H, int W, int oH, int oW, void* next_state,
+                         long long n_sb, long long n_sy, int n_pitch, int aux_mode, void* aux_hi,
+                         void* aux_lo, uint32_t* next_raw_bits, float threshold, int update_mode) {
+  CB_CHECK_ARG(x && idx && count && dil_bits && out && next_state && next_raw_bits,
+               "maxpool2x2_detect: null pointer");
+  if (B == 0 || H == 0 || W == 0 || C == 0) return 0;
+  const size_t es = cb::esize(dtype);
+  const int vec = (int)(16 / es);
+  const bool ok = (x_pitch % vec) == 0 && x_pitch == o_pitch && o_pitch == n_pitch && x_pitch >= C &&
+                  (C + vec - 1) / vec * vec == x_pitch && ((x_sy * es) % 16) == 0 &&
+                  ((o_sy * es) % 16) == 0 && ((n_sy * es) % 16) == 0 && ((x_sb * es) % 16) == 0 &&
+                  ((o_sb * es) % 16) == 0 && ((n_sb * es) % 16) == 0 && ((uintptr_t)x % 16) == 0 &&
+                  ((uintptr_t)out % 16) == 0 && ((uintptr_t)next_state % 16) == 0;
+  CB_CHECK_ARG(ok, "maxpool2x2_detect: needs pixel-major, 16-byte aligned tensors of equal pitch");
+  const int cpp = x_pitch / vec;
+  int glog = 0;
+  while ((1 << glog) < cpp && glog < 5) ++glog;
+  const unsigned grid = (unsigned)(sm_count() * 16);
+  cudaStream_t s = (cudaStream_t)stream;
+#define CB_MPD(U_)                                                                                \
+  CB_DISPATCH_DTYPE(dtype, {                                                                      \
+    AuxPlanes aux;                                                                                \
+    if (int rc = make_aux<T>(aux, aux_mode, aux_hi, aux_lo, next_state, C)) return rc;            \
+    cb::launch_pdl(maxpool2x2_detect_kernel<T, VEC, U_>, grid, 256, 0, s, (const T*)x, x_sb,     \
+                   x_sy, x_pitch, idx, count, dil_bits, (T*)out, o_sb, o_sy, o_pitch, cpp, glog, \
+                   H, W, oH, oW, (T*)next_state, n_sb, n_sy, n_pitch, aux, next_raw_bits,         \
+                   thr_cast<T>(threshold));                                                       \
+  })
+  switch (update_mode) {
+    case CB_UPDATE_NONE: CB_MPD(CB_UPDATE_NONE); break;
+    case CB_UPDATE_CHANGED: CB_MPD(CB_UPDATE_CHANGED); break;
+    case CB_UPDATE_ALL: CB_MPD(CB_UPDATE_ALL); break;
+    default: return cb::fail(2, "maxpool2x2_detect: bad update_mode %d", update_mode);
+  }
+#undef CB_MPD
+  CB_CHECK_LAUNCH("maxpool2x2_detect");
+  return 0;
+}
+
 int cb_gen_xmatrix(void* stream, int dtype, void* columns, const void* input, const int32_t* idx,
                    int kW, int kH, int C, int W, int H, int n) {
   if (n <= 0) return 0;

@@ -9,6 +9,7 @@
 // Traffic per distinct window: 4*C*s read + C*s written.
 #pragma once
 #include "cb_common.cuh"
+#include "detect.cuh"
 
 namespace cb {
 
@@ -136,6 +137,96 @@ maxpool2x2_vec_kernel(const T* __restrict__ x, long long x_sb, long long x_sy, i
         er[e] = v;
       }
       st16(o + cc * VEC, res);
+    }
+  }
+}
+
+// Pool + downstream change detection in one pass (pixel-major only): the lane group that
+// recomputes a pooled pixel still holds its new channel values, so it thresholds them against the
+// NEXT layer's previous-input state right away, ORs the change bit into that layer's (pre-cleared)
+// raw bitmap and maintains its state / operand planes.  Replaces three launches of the candidate
+// path (pool, pooled compaction, sparse detection) and is exact for the same reason candidate
+// detection is: only re-pooled pixels can differ from what the next layer saw last frame.
+template <typename T, int VEC, int UPDATE>
+__global__ void __launch_bounds__(256)
+maxpool2x2_detect_kernel(const T* __restrict__ x, long long x_sb, long long x_sy, int xp,
+                         const int32_t* __restrict__ idx, const int32_t* __restrict__ count,
+                         const uint32_t* __restrict__ bits, T* __restrict__ out, long long o_sb,
+                         long long o_sy, int op, int cpp, int glog, int H, int W, int oH, int oW,
+                         T* __restrict__ nst, long long n_sb, long long n_sy, int np, AuxPlanes aux,
+                         uint32_t* __restrict__ nbits, T thr) {
+  pdl_prologue();
+  const int n = *count;
+  const int lane = threadIdx.x & 31;
+  const int G = 1 << glog, ppw = 32 >> glog;
+  const int sub = lane >> glog, gl = lane & (G - 1);
+  const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (sub * G);
+  const int P = H * W, Wd = (W + 31) >> 5, oWd = (oW + 31) >> 5;
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long j0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * ppw;
+       j0 < n; j0 += nwarps * ppw) {
+    const long long j = j0 + sub;
+    bool work = j < n;
+    int b = 0, yo = 0, xo = 0;
+    if (work) {
+      const int pix = __ldg(idx + j);
+      b = pix / P;
+      const int p = pix - b * P;
+      const int y = p / W, xx = p - y * W;
+      yo = y >> 1;
+      xo = xx >> 1;
+      work = yo < oH && xo < oW;
+      if (work) {                              // first changed pixel of the window owns it
+        const long long r = (long long)b * H + y;
+        if (xx & 1) work = !bit_at(bits, r, Wd, xx - 1);
+        if (work && (y & 1)) {
+          const int xe = xx & ~1;
+          work = !bit_at(bits, r - 1, Wd, xe) && !(xe + 1 < W && bit_at(bits, r - 1, Wd, xe + 1));
+        }
+      }
+    }
+    const int y0 = yo * 2, x0 = xo * 2;
+    const bool hy = y0 + 1 < H, hx = x0 + 1 < W;
+    const T* base = x + b * x_sb + y0 * x_sy + (long long)x0 * xp;
+    T* o = out + b * o_sb + yo * o_sy + (long long)xo * op;
+    T* ns = nst + b * n_sb + yo * n_sy + (long long)xo * np;
+    const long long opix = ((long long)b * oH + yo) * oW + xo;
+    bool f = false;
+    if (work) {
+      for (int cc = gl; cc < cpp; cc += G) {
+        const T* q = base + cc * VEC;
+        uint4 v00 = ldg16(q), v01 = v00, v10 = v00, v11 = v00;
+        if (hx) v01 = ldg16(q + xp);
+        if (hy) {
+          v10 = ldg16(q + x_sy);
+          v11 = hx ? ldg16(q + x_sy + xp) : v10;
+        }
+        const uint4 sv = ld16(ns + cc * VEC);
+        uint4 res;
+        const T* e00 = reinterpret_cast<const T*>(&v00);
+        const T* e01 = reinterpret_cast<const T*>(&v01);
+        const T* e10 = reinterpret_cast<const T*>(&v10);
+        const T* e11 = reinterpret_cast<const T*>(&v11);
+        T* er = reinterpret_cast<T*>(&res);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          T v = max_keep(neg_inf<T>(), e00[e]);
+          v = max_keep(v, e01[e]);
+          v = max_keep(v, e10[e]);
+          v = max_keep(v, e11[e]);
+          er[e] = v;
+        }
+        st16(o + cc * VEC, res);
+        f |= Chunk<T>::changed(sv, res, thr);
+        if (UPDATE == CB_UPDATE_ALL) store_state<T>(ns + cc * VEC, res, aux, opix, cc * VEC);
+      }
+    }
+    const bool chg = (__ballot_sync(0xffffffffu, f) & gmask) != 0u;
+    if (work && chg) {
+      if (gl == 0) atomicOr(nbits + ((long long)b * oH + yo) * oWd + (xo >> 5), 1u << (xo & 31));
+      if (UPDATE == CB_UPDATE_CHANGED)          // feedback: accept the new pooled pixel
+        for (int cc = gl; cc < cpp; cc += G)
+          store_state<T>(ns + cc * VEC, ld16(o + cc * VEC), aux, opix, cc * VEC);
     }
   }
 }

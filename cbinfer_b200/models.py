@@ -31,7 +31,7 @@ def sceneLabelingBaseline(seed=0):
     return m
 
 
-def enableCandidateDetection(m):
+def enableCandidateDetection(m, fusePool=True):
     """B200 extension (no reference counterpart): inside every nn.Sequential, let each CB layer
     hand its change set to a directly following CB layer as detection *candidates*, so that layer
     thresholds only the pixels that were just rewritten instead of re-scanning its whole input.
@@ -47,6 +47,8 @@ def enableCandidateDetection(m):
                 elif type(a) is CBPoolMax2d:
                     a.propPooledIndexes = True
                     b.candidateDetect = True
+                    if fusePool:             # pooling + b's detection in one kernel
+                        a._fusedNext = [b]
     return m
 
 

@@ -161,6 +161,18 @@ int cb_maxpool2x2(void* stream, int dtype,
                   void* out, long long o_sb, long long o_sc, long long o_sy, long long o_sx,
                   int B, int C, int H, int W, int oH, int oW);
 
+/* cb_maxpool2x2 fused with the NEXT layer's change detection (pixel-major tensors of equal pitch
+ * only): every re-pooled pixel is thresholded against next_state on the spot, its bit OR-ed into
+ * next_raw_bits (which the caller keeps cleared, see cb_dilate_compact clear_raw) and next_state /
+ * its auxiliary planes are maintained per update_mode -- i.e. cb_maxpool2x2 + cb_pool_compact +
+ * cb_change_detect_sparse in one launch, with identical results.  dil_bits is required. */
+int cb_maxpool2x2_detect(void* stream, int dtype, const void* x, long long x_sb, long long x_sy,
+                         int x_pitch, const int32_t* idx, const int32_t* count,
+                         const uint32_t* dil_bits, void* out, long long o_sb, long long o_sy,
+                         int o_pitch, int B, int C, int H, int W, int oH, int oW, void* next_state,
+                         long long n_sb, long long n_sy, int n_pitch, int aux_mode, void* aux_hi,
+                         void* aux_lo, uint32_t* next_raw_bits, float threshold, int update_mode);
+
 /* ---- staged (unfused) ops in the reference's planar layout --------------------------------
  * 1:1 replacements used by the op-level wrappers and parity tests. n is a host count here,
  * exactly as in the reference signatures. */
