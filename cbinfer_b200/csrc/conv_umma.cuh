@@ -608,11 +608,23 @@ int launch_conv_umma(cudaStream_t s, int dtype, const void* state, const void* s
       return fail(3, "conv_update: cannot reserve %d bytes of shared memory", C::SMEM_BYTES);
     attr_dev = dev;
   }
+  // shared memory actually needed: stages + alignment slack + ctrl + the K-chunk table of THIS
+  // layer (small layers then fit a third CTA per SM -> more gather stages in flight)
+  const int num_kb = KpPad / C::BK;
+  const int table_entries = num_kb * 8 <= C::TABLE_MAX ? num_kb * 8 : 0;
+  const int smem_bytes = C::STAGES * C::STAGE_BYTES + 1024 + 2048 + table_entries * 8;
+  int occ = C::CTAS_PER_SM;
+  if (!DEEP) {
+    int q = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, UM_THREADS, smem_bytes) == cudaSuccess &&
+        q > occ)
+      occ = q > 4 ? 4 : q;
+  }
   const long long max_tiles = (((long long)B * H * W + UM_BM - 1) / UM_BM) * (CoutPad / BN);
-  long long grid = (long long)sm_count() * C::CTAS_PER_SM;
+  long long grid = (long long)sm_count() * occ;
   if (grid > max_tiles) grid = max_tiles;
   if (grid < 1) grid = 1;
-  cb::launch_pdl(kern, (unsigned)grid, UM_THREADS, C::SMEM_BYTES, s, map, (const T*)state, (const T*)state_lo, Cp,
+  cb::launch_pdl(kern, (unsigned)grid, UM_THREADS, (size_t)smem_bytes, s, map, (const T*)state, (const T*)state_lo, Cp,
                                                         idx, count, bias,
                                                         (TO*)out, Op, H, W, Cout, CoutPad, kH, kW,
                                                         Kp, relu, sel_lo, sel_hi);
