@@ -15,9 +15,9 @@
 namespace cb {
 
 constexpr int kCompactThreads = 512;
-constexpr int kCompactWPT = 4;                               // words per thread
-constexpr int kCompactTile = kCompactThreads * kCompactWPT;  // words per tile (65536 pixels)
-constexpr int kCompactWin = 7168;                            // staged raw window (words, 28 KB)
+constexpr int kCompactWPT = 2;                               // words per thread
+constexpr int kCompactTile = kCompactThreads * kCompactWPT;  // words per tile (32768 pixels)
+constexpr int kCompactWin = 6144;                            // staged raw window (words, 24 KB)
 
 struct CompactHeader {                         // first 16 bytes of the workspace
   unsigned reserved, done, epoch, pad;
@@ -192,31 +192,26 @@ dilate_compact_kernel(const uint32_t* __restrict__ raw, uint32_t* __restrict__ d
   }
   __syncthreads();
 
-  // ---- expand set bits to ascending pixel indices: warp-cooperative, one coalesced store per
-  //      non-zero word (lane i writes the index of bit i) -----------------------------------------
+  // ---- expand set bits to ascending pixel indices ------------------------------------------
   int o = s_base + s_warp[wid] + (incl - cnt);
 #pragma unroll
   for (int i = 0; i < kCompactWPT; ++i) {
     const int w = w0 + i;
-    const bool valid = w < nwords;
-    const int j = valid ? w % Wd : 0;
-    const int r = valid ? w / Wd : 0;                        // r = b*H + y
+    if (w >= nwords) break;
+    const int j = w % Wd;
+    const int r = w / Wd;                                    // r = b*H + y
     const int pix0 = r * W + j * 32;
-    unsigned todo = __ballot_sync(0xffffffffu, valid && d[i] != 0u);
-    while (todo) {
-      const int src = __ffs(todo) - 1;
-      todo &= todo - 1;
-      const unsigned dd = __shfl_sync(0xffffffffu, d[i], src);
-      const int oo = __shfl_sync(0xffffffffu, o, src);
-      const int pp = __shfl_sync(0xffffffffu, pix0, src);
-      if ((dd >> lane) & 1u) idx[oo + __popc(dd & ((1u << lane) - 1u))] = pp + lane;
+    unsigned dd = d[i];
+    while (dd) {
+      const int bit = __ffs(dd) - 1;
+      idx[o++] = pix0 + bit;
+      dd &= dd - 1;
     }
-    if (valid && dil_map) {
+    if (dil_map) {
       const int n = min(32, W - j * 32);
       int8_t* m = dil_map + pix0;
       for (int q = 0; q < n; ++q) m[q] = (int8_t)((d[i] >> q) & 1u);
     }
-    o += __popc(d[i]);
   }
 
   // ---- leave the workspace clean for the next launch ---------------------------------------

@@ -146,6 +146,7 @@ __host__ __device__ inline uint32_t umma_idesc(int fmt, int N) {
 }
 
 // ---- configuration -----------------------------------------------------------------------------
+constexpr int UM_CTRL_BYTES = 1280;            // barriers + TMEM base + row table
 // DEEP: one CTA per SM with as many stages as fit (used when few tiles exist: latency, not
 // occupancy, is then the limiter).
 template <typename T, bool SPLIT3, int BN, bool DEEP = false>
@@ -165,7 +166,7 @@ struct UmmaCfg {
                                 : (BUDGET / STAGE_BYTES) > 8 ? 8 : (BUDGET / STAGE_BYTES);
   static constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
   static constexpr int TABLE_MAX = 1024;        // chunk-offset table entries (8 KB)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 2048 /*ctrl*/ +
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + UM_CTRL_BYTES +
                                     TABLE_MAX * 8;
 };
 
@@ -175,7 +176,7 @@ struct UmmaCtrl {                              // lives after the stage buffers
   int pix[UM_BM];
   int yx[UM_BM];
 };
-static_assert(sizeof(UmmaCtrl) <= 2048, "ctrl block too large");
+static_assert(sizeof(UmmaCtrl) <= UM_CTRL_BYTES, "ctrl block too large");
 
 // Incremental (ky,kx,ci) decode of this thread's K position: advances by one stage (BK elements)
 // per call, in stage order, without integer divisions in the hot loop.
@@ -220,9 +221,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
   if (mtiles < sel_lo || mtiles >= sel_hi) return;
   if ((int)blockIdx.x >= total_tiles) return;             // uniform: before any barrier / alloc
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if (smem_u32(smem) & 1023u) __trap();                   // SWIZZLE_128B tiles need 1024-byte alignment
   UmmaCtrl* ctrl = reinterpret_cast<UmmaCtrl*>(smem + C::STAGES * C::STAGE_BYTES);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int num_kb = (Kp + C::BK - 1) / C::BK;
@@ -230,8 +231,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
   const int ph = (kH - 1) / 2, pw = (kW - 1) / 2;
   // Per 16-byte K chunk q (k = q*VEC): element offset of its filter tap relative to the pixel and
   // the tap's (dy,dx); built once per CTA so the gather loop has no divisions.
-  int2* ktab = reinterpret_cast<int2*>(reinterpret_cast<uint8_t*>(ctrl) + 2048);
+  int2* ktab = reinterpret_cast<int2*>(reinterpret_cast<uint8_t*>(ctrl) + UM_CTRL_BYTES);
   const bool use_table = num_kb * 8 <= C::TABLE_MAX;
+  const uint32_t ktab_s = smem_u32(ktab);
   if (use_table) {
     for (int q = tid; q < num_kb * 8; q += UM_THREADS) {
       const int k = q * C::VEC;
@@ -318,7 +320,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
         long long koff;
         bool kvalid;
         if (use_table) {
-          const int2 e = ktab[kb * 8 + c];
+          int2 e;                                            // explicit ld.shared (not a generic LD)
+          asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];"
+                       : "=r"(e.x), "=r"(e.y)
+                       : "r"(ktab_s + (uint32_t)((kb * 8 + c) * 8)));
           koff = e.x;
           dy = e.y >> 16;
           dx = (int)(short)(e.y & 0xffff);
@@ -612,7 +617,9 @@ int launch_conv_umma(cudaStream_t s, int dtype, const void* state, const void* s
   // layer (small layers then fit a third CTA per SM -> more gather stages in flight)
   const int num_kb = KpPad / C::BK;
   const int table_entries = num_kb * 8 <= C::TABLE_MAX ? num_kb * 8 : 0;
-  const int smem_bytes = C::STAGES * C::STAGE_BYTES + 1024 + 2048 + table_entries * 8;
+  // (the 1024-byte alignment slack is only needed if the dynamic smem window is not already
+  //  1024-aligned; it is when the kernel has no static shared memory, which the kernel checks)
+  const int smem_bytes = C::STAGES * C::STAGE_BYTES + UM_CTRL_BYTES + table_entries * 8;
   int occ = C::CTAS_PER_SM;
   if (!DEEP) {
     int q = 0;

@@ -33,7 +33,7 @@ def test_size_helpers():
     assert C.cb_bitmap_words(2, 480, 640) == 2 * 480 * 20
     assert C.cb_channel_pitch(0, 3) == 4 and C.cb_channel_pitch(0, 185) == 188
     assert C.cb_channel_pitch(1, 3) == 8 and C.cb_channel_pitch(2, 185) == 192
-    assert C.cb_compact_ws_bytes(1, 480, 640) >= 16 + 8 * ((9600 + 2047) // 2048)   # header + one status word per tile
+    assert C.cb_compact_ws_bytes(1, 480, 640) >= 16 + 8 * ((9600 + 1023) // 1024)   # header + one status word per 1024-word tile
     # simt packing: fp32 [Kp][CoutP]
     assert C.cb_packed_weight_bytes(0, 0, 16, 3, 7, 7) == 49 * 4 * 16 * 4
     # tc3x packing: 2 planes x CoutPad(64) x KpPad(196->224) fp32
