@@ -39,8 +39,11 @@ int sm_count() {
 bool pdl_enabled() {
   static int cached = -1;
   if (cached < 0) {
+    // Off by default: a dependent grid that becomes resident early may see stale L1 / read-only
+    // (ld.global.nc) lines of buffers its predecessor is still writing (observed as wrong results
+    // inside CUDA graphs); measured gain was only ~2 %.  CBINFER_PDL=1 enables it for experiments.
     const char* e = getenv("CBINFER_PDL");
-    cached = (e && e[0] == '0') ? 0 : 1;
+    cached = (e && e[0] == '1') ? 1 : 0;
   }
   return cached != 0;
 }

@@ -32,7 +32,8 @@ bool pdl_enabled();
 // "my dependents may be scheduled" + "wait until the grids I depend on have completed and their
 // writes are visible" -- and is launched with programmatic stream serialisation, so the next
 // kernel of the stream is already resident when its predecessor drains (no launch gap between the
-// ~20 dependent kernels of a frame; also inside CUDA graphs).  CBINFER_PDL=0 turns it off.
+// ~20 dependent kernels of a frame; also inside CUDA graphs).  Experimental, enabled only with
+// CBINFER_PDL=1 (see pdl_enabled()); without the launch attribute both instructions are no-ops.
 __device__ __forceinline__ void pdl_prologue() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
