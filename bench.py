@@ -297,8 +297,8 @@ def main():
     # my kernels per step and group: per CBConv2d detect + dilate/compact + conv; per pool 1 (+1
     # pooled compaction when it hands candidates on)
     # dense scan: 5 x (detect, compact, conv) + 2 pools = 17; candidate path: the two pools also run
-    # the next conv's detection (15 launches)
-    my_launches_per_step = G * (17 if args.dense_scan else 15)
+    # the next conv's detection and the two 1x1 layers detect+compact in one launch (13 launches)
+    my_launches_per_step = G * (17 if args.dense_scan else 13)
 
     def step(t):
         static_in.copy_(frames[t])
@@ -428,7 +428,8 @@ def kernel_roofline(args, model, frames, dev, tdt):
     rec = {}
     cur = {"layer": None}
     orig = {n: getattr(cg, n) for n in ("detect", "detect_sparse", "dilate_compact", "pool_compact",
-                                        "conv_update", "maxPool2d", "maxPool2d_detect")}
+                                        "conv_update", "maxPool2d", "maxPool2d_detect",
+                                        "detect_compact_sparse")}
 
     def timed(name):
         fn = orig[name]

@@ -23,7 +23,8 @@ _DTYPES = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
 SYMBOLS = [
     "cb_version", "cb_last_error", "cb_device_info", "cb_bitmap_row_words", "cb_bitmap_words",
     "cb_compact_ws_bytes", "cb_channel_pitch", "cb_packed_weight_bytes", "cb_change_detect",
-    "cb_dilate_compact", "cb_map_to_bits", "cb_change_detect_sparse", "cb_pool_compact", "cb_maxpool2x2_detect", "cb_pack_weights", "cb_conv_update", "cb_maxpool2x2",
+    "cb_dilate_compact", "cb_map_to_bits", "cb_change_detect_sparse", "cb_pool_compact", "cb_maxpool2x2_detect",
+    "cb_detect_compact_ws_bytes", "cb_detect_compact_sparse", "cb_pack_weights", "cb_conv_update", "cb_maxpool2x2",
     "cb_gen_xmatrix", "cb_matrix_mult", "cb_update_output", "cb_fg_update",
 ]
 
@@ -56,6 +57,9 @@ def _load():
         "cb_map_to_bits": (i32, [vp, vp, vp, i32, i32, i32]),
         "cb_change_detect_sparse": (i32, [vp, i32, vp, i64, i64, i64, i64, vp, i64, i64, i64, i64, i32,
                                           vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, i32, i32]),
+        "cb_detect_compact_ws_bytes": (sz, [i32, i32, i32]),
+        "cb_detect_compact_sparse": (i32, [vp, i32, vp, i64, i64, i64, i64, vp, i64, i64, i64, i64, i32,
+                                           vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, i32]),
         "cb_pool_compact": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32]),
         "cb_pack_weights": (i32, [vp, i32, i32, vp, vp, i32, i32, i32, i32]),
         "cb_conv_update": (i32, [vp, i32, i32, vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32,

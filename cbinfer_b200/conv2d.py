@@ -321,8 +321,17 @@ class CBConv2d(nn.Module):
             # honoured as a copy -- the state always owns its memory.
             mode = _lib.UPDATE_CHANGED if self.feedbackLoop else _lib.UPDATE_ALL
             sparse_next = bool(getattr(self, 'candidateDetect', False))
+            fused11 = (candidates is not None and tuple(self.kernel_size) == (1, 1)
+                       and not self.saveChangeMap and input.stride(1) == 1)
             if detected:
                 pass                     # the upstream pool kernel already did it
+            elif fused11:
+                # no dilation needed: candidate detection + ordered compaction in one launch
+                if "dcs_ws" not in s:
+                    s["dcs_ws"] = torch.zeros(_lib.C.cb_detect_compact_ws_bytes(B, H, W),
+                                              dtype=torch.uint8, device=dev)
+                cg.detect_compact_sparse(input, self.prevInput, self.threshold, mode, candidates,
+                                         s["idx"], s["count"], s["dcs_ws"], aux=aux_arg)
             elif candidates is not None:
                 cg.detect_sparse(input, self.prevInput, s["raw_bits"], self.threshold, mode,
                                  candidates, aux=aux_arg,
@@ -331,16 +340,11 @@ class CBConv2d(nn.Module):
                 cg.detect(input, self.prevInput, s["raw_bits"], self.threshold, mode, aux=aux_arg)
             self._fresh = False
             self._lastThr = self.threshold
-            dil_map = s.get("dil_map") if self.saveChangeMap else None
-            # a layer on the candidate path lets the compaction zero the raw bitmap once it has
-            # been consumed, so the next frame's candidate detection needs no memset
-            cg.dilate_compact(s["raw_bits"], (B, H, W), self.kernel_size, s["idx"], s["count"],
-                              s["ws"], dil_bits=s["dil_bits"], dil_map=dil_map,
-                              clear_raw=sparse_next)
-            s["raw_clear"] = sparse_next
-            if self.saveChangeMap:
-                self.changeMap = dil_map[0] if B == 1 else dil_map
-            changeIndexes = ChangeIndexes(s["idx"], s["count"], (B, H, W), bits=s["dil_bits"])
+            if not detected and fused11:
+                s["raw_clear"] = False
+                changeIndexes = ChangeIndexes(s["idx"], s["count"], (B, H, W), bits=None)
+            else:
+                changeIndexes = self._compact(s, B, H, W, sparse_next)
         else:
             if not isinstance(changeIndexes, ChangeIndexes):
                 assert(changeIndexes.dim() == 1)
@@ -360,6 +364,18 @@ class CBConv2d(nn.Module):
             return 'changeIndexes', self.prevOutput, changeIndexes
         else:
             return self.prevOutput
+
+    def _compact(self, s, B, H, W, sparse_next):
+        """dilate the raw bitmap by the filter footprint and compact it to the index list."""
+        dil_map = s.get("dil_map") if self.saveChangeMap else None
+        # a layer on the candidate path lets the compaction zero the raw bitmap once it has been
+        # consumed, so the next frame's candidate detection needs no memset
+        cg.dilate_compact(s["raw_bits"], (B, H, W), self.kernel_size, s["idx"], s["count"],
+                          s["ws"], dil_bits=s["dil_bits"], dil_map=dil_map, clear_raw=sparse_next)
+        s["raw_clear"] = sparse_next
+        if self.saveChangeMap:
+            self.changeMap = dil_map[0] if B == 1 else dil_map
+        return ChangeIndexes(s["idx"], s["count"], (B, H, W), bits=s["dil_bits"])
 
     def _gatherStats(self, input):
         """op-count bookkeeping of conv2d.py:201-218 (dense torch ops, only when enabled)."""

@@ -259,6 +259,25 @@ int cb_maxpool2x2(void* stream, int dtype, const void* x, long long x_sb, long l
   return 0;
 }
 
+size_t cb_detect_compact_ws_bytes(int B, int H, int W) { return 16 + (size_t)B * H * W + 16; }
+
+int cb_detect_compact_sparse(void* stream, int dtype, const void* x, long long x_sb, long long x_sc,
+                             long long x_sy, long long x_sx, void* state, long long s_sb,
+                             long long s_sc, long long s_sy, long long s_sx, int aux_mode,
+                             void* aux_hi, void* aux_lo, const int32_t* candidates,
+                             const int32_t* n_candidates, int32_t* idx, int32_t* count,
+                             uint32_t* bits, void* ws, int B, int C, int H, int W, float threshold,
+                             int update_mode) {
+  CB_CHECK_ARG(x && state && candidates && n_candidates && idx && count && ws,
+               "detect_compact_sparse: null pointer");
+  CB_CHECK_ARG(idx != candidates, "detect_compact_sparse: idx must not alias candidates");
+  CB_DISPATCH_DTYPE(dtype, return (launch_detect_compact_sparse<T, VEC>(
+                               (cudaStream_t)stream, x, x_sb, x_sc, x_sy, x_sx, state, s_sb, s_sc,
+                               s_sy, s_sx, aux_mode, aux_hi, aux_lo, candidates, n_candidates, idx,
+                               count, bits, ws, B, C, H, W, threshold, update_mode)));
+  return 0;
+}
+
 int cb_maxpool2x2_detect(void* stream, int dtype, const void* x, long long x_sb, long long x_sy,
                          int x_pitch, const int32_t* idx, const int32_t* count,
                          const uint32_t* dil_bits, void* out, long long o_sb, long long o_sy,
