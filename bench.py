@@ -297,8 +297,8 @@ def main():
     # my kernels per step and group: per CBConv2d detect + dilate/compact + conv; per pool 1 (+1
     # pooled compaction when it hands candidates on)
     # dense scan: 5 x (detect, compact, conv) + 2 pools = 17; candidate path: the two pools also run
-    # the next conv's detection and the two 1x1 layers detect+compact in one launch (13 launches)
-    my_launches_per_step = G * (17 if args.dense_scan else 13)
+    # the next conv's detection (15 launches)
+    my_launches_per_step = G * (17 if args.dense_scan else 15)
 
     def step(t):
         static_in.copy_(frames[t])

@@ -171,6 +171,7 @@ class CBConv2d(nn.Module):
         # extension: treat indices received from upstream as *candidates* for the thresholded
         # detection instead of as the final change set (exact, see cb_change_detect_sparse)
         self.candidateDetect = False
+        self.fuse1x1 = False      # extension: detect+compact in one launch for 1x1 layers
 
     # ---- state ---------------------------------------------------------------------------
     def clearMemory(self):
@@ -321,7 +322,10 @@ class CBConv2d(nn.Module):
             # honoured as a copy -- the state always owns its memory.
             mode = _lib.UPDATE_CHANGED if self.feedbackLoop else _lib.UPDATE_ALL
             sparse_next = bool(getattr(self, 'candidateDetect', False))
+            # (measured: one launch fewer, but its serial compaction tail makes it slower than the
+            #  two-kernel path once there are >~10k candidates, so it is opt-in: fuse1x1=True)
             fused11 = (candidates is not None and tuple(self.kernel_size) == (1, 1)
+                       and getattr(self, 'fuse1x1', False)
                        and not self.saveChangeMap and input.stride(1) == 1)
             if detected:
                 pass                     # the upstream pool kernel already did it

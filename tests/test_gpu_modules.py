@@ -227,7 +227,8 @@ def test_candidate_detection_equals_dense_scan(feedback, dt, save_maps):
         for c in m.modules():
             if type(c) is cb.CBConv2d:
                 c.feedbackLoop = feedback
-                c.saveChangeMap = save_maps     # False also exercises the fused 1x1 detect+compact
+                c.saveChangeMap = save_maps
+                c.fuse1x1 = not save_maps       # also exercise the fused 1x1 detect+compact
         ms.append(m)
     for t, f in enumerate(frames):
         outs = [m(f) for m in ms]
