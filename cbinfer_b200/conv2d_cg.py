@@ -209,7 +209,7 @@ def bf16_pair(x):
 def bf16_planes(state_buf, C_):
     """pixel-major bf16 hi/lo planes [B,H,W,pitch16] of a pixel-major fp32 buffer."""
     B, H, W, _ = state_buf.shape
-    p16 = (C_ + 7) // 8 * 8
+    p16 = C.cb_plane_pitch16(C_)
     hi = torch.zeros(B, H, W, p16, dtype=torch.bfloat16, device=state_buf.device)
     lo = torch.zeros_like(hi)
     h, l = bf16_pair(state_buf[..., :C_])

@@ -86,6 +86,7 @@ int cb_device_info(int* sms, int* major, int* minor) {
 int cb_bitmap_row_words(int W) { return (W + 31) / 32; }
 size_t cb_bitmap_words(int B, int H, int W) { return (size_t)B * H * ((W + 31) / 32); }
 size_t cb_compact_ws_bytes(int B, int H, int W) { return cb::compact_ws_bytes(cb_bitmap_words(B, H, W)); }
+int cb_plane_pitch16(int C) { return cb::pitch16_of(C); }
 int cb_channel_pitch(int dtype, int C) {
   const int v = 16 / cb::esize(dtype);
   return (C + v - 1) / v * v;
@@ -177,7 +178,7 @@ int cb_map_to_bits(void* stream, const int8_t* map, uint32_t* bits, int B, int H
 }
 
 size_t cb_packed_weight_bytes(int dtype, int gemm, int Cout, int Cin, int kH, int kW) {
-  const int Cp = gemm == CB_GEMM_TC_BF16X3 ? (Cin + 7) / 8 * 8 : cb_channel_pitch(dtype, Cin);
+  const int Cp = gemm == CB_GEMM_TC_BF16X3 ? cb::pitch16_of(Cin) : cb_channel_pitch(dtype, Cin);
   if (gemm == CB_GEMM_SIMT_F32) {
     const int CoutP = (Cout + 3) / 4 * 4;
     return (size_t)kH * kW * Cp * CoutP * sizeof(float);
@@ -188,7 +189,7 @@ size_t cb_packed_weight_bytes(int dtype, int gemm, int Cout, int Cin, int kH, in
 int cb_pack_weights(void* stream, int dtype, int gemm, const void* weight, void* packed, int Cout,
                     int Cin, int kH, int kW) {
   CB_CHECK_ARG(weight && packed, "pack_weights: null pointer");
-  const int Cp = gemm == CB_GEMM_TC_BF16X3 ? (Cin + 7) / 8 * 8 : cb_channel_pitch(dtype, Cin);
+  const int Cp = gemm == CB_GEMM_TC_BF16X3 ? cb::pitch16_of(Cin) : cb_channel_pitch(dtype, Cin);
   cudaStream_t s = (cudaStream_t)stream;
   if (gemm == CB_GEMM_SIMT_F32) {
     const int CoutP = (Cout + 3) / 4 * 4;
@@ -206,7 +207,7 @@ int cb_conv_update(void* stream, int dtype, int gemm, const void* state, const v
                    const float* bias, void* out, int pitch_out, int B, int H, int W, int Cin,
                    int Cout, int kH, int kW, int relu) {
   CB_CHECK_ARG(state && idx && count && packed_w && bias && out, "conv_update: null pointer");
-  const int want_pitch = gemm == CB_GEMM_TC_BF16X3 ? (Cin + 7) / 8 * 8 : cb_channel_pitch(dtype, Cin);
+  const int want_pitch = gemm == CB_GEMM_TC_BF16X3 ? cb::pitch16_of(Cin) : cb_channel_pitch(dtype, Cin);
   CB_CHECK_ARG(pitch_in == want_pitch, "conv_update: pitch_in %d != channel pitch %d", pitch_in,
                want_pitch);
   CB_CHECK_ARG(pitch_out >= Cout, "conv_update: pitch_out < Cout");

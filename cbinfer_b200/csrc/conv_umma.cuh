@@ -71,6 +71,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 // 16-byte async copy global -> shared (LDGSTS); src_bytes = 0 zero-fills (out-of-image taps)
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes)
+               : "memory");
+}
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes)
                : "memory");
@@ -232,11 +236,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
   // Per 16-byte K chunk q (k = q*VEC): element offset of its filter tap relative to the pixel and
   // the tap's (dy,dx); built once per CTA so the gather loop has no divisions.
   int2* ktab = reinterpret_cast<int2*>(reinterpret_cast<uint8_t*>(ctrl) + UM_CTRL_BYTES);
-  const bool use_table = num_kb * 8 <= C::TABLE_MAX;
+  // 8-byte taps (Cp == 4 sixteen-bit channels, e.g. an RGB input layer's bf16 planes): a 16-byte
+  // chunk holds two taps, gathered as two 8-byte copies with their own bounds test
+  const bool half_taps = sizeof(T) == 2 && Cp == 4;
+  const int upc = half_taps ? 2 : 1;                        // table units per 16-byte chunk
+  const bool use_table = num_kb * 8 * upc <= C::TABLE_MAX;
   const uint32_t ktab_s = smem_u32(ktab);
   if (use_table) {
-    for (int q = tid; q < num_kb * 8; q += UM_THREADS) {
-      const int k = q * C::VEC;
+    for (int q = tid; q < num_kb * 8 * upc; q += UM_THREADS) {
+      const int k = q * (C::VEC / upc);
       int2 e = make_int2(0, (int)0x80008000u);             // k beyond K: dy = dx = -32768 (invalid)
       if (k < Kp) {
         const int tap = k / Cp, ci = k - tap * Cp;
@@ -316,6 +324,26 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&ctrl->empty[stage], phase ^ 1u);
         const uint32_t a_hi = smem_u32(smem + stage * C::STAGE_BYTES);
+        if (half_taps) {                                     // (always table-driven: K is tiny)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            int2 e;
+            asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];"
+                         : "=r"(e.x), "=r"(e.y)
+                         : "r"(ktab_s + (uint32_t)(((kb * 8 + c) * 2 + h) * 8)));
+            const int dy = e.y >> 16, dx = (int)(short)(e.y & 0xffff);
+#pragma unroll
+            for (int it = 0; it < RPT; ++it) {
+              const bool ok = (unsigned)(ry[it] + dy) < (unsigned)H && (unsigned)(rx[it] + dx) < (unsigned)W;
+              const T* src = ok ? rbase[it] + e.x : state;
+              cp_async8(a_hi + soff[it] + 8 * h, src, ok ? 8u : 0u);
+              if (SPLIT3) cp_async8(a_hi + C::A_BYTES + soff[it] + 8 * h, src + lo_delta, ok ? 8u : 0u);
+            }
+          }
+          cp_async_arrive_noinc(&ctrl->full[stage]);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+          continue;
+        }
         int dy, dx;
         long long koff;
         bool kvalid;
@@ -616,7 +644,8 @@ int launch_conv_umma(cudaStream_t s, int dtype, const void* state, const void* s
   // shared memory actually needed: stages + alignment slack + ctrl + the K-chunk table of THIS
   // layer (small layers then fit a third CTA per SM -> more gather stages in flight)
   const int num_kb = KpPad / C::BK;
-  const int table_entries = num_kb * 8 <= C::TABLE_MAX ? num_kb * 8 : 0;
+  const int upc = (sizeof(T) == 2 && Cp == 4) ? 2 : 1;
+  const int table_entries = num_kb * 8 * upc <= C::TABLE_MAX ? num_kb * 8 * upc : 0;
   // (the 1024-byte alignment slack is only needed if the dynamic smem window is not already
   //  1024-aligned; it is when the kernel has no static shared memory, which the kernel checks)
   const int smem_bytes = C::STAGES * C::STAGE_BYTES + UM_CTRL_BYTES + table_entries * 8;
@@ -677,6 +706,8 @@ inline int umma_conv_update(cudaStream_t s, int dtype, int gemm, const void* sta
   const int bn = umma_bn(gemm, Cout), CoutPad = umma_cout_pad(gemm, Cout);
   const bool split3 = gemm == CB_GEMM_TC_3X && dtype == CB_F32;
   const bool bf16x3 = gemm == CB_GEMM_TC_BF16X3;
+  CB_CHECK_ARG(!(bf16x3 && Cp == 4) || kH * kW <= 256,
+               "conv_update: 8-byte-tap layers support up to 256 filter taps");
   CB_CHECK_ARG(!(split3 || bf16x3) || (state_lo && ((uintptr_t)state_lo % 16) == 0),
                "conv_update: the 3x modes need their 16-byte aligned lo operand plane (state_lo)");
   // Tiling policy.  Large N tiles minimise the im2col re-gather (the kernel is L2-bound on big

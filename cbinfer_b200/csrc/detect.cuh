@@ -34,7 +34,7 @@ __device__ __forceinline__ uint4 merge_tail(uint4 xv, const uint4& sv, int tail)
 //           the tensor rate and half the bytes of 3xTF32), pixel-major with their own pitch.
 struct AuxPlanes {
   int mode;
-  int pitch16;               // mode 2: bf16 elements per pixel (multiple of 8)
+  int pitch16;               // mode 2: bf16 elements per pixel (pitch16_of(C))
   long long lo_off;          // mode 1: element offset state -> lo plane (same strides as the state)
   __nv_bfloat16* hi16;       // mode 2
   __nv_bfloat16* lo16;
@@ -281,7 +281,7 @@ inline int make_aux(AuxPlanes& aux, int aux_mode, void* aux_hi, void* aux_lo, co
   CB_CHECK_ARG(aux_hi && aux_lo && ((uintptr_t)aux_hi % 16) == 0 && ((uintptr_t)aux_lo % 16) == 0,
                "change_detect: bad bf16 operand planes");
   aux.mode = 2;
-  aux.pitch16 = (C + 7) / 8 * 8;
+  aux.pitch16 = pitch16_of(C);
   aux.hi16 = (__nv_bfloat16*)aux_hi;
   aux.lo16 = (__nv_bfloat16*)aux_lo;
   return 0;

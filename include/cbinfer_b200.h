@@ -56,7 +56,7 @@ extern "C" {
 #define CB_AUX_NONE 0
 #define CB_AUX_TF32_LO 1     /* aux_lo: fp32 plane v - trunc_tf32(v), same strides as the state    */
 #define CB_AUX_BF16_PAIR 2   /* aux_hi / aux_lo: bf16 planes bf16(v), bf16(v - hi); pixel-major,
-                                pitch = C rounded up to 8                                          */
+                                pitch = cb_plane_pitch16(C): 4 for C <= 4, else C rounded up to 8  */
 
 /* ---- library ---------------------------------------------------------------------------- */
 int cb_version(void);
@@ -69,6 +69,7 @@ int cb_bitmap_row_words(int W);                       /* ceil(W/32)             
 size_t cb_bitmap_words(int B, int H, int W);          /* B*H*ceil(W/32)                         */
 size_t cb_compact_ws_bytes(int B, int H, int W);      /* workspace of cb_dilate_compact         */
 int cb_channel_pitch(int dtype, int C);               /* C rounded up to 16 bytes               */
+int cb_plane_pitch16(int C);                          /* pitch of the CB_AUX_BF16_PAIR planes   */
 size_t cb_packed_weight_bytes(int dtype, int gemm, int Cout, int Cin, int kH, int kW);
 
 /* ---- change detection ---------------------------------------------------------------------

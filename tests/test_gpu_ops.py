@@ -183,7 +183,7 @@ def test_detect_update_all_and_special_values(cbm, orc):
             xin = x1 if layout == "narrow" else cg.pixel_major(shape, torch.float32, "cuda", 0)[0].copy_(x1)
         lo.copy_(cg.tf32_lo(x0))
         s = cg.alloc_scratch((shape[0], shape[2], shape[3]), "cuda")
-        p16 = (shape[1] + 7) // 8 * 8
+        p16 = cbm['lib'].C.cb_plane_pitch16(shape[1])
         h16 = torch.zeros(shape[0], shape[2], shape[3], p16, dtype=torch.bfloat16, device="cuda")
         l16 = torch.zeros_like(h16)
         eh, el = cg.bf16_pair(x0.permute(0, 2, 3, 1))
