@@ -497,9 +497,17 @@ def kernel_roofline(args, model, frames, dev, tdt):
     top = next((r for r in table if "achieved" in r), None)
     out = {"kernels": table, "kernel_us_per_step": round(total, 1), "peaks_source": src}
     if top:
-        out["roofline"] = {"kernel": "%s[%s]" % (top["kernel"], top["layer"]), "bound": top["bound"],
+        key = "%s[%s]" % (top["kernel"], top["layer"])
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(REPO, "profiles", "r01_traffic.json"))).get(key, {}).get("bytes")
+        except Exception:
+            pass
+        out["roofline"] = {"kernel": key, "bound": top["bound"],
                            "achieved": top["achieved"], "peak": top["peak"], "unit": top["unit"],
-                           "frac": top["frac"], "traffic": None,
+                           "frac": top["frac"], "traffic": traffic,
+                           "tensor_work_frac": (3.0 * top["frac"] if top["bound"] == "tensor" and args.dtype == "f32"
+                                                and args.gemm in ("auto", "bf16x3", "tc3x") else top["frac"]),
                            "share_of_step": top["us"] / total if total else None,
                            "note": "fp32 data runs 3xTF32 (3 MMAs per product): peak = bf16 burst / 2, achieved counts "
                                    "algorithmic FLOPs 2*n*K*Cout once" if top["bound"] == "tensor" and args.dtype == "f32" else ""}

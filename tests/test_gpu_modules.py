@@ -3,6 +3,7 @@ restatement of the reference flow (oracle.OracleCBConv2d / OracleCBPoolMax2d), a
 nn.Conv2d at threshold 0, and against the UNMODIFIED reference kernels (oracle/_ref, JIT-compiled
 from their compute_52/61 PTX) run on the same GPU."""
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -406,3 +407,30 @@ def test_reference_cuda_fg_kernels():
     torch.cuda.synchronize()
     assert int(cnt.item()) == nchg
     np.testing.assert_allclose(out.cpu().numpy(), out_ref.cpu().numpy(), rtol=1e-5, atol=1e-4)
+
+
+def test_eval_tools_and_threshold_tuner(tmp_path):
+    """reference harness surface: inferFrameset / inferFramesetBenchmark (evalTools.py:7-49) and the
+    greedy threshold search (pycbinfer/__init__.py:98-144) run end to end on the CUDA backend."""
+    import cbinfer_b200 as cb
+    from cbinfer_b200 import evalTools, models, video
+    base = models.sceneLabelingBaseline().cuda()
+    m = models.sceneLabelingCBinfer(base, experimentIdx=6, threshold=0.0)
+    frames = video.sequence(1, 48, 64, 5, 0.1)
+    out = evalTools.inferFrameset(m, frames)
+    with torch.no_grad():
+        ref = base(frames[-1].cuda())
+    assert _rel(to_val(out), to_val(ref)) <= 2e-4
+    wall, dev = evalTools.inferFramesetBenchmark(m, frames)
+    assert wall > 0 and dev > 0 and len(evalTools.changeStatistics(m)) == 5
+    assert os.path.exists(evalTools.writeTable("t", [[1, 2]], header=["a", "b"], directory=str(tmp_path)))
+
+    class Reader(object):
+        def getDataFrames(self, seqName, numFrames):
+            return frames[:numFrames + 1], None
+
+    mods = evalTools.getCBconvLayers(m)
+    cb.tuneThresholdParameters(Reader(), ["s0"], 3, lambda f: base(f.cuda()), lambda f: f, base, m,
+                               lambda o, t: float((o - t).abs().mean()), mods[:2], 1e-3,
+                               initThreshold=1e-3, thresholdIncrFactor=2.0)
+    assert all(c.threshold >= 1e-3 for c in mods[:2])
