@@ -509,8 +509,10 @@ def kernel_roofline(args, model, frames, dev, tdt):
                            "tensor_work_frac": (3.0 * top["frac"] if top["bound"] == "tensor" and args.dtype == "f32"
                                                 and args.gemm in ("auto", "bf16x3", "tc3x") else top["frac"]),
                            "share_of_step": top["us"] / total if total else None,
-                           "note": "fp32 data runs 3xTF32 (3 MMAs per product): peak = bf16 burst / 2, achieved counts "
-                                   "algorithmic FLOPs 2*n*K*Cout once" if top["bound"] == "tensor" and args.dtype == "f32" else ""}
+                           "note": ("fp32 data: %s split, 3 tensor-core MMAs per product; peak = %s; `achieved` counts the "
+                                    "algorithmic FLOPs 2*n*K*Cout once, tensor_work_frac counts the 3x MMA work"
+                                    % (("3xTF32", "bf16 burst / 2") if args.gemm == "tc3x" else ("3xBF16", "bf16 burst")))
+                           if top["bound"] == "tensor" and args.dtype == "f32" and args.gemm in ("auto", "bf16x3", "tc3x") else ""}
     return out
 
 

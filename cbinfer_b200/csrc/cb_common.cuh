@@ -40,19 +40,36 @@ __device__ __forceinline__ void pdl_prologue() {
 }
 
 template <typename... KArgs, typename... Args>
-inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
-                       Args&&... args) {
+inline void launch_cluster(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                           cudaStream_t s, unsigned cluster_x, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  unsigned na = 0;
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (cluster_x > 1) {                         // thread-block cluster (cluster_x, 1, 1)
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = cluster_x;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = na;
   cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                       Args&&... args) {
+  launch_cluster(kern, grid, block, smem, s, 1u, static_cast<Args&&>(args)...);
 }
 
 // ---- dtype traits --------------------------------------------------------------------------

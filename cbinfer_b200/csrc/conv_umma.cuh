@@ -70,6 +70,58 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
   }
 }
+// ---- thread-block cluster helpers (split-K reduction over distributed shared memory) ----------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t local_smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok = 0;
+  long long t0 = 0;
+  for (uint32_t spins = 0;; ++spins) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if ((spins & 1023u) == 1023u) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ll) __trap();
+    }
+  }
+}
+__device__ __forceinline__ float4 ld_cluster_f4(uint32_t cluster_addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(cluster_addr));
+  return v;
+}
+
 // 16-byte async copy global -> shared (LDGSTS); src_bytes = 0 zero-fills (out-of-image taps)
 __device__ __forceinline__ void cp_async8(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes)
@@ -165,17 +217,19 @@ struct UmmaCfg {
   static constexpr int STAGE_BYTES = NSPLIT * (A_BYTES + B_BYTES);
   // two CTAs per SM (<= ~100 KB each) unless a stage is so large that only one CTA fits
   static constexpr int CTAS_PER_SM = (DEEP || STAGE_BYTES > 48 * 1024) ? 1 : 2;
-  static constexpr int BUDGET = CTAS_PER_SM == 1 ? 200 * 1024 : 98 * 1024;
+  static constexpr int RED_BYTES = DEEP ? UM_BM * BN * 4 : 0;   // split-K partial tile (fp32)
+  static constexpr int BUDGET = DEEP ? 200 * 1024 - RED_BYTES : (CTAS_PER_SM == 1 ? 200 * 1024 : 98 * 1024);
   static constexpr int STAGES = (BUDGET / STAGE_BYTES) < 2 ? 2
                                 : (BUDGET / STAGE_BYTES) > 8 ? 8 : (BUDGET / STAGE_BYTES);
   static constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
   static constexpr int TABLE_MAX = 1024;        // chunk-offset table entries (8 KB)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + UM_CTRL_BYTES +
-                                    TABLE_MAX * 8;
+                                    TABLE_MAX * 8 + RED_BYTES;
 };
 
 struct UmmaCtrl {                              // lives after the stage buffers
   uint64_t full[8], empty[8], tmem_full, tmem_empty;
+  uint64_t red_full, red_free;                 // split-K: partials delivered / partial buffer free
   uint32_t tmem_base, pad;
   int pix[UM_BM];
   int yx[UM_BM];
@@ -223,7 +277,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
   // sel window: two tilings of the same layer may be launched back to back; the change count
   // (known only on the device) decides which one does the work
   if (mtiles < sel_lo || mtiles >= sel_hi) return;
-  if ((int)blockIdx.x >= total_tiles) return;             // uniform: before any barrier / alloc
+  // split-K: groups of KS consecutive CTAs of a cluster work on the same tile, each on 1/KS of
+  // the K range; the group's first CTA sums the partial accumulators through distributed shared
+  // memory.  KS is chosen HERE from the change count: the widest split (a power of two dividing
+  // the launched cluster size) for which all tiles still run in one wave, else no split.
+  const uint32_t KSmax = DEEP ? cluster_nctarank() : 1u, crank = DEEP ? cluster_ctarank() : 0u;
+  uint32_t KS = KSmax;
+  while (KS > 1 && (long long)total_tiles * KS > (long long)gridDim.x) KS >>= 1;
+  const uint32_t krank = crank & (KS - 1), leader = crank - krank;
+  const int tile0 = (int)(blockIdx.x / KS), tile_step = (int)(gridDim.x / KS);
+  if (tile0 >= total_tiles) {                             // group-uniform: before any barrier / alloc
+    if (KSmax > 1) { cluster_sync_all(); cluster_sync_all(); }   // busy peers still sync twice
+    return;
+  }
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
@@ -231,6 +297,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
   UmmaCtrl* ctrl = reinterpret_cast<UmmaCtrl*>(smem + C::STAGES * C::STAGE_BYTES);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int num_kb = (Kp + C::BK - 1) / C::BK;
+  const int kb0 = (int)((long long)num_kb * krank / KS), kb1 = (int)((long long)num_kb * (krank + 1) / KS);
   constexpr int TMA_WARP = UM_PRODUCERS / 32, MMA_WARP = TMA_WARP + 1;
   const int ph = (kH - 1) / 2, pw = (kW - 1) / 2;
   // Per 16-byte K chunk q (k = q*VEC): element offset of its filter tap relative to the pixel and
@@ -263,6 +330,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
     }
     mbar_init(&ctrl->tmem_full, 1);
     mbar_init(&ctrl->tmem_empty, UM_PRODUCERS);
+    mbar_init(&ctrl->red_full, (KS > 1 ? KS - 1 : 1) * UM_PRODUCERS);
+    mbar_init(&ctrl->red_free, UM_PRODUCERS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == MMA_WARP) {                                  // TMEM allocation (one warp)
@@ -277,12 +346,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (DEEP && KSmax > 1) cluster_sync_all();               // peers' barriers exist before remote arrives
   const uint32_t tmem_base = ctrl->tmem_base;
   const int P = H * W;
 
   if (warp < TMA_WARP) {
     // =============================== gather producers + epilogue ============================
-    uint32_t stage = 0, phase = 0, acc_phase = 0;
+    uint32_t stage = 0, phase = 0, acc_phase = 0, red_phase = 0;
     const int c = tid & 7;                                  // my 16-byte chunk column
     const int r0 = tid >> 3;                                // my rows: r0 + RSTEP*it
     uint32_t soff[RPT];                                     // swizzled smem offsets of my chunks
@@ -291,7 +361,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
       const int r = r0 + RSTEP * it;
       soff[it] = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
     }
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < total_tiles; tile += tile_step) {
       const int mt = tile / ntiles, nt = tile - mt * ntiles;
       if (tid < UM_BM) {                                    // row table of this tile
         const int j = mt * UM_BM + tid;
@@ -318,10 +388,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
       }
       const long long lo_delta = SPLIT3 ? (state_lo - state) : 0;
       KCursor cur;
-      cur.init(c * C::VEC, Cp, kW);
+      cur.init(kb0 * C::BK + c * C::VEC, Cp, kW);
       // Gather = async 16-byte copies straight into the swizzled UMMA tile (zero-filled outside
       // the image / beyond K); no register staging, so up to STAGES stages of loads are in flight.
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&ctrl->empty[stage], phase ^ 1u);
         const uint32_t a_hi = smem_u32(smem + stage * C::STAGE_BYTES);
         if (half_taps) {                                     // (always table-driven: K is tiny)
@@ -386,11 +456,51 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
       constexpr int NGROUP = UM_PRODUCERS / 128;             // warps sharing a lane quarter
       constexpr int COLS = (BN / NGROUP) < 16 ? 16 : (BN / NGROUP);
       const int cbeg = (warp >> 2) * COLS;
+      // split-K partial buffer: float4 slot ((it*4 + i4) * 256 + tid) -> conflict-free, and the
+      // same thread owns the same (row, columns) on every rank
+      float4* red = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(ktab) + C::TABLE_MAX * 8);
+      if (DEEP && KS > 1 && krank != 0) {
+        mbar_wait_cluster(&ctrl->red_free, red_phase ^ 1u);  // rank 0 has consumed my last partial
+        int it = 0;
 #pragma unroll 1
-      for (int c0 = cbeg; c0 < cbeg + COLS && c0 < BN; c0 += 16) {
+        for (int c0 = cbeg; c0 < cbeg + COLS && c0 < BN; c0 += 16, ++it) {
+          uint32_t acc[16];
+          tmem_ld16(trow + (uint32_t)c0, acc);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i4 = 0; i4 < 4; ++i4)
+            red[(it * 4 + i4) * UM_PRODUCERS + tid] =
+                make_float4(__uint_as_float(acc[4 * i4]), __uint_as_float(acc[4 * i4 + 1]),
+                            __uint_as_float(acc[4 * i4 + 2]), __uint_as_float(acc[4 * i4 + 3]));
+        }
+        tc_fence_before();
+        mbar_arrive(&ctrl->tmem_empty);
+        mbar_arrive_remote(map_to_rank(smem_u32(&ctrl->red_full), leader));   // release: partial visible
+        red_phase ^= 1u;
+        acc_phase ^= 1u;
+        asm volatile("bar.sync 1, %0;" ::"n"(UM_PRODUCERS) : "memory");
+        continue;
+      }
+      if (DEEP && KS > 1) mbar_wait_cluster(&ctrl->red_full, red_phase);   // all partials delivered
+      int it = 0;
+#pragma unroll 1
+      for (int c0 = cbeg; c0 < cbeg + COLS && c0 < BN; c0 += 16, ++it) {
         uint32_t acc[16];
         tmem_ld16(trow + (uint32_t)c0, acc);
         tmem_ld_wait();
+        if (DEEP && KS > 1) {
+          for (uint32_t r = 1; r < KS; ++r) {
+#pragma unroll
+            for (int i4 = 0; i4 < 4; ++i4) {
+              const float4 p = ld_cluster_f4(
+                  map_to_rank(smem_u32(&red[(it * 4 + i4) * UM_PRODUCERS + tid]), leader + r));
+              acc[4 * i4] = __float_as_uint(__uint_as_float(acc[4 * i4]) + p.x);
+              acc[4 * i4 + 1] = __float_as_uint(__uint_as_float(acc[4 * i4 + 1]) + p.y);
+              acc[4 * i4 + 2] = __float_as_uint(__uint_as_float(acc[4 * i4 + 2]) + p.z);
+              acc[4 * i4 + 3] = __float_as_uint(__uint_as_float(acc[4 * i4 + 3]) + p.w);
+            }
+          }
+        }
         const int co0 = nt * BN + c0;
         if (pix >= 0 && co0 < Cout) {
           float f[16];
@@ -425,6 +535,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
       }
       tc_fence_before();
       mbar_arrive(&ctrl->tmem_empty);
+      if (DEEP && KS > 1) {                                  // the peers may reuse their partial buffers
+        for (uint32_t r = 1; r < KS; ++r) mbar_arrive_remote(map_to_rank(smem_u32(&ctrl->red_free), leader + r));
+        red_phase ^= 1u;
+      }
       acc_phase ^= 1u;
       asm volatile("bar.sync 1, %0;" ::"n"(UM_PRODUCERS) : "memory");   // row table reused next tile
     }
@@ -432,9 +546,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
     // =============================== TMA producer: weight tiles ==============================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
         const int nt = tile % ntiles;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&ctrl->empty[stage], phase ^ 1u);
           uint8_t* b_hi = smem + stage * C::STAGE_BYTES + C::NSPLIT * C::A_BYTES;
           mbar_arrive_expect_tx(&ctrl->full[stage], (uint32_t)(C::NSPLIT * C::B_BYTES));
@@ -453,10 +567,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
       const uint32_t idesc =
           umma_idesc(sizeof(T) == 4 ? 2 : (std::is_same<T, __half>::value ? 0 : 1), BN);
       uint32_t stage = 0, phase = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
         mbar_wait(&ctrl->tmem_empty, acc_phase ^ 1u);        // epilogue drained the accumulator
         tc_fence_after();
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&ctrl->full[stage], phase);
           fence_proxy_async_smem();                          // cp.async writes -> async proxy (UMMA)
           tc_fence_after();
@@ -467,7 +581,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
 #pragma unroll
           for (int ks = 0; ks < C::BK / C::UK; ++ks) {
             const uint32_t adv = (uint32_t)(ks * 32);        // 32 bytes of K per instruction
-            const uint32_t first = (kb | ks) ? 1u : 0u;
+            const uint32_t first = (kb != kb0 || ks) ? 1u : 0u;
             if (SPLIT3) {
               umma<KIND>(tmem_base, umma_desc(a_lo + adv), umma_desc(b_hi + adv), idesc, first);
               umma<KIND>(tmem_base, umma_desc(a_hi + adv), umma_desc(b_lo + adv), idesc, 1u);
@@ -487,6 +601,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
 
   tc_fence_before();
   __syncthreads();
+  if (DEEP && KSmax > 1) cluster_sync_all();               // nobody leaves while peers may touch its smem
   if (warp == MMA_WARP) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
@@ -612,7 +727,7 @@ int launch_conv_umma(cudaStream_t s, int dtype, const void* state, const void* s
                      const int32_t* idx,
                      const int32_t* count, const void* packed, const float* bias, void* out,
                      int Op, int B, int H, int W, int Cout, int CoutPad, int kH, int kW, int relu,
-                     int sel_lo, int sel_hi) {
+                     int sel_lo, int sel_hi, int ksplit) {
   using C = UmmaCfg<T, SPLIT3, BN, DEEP>;
   const int Kp = kH * kW * Cp;
   const int KpPad = umma_kp_pad_es((int)sizeof(T), Cp, kH, kW);
@@ -648,7 +763,8 @@ int launch_conv_umma(cudaStream_t s, int dtype, const void* state, const void* s
   const int table_entries = num_kb * 8 * upc <= C::TABLE_MAX ? num_kb * 8 * upc : 0;
   // (the 1024-byte alignment slack is only needed if the dynamic smem window is not already
   //  1024-aligned; it is when the kernel has no static shared memory, which the kernel checks)
-  const int smem_bytes = C::STAGES * C::STAGE_BYTES + UM_CTRL_BYTES + table_entries * 8;
+  const int smem_bytes = DEEP ? C::STAGES * C::STAGE_BYTES + UM_CTRL_BYTES + C::TABLE_MAX * 8 + C::RED_BYTES
+                              : C::STAGES * C::STAGE_BYTES + UM_CTRL_BYTES + table_entries * 8;
   int occ = C::CTAS_PER_SM;
   if (!DEEP) {
     int q = 0;
@@ -657,10 +773,43 @@ int launch_conv_umma(cudaStream_t s, int dtype, const void* state, const void* s
       occ = q > 4 ? 4 : q;
   }
   const long long max_tiles = (((long long)B * H * W + UM_BM - 1) / UM_BM) * (CoutPad / BN);
-  long long grid = (long long)sm_count() * occ;
+  // split-K (deep variant only): clusters of `ks` CTAs share a tile; keep ks <= stages / 4
+  int ks = DEEP ? ksplit : 1;
+  while (ks > 1 && num_kb / ks < 4) ks >>= 1;
+  long long grid = (long long)sm_count() * occ / ks;       // clusters
+  if (ks > 1) {
+    // co-resident clusters of this size (GPC boundaries strand a few SMs); fall back to smaller
+    // clusters when the big ones would leave more than ~15 % of the SMs unused
+    static thread_local int act[4] = {-1, -1, -1, -1}, act_dev = -1;
+    if (act_dev != dev) { act[0] = act[1] = act[2] = act[3] = -1; act_dev = dev; }
+    for (; ks > 1; ks >>= 1) {
+      const int slot = ks == 8 ? 3 : ks == 4 ? 2 : 1;
+      if (act[slot] < 0) {
+        cudaLaunchConfig_t qc = {};
+        qc.gridDim = dim3((unsigned)(sm_count() / ks * ks));
+        qc.blockDim = dim3(UM_THREADS);
+        qc.dynamicSmemBytes = (size_t)smem_bytes;
+        cudaLaunchAttribute qa[1];
+        qa[0].id = cudaLaunchAttributeClusterDimension;
+        qa[0].val.clusterDim.x = (unsigned)ks;
+        qa[0].val.clusterDim.y = qa[0].val.clusterDim.z = 1;
+        qc.attrs = qa;
+        qc.numAttrs = 1;
+        int nclusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&nclusters, kern, &qc) != cudaSuccess) {
+          cudaGetLastError();
+          nclusters = 0;
+        }
+        act[slot] = nclusters;
+      }
+      if ((long long)act[slot] * ks * 100 >= (long long)sm_count() * 85) break;
+    }
+    grid = ks > 1 ? act[ks == 8 ? 3 : ks == 4 ? 2 : 1] : (long long)sm_count() * occ;
+  }
   if (grid > max_tiles) grid = max_tiles;
   if (grid < 1) grid = 1;
-  cb::launch_pdl(kern, (unsigned)grid, UM_THREADS, (size_t)smem_bytes, s, map, (const T*)state, (const T*)state_lo, Cp,
+  grid *= ks;
+  cb::launch_cluster(kern, (unsigned)grid, UM_THREADS, (size_t)smem_bytes, s, (unsigned)ks, map, (const T*)state, (const T*)state_lo, Cp,
                                                         idx, count, bias,
                                                         (TO*)out, Op, H, W, Cout, CoutPad, kH, kW,
                                                         Kp, relu, sel_lo, sel_hi);
@@ -673,12 +822,12 @@ int dispatch_bn(int bn, cudaStream_t s, int dtype, const void* state, const void
                 const int32_t* idx,
                 const int32_t* count, const void* packed, const float* bias, void* out, int Op,
                 int B, int H, int W, int Cout, int CoutPad, int kH, int kW, int relu, int sel_lo,
-                int sel_hi) {
+                int sel_hi, int ksplit) {
 #define CB_BN(N)                                                                              \
   case N:                                                                                     \
     return launch_conv_umma<T, TO, SPLIT3, N, DEEP>(s, dtype, state, state_lo, Cp, idx, count, packed, bias, out, \
                                           Op, B, H, W, Cout, CoutPad, kH, kW, relu, sel_lo,   \
-                                          sel_hi);
+                                          sel_hi, ksplit);
   if (DEEP) {                                  // the deep variant only exists for N tiles <= 64
     switch (bn) {
       CB_BN(16) CB_BN(32) CB_BN(64)
@@ -714,27 +863,27 @@ inline int umma_conv_update(cudaStream_t s, int dtype, int gemm, const void* sta
   // layers) but give few CTAs when few pixels changed; the count is only known on the device, so
   // when a small change set is plausible (expected tiles at 10 % change < half the SMs) a second,
   // finer tiling is launched as well and each kernel checks the count to see whether it is its turn.
-  auto run_t = [&](auto deep_tag, int tile_n, int lo, int hi) -> int {
+  auto run_t = [&](auto deep_tag, int tile_n, int lo, int hi, int ksplit = 1) -> int {
     constexpr bool DP = decltype(deep_tag)::value;
     if (bf16x3)
       return dispatch_bn<__nv_bfloat16, float, true, DP>(tile_n, s, dtype, state, state_lo, Cp, idx,
                                                          count, packed, bias, out, Op, B, H, W,
-                                                         Cout, CoutPad, kH, kW, relu, lo, hi);
+                                                         Cout, CoutPad, kH, kW, relu, lo, hi, ksplit);
     switch (dtype) {
       case CB_F32:
         return split3 ? dispatch_bn<float, float, true, DP>(tile_n, s, dtype, state, state_lo, Cp, idx, count,
                                                  packed, bias, out, Op, B, H, W, Cout, CoutPad, kH,
-                                                 kW, relu, lo, hi)
+                                                 kW, relu, lo, hi, ksplit)
                       : dispatch_bn<float, float, false, DP>(tile_n, s, dtype, state, state_lo, Cp, idx, count,
                                                   packed, bias, out, Op, B, H, W, Cout, CoutPad,
-                                                  kH, kW, relu, lo, hi);
+                                                  kH, kW, relu, lo, hi, ksplit);
       case CB_F16:
         return dispatch_bn<__half, __half, false, DP>(tile_n, s, dtype, state, state_lo, Cp, idx, count, packed,
-                                          bias, out, Op, B, H, W, Cout, CoutPad, kH, kW, relu, lo, hi);
+                                          bias, out, Op, B, H, W, Cout, CoutPad, kH, kW, relu, lo, hi, ksplit);
       case CB_BF16:
         return dispatch_bn<__nv_bfloat16, __nv_bfloat16, false, DP>(tile_n, s, dtype, state, state_lo, Cp, idx, count,
                                                  packed, bias, out, Op, B, H, W, Cout, CoutPad, kH,
-                                                 kW, relu, lo, hi);
+                                                 kW, relu, lo, hi, ksplit);
       default: return fail(2, "conv_update: bad dtype %d", dtype);
     }
   };
@@ -749,7 +898,18 @@ inline int umma_conv_update(cudaStream_t s, int dtype, int gemm, const void* sta
     // switch point: the coarse tiling takes over once it alone fills ~2/3 of the SMs
     int m_switch = (2 * sms / 3) / (CoutPad / bn);
     if (m_switch < 1) m_switch = 1;
-    const int rc = run_t(std::true_type{}, bn_small, 0, m_switch);
+    // split-K over thread-block clusters: few tiles x long K (small maps, big filters) would
+    // otherwise leave most SMs idle and each busy SM limited by its own L2 ingest rate
+    const int num_kb = umma_kp_pad_es(umma_operand_es(dtype, gemm), Cp, kH, kW) /
+                       (UM_ROW_BYTES / umma_operand_es(dtype, gemm));
+    static const int ks_max = [] {
+      const char* e = getenv("CBINFER_KSPLIT");              // tuning knob: cap (1 disables)
+      const int v = e ? atoi(e) : 8;
+      return v < 1 ? 1 : v > 8 ? 8 : v;
+    }();
+    int ksplit = 1;
+    while (ksplit < ks_max && num_kb / (ksplit * 2) >= 6) ksplit *= 2;   // the kernel narrows it
+    const int rc = run_t(std::true_type{}, bn_small, 0, m_switch, ksplit);
     if (rc) return rc;
     return run_t(std::false_type{}, bn, m_switch, 0x7fffffff);
   }

@@ -99,8 +99,8 @@ detect_vec_kernel(const T* __restrict__ x, long long x_sb, long long x_sy, int x
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int wpw = 1 << wlog;
   const int part = wid & (wpw - 1), slot = wid >> wlog;
-  const long long word = (long long)blockIdx.x * (kDetWarps >> wlog) + slot;
-  const bool active = word < (long long)B * H * Wd;
+  const int word = blockIdx.x * (kDetWarps >> wlog) + slot;      // < 2^31 words (host-checked)
+  const bool active = word < B * H * Wd;
   if (wlog > 0) {
     if (threadIdx.x < kDetWarps) s_word[threadIdx.x] = 0u;
     __syncthreads();
@@ -117,10 +117,10 @@ detect_vec_kernel(const T* __restrict__ x, long long x_sb, long long x_sy, int x
   long long pixbase = 0;
   unsigned wordbits = 0;
   if (active) {
-    const int j = (int)(word % Wd);
-    const long long r = word / Wd;
-    const int y = (int)(r % H);
-    const int b = (int)(r / H);
+    const int j = word % Wd;
+    const int r = word / Wd;
+    const int y = r % H;
+    const int b = r / H;
     const int x0 = j * 32;
     const int npx = min(32, W - x0);
     xb = x + b * x_sb + y * x_sy + (long long)x0 * xp;
@@ -309,12 +309,12 @@ int launch_detect(cudaStream_t stream, const void* x, long long x_sb, long long 
                          ((uintptr_t)state % 16) == 0;
   const int cpv = (C + VEC - 1) / VEC;
   const unsigned magic = cpv > 1 ? (unsigned)((0x100000000ull + cpv - 1) / cpv) : 0u;
-  // warps per word: keep >= 2 load batches (of U*32 chunks) per warp, at most one block per word
+  // warps per word: keep >= 4 load batches (of U*32 chunks) per warp, at most one block per word
   int wlog = 0;
-  while (wlog < 3 && (32 * cpv) / (1 << (wlog + 1)) >= 2 * 4 * 32) ++wlog;
+  while (wlog < 3 && (32 * cpv) / (1 << (wlog + 1)) >= 4 * 4 * 32) ++wlog;
   const long long vec_blocks = (words + (kDetWarps >> wlog) - 1) / (kDetWarps >> wlog);
   const long long blocks = vec_ok ? vec_blocks : (words + 7) / 8;
-  CB_CHECK_ARG(blocks < (1ll << 31), "change_detect: image too large");
+  CB_CHECK_ARG(blocks < (1ll << 31) && words < (1ll << 31), "change_detect: image too large");
   dim3 grid((unsigned)blocks), block(256);
 #define CB_DET(U_)                                                                             \
   if (vec_ok) {                                                                                \

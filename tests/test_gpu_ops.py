@@ -234,6 +234,9 @@ CONV_CASES = [  # B, Cin, Cout, H, W, kH, kW, frac, relu
     (1, 128, 19, 6, 7, 3, 3, 1.00, True),
     (1, 5, 6, 9, 14, 5, 3, 0.60, True),
     (1, 40, 130, 6, 5, 3, 3, 1.00, False),
+    (1, 64, 64, 46, 46, 7, 7, 0.50, True),      # split-K clusters, one tile per cluster
+    (1, 128, 128, 46, 46, 7, 7, 1.00, True),    # split-K clusters, several tiles per cluster
+    (1, 128, 96, 30, 40, 3, 3, 0.70, False),    # 2-way split-K
 ]
 
 
