@@ -22,7 +22,7 @@ _DTYPES = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
 # every symbol include/cbinfer_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "cb_version", "cb_last_error", "cb_device_info", "cb_bitmap_row_words", "cb_bitmap_words",
-    "cb_compact_ws_bytes", "cb_channel_pitch", "cb_plane_pitch16", "cb_packed_weight_bytes", "cb_change_detect",
+    "cb_compact_ws_bytes", "cb_channel_pitch", "cb_plane_pitch16", "cb_packed_weight_bytes", "cb_change_detect", "cb_change_detect_u8",
     "cb_dilate_compact", "cb_map_to_bits", "cb_change_detect_sparse", "cb_pool_compact", "cb_maxpool2x2_detect",
     "cb_detect_compact_ws_bytes", "cb_detect_compact_sparse", "cb_pack_weights", "cb_conv_update", "cb_maxpool2x2",
     "cb_gen_xmatrix", "cb_matrix_mult", "cb_update_output", "cb_fg_update",
@@ -54,6 +54,8 @@ def _load():
         "cb_packed_weight_bytes": (sz, [i32] * 6),
         "cb_change_detect": (i32, [vp, i32, vp, i64, i64, i64, i64, vp, i64, i64, i64, i64, i32, vp, vp,
                                    vp, i32, i32, i32, i32, f32, i32]),
+        "cb_change_detect_u8": (i32, [vp, vp, i64, i64, i64, i64, vp, i64, i64, i64, i64, i32, vp, vp, vp,
+                                      i32, i32, i32, i32, f32, f32, f32, i32]),
         "cb_dilate_compact": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32]),
         "cb_map_to_bits": (i32, [vp, vp, vp, i32, i32, i32]),
         "cb_change_detect_sparse": (i32, [vp, i32, vp, i64, i64, i64, i64, vp, i64, i64, i64, i64, i32,

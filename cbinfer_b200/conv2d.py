@@ -172,6 +172,8 @@ class CBConv2d(nn.Module):
         # detection instead of as the final change set (exact, see cb_change_detect_sparse)
         self.candidateDetect = False
         self.fuse1x1 = False      # extension: detect+compact in one launch for 1x1 layers
+        # extension: (divisor, bias) applied to uint8 input frames inside the detection kernel
+        self.inputNorm = None
 
     # ---- state ---------------------------------------------------------------------------
     def clearMemory(self):
@@ -280,6 +282,18 @@ class CBConv2d(nn.Module):
         _lib.require_cuda(input)
         B, _, H, W = input.shape
         dev, dt = input.device, input.dtype
+        # uint8 frames (decoder output) are normalised inside the detection kernel:
+        # value = u8 / divisor + bias with inputNorm = (divisor, bias); the layer computes in fp32
+        u8norm = None
+        if dt == torch.uint8:
+            u8norm = getattr(self, 'inputNorm', None)
+            if u8norm is None:
+                raise _lib.CBinferError("uint8 input needs CBConv2d.inputNorm = (divisor, bias), e.g. "
+                                        "(255.0, 0.0) for the scene reader's frame/255")
+            if changeIndexes is not None or self.gatherComputationStats or self.in_channels > 4:
+                input = input.float().div(u8norm[0]).add(u8norm[1])     # rare paths: plain fp32
+                u8norm = None
+            dt = torch.float32
 
         if self.prevInput.size() != input.size() or self.prevInput.dtype != dt or self._inBuf is None:
             self.prevInput, self._inBuf = cg.pixel_major(input.shape, dt, dev, _INF)   # :192-194
@@ -340,6 +354,9 @@ class CBConv2d(nn.Module):
                 cg.detect_sparse(input, self.prevInput, s["raw_bits"], self.threshold, mode,
                                  candidates, aux=aux_arg,
                                  bits_are_clear=s.get("raw_clear", False))
+            elif u8norm is not None:
+                cg.detect_u8(input, self.prevInput, s["raw_bits"], self.threshold, mode,
+                             u8norm[0], u8norm[1], aux=aux_arg)
             else:
                 cg.detect(input, self.prevInput, s["raw_bits"], self.threshold, mode, aux=aux_arg)
             self._fresh = False
@@ -430,6 +447,6 @@ class CBConv2d(nn.Module):
         for name, val in (('saveChangeMap', False), ('propChangeIndexes', False),
                           ('gatherComputationStats', False), ('finegrained', False),
                           ('copyInput', True), ('feedbackLoop', False), ('gemmMode', 'auto'),
-                          ('candidateDetect', False)):
+                          ('candidateDetect', False), ('fuse1x1', False), ('inputNorm', None)):
             if not(hasattr(self, name)):
                 setattr(self, name, val)

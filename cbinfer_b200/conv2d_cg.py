@@ -111,6 +111,20 @@ def detect(x, state, raw_bits, threshold, update_mode, aux=None):
                              raw_bits.data_ptr(), B, Cc, H, W, float(threshold), int(update_mode)))
 
 
+def detect_u8(x, state, raw_bits, threshold, update_mode, divisor, bias, aux=None):
+    """cb_change_detect_u8: detection on a uint8 frame normalised on the fly as u8/divisor + bias
+    (the readers' /255 resp. /256 - 0.5); `state` is the fp32 pixel-major state.  Bit-identical to
+    :func:`detect` on ``x.float() / divisor + bias``."""
+    require_cuda(x, state, raw_bits)
+    B, Cc, H, W = x.shape
+    assert x.dtype == torch.uint8 and state.dtype == torch.float32 and state.shape == x.shape
+    mode, hi, lo = _aux_args(aux, state)
+    check(C.cb_change_detect_u8(stream_ptr(x.device), x.data_ptr(), *_strides4(x),
+                                state.data_ptr(), *_strides4(state), mode, hi, lo,
+                                raw_bits.data_ptr(), B, Cc, H, W, float(divisor), float(bias),
+                                float(threshold), int(update_mode)))
+
+
 def detect_sparse(x, state, raw_bits, threshold, update_mode, candidates, aux=None,
                   bits_are_clear=False):
     """cb_change_detect_sparse: the detection test at the candidate pixels only (see the header

@@ -106,6 +106,18 @@ int cb_change_detect(void* stream, int dtype, const void* x, long long x_sb, lon
   return 0;
 }
 
+int cb_change_detect_u8(void* stream, const uint8_t* x, long long x_sb, long long x_sc,
+                        long long x_sy, long long x_sx, float* state, long long s_sb, long long s_sc,
+                        long long s_sy, long long s_sx, int aux_mode, void* aux_hi, void* aux_lo,
+                        uint32_t* raw_bits, int B, int C, int H, int W, float divisor, float bias,
+                        float threshold, int update_mode) {
+  CB_CHECK_ARG(x && state && raw_bits, "change_detect_u8: null pointer");
+  CB_CHECK_ARG(B >= 0 && C > 0 && H >= 0 && W >= 0, "change_detect_u8: bad shape");
+  return launch_detect_u8((cudaStream_t)stream, x, x_sb, x_sc, x_sy, x_sx, state, s_sb, s_sc, s_sy,
+                          s_sx, aux_mode, aux_hi, aux_lo, raw_bits, B, C, H, W, divisor, bias,
+                          threshold, update_mode);
+}
+
 int cb_dilate_compact(void* stream, const uint32_t* raw_bits, uint32_t* dil_bits, int8_t* dil_map,
                       int32_t* idx, int32_t* count, void* ws, int B, int H, int W, int kHHalf,
                       int kWHalf, int clear_raw) {

@@ -257,6 +257,45 @@ detect_generic_kernel(const T* __restrict__ x, long long x_sb, long long x_sc, l
   if (lane == 0) bits[warp] = word;
 }
 
+// uint8 frame ingest (decoder / camera output, any strides: HWC interleaved or planar) against a
+// pixel-major fp32 state whose pixel is one 16-byte chunk (C <= 4).  The normalisation of the
+// reference's readers -- frame/255 (sceneLabeling/videoSequenceReader.py:65), frame/256 - 0.5
+// (openPose/PoseDetector.py:72) -- is applied on the fly with IEEE division and addition, so the
+// result is bit-identical to detecting on the host-normalised fp32 frame, at a quarter of the
+// host->device bytes.
+template <int UPDATE>
+__global__ void __launch_bounds__(256)
+detect_u8_kernel(const uint8_t* __restrict__ x, long long x_sb, long long x_sc, long long x_sy,
+                 long long x_sx, float* __restrict__ st, long long s_sb, long long s_sy,
+                 AuxPlanes aux, uint32_t* __restrict__ bits, int B, int H, int W, int C, int Wd,
+                 float divisor, float bias, float thr) {
+  pdl_prologue();
+  const int lane = threadIdx.x & 31;
+  const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (warp >= (long long)B * H * Wd) return;
+  const int j = (int)(warp % Wd);
+  const long long r = warp / Wd;
+  const int y = (int)(r % H);
+  const int b = (int)(r / H);
+  const int xx = j * 32 + lane;
+  bool f = false;
+  if (xx < W) {
+    const uint8_t* xp = x + b * x_sb + y * x_sy + xx * x_sx;
+    float* sp = st + b * s_sb + y * s_sy + (long long)xx * 4;
+    const uint4 sv = ld16(sp);
+    uint4 nv = sv;                             // pad lanes keep the state's (zero) value
+    float* ne = reinterpret_cast<float*>(&nv);
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (c < C) ne[c] = __fadd_rn(__fdiv_rn((float)xp[c * x_sc], divisor), bias);
+    f = Chunk<float>::changed(sv, nv, thr);
+    if (UPDATE == CB_UPDATE_ALL || (UPDATE == CB_UPDATE_CHANGED && f))
+      store_state<float>(sp, nv, aux, ((long long)b * H + y) * W + xx, 0);
+  }
+  const unsigned word = __ballot_sync(0xffffffffu, f);
+  if (lane == 0) bits[warp] = word;
+}
+
 template <typename T> __host__ __device__ inline T thr_cast(float t);
 template <> __host__ __device__ inline float thr_cast<float>(float t) { return t; }
 template <> __host__ __device__ inline __half thr_cast<__half>(float t) { return __float2half_rn(t); }
@@ -343,6 +382,38 @@ int launch_detect(cudaStream_t stream, const void* x, long long x_sb, long long 
   }
 #undef CB_DET
   CB_CHECK_LAUNCH("change_detect");
+  return 0;
+}
+
+
+inline int launch_detect_u8(cudaStream_t stream, const void* x, long long x_sb, long long x_sc,
+                            long long x_sy, long long x_sx, void* state, long long s_sb,
+                            long long s_sc, long long s_sy, long long s_sx, int aux_mode,
+                            void* aux_hi, void* aux_lo, uint32_t* bits, int B, int C, int H, int W,
+                            float divisor, float bias, float threshold, int update) {
+  const int Wd = (W + 31) / 32;
+  const long long words = (long long)B * H * Wd;
+  if (words == 0) return 0;
+  CB_CHECK_ARG(C <= 4 && s_sc == 1 && s_sx == 4 && (s_sy % 4) == 0 && (s_sb % 4) == 0 &&
+                   ((uintptr_t)state % 16) == 0,
+               "change_detect_u8: needs <= 4 channels and a pixel-major fp32 state of pitch 4");
+  CB_CHECK_ARG(divisor != 0.f, "change_detect_u8: divisor must be non-zero");
+  AuxPlanes aux;
+  if (int rc = make_aux<float>(aux, aux_mode, aux_hi, aux_lo, state, C)) return rc;
+  const long long blocks = (words + 7) / 8;
+  CB_CHECK_ARG(blocks < (1ll << 31), "change_detect_u8: image too large");
+#define CB_DET8(U_)                                                                              \
+  cb::launch_pdl(detect_u8_kernel<U_>, dim3((unsigned)blocks), dim3(256), 0, stream,            \
+                 (const uint8_t*)x, x_sb, x_sc, x_sy, x_sx, (float*)state, s_sb, s_sy, aux, bits, \
+                 B, H, W, C, Wd, divisor, bias, threshold);
+  switch (update) {
+    case CB_UPDATE_NONE: CB_DET8(CB_UPDATE_NONE) break;
+    case CB_UPDATE_CHANGED: CB_DET8(CB_UPDATE_CHANGED) break;
+    case CB_UPDATE_ALL: CB_DET8(CB_UPDATE_ALL) break;
+    default: return fail(2, "change_detect_u8: bad update_mode %d", update);
+  }
+#undef CB_DET8
+  CB_CHECK_LAUNCH("change_detect_u8");
   return 0;
 }
 

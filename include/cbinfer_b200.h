@@ -87,6 +87,20 @@ int cb_change_detect(void* stream, int dtype,
                      int aux_mode, void* aux_hi, void* aux_lo, uint32_t* raw_bits, int B, int C,
                      int H, int W, float threshold, int update_mode);
 
+/* ---- uint8 frame ingest --------------------------------------------------------------------
+ * cb_change_detect for a uint8 frame (camera / decoder output; strides in bytes, HWC or planar)
+ * against a pixel-major fp32 state of pitch 4 (C <= 4).  The frame value is
+ *   v = (float)u8 / divisor + bias      (IEEE division and addition, no contraction)
+ * which is the normalisation the reference's readers apply on the host before the first layer:
+ * /255 (sceneLabeling/videoSequenceReader.py:65), /256 - 0.5 (openPose/PoseDetector.py:72).
+ * Bit-identical to cb_change_detect on the host-normalised fp32 frame; a quarter of the bytes
+ * cross PCIe.  No reference counterpart (detection on uint8 frames). */
+int cb_change_detect_u8(void* stream, const uint8_t* x, long long x_sb, long long x_sc,
+                        long long x_sy, long long x_sx, float* state, long long s_sb, long long s_sc,
+                        long long s_sy, long long s_sx, int aux_mode, void* aux_hi, void* aux_lo,
+                        uint32_t* raw_bits, int B, int C, int H, int W, float divisor, float bias,
+                        float threshold, int update_mode);
+
 /* ---- propagation + compaction -------------------------------------------------------------
  * replaces: the scatter-dilate inside changeDetection_kernel (cbconv2d_cg_backend.cu:62-72),
  *           changePropagation (conv2d_cg.py:15-19 -> cbconv2d_cg_backend.cu:101-136) and

@@ -434,3 +434,64 @@ def test_eval_tools_and_threshold_tuner(tmp_path):
                                lambda o, t: float((o - t).abs().mean()), mods[:2], 1e-3,
                                initThreshold=1e-3, thresholdIncrFactor=2.0)
     assert all(c.threshold >= 1e-3 for c in mods[:2])
+
+
+@pytest.mark.parametrize("layout", ["hwc", "planar"])
+@pytest.mark.parametrize("norm", [(255.0, 0.0), (256.0, -0.5)])
+def test_uint8_ingest_bit_identical_to_normalised_fp32(layout, norm):
+    """uint8 frames normalised inside the detection kernel (the readers' /255 resp. /256 - 0.5,
+    sceneLabeling/videoSequenceReader.py:65, openPose/PoseDetector.py:72) give bit-identical change
+    maps, states and outputs to feeding the host-normalised fp32 frame."""
+    import cbinfer_b200 as cb
+    from cbinfer_b200 import models
+    base = models.sceneLabelingBaseline().cuda()
+    g = torch.Generator().manual_seed(3)
+    B, H, W = 2, 40, 70
+    f8 = [torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8)]
+    for t in range(4):
+        nxt = f8[-1].clone()
+        y0, x0 = 5 + 3 * t, 11 + 7 * t
+        nxt[:, y0:y0 + 9, x0:x0 + 13] = torch.randint(0, 256, (B, 9, 13, 3), generator=g, dtype=torch.uint8)
+        nxt[0, 0, 0, 1] = (int(nxt[0, 0, 0, 1]) + 1) % 256      # a one-level change, below threshold
+        f8.append(nxt)
+    ms = [models.sceneLabelingCBinfer(base, experimentIdx=6, threshold=0.02, candidateDetect=True)
+          for _ in range(2)]
+    first = [c for c in ms[1].modules() if type(c) is cb.CBConv2d][0]
+    first.inputNorm = norm
+    for c in ms[0].modules():
+        if type(c) is cb.CBConv2d:
+            c.saveChangeMap = True
+    for c in ms[1].modules():
+        if type(c) is cb.CBConv2d:
+            c.saveChangeMap = True
+    for t, f in enumerate(f8):
+        nchw = f.permute(0, 3, 1, 2)                       # HWC memory seen as NCHW (strided view)
+        if layout == "planar":
+            nchw = nchw.contiguous()
+        ref = ms[0](nchw.float().div(norm[0]).add(norm[1]).cuda())
+        got = ms[1](nchw.cuda() if layout == "planar" else f.cuda().permute(0, 3, 1, 2))
+        assert torch.equal(ref, got), t
+        a = [c for c in ms[0].modules() if type(c) is cb.CBConv2d][0]
+        assert torch.equal(a.prevInput, first.prevInput) and torch.equal(a.changeMap, first.changeMap), t
+    m3 = models.sceneLabelingCBinfer(base, experimentIdx=6, threshold=0.02)
+    with pytest.raises(cb._lib.CBinferError):
+        m3(f8[0].permute(0, 3, 1, 2).cuda())               # no inputNorm: refuse uint8
+
+
+def test_save_load_converted_model_roundtrip(tmp_path):
+    """the reference's deployment flow: clearMemory(model); torch.save(model, path); torch.load
+    (pycbinfer/__init__.py:144, sceneLabeling/modelLoader.py:28-33)."""
+    import cbinfer_b200 as cb
+    from cbinfer_b200 import models, video
+    base = models.sceneLabelingBaseline().cuda()
+    m = models.sceneLabelingCBinfer(base, experimentIdx=6, threshold=0.03, candidateDetect=True)
+    frames = [f.cuda() for f in video.sequence(1, 48, 64, 4, 0.1)]
+    outs = [m(f).clone() for f in frames]
+    cb.clearMemory(m)
+    assert all(t.numel() == 0 for t in cb.getStateTensors(m))
+    path = str(tmp_path / "model.net")
+    torch.save(m, path)
+    m2 = torch.load(path, weights_only=False)
+    assert repr(m2) == repr(m)
+    for f, o in zip(frames, outs):
+        assert torch.equal(m2(f), o)
