@@ -112,10 +112,22 @@ def getStateTensors(net):
     return state
 
 
+def shareWorkspace(net):
+    """Let all CBConv2d layers of one model instance share one stream-K workspace (their launches
+    are ordered).  Models that may run concurrently must not share: call this per instance."""
+    holder = None
+    for m in net.modules():
+        if type(m) == CBConv2d:
+            if holder is None:
+                holder = m._workspace_holder()
+            m._wsHolder = holder
+    return net
+
+
 def convert(m, ignoreList=[], threshold=1e-1):
     m1, changed = convertRecur(m, ignoreList=ignoreList, threshold=threshold)
     mout = mergeReLURecur(m1)
-    return mout
+    return shareWorkspace(mout)
 
 
 def convertPools(m):

@@ -24,7 +24,7 @@ SYMBOLS = [
     "cb_version", "cb_last_error", "cb_device_info", "cb_bitmap_row_words", "cb_bitmap_words",
     "cb_compact_ws_bytes", "cb_channel_pitch", "cb_plane_pitch16", "cb_packed_weight_bytes", "cb_change_detect", "cb_change_detect_u8",
     "cb_dilate_compact", "cb_map_to_bits", "cb_change_detect_sparse", "cb_pool_compact", "cb_maxpool2x2_detect",
-    "cb_detect_compact_ws_bytes", "cb_detect_compact_sparse", "cb_pack_weights", "cb_conv_update", "cb_maxpool2x2",
+    "cb_detect_compact_ws_bytes", "cb_detect_compact_sparse", "cb_pack_weights", "cb_conv_ws_bytes", "cb_conv_update", "cb_maxpool2x2",
     "cb_gen_xmatrix", "cb_matrix_mult", "cb_update_output", "cb_fg_update",
 ]
 
@@ -40,6 +40,7 @@ def _load():
                     "cbinfer_b200: libcbinfer_sm100.so is missing and could not be built (%s). "
                     "There is no CPU or fallback path." % (e,))
             path = _build.LIB
+    path = os.environ.get("CBINFER_LIB", path)       # experiments: an alternative build of the library
     lib = ctypes.CDLL(path)
     vp, i32, i64, f32, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_size_t
     sig = {
@@ -65,8 +66,9 @@ def _load():
                                            vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, i32]),
         "cb_pool_compact": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32]),
         "cb_pack_weights": (i32, [vp, i32, i32, vp, vp, i32, i32, i32, i32]),
+        "cb_conv_ws_bytes": (sz, []),
         "cb_conv_update": (i32, [vp, i32, i32, vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32,
-                                 i32, i32, i32, i32, i32]),
+                                 i32, i32, i32, i32, i32, vp, sz]),
         "cb_maxpool2x2": (i32, [vp, i32, vp, i64, i64, i64, i64, vp, vp, vp, vp, i64, i64, i64,
                                 i64, i32, i32, i32, i32, i32, i32]),
         "cb_maxpool2x2_detect": (i32, [vp, i32, vp, i64, i64, i32, vp, vp, vp, vp, i64, i64, i32,

@@ -174,6 +174,7 @@ class CBConv2d(nn.Module):
         self.fuse1x1 = False      # extension: detect+compact in one launch for 1x1 layers
         # extension: (divisor, bias) applied to uint8 input frames inside the detection kernel
         self.inputNorm = None
+        self._wsHolder = cg.ConvWorkspace()    # shared per model by pycbinfer.convert()
 
     # ---- state ---------------------------------------------------------------------------
     def clearMemory(self):
@@ -188,6 +189,8 @@ class CBConv2d(nn.Module):
         self._fresh = True        # state holds +inf: the next detection must be a full scan
         self._lastThr = None
         self.changeMap = None
+        if getattr(self, '_wsHolder', None) is not None:
+            self._wsHolder.clear()
         if hasattr(self, 'compStats'):
             self.compStats = None
 
@@ -379,12 +382,21 @@ class CBConv2d(nn.Module):
         cg.conv_update(self._inBuf, changeIndexes, packed, bias32, self._outBuf, self.in_channels,
                        self.out_channels, self.kernel_size, self.withReLU, gemm,
                        lo_buf=aux[2] if aux is not None and aux[0] == 'tf32' else None,
-                       planes16=aux[1:] if aux is not None and aux[0] == 'bf16' else None)  # :242-251
+                       planes16=aux[1:] if aux is not None and aux[0] == 'bf16' else None,
+                       ws=self._workspace(dev))                                        # :242-251
 
         if self.propChangeIndexes:
             return 'changeIndexes', self.prevOutput, changeIndexes
         else:
             return self.prevOutput
+
+    def _workspace_holder(self):
+        if getattr(self, '_wsHolder', None) is None:
+            self._wsHolder = cg.ConvWorkspace()
+        return self._wsHolder
+
+    def _workspace(self, dev):
+        return self._workspace_holder().get(dev)
 
     def _compact(self, s, B, H, W, sparse_next):
         """dilate the raw bitmap by the filter footprint and compact it to the index list."""

@@ -17,6 +17,8 @@ exist in this repo only inside ``oracle/`` as the parity checker.
 The fused per-frame path used by ``CBConv2d`` (``detect`` -> ``dilate_compact`` ->
 ``conv_update``) is exposed as well.
 """
+import os
+
 import torch
 
 from . import _lib
@@ -232,8 +234,33 @@ def bf16_planes(state_buf, C_):
     return hi, lo
 
 
+class ConvWorkspace(object):
+    """Stream-K workspace of cb_conv_update (cb_conv_ws_bytes() of zeroed device memory; the kernel
+    leaves it clean).  Launches that may overlap need their own: one holder per model instance,
+    shared by its layers (a model's layers run in order).  Not pickled."""
+
+    def __init__(self):
+        self.buf = None
+
+    def get(self, device):
+        if os.environ.get("CBINFER_STREAMK", "1") == "0":
+            return None
+        if self.buf is None or self.buf.device != device:
+            self.buf = torch.zeros(C.cb_conv_ws_bytes(), dtype=torch.uint8, device=device)
+        return self.buf
+
+    def clear(self):
+        self.buf = None
+
+    def __getstate__(self):
+        return {}
+
+    def __setstate__(self, state):
+        self.buf = None
+
+
 def conv_update(state_buf, changes, packed_w, bias_f32, out_buf, Cin, Cout, filtSize, relu, gemm,
-                lo_buf=None, planes16=None):
+                lo_buf=None, planes16=None, ws=None):
     """cb_conv_update on pixel-major buffers [B,H,W,pitch].  GEMM_TC_3X (fp32) consumes the tf32
     remainder plane `lo_buf`, GEMM_TC_BF16X3 the bf16 hi/lo planes `planes16`; both are derived
     on the fly when the caller does not maintain them (cb_change_detect can)."""
@@ -253,7 +280,9 @@ def conv_update(state_buf, changes, packed_w, bias_f32, out_buf, Cin, Cout, filt
                            pitch, changes.buffer.data_ptr(),
                            changes.count.data_ptr(), packed_w.data_ptr(), bias_f32.data_ptr(),
                            out_buf.data_ptr(), out_buf.shape[3], B, H, W, Cin, Cout,
-                           filtSize[0], filtSize[1], int(bool(relu))))
+                           filtSize[0], filtSize[1], int(bool(relu)),
+                           ws.data_ptr() if ws is not None else None,
+                           ws.numel() if ws is not None else 0))
 
 
 def pixel_major(shape, dtype, device, fill):

@@ -214,10 +214,15 @@ int cb_pack_weights(void* stream, int dtype, int gemm, const void* weight, void*
   return cb::umma_pack_weights(s, dtype, gemm, weight, packed, Cout, Cin, Cp, kH, kW);
 }
 
+size_t cb_conv_ws_bytes(void) {
+  // flags + one fp32 partial tile per resident CTA slot; 256 KB per SM covers every tiling
+  return (size_t)cb::UM_SK_FLAG_BYTES + (size_t)sm_count() * 256 * 1024;
+}
+
 int cb_conv_update(void* stream, int dtype, int gemm, const void* state, const void* state_lo,
                    int pitch_in, const int32_t* idx, const int32_t* count, const void* packed_w,
                    const float* bias, void* out, int pitch_out, int B, int H, int W, int Cin,
-                   int Cout, int kH, int kW, int relu) {
+                   int Cout, int kH, int kW, int relu, void* ws, size_t ws_bytes) {
   CB_CHECK_ARG(state && idx && count && packed_w && bias && out, "conv_update: null pointer");
   const int want_pitch = gemm == CB_GEMM_TC_BF16X3 ? cb::pitch16_of(Cin) : cb_channel_pitch(dtype, Cin);
   CB_CHECK_ARG(pitch_in == want_pitch, "conv_update: pitch_in %d != channel pitch %d", pitch_in,
@@ -237,7 +242,7 @@ int cb_conv_update(void* stream, int dtype, int gemm, const void* state, const v
     return 0;
   }
   return cb::umma_conv_update(s, dtype, gemm, state, state_lo, pitch_in, idx, count, packed_w, bias, out,
-                              pitch_out, B, H, W, Cin, Cout, kH, kW, relu);
+                              pitch_out, B, H, W, Cin, Cout, kH, kW, relu, ws, ws_bytes);
 }
 
 int cb_maxpool2x2(void* stream, int dtype, const void* x, long long x_sb, long long x_sc,

@@ -127,7 +127,15 @@ __device__ __forceinline__ void cp_async8(uint32_t dst, const void* src, uint32_
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes)
                : "memory");
 }
+#ifndef CB_GATHER_CA
+#define CB_GATHER_CA 0
+#endif
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+#if CB_GATHER_CA
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes)
+               : "memory");
+  return;
+#endif
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes)
                : "memory");
 }
@@ -257,6 +265,46 @@ struct KCursor {
   }
 };
 
+// Work segments (tile, K blocks [kb0, kb1)) of one CTA, walked identically by every warp role.
+//   static  : tiles tile0, tile0 + step, ... each over the CTA's fixed K range
+//   stream-K: the (tile, kb) space is cut into gridDim.x equal contiguous ranges, so every CTA gets
+//             the same amount of work whatever the change count; tiles cut by a range boundary
+//             are finished by the CTA holding their first K blocks (it reaches them last), the
+//             others park their partial accumulators in a global workspace.
+struct TileSeg {
+  int tile, kb0, kb1;
+  int step, total, nkb;
+  long long u, u1;
+  bool sk;
+  __device__ __forceinline__ void init_static(int tile0, int step_, int total_, int k0, int k1) {
+    sk = false; tile = tile0 - step_; step = step_; total = total_; kb0 = k0; kb1 = k1;
+    nkb = 0; u = u1 = 0;
+  }
+  __device__ __forceinline__ void init_sk(long long u0, long long u1_, int num_kb) {
+    sk = true; u = u0; u1 = u1_; nkb = num_kb; tile = 0; kb0 = kb1 = 0; step = total = 0;
+  }
+  __device__ __forceinline__ bool next() {
+    if (!sk) { tile += step; return tile < total; }
+    if (u >= u1) return false;
+    tile = (int)(u / nkb);
+    kb0 = (int)(u - (long long)tile * nkb);
+    const long long left = u1 - u;
+    kb1 = (left < (long long)(nkb - kb0)) ? kb0 + (int)left : nkb;
+    u += kb1 - kb0;
+    return true;
+  }
+};
+constexpr int UM_SK_FLAG_BYTES = 4096;       // stream-K workspace: per-CTA flags, then partial tiles
+
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // packed weights: [NSPLIT][CoutPad][KpPad] elements of T (K-major); tensor map dims {KpPad, NSPLIT*CoutPad}
 // T = operand element type in the state planes / shared memory, TO = element type of `out`
 // (TO != T only for 3xBF16: bf16 hi/lo operand planes of an fp32 layer).
@@ -265,7 +313,8 @@ __global__ void __launch_bounds__(UM_THREADS)
 conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__ state,
                  const T* __restrict__ state_lo, int Cp, const int32_t* __restrict__ idx, const int32_t* __restrict__ count,
                  const float* __restrict__ bias, TO* __restrict__ out, int Op, int H, int W,
-                 int Cout, int CoutPad, int kH, int kW, int Kp, int relu, int sel_lo, int sel_hi) {
+                 int Cout, int CoutPad, int kH, int kW, int Kp, int relu, int sel_lo, int sel_hi,
+                 uint32_t* __restrict__ sk_ws) {
   pdl_prologue();
   using C = UmmaCfg<T, SPLIT3, BN, DEEP>;
   constexpr int RPT = UM_BM * 8 / UM_PRODUCERS;            // 16-byte chunks per thread per stage
@@ -286,7 +335,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
   while (KS > 1 && (long long)total_tiles * KS > (long long)gridDim.x) KS >>= 1;
   const uint32_t krank = crank & (KS - 1), leader = crank - krank;
   const int tile0 = (int)(blockIdx.x / KS), tile_step = (int)(gridDim.x / KS);
-  if (tile0 >= total_tiles) {                             // group-uniform: before any barrier / alloc
+  const bool sk = !DEEP && sk_ws != nullptr;              // stream-K (never together with clusters)
+  if (!sk && tile0 >= total_tiles) {                      // group-uniform: before any barrier / alloc
     if (KSmax > 1) { cluster_sync_all(); cluster_sync_all(); }   // busy peers still sync twice
     return;
   }
@@ -297,7 +347,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
   UmmaCtrl* ctrl = reinterpret_cast<UmmaCtrl*>(smem + C::STAGES * C::STAGE_BYTES);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int num_kb = (Kp + C::BK - 1) / C::BK;
-  const int kb0 = (int)((long long)num_kb * krank / KS), kb1 = (int)((long long)num_kb * (krank + 1) / KS);
+  TileSeg seg0;
+  const long long sk_units = (long long)total_tiles * num_kb;
+  if (sk)
+    seg0.init_sk(sk_units * blockIdx.x / gridDim.x, sk_units * (blockIdx.x + 1) / gridDim.x, num_kb);
+  else
+    seg0.init_static(tile0, tile_step, total_tiles, (int)((long long)num_kb * krank / KS),
+                     (int)((long long)num_kb * (krank + 1) / KS));
+  float4* const sk_part = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(sk_ws) + UM_SK_FLAG_BYTES);
+  constexpr int SK_SLOT = UM_BM * BN / 4;                   // float4 per partial tile
   constexpr int TMA_WARP = UM_PRODUCERS / 32, MMA_WARP = TMA_WARP + 1;
   const int ph = (kH - 1) / 2, pw = (kW - 1) / 2;
   // Per 16-byte K chunk q (k = q*VEC): element offset of its filter tap relative to the pixel and
@@ -361,7 +419,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
       const int r = r0 + RSTEP * it;
       soff[it] = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
     }
-    for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+    TileSeg sg = seg0;
+    while (sg.next()) {
+      const int tile = sg.tile, kb0 = sg.kb0, kb1 = sg.kb1;
       const int mt = tile / ntiles, nt = tile - mt * ntiles;
       if (tid < UM_BM) {                                    // row table of this tile
         const int j = mt * UM_BM + tid;
@@ -482,12 +542,69 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
         continue;
       }
       if (DEEP && KS > 1) mbar_wait_cluster(&ctrl->red_full, red_phase);   // all partials delivered
+      // ---- stream-K: a tile cut by a range boundary -----------------------------------------
+      int sk_c0 = 0, sk_c1 = 0;                              // contributors [sk_c0, sk_c1) to wait for
+      if (!DEEP && sk && kb0 > 0) {
+        // not the tile's first K blocks: park the partial accumulator, raise my flag, move on
+        float4* slot = sk_part + (long long)blockIdx.x * SK_SLOT;
+        int it2 = 0;
+#pragma unroll 1
+        for (int c0 = cbeg; c0 < cbeg + COLS && c0 < BN; c0 += 16, ++it2) {
+          uint32_t acc[16];
+          tmem_ld16(trow + (uint32_t)c0, acc);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i4 = 0; i4 < 4; ++i4)
+            __stcg(&slot[(it2 * 4 + i4) * UM_PRODUCERS + tid],
+                   make_float4(__uint_as_float(acc[4 * i4]), __uint_as_float(acc[4 * i4 + 1]),
+                               __uint_as_float(acc[4 * i4 + 2]), __uint_as_float(acc[4 * i4 + 3])));
+        }
+        __threadfence();
+        tc_fence_before();
+        mbar_arrive(&ctrl->tmem_empty);
+        acc_phase ^= 1u;
+        asm volatile("bar.sync 1, %0;" ::"n"(UM_PRODUCERS) : "memory");
+        if (tid == 0) st_release_gpu(sk_ws + blockIdx.x, 1u);
+        continue;
+      }
+      if (!DEEP && sk && kb1 < num_kb) {
+        // the tile's first K blocks, reached at the END of my range: the CTAs after me hold the
+        // rest and processed it at the START of theirs
+        sk_c0 = (int)blockIdx.x + 1;
+        sk_c1 = sk_c0;
+        const long long tile_end = (long long)(tile + 1) * num_kb;
+        while (sk_c1 < (int)gridDim.x && sk_units * sk_c1 / gridDim.x < tile_end) ++sk_c1;
+        if (tid == 0) {
+          for (int cta = sk_c0; cta < sk_c1; ++cta) {
+            long long t0 = 0;
+            for (uint32_t spins = 0; ld_acquire_gpu(sk_ws + cta) == 0u; ++spins) {
+              if ((spins & 1023u) == 1023u) {
+                const long long now = clock64();
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > 4000000000ll) __trap();
+              }
+            }
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(UM_PRODUCERS) : "memory");
+      }
       int it = 0;
 #pragma unroll 1
       for (int c0 = cbeg; c0 < cbeg + COLS && c0 < BN; c0 += 16, ++it) {
         uint32_t acc[16];
         tmem_ld16(trow + (uint32_t)c0, acc);
         tmem_ld_wait();
+        for (int cta = sk_c0; cta < sk_c1; ++cta) {          // stream-K partials (fixed order)
+          const float4* slot = sk_part + (long long)cta * SK_SLOT;
+#pragma unroll
+          for (int i4 = 0; i4 < 4; ++i4) {
+            const float4 p = __ldcg(&slot[(it * 4 + i4) * UM_PRODUCERS + tid]);
+            acc[4 * i4] = __float_as_uint(__uint_as_float(acc[4 * i4]) + p.x);
+            acc[4 * i4 + 1] = __float_as_uint(__uint_as_float(acc[4 * i4 + 1]) + p.y);
+            acc[4 * i4 + 2] = __float_as_uint(__uint_as_float(acc[4 * i4 + 2]) + p.z);
+            acc[4 * i4 + 3] = __float_as_uint(__uint_as_float(acc[4 * i4 + 3]) + p.w);
+          }
+        }
         if (DEEP && KS > 1) {
           for (uint32_t r = 1; r < KS; ++r) {
 #pragma unroll
@@ -541,13 +658,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
       }
       acc_phase ^= 1u;
       asm volatile("bar.sync 1, %0;" ::"n"(UM_PRODUCERS) : "memory");   // row table reused next tile
+      if (sk_c1 > sk_c0 && tid == 0)                          // partials consumed: leave the flags clean
+        for (int cta = sk_c0; cta < sk_c1; ++cta) sk_ws[cta] = 0u;
     }
   } else if (warp == TMA_WARP) {
     // =============================== TMA producer: weight tiles ==============================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
-        const int nt = tile % ntiles;
+      TileSeg sg = seg0;
+      while (sg.next()) {
+        const int nt = sg.tile % ntiles, kb0 = sg.kb0, kb1 = sg.kb1;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&ctrl->empty[stage], phase ^ 1u);
           uint8_t* b_hi = smem + stage * C::STAGE_BYTES + C::NSPLIT * C::A_BYTES;
@@ -567,7 +687,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
       const uint32_t idesc =
           umma_idesc(sizeof(T) == 4 ? 2 : (std::is_same<T, __half>::value ? 0 : 1), BN);
       uint32_t stage = 0, phase = 0, acc_phase = 0;
-      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+      TileSeg sg = seg0;
+      while (sg.next()) {
+        const int kb0 = sg.kb0, kb1 = sg.kb1;
         mbar_wait(&ctrl->tmem_empty, acc_phase ^ 1u);        // epilogue drained the accumulator
         tc_fence_after();
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -727,7 +849,7 @@ int launch_conv_umma(cudaStream_t s, int dtype, const void* state, const void* s
                      const int32_t* idx,
                      const int32_t* count, const void* packed, const float* bias, void* out,
                      int Op, int B, int H, int W, int Cout, int CoutPad, int kH, int kW, int relu,
-                     int sel_lo, int sel_hi, int ksplit) {
+                     int sel_lo, int sel_hi, int ksplit, void* ws, size_t ws_bytes) {
   using C = UmmaCfg<T, SPLIT3, BN, DEEP>;
   const int Kp = kH * kW * Cp;
   const int KpPad = umma_kp_pad_es((int)sizeof(T), Cp, kH, kW);
@@ -806,13 +928,20 @@ int launch_conv_umma(cudaStream_t s, int dtype, const void* state, const void* s
     }
     grid = ks > 1 ? act[ks == 8 ? 3 : ks == 4 ? 2 : 1] : (long long)sm_count() * occ;
   }
-  if (grid > max_tiles) grid = max_tiles;
+  // stream-K (coarse variant, K long enough to be worth cutting): every resident CTA slot gets an
+  // equal share of the (tile, K block) space; needs flags + one partial tile per CTA of workspace
+  uint32_t* sk_ws = nullptr;
+  if (!DEEP && ws && num_kb >= 8 &&
+      ws_bytes >= (size_t)UM_SK_FLAG_BYTES + (size_t)grid * UM_BM * BN * sizeof(float) &&
+      grid * sizeof(uint32_t) <= (size_t)UM_SK_FLAG_BYTES)
+    sk_ws = (uint32_t*)ws;
+  if (!sk_ws && grid > max_tiles) grid = max_tiles;
   if (grid < 1) grid = 1;
   grid *= ks;
   cb::launch_cluster(kern, (unsigned)grid, UM_THREADS, (size_t)smem_bytes, s, (unsigned)ks, map, (const T*)state, (const T*)state_lo, Cp,
                                                         idx, count, bias,
                                                         (TO*)out, Op, H, W, Cout, CoutPad, kH, kW,
-                                                        Kp, relu, sel_lo, sel_hi);
+                                                        Kp, relu, sel_lo, sel_hi, sk_ws);
   CB_CHECK_LAUNCH("conv_update(umma)");
   return 0;
 }
@@ -822,12 +951,12 @@ int dispatch_bn(int bn, cudaStream_t s, int dtype, const void* state, const void
                 const int32_t* idx,
                 const int32_t* count, const void* packed, const float* bias, void* out, int Op,
                 int B, int H, int W, int Cout, int CoutPad, int kH, int kW, int relu, int sel_lo,
-                int sel_hi, int ksplit) {
+                int sel_hi, int ksplit, void* ws, size_t ws_bytes) {
 #define CB_BN(N)                                                                              \
   case N:                                                                                     \
     return launch_conv_umma<T, TO, SPLIT3, N, DEEP>(s, dtype, state, state_lo, Cp, idx, count, packed, bias, out, \
                                           Op, B, H, W, Cout, CoutPad, kH, kW, relu, sel_lo,   \
-                                          sel_hi, ksplit);
+                                          sel_hi, ksplit, ws, ws_bytes);
   if (DEEP) {                                  // the deep variant only exists for N tiles <= 64
     switch (bn) {
       CB_BN(16) CB_BN(32) CB_BN(64)
@@ -844,7 +973,7 @@ int dispatch_bn(int bn, cudaStream_t s, int dtype, const void* state, const void
 inline int umma_conv_update(cudaStream_t s, int dtype, int gemm, const void* state,
                             const void* state_lo, int Cp, const int32_t* idx, const int32_t* count, const void* packed,
                             const float* bias, void* out, int Op, int B, int H, int W, int Cin,
-                            int Cout, int kH, int kW, int relu) {
+                            int Cout, int kH, int kW, int relu, void* ws, size_t ws_bytes) {
   (void)Cin;
   CB_CHECK_ARG(gemm == CB_GEMM_TC || gemm == CB_GEMM_TC_3X || gemm == CB_GEMM_TC_BF16X3,
                "conv_update: bad gemm mode %d", gemm);
@@ -868,22 +997,22 @@ inline int umma_conv_update(cudaStream_t s, int dtype, int gemm, const void* sta
     if (bf16x3)
       return dispatch_bn<__nv_bfloat16, float, true, DP>(tile_n, s, dtype, state, state_lo, Cp, idx,
                                                          count, packed, bias, out, Op, B, H, W,
-                                                         Cout, CoutPad, kH, kW, relu, lo, hi, ksplit);
+                                                         Cout, CoutPad, kH, kW, relu, lo, hi, ksplit, ws, ws_bytes);
     switch (dtype) {
       case CB_F32:
         return split3 ? dispatch_bn<float, float, true, DP>(tile_n, s, dtype, state, state_lo, Cp, idx, count,
                                                  packed, bias, out, Op, B, H, W, Cout, CoutPad, kH,
-                                                 kW, relu, lo, hi, ksplit)
+                                                 kW, relu, lo, hi, ksplit, ws, ws_bytes)
                       : dispatch_bn<float, float, false, DP>(tile_n, s, dtype, state, state_lo, Cp, idx, count,
                                                   packed, bias, out, Op, B, H, W, Cout, CoutPad,
-                                                  kH, kW, relu, lo, hi, ksplit);
+                                                  kH, kW, relu, lo, hi, ksplit, ws, ws_bytes);
       case CB_F16:
         return dispatch_bn<__half, __half, false, DP>(tile_n, s, dtype, state, state_lo, Cp, idx, count, packed,
-                                          bias, out, Op, B, H, W, Cout, CoutPad, kH, kW, relu, lo, hi, ksplit);
+                                          bias, out, Op, B, H, W, Cout, CoutPad, kH, kW, relu, lo, hi, ksplit, ws, ws_bytes);
       case CB_BF16:
         return dispatch_bn<__nv_bfloat16, __nv_bfloat16, false, DP>(tile_n, s, dtype, state, state_lo, Cp, idx, count,
                                                  packed, bias, out, Op, B, H, W, Cout, CoutPad, kH,
-                                                 kW, relu, lo, hi, ksplit);
+                                                 kW, relu, lo, hi, ksplit, ws, ws_bytes);
       default: return fail(2, "conv_update: bad dtype %d", dtype);
     }
   };

@@ -14,7 +14,7 @@ import copy
 import torch
 import torch.nn as nn
 
-from . import CBConv2d, CBPoolMax2d, convert, convertPools
+from . import CBConv2d, CBPoolMax2d, convert, convertPools, shareWorkspace
 
 
 def sceneLabelingBaseline(seed=0):
@@ -171,4 +171,4 @@ def poseModelCBinfer(pose, threshold=1e-1, feedbackLoop=True, pools=True):
         if type(mm) is CBConv2d:
             mm.feedbackLoop = feedbackLoop
             mm.copyInput = False
-    return m.eval()
+    return shareWorkspace(m).eval()

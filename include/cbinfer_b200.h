@@ -169,13 +169,18 @@ int cb_map_to_bits(void* stream, const int8_t* map, uint32_t* bits, int B, int H
  * cb_pack_weights with the same dtype/gemm/shape.  *count is read on the device.
  * Operands per mode: CB_GEMM_SIMT_F32 / CB_GEMM_TC: `state` only.  CB_GEMM_TC_3X (fp32): `state`
  * plus `state_lo` = the CB_AUX_TF32_LO plane.  CB_GEMM_TC_BF16X3 (fp32 output): `state` and
- * `state_lo` are the CB_AUX_BF16_PAIR planes (hi, lo) and pitch_in is their pitch. */
+ * `state_lo` are the CB_AUX_BF16_PAIR planes (hi, lo) and pitch_in is their pitch.
+ * ws / ws_bytes: optional stream-K workspace (cb_conv_ws_bytes() of device memory, zeroed once at
+ * allocation, private to the calling stream; the kernel leaves it clean).  With it the tensor-core
+ * path cuts the (tile, K block) space into equal shares per CTA, so the run time follows the
+ * change count instead of jumping at tile-wave boundaries; NULL keeps whole tiles per CTA. */
+size_t cb_conv_ws_bytes(void);
 int cb_pack_weights(void* stream, int dtype, int gemm, const void* weight /*[Cout,Cin,kH,kW]*/,
                     void* packed, int Cout, int Cin, int kH, int kW);
 int cb_conv_update(void* stream, int dtype, int gemm, const void* state, const void* state_lo,
                    int pitch_in, const int32_t* idx, const int32_t* count, const void* packed_w,
                    const float* bias, void* out, int pitch_out, int B, int H, int W, int Cin,
-                   int Cout, int kH, int kW, int relu);
+                   int Cout, int kH, int kW, int relu, void* ws, size_t ws_bytes);
 
 /* ---- change-based 2x2/stride-2 max pooling ------------------------------------------------
  * replaces: maxPool2d (conv2d_cg.py:33-37 -> cbconv2d_cg_backend.cu:199-240, half :207-250).

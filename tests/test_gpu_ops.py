@@ -289,6 +289,56 @@ def test_conv_update(cbm, orc, mode, dt, case):
     assert float(obuf[..., Cout:].abs().sum()) == 0.0
 
 
+SK_CASES = [  # mode, dt, B, Cin, Cout, H, W, k, frac   (all reach the coarse tiling: stream-K applies)
+    ("bf16x3", "f32", 8, 64, 256, 60, 80, 7, 0.60),
+    ("bf16x3", "f32", 4, 16, 64, 120, 160, 7, 0.50),
+    ("bf16x3", "f32", 1, 128, 128, 120, 160, 3, 1.00),
+    ("tc3x", "f32", 2, 64, 64, 120, 160, 3, 0.90),
+    ("tc", "f32", 2, 64, 96, 120, 160, 3, 0.80),
+    ("tc", "bf16", 1, 64, 64, 120, 160, 3, 1.00),
+    ("tc", "f16", 2, 32, 256, 100, 120, 5, 0.70),
+]
+
+
+@pytest.mark.parametrize("case", SK_CASES)
+def test_conv_update_stream_k(cbm, case):
+    """stream-K (equal shares of the (tile, K block) space per CTA, partial tiles summed through the
+    workspace) against whole tiles per CTA and against dense F.conv2d; the workspace is left clean."""
+    import torch.nn.functional as F
+    cg, lib, cb = cbm["cg"], cbm["lib"], cbm["cb"]
+    mode, dt, B, Cin, Cout, H, W, k, frac = case
+    tdt = TORCH_DT[dt]
+    gemm = cb.CBConv2d.GEMM_MODES[mode]
+    torch.backends.cudnn.allow_tf32 = False
+    state, sbuf = cg.pixel_major((B, Cin, H, W), tdt, "cuda", 0)
+    state.copy_(rand_tensor((B, Cin, H, W), dt, seed=Cin + H))
+    w = rand_tensor((Cout, Cin, k, k), dt, seed=11, scale=(Cin * k * k) ** -0.5).cuda()
+    bias = rand_tensor((Cout,), dt, seed=12).cuda()
+    g = torch.Generator().manual_seed(5)
+    sel = torch.nonzero(torch.rand(B * H * W, generator=g) < frac).view(-1).int().cuda()
+    ci = cg.ChangeIndexes.from_tensor(sel, (B, H, W))
+    packed = cg.pack_weights(w, gemm)
+    ws = torch.zeros(lib.C.cb_conv_ws_bytes(), dtype=torch.uint8, device="cuda")
+    outs = []
+    for use_ws in (None, ws, ws):
+        out, obuf = cg.pixel_major((B, Cout, H, W), tdt, "cuda", 0)
+        out.fill_(3.0)
+        cg.conv_update(sbuf, ci, packed, bias.float().contiguous(), obuf, Cin, Cout, (k, k), True, gemm,
+                       ws=use_ws)
+        torch.cuda.synchronize()
+        outs.append(out.float())
+    assert int(ws.view(torch.int32)[:1024].abs().sum()) == 0          # flags left clean
+    assert torch.equal(outs[1], outs[2])                                # deterministic, reusable
+    ref = F.relu(F.conv2d(state.float(), w.float(), bias.float(), padding=k // 2))
+    touched = torch.zeros(B * H * W, dtype=torch.bool, device="cuda")
+    touched[sel.long()] = True
+    tm = touched.view(B, 1, H, W).expand(B, Cout, H, W)
+    scale = float(ref.abs().max())
+    for o in outs[:2]:
+        assert float((o[~tm] - 3.0).abs().max()) == 0.0                  # untouched pixels untouched
+        assert float((o[tm] - ref[tm]).abs().max()) / scale <= CONV_TOL[(mode, dt)]
+
+
 def test_conv_update_zero_changes_is_noop(cbm):
     cg, lib = cbm["cg"], cbm["lib"]
     state, sbuf = cg.pixel_major((1, 16, 8, 8), torch.float32, "cuda", 1.0)
