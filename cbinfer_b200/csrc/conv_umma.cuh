@@ -931,10 +931,14 @@ int launch_conv_umma(cudaStream_t s, int dtype, const void* state, const void* s
   // stream-K (coarse variant, K long enough to be worth cutting): every resident CTA slot gets an
   // equal share of the (tile, K block) space; needs flags + one partial tile per CTA of workspace
   uint32_t* sk_ws = nullptr;
-  if (!DEEP && ws && num_kb >= 8 &&
-      ws_bytes >= (size_t)UM_SK_FLAG_BYTES + (size_t)grid * UM_BM * BN * sizeof(float) &&
-      grid * sizeof(uint32_t) <= (size_t)UM_SK_FLAG_BYTES)
-    sk_ws = (uint32_t*)ws;
+  if (!DEEP && ws && num_kb >= 8 && ws_bytes > (size_t)UM_SK_FLAG_BYTES) {
+    const long long slots = (long long)((ws_bytes - UM_SK_FLAG_BYTES) / ((size_t)UM_BM * BN * sizeof(float)));
+    if (slots >= sm_count() / 2) {                           // enough partial-tile slots to be useful
+      if (grid > slots) grid = slots;
+      if (grid * (long long)sizeof(uint32_t) > UM_SK_FLAG_BYTES) grid = UM_SK_FLAG_BYTES / sizeof(uint32_t);
+      sk_ws = (uint32_t*)ws;
+    }
+  }
   if (!sk_ws && grid > max_tiles) grid = max_tiles;
   if (grid < 1) grid = 1;
   grid *= ks;

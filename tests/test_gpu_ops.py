@@ -335,7 +335,8 @@ def test_conv_update_stream_k(cbm, case):
     tm = touched.view(B, 1, H, W).expand(B, Cout, H, W)
     scale = float(ref.abs().max())
     for o in outs[:2]:
-        assert float((o[~tm] - 3.0).abs().max()) == 0.0                  # untouched pixels untouched
+        if not bool(touched.all()):
+            assert float((o[~tm] - 3.0).abs().max()) == 0.0              # untouched pixels untouched
         assert float((o[tm] - ref[tm]).abs().max()) / scale <= CONV_TOL[(mode, dt)]
 
 
