@@ -30,8 +30,11 @@
 namespace cb {
 
 constexpr int UM_BM = 128;                     // rows per tile (UMMA M, cta_group::1)
-constexpr int UM_PRODUCERS = 256;              // gather / epilogue threads (warps 0-7)
-constexpr int UM_THREADS = UM_PRODUCERS + 64;  // + TMA warp + MMA warp
+constexpr int UM_PRODUCERS = 256;              // gather threads (warps 0-7)
+// epilogue threads: warps 10.. ; one warp per TMEM lane quarter for narrow N tiles (keeps the CTA
+// small enough for 2 CTAs/SM), two per quarter (splitting the columns) for N tiles >= 128
+__host__ __device__ constexpr int um_epi(int bn) { return bn >= 128 ? 256 : 128; }
+__host__ __device__ constexpr int um_threads(int bn) { return UM_PRODUCERS + 64 + um_epi(bn); }  // + TMA warp + MMA warp
 constexpr int UM_ROW_BYTES = 128;              // K bytes per stage row = one swizzle-128B span
 
 // ---- PTX wrappers ----------------------------------------------------------------------------
@@ -210,7 +213,7 @@ __host__ __device__ inline uint32_t umma_idesc(int fmt, int N) {
 }
 
 // ---- configuration -----------------------------------------------------------------------------
-constexpr int UM_CTRL_BYTES = 1280;            // barriers + TMEM base + row table
+constexpr int UM_CTRL_BYTES = 2304;            // barriers + TMEM base + row table
 // DEEP: one CTA per SM with as many stages as fit (used when few tiles exist: latency, not
 // occupancy, is then the limiter).
 template <typename T, bool SPLIT3, int BN, bool DEEP = false>
@@ -229,18 +232,22 @@ struct UmmaCfg {
   static constexpr int BUDGET = DEEP ? 200 * 1024 - RED_BYTES : (CTAS_PER_SM == 1 ? 200 * 1024 : 98 * 1024);
   static constexpr int STAGES = (BUDGET / STAGE_BYTES) < 2 ? 2
                                 : (BUDGET / STAGE_BYTES) > 8 ? 8 : (BUDGET / STAGE_BYTES);
-  static constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  // two accumulators: the epilogue warps drain one while the MMA warp fills the other
+  static constexpr int TMEM_COLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128
+                                   : 2 * BN <= 256 ? 256 : 512;
   static constexpr int TABLE_MAX = 1024;        // chunk-offset table entries (8 KB)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + UM_CTRL_BYTES +
                                     TABLE_MAX * 8 + RED_BYTES;
 };
 
 struct UmmaCtrl {                              // lives after the stage buffers
-  uint64_t full[8], empty[8], tmem_full, tmem_empty;
+  uint64_t full[8], empty[8];
+  uint64_t tmem_full[2], tmem_empty[2];        // per accumulator: MMAs done / drained
+  uint64_t tab_full[2];                        // per row table: written by the gather warps
   uint64_t red_full, red_free;                 // split-K: partials delivered / partial buffer free
   uint32_t tmem_base, pad;
-  int pix[UM_BM];
-  int yx[UM_BM];
+  int pix[2][UM_BM];                           // row tables (pixel index or -1), double-buffered
+  int yx[2][UM_BM];
 };
 static_assert(sizeof(UmmaCtrl) <= UM_CTRL_BYTES, "ctrl block too large");
 
@@ -309,7 +316,7 @@ __device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
 // T = operand element type in the state planes / shared memory, TO = element type of `out`
 // (TO != T only for 3xBF16: bf16 hi/lo operand planes of an fp32 layer).
 template <typename T, typename TO, bool SPLIT3, int BN, bool DEEP>
-__global__ void __launch_bounds__(UM_THREADS)
+__global__ void __launch_bounds__(um_threads(BN))
 conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__ state,
                  const T* __restrict__ state_lo, int Cp, const int32_t* __restrict__ idx, const int32_t* __restrict__ count,
                  const float* __restrict__ bias, TO* __restrict__ out, int Op, int H, int W,
@@ -317,6 +324,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
                  uint32_t* __restrict__ sk_ws) {
   pdl_prologue();
   using C = UmmaCfg<T, SPLIT3, BN, DEEP>;
+  constexpr int UM_EPI = um_epi(BN), UM_THREADS = um_threads(BN);
   constexpr int RPT = UM_BM * 8 / UM_PRODUCERS;            // 16-byte chunks per thread per stage
   constexpr int RSTEP = UM_PRODUCERS / 8;                  // row stride between a thread's chunks
   const int n = *count;
@@ -356,7 +364,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
                      (int)((long long)num_kb * (krank + 1) / KS));
   float4* const sk_part = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(sk_ws) + UM_SK_FLAG_BYTES);
   constexpr int SK_SLOT = UM_BM * BN / 4;                   // float4 per partial tile
-  constexpr int TMA_WARP = UM_PRODUCERS / 32, MMA_WARP = TMA_WARP + 1;
+  constexpr int TMA_WARP = UM_PRODUCERS / 32, MMA_WARP = TMA_WARP + 1, EPI_WARP0 = MMA_WARP + 1;
   const int ph = (kH - 1) / 2, pw = (kW - 1) / 2;
   // Per 16-byte K chunk q (k = q*VEC): element offset of its filter tap relative to the pixel and
   // the tap's (dy,dx); built once per CTA so the gather loop has no divisions.
@@ -386,10 +394,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
       mbar_init(&ctrl->full[s], UM_PRODUCERS + 1);
       mbar_init(&ctrl->empty[s], 1);
     }
-    mbar_init(&ctrl->tmem_full, 1);
-    mbar_init(&ctrl->tmem_empty, UM_PRODUCERS);
-    mbar_init(&ctrl->red_full, (KS > 1 ? KS - 1 : 1) * UM_PRODUCERS);
-    mbar_init(&ctrl->red_free, UM_PRODUCERS);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&ctrl->tmem_full[b], 1);
+      mbar_init(&ctrl->tmem_empty[b], UM_EPI);
+      mbar_init(&ctrl->tab_full[b], 1);
+    }
+    mbar_init(&ctrl->red_full, (KS > 1 ? KS - 1 : 1) * UM_EPI);
+    mbar_init(&ctrl->red_free, UM_EPI);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == MMA_WARP) {                                  // TMEM allocation (one warp)
@@ -409,8 +420,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
   const int P = H * W;
 
   if (warp < TMA_WARP) {
-    // =============================== gather producers + epilogue ============================
-    uint32_t stage = 0, phase = 0, acc_phase = 0, red_phase = 0;
+    // =============================== gather producers ========================================
+    uint32_t stage = 0, phase = 0, sidx = 0;
     const int c = tid & 7;                                  // my 16-byte chunk column
     const int r0 = tid >> 3;                                // my rows: r0 + RSTEP*it
     uint32_t soff[RPT];                                     // swizzled smem offsets of my chunks
@@ -422,8 +433,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
     TileSeg sg = seg0;
     while (sg.next()) {
       const int tile = sg.tile, kb0 = sg.kb0, kb1 = sg.kb1;
-      const int mt = tile / ntiles, nt = tile - mt * ntiles;
+      const int mt = tile / ntiles;
+      const uint32_t buf = sidx & 1u, use = sidx >> 1;
+      ++sidx;
       if (tid < UM_BM) {                                    // row table of this tile
+        // the table (and accumulator) `buf` was last used two segments ago: drained yet?
+        mbar_wait(&ctrl->tmem_empty[buf], (use & 1u) ^ 1u);
         const int j = mt * UM_BM + tid;
         int pix = -1, yx = 0;
         if (j < n) {
@@ -432,16 +447,17 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
           const int yy = p / W;
           yx = (yy << 16) | (p - yy * W);
         }
-        ctrl->pix[tid] = pix;
-        ctrl->yx[tid] = yx;
+        ctrl->pix[buf][tid] = pix;
+        ctrl->yx[buf][tid] = yx;
       }
       asm volatile("bar.sync 1, %0;" ::"n"(UM_PRODUCERS) : "memory");   // producers only
+      if (tid == 0) mbar_arrive(&ctrl->tab_full[buf]);      // release: the epilogue may read the table
       // per-row source pointers (pixel base) and coordinates of my RPT rows
       const T* rbase[RPT];
       int ry[RPT], rx[RPT];
 #pragma unroll
       for (int it = 0; it < RPT; ++it) {
-        const int pix = ctrl->pix[r0 + RSTEP * it], yx = ctrl->yx[r0 + RSTEP * it];
+        const int pix = ctrl->pix[buf][r0 + RSTEP * it], yx = ctrl->yx[buf][r0 + RSTEP * it];
         rbase[it] = state + (long long)(pix < 0 ? 0 : pix) * Cp;
         ry[it] = pix < 0 ? -0x40000000 : (yx >> 16);        // invalid rows fail every bounds test
         rx[it] = yx & 0xffff;
@@ -504,19 +520,33 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
         cp_async_arrive_noinc(&ctrl->full[stage]);
         if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
       }
+    }
+  } else if (warp >= EPI_WARP0) {
+    // =============================== epilogue: TMEM -> bias / ReLU -> scatter ================
+    // One or two warps per TMEM lane quarter (warp % 4; two split the columns) drain accumulator
+    // `buf` while the MMA warp fills the other one and the gather warps fetch the next segment.
+    const int etid = tid - EPI_WARP0 * 32;
+    const int q = warp & 3;                                  // TMEM lane quarter of this warp
+    const int row = q * 32 + lane;
+    uint32_t sidx = 0, red_phase = 0;
+    TileSeg sg = seg0;
+    while (sg.next()) {
+      const int tile = sg.tile, kb0 = sg.kb0, kb1 = sg.kb1;
+      const int nt = tile % ntiles;
+      const uint32_t buf = sidx & 1u, use = sidx >> 1;
+      ++sidx;
       // ---- epilogue: TMEM -> registers -> bias / ReLU -> scatter -------------------------
-      mbar_wait(&ctrl->tmem_full, acc_phase);
+      mbar_wait(&ctrl->tab_full[buf], use & 1u);             // row table written
+      mbar_wait(&ctrl->tmem_full[buf], use & 1u);            // accumulator complete
       tc_fence_after();
-      const int q = warp & 3;                                // TMEM lane quarter of this warp
-      const int row = q * 32 + lane;
-      const int pix = ctrl->pix[row];
-      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+      const int pix = ctrl->pix[buf][row];
+      const uint32_t trow = tmem_base + buf * (uint32_t)BN + ((uint32_t)(q * 32) << 16);
       TO* orow = out + (long long)(pix < 0 ? 0 : pix) * Op;
       constexpr int OVEC = 16 / (int)sizeof(TO);
-      constexpr int NGROUP = UM_PRODUCERS / 128;             // warps sharing a lane quarter
+      constexpr int NGROUP = UM_EPI / 128;                   // warps sharing a lane quarter
       constexpr int COLS = (BN / NGROUP) < 16 ? 16 : (BN / NGROUP);
-      const int cbeg = (warp >> 2) * COLS;
-      // split-K partial buffer: float4 slot ((it*4 + i4) * 256 + tid) -> conflict-free, and the
+      const int cbeg = ((warp - EPI_WARP0) >> 2) * COLS;
+      // split-K partial buffer: float4 slot ((it*4 + i4) * 128 + etid) -> conflict-free, and the
       // same thread owns the same (row, columns) on every rank
       float4* red = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(ktab) + C::TABLE_MAX * 8);
       if (DEEP && KS > 1 && krank != 0) {
@@ -529,16 +559,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
           tmem_ld_wait();
 #pragma unroll
           for (int i4 = 0; i4 < 4; ++i4)
-            red[(it * 4 + i4) * UM_PRODUCERS + tid] =
+            red[(it * 4 + i4) * UM_EPI + etid] =
                 make_float4(__uint_as_float(acc[4 * i4]), __uint_as_float(acc[4 * i4 + 1]),
                             __uint_as_float(acc[4 * i4 + 2]), __uint_as_float(acc[4 * i4 + 3]));
         }
         tc_fence_before();
-        mbar_arrive(&ctrl->tmem_empty);
+        mbar_arrive(&ctrl->tmem_empty[buf]);
         mbar_arrive_remote(map_to_rank(smem_u32(&ctrl->red_full), leader));   // release: partial visible
         red_phase ^= 1u;
-        acc_phase ^= 1u;
-        asm volatile("bar.sync 1, %0;" ::"n"(UM_PRODUCERS) : "memory");
         continue;
       }
       if (DEEP && KS > 1) mbar_wait_cluster(&ctrl->red_full, red_phase);   // all partials delivered
@@ -555,16 +583,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
           tmem_ld_wait();
 #pragma unroll
           for (int i4 = 0; i4 < 4; ++i4)
-            __stcg(&slot[(it2 * 4 + i4) * UM_PRODUCERS + tid],
+            __stcg(&slot[(it2 * 4 + i4) * UM_EPI + etid],
                    make_float4(__uint_as_float(acc[4 * i4]), __uint_as_float(acc[4 * i4 + 1]),
                                __uint_as_float(acc[4 * i4 + 2]), __uint_as_float(acc[4 * i4 + 3])));
         }
         __threadfence();
         tc_fence_before();
-        mbar_arrive(&ctrl->tmem_empty);
-        acc_phase ^= 1u;
-        asm volatile("bar.sync 1, %0;" ::"n"(UM_PRODUCERS) : "memory");
-        if (tid == 0) st_release_gpu(sk_ws + blockIdx.x, 1u);
+        mbar_arrive(&ctrl->tmem_empty[buf]);
+        asm volatile("bar.sync 2, %0;" ::"n"(UM_EPI) : "memory");
+        if (etid == 0) st_release_gpu(sk_ws + blockIdx.x, 1u);
         continue;
       }
       if (!DEEP && sk && kb1 < num_kb) {
@@ -574,7 +601,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
         sk_c1 = sk_c0;
         const long long tile_end = (long long)(tile + 1) * num_kb;
         while (sk_c1 < (int)gridDim.x && sk_units * sk_c1 / gridDim.x < tile_end) ++sk_c1;
-        if (tid == 0) {
+        if (etid == 0) {
           for (int cta = sk_c0; cta < sk_c1; ++cta) {
             long long t0 = 0;
             for (uint32_t spins = 0; ld_acquire_gpu(sk_ws + cta) == 0u; ++spins) {
@@ -586,7 +613,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
             }
           }
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(UM_PRODUCERS) : "memory");
+        asm volatile("bar.sync 2, %0;" ::"n"(UM_EPI) : "memory");
       }
       int it = 0;
 #pragma unroll 1
@@ -598,7 +625,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
           const float4* slot = sk_part + (long long)cta * SK_SLOT;
 #pragma unroll
           for (int i4 = 0; i4 < 4; ++i4) {
-            const float4 p = __ldcg(&slot[(it * 4 + i4) * UM_PRODUCERS + tid]);
+            const float4 p = __ldcg(&slot[(it * 4 + i4) * UM_EPI + etid]);
             acc[4 * i4] = __float_as_uint(__uint_as_float(acc[4 * i4]) + p.x);
             acc[4 * i4 + 1] = __float_as_uint(__uint_as_float(acc[4 * i4 + 1]) + p.y);
             acc[4 * i4 + 2] = __float_as_uint(__uint_as_float(acc[4 * i4 + 2]) + p.z);
@@ -610,7 +637,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
 #pragma unroll
             for (int i4 = 0; i4 < 4; ++i4) {
               const float4 p = ld_cluster_f4(
-                  map_to_rank(smem_u32(&red[(it * 4 + i4) * UM_PRODUCERS + tid]), leader + r));
+                  map_to_rank(smem_u32(&red[(it * 4 + i4) * UM_EPI + etid]), leader + r));
               acc[4 * i4] = __float_as_uint(__uint_as_float(acc[4 * i4]) + p.x);
               acc[4 * i4 + 1] = __float_as_uint(__uint_as_float(acc[4 * i4 + 1]) + p.y);
               acc[4 * i4 + 2] = __float_as_uint(__uint_as_float(acc[4 * i4 + 2]) + p.z);
@@ -651,15 +678,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
         }
       }
       tc_fence_before();
-      mbar_arrive(&ctrl->tmem_empty);
+      mbar_arrive(&ctrl->tmem_empty[buf]);
       if (DEEP && KS > 1) {                                  // the peers may reuse their partial buffers
         for (uint32_t r = 1; r < KS; ++r) mbar_arrive_remote(map_to_rank(smem_u32(&ctrl->red_free), leader + r));
         red_phase ^= 1u;
       }
-      acc_phase ^= 1u;
-      asm volatile("bar.sync 1, %0;" ::"n"(UM_PRODUCERS) : "memory");   // row table reused next tile
-      if (sk_c1 > sk_c0 && tid == 0)                          // partials consumed: leave the flags clean
-        for (int cta = sk_c0; cta < sk_c1; ++cta) sk_ws[cta] = 0u;
+      if (sk_c1 > sk_c0) {                                   // partials consumed: leave the flags clean
+        asm volatile("bar.sync 2, %0;" ::"n"(UM_EPI) : "memory");
+        if (etid == 0)
+          for (int cta = sk_c0; cta < sk_c1; ++cta) sk_ws[cta] = 0u;
+      }
     }
   } else if (warp == TMA_WARP) {
     // =============================== TMA producer: weight tiles ==============================
@@ -680,17 +708,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
         }
       }
     }
-  } else {
+  } else if (warp == MMA_WARP) {
     // =============================== MMA issuer ==============================================
     if (lane == 0) {
       constexpr int KIND = sizeof(T) == 4 ? 0 : 1;
       const uint32_t idesc =
           umma_idesc(sizeof(T) == 4 ? 2 : (std::is_same<T, __half>::value ? 0 : 1), BN);
-      uint32_t stage = 0, phase = 0, acc_phase = 0;
+      uint32_t stage = 0, phase = 0, sidx = 0;
       TileSeg sg = seg0;
       while (sg.next()) {
         const int kb0 = sg.kb0, kb1 = sg.kb1;
-        mbar_wait(&ctrl->tmem_empty, acc_phase ^ 1u);        // epilogue drained the accumulator
+        const uint32_t buf = sidx & 1u, use = sidx >> 1;
+        ++sidx;
+        const uint32_t tmem_d = tmem_base + buf * (uint32_t)BN;
+        mbar_wait(&ctrl->tmem_empty[buf], (use & 1u) ^ 1u);  // epilogue drained this accumulator
         tc_fence_after();
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&ctrl->full[stage], phase);
@@ -705,18 +736,17 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
             const uint32_t adv = (uint32_t)(ks * 32);        // 32 bytes of K per instruction
             const uint32_t first = (kb != kb0 || ks) ? 1u : 0u;
             if (SPLIT3) {
-              umma<KIND>(tmem_base, umma_desc(a_lo + adv), umma_desc(b_hi + adv), idesc, first);
-              umma<KIND>(tmem_base, umma_desc(a_hi + adv), umma_desc(b_lo + adv), idesc, 1u);
-              umma<KIND>(tmem_base, umma_desc(a_hi + adv), umma_desc(b_hi + adv), idesc, 1u);
+              umma<KIND>(tmem_d, umma_desc(a_lo + adv), umma_desc(b_hi + adv), idesc, first);
+              umma<KIND>(tmem_d, umma_desc(a_hi + adv), umma_desc(b_lo + adv), idesc, 1u);
+              umma<KIND>(tmem_d, umma_desc(a_hi + adv), umma_desc(b_hi + adv), idesc, 1u);
             } else {
-              umma<KIND>(tmem_base, umma_desc(a_hi + adv), umma_desc(b_hi + adv), idesc, first);
+              umma<KIND>(tmem_d, umma_desc(a_hi + adv), umma_desc(b_hi + adv), idesc, first);
             }
           }
           umma_commit(&ctrl->empty[stage]);                  // frees the smem stage when done
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&ctrl->tmem_full);                       // accumulator complete
-        acc_phase ^= 1u;
+        umma_commit(&ctrl->tmem_full[buf]);                  // accumulator complete
       }
     }
   }
@@ -890,10 +920,11 @@ int launch_conv_umma(cudaStream_t s, int dtype, const void* state, const void* s
   int occ = C::CTAS_PER_SM;
   if (!DEEP) {
     int q = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, UM_THREADS, smem_bytes) == cudaSuccess &&
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, um_threads(BN), smem_bytes) == cudaSuccess &&
         q > occ)
       occ = q > 4 ? 4 : q;
   }
+  if (occ > 512 / C::TMEM_COLS) occ = 512 / C::TMEM_COLS;     // two accumulators per CTA must fit TMEM
   const long long max_tiles = (((long long)B * H * W + UM_BM - 1) / UM_BM) * (CoutPad / BN);
   // split-K (deep variant only): clusters of `ks` CTAs share a tile; keep ks <= stages / 4
   int ks = DEEP ? ksplit : 1;
@@ -909,7 +940,7 @@ int launch_conv_umma(cudaStream_t s, int dtype, const void* state, const void* s
       if (act[slot] < 0) {
         cudaLaunchConfig_t qc = {};
         qc.gridDim = dim3((unsigned)(sm_count() / ks * ks));
-        qc.blockDim = dim3(UM_THREADS);
+        qc.blockDim = dim3(um_threads(BN));
         qc.dynamicSmemBytes = (size_t)smem_bytes;
         cudaLaunchAttribute qa[1];
         qa[0].id = cudaLaunchAttributeClusterDimension;
@@ -942,7 +973,7 @@ int launch_conv_umma(cudaStream_t s, int dtype, const void* state, const void* s
   if (!sk_ws && grid > max_tiles) grid = max_tiles;
   if (grid < 1) grid = 1;
   grid *= ks;
-  cb::launch_cluster(kern, (unsigned)grid, UM_THREADS, (size_t)smem_bytes, s, (unsigned)ks, map, (const T*)state, (const T*)state_lo, Cp,
+  cb::launch_cluster(kern, (unsigned)grid, um_threads(BN), (size_t)smem_bytes, s, (unsigned)ks, map, (const T*)state, (const T*)state_lo, Cp,
                                                         idx, count, bias,
                                                         (TO*)out, Op, H, W, Cout, CoutPad, kH, kW,
                                                         Kp, relu, sel_lo, sel_hi, sk_ws);
