@@ -416,7 +416,7 @@ def main():
     # ---- extras on rank 0 at N=1: kernel table / roofline, dense cuDNN, single-stream latency, CPU ----
     if rank == 0 and not args.no_extras:
         try:
-            result.update(kernel_roofline(args, model, frames, dev, tdt))
+            result.update(kernel_roofline(args, model, frames, dev, tdt, elapsed_ms / K * 1e3))
         except Exception as e:                                   # never lose the headline line
             result["roofline_error"] = repr(e)
         try:
@@ -444,7 +444,7 @@ def main():
         dist.destroy_process_group()
 
 
-def kernel_roofline(args, model, frames, dev, tdt):
+def kernel_roofline(args, model, frames, dev, tdt, step_us):
     """Per-kernel CUDA-event timing of the same frames (eager, one event pair per launch) and the
     roofline of the dominant kernel.  Algorithmic bytes / FLOPs per launch: DESIGN.md section 4."""
     import torch
@@ -542,7 +542,9 @@ def kernel_roofline(args, model, frames, dev, tdt):
                            "frac": top["frac"], "traffic": traffic,
                            "tensor_work_frac": (3.0 * top["frac"] if top["bound"] == "tensor" and args.dtype == "f32"
                                                 and args.gemm in ("auto", "bf16x3", "tc3x") else top["frac"]),
-                           "share_of_step": top["us"] / total if total else None,
+                           # share of the timed (graph-replay) step; the eager per-launch timings of the
+                           # small kernels include launch gaps, so their sum is not the denominator
+                           "share_of_step": top["us"] / step_us if step_us else None,
                            "note": ("fp32 data: %s split, 3 tensor-core MMAs per product; peak = %s; `achieved` counts the "
                                     "algorithmic FLOPs 2*n*K*Cout once, tensor_work_frac counts the 3x MMA work"
                                     % (("3xTF32", "bf16 burst / 2") if args.gemm == "tc3x" else ("3xBF16", "bf16 burst")))
