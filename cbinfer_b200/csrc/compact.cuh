@@ -14,9 +14,15 @@
 
 namespace cb {
 
-constexpr int kCompactThreads = 512;
-constexpr int kCompactWPT = 2;                               // words per thread
-constexpr int kCompactTile = kCompactThreads * kCompactWPT;  // words per tile (32768 pixels)
+#ifndef CB_COMPACT_THREADS
+#define CB_COMPACT_THREADS 512
+#endif
+#ifndef CB_COMPACT_WPT
+#define CB_COMPACT_WPT 1
+#endif
+constexpr int kCompactThreads = CB_COMPACT_THREADS;
+constexpr int kCompactWPT = CB_COMPACT_WPT;                  // words per thread
+constexpr int kCompactTile = kCompactThreads * kCompactWPT;  // words per tile (16384 pixels; measured best of 256..2048)
 constexpr int kCompactWin = 6144;                            // staged raw window (words, 24 KB)
 
 struct CompactHeader {                         // first 16 bytes of the workspace
