@@ -340,6 +340,52 @@ def test_conv_update_stream_k(cbm, case):
         assert float((o[tm] - ref[tm]).abs().max()) / scale <= CONV_TOL[(mode, dt)]
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_conv_update_random_shapes(cbm, seed):
+    """seeded sweep over odd shapes, change counts and tilings (fine / coarse variant, cluster
+    split-K widths, stream-K cuts) against dense F.conv2d; unchanged pixels must stay untouched."""
+    import random
+    import torch.nn.functional as F
+    cg, lib, cb = cbm["cg"], cbm["lib"], cbm["cb"]
+    rnd = random.Random(1234 + seed)
+    torch.backends.cudnn.allow_tf32 = False
+    ws = torch.zeros(lib.C.cb_conv_ws_bytes(), dtype=torch.uint8, device="cuda")
+    for case in range(8):
+        mode, dt = rnd.choice([("bf16x3", "f32"), ("bf16x3", "f32"), ("tc3x", "f32"), ("tc", "bf16"), ("tc", "f16")])
+        B = rnd.choice([1, 1, 2, 5])
+        Cin = rnd.choice([3, 4, 8, 16, 24, 40, 64, 128, 185])
+        Cout = rnd.choice([8, 16, 19, 38, 64, 96, 128, 130, 256])
+        k = rnd.choice([1, 3, 3, 5, 7])
+        H, W = rnd.randint(5, 70), rnd.randint(5, 90)
+        frac = rnd.choice([0.02, 0.1, 0.3, 0.6, 1.0])
+        tdt, gemm = TORCH_DT[dt], cb.CBConv2d.GEMM_MODES[mode]
+        g = torch.Generator().manual_seed(seed * 100 + case)
+        state, sbuf = cg.pixel_major((B, Cin, H, W), tdt, "cuda", 0)
+        state.copy_((torch.rand(B, Cin, H, W, generator=g) - 0.5).to(tdt))
+        w = ((torch.rand(Cout, Cin, k, k, generator=g) - 0.5) * 2 * (Cin * k * k) ** -0.5).to(tdt).cuda()
+        bias = (torch.rand(Cout, generator=g) - 0.5).to(tdt).cuda()
+        sel = torch.nonzero(torch.rand(B * H * W, generator=g) < frac).view(-1).int().cuda()
+        ci = cg.ChangeIndexes.from_tensor(sel, (B, H, W))
+        out, obuf = cg.pixel_major((B, Cout, H, W), tdt, "cuda", 0)
+        out.fill_(2.0)
+        cg.conv_update(sbuf, ci, cg.pack_weights(w, gemm), bias.float().contiguous(), obuf, Cin, Cout,
+                       (k, k), False, gemm, ws=ws if case % 4 else None)
+        torch.cuda.synchronize()
+        ref = F.conv2d(state.float(), w.float(), bias.float(), padding=k // 2)
+        touched = torch.zeros(B * H * W, dtype=torch.bool, device="cuda")
+        touched[sel.long()] = True
+        tm = touched.view(B, 1, H, W).expand(B, Cout, H, W)
+        o = out.float()
+        info = (seed, case, mode, dt, B, Cin, Cout, H, W, k, frac, int(sel.numel()))
+        if not bool(touched.all()):
+            assert float((o[~tm] - 2.0).abs().max()) == 0.0, info
+        if bool(touched.any()):
+            err = float((o[tm] - ref[tm]).abs().max()) / (float(ref.abs().max()) + 1e-30)
+            assert err <= CONV_TOL[(mode, dt)], (err,) + info
+        assert float(obuf[..., Cout:].abs().sum()) == 0.0, info
+    assert int(ws.view(torch.int32)[:1024].abs().sum()) == 0
+
+
 def test_conv_update_zero_changes_is_noop(cbm):
     cg, lib = cbm["cg"], cbm["lib"]
     state, sbuf = cg.pixel_major((1, 16, 8, 8), torch.float32, "cuda", 1.0)
