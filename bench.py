@@ -386,6 +386,7 @@ def main():
         barrier()
         u8_fps, u8_ms = streams.whole_job_rate(S * K, u8_wall_ms, dev)
         e2e_u8 = {"value": u8_fps, "unit": "frames/s", "ms_per_step": u8_ms / K,
+                  "h2d_gbs": pinned8[0].numel() / (u8_ms / K * 1e-3) / 1e9,
                   "h2d_bytes_per_step": pinned8[0].numel(), "d2h_bytes_per_step": d2h,
                   "checksum": float(pipe8.out_host[last].float().abs().sum()),
                   "path": "as e2e, but the pinned host frames are uint8 and are normalised (u8/255) inside "
@@ -406,6 +407,7 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / K, "checksum": e2e_checksum,
+                "h2d_gbs": h2d / (e2e_ms / K * 1e-3) / 1e9,     # PCIe roofline of this leg (Gen5 x16 ~ 55 GB/s)
                 "path": "runtime.FramePipeline: per step pinned H2D of the frames, one graph replay, D2H of the "
                         "logits; copies of neighbouring steps overlap compute (3 streams); host wall clock"},
         "gpu_launches": my_launches_per_step * K,
