@@ -452,6 +452,41 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
       }
       asm volatile("bar.sync 1, %0;" ::"n"(UM_PRODUCERS) : "memory");   // producers only
       if (tid == 0) mbar_arrive(&ctrl->tab_full[buf]);      // release: the epilogue may read the table
+      const long long lo_delta = SPLIT3 ? (state_lo - state) : 0;
+      if (half_taps) {
+        // 8-byte taps: lane = (row pair, chunk, half) so that one warp instruction writes both
+        // halves of 16 chunks of 2 rows -- all 32 banks of the 128B-swizzled tile (2 wavefronts
+        // instead of ~6 with a fixed half per instruction) -- and reads 16 consecutive taps per row
+        const int hh = tid & 1, c2 = (tid >> 1) & 7, q0 = tid >> 4;      // rows q0 + 16*it
+        constexpr int HR = UM_BM / 16;
+        int hpix[HR], hyx[HR];
+#pragma unroll
+        for (int it = 0; it < HR; ++it) {
+          hpix[it] = ctrl->pix[buf][q0 + 16 * it];
+          hyx[it] = ctrl->yx[buf][q0 + 16 * it];
+        }
+        const uint32_t hoff = (uint32_t)((q0 >> 3) * 1024 + (q0 & 7) * 128 + ((c2 ^ (q0 & 7)) << 4) + 8 * hh);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&ctrl->empty[stage], phase ^ 1u);
+          const uint32_t a_hi = smem_u32(smem + stage * C::STAGE_BYTES) + hoff;
+          int2 e;
+          asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];"
+                       : "=r"(e.x), "=r"(e.y)
+                       : "r"(ktab_s + (uint32_t)(((kb * 8 + c2) * 2 + hh) * 8)));
+          const int dy = e.y >> 16, dx = (int)(short)(e.y & 0xffff);
+#pragma unroll
+          for (int it = 0; it < HR; ++it) {
+            const bool ok = hpix[it] >= 0 && (unsigned)((hyx[it] >> 16) + dy) < (unsigned)H &&
+                            (unsigned)((hyx[it] & 0xffff) + dx) < (unsigned)W;
+            const T* src = ok ? state + ((long long)hpix[it] * 4 + e.x) : state;
+            cp_async8(a_hi + it * 2048, src, ok ? 8u : 0u);
+            if (SPLIT3) cp_async8(a_hi + C::A_BYTES + it * 2048, src + lo_delta, ok ? 8u : 0u);
+          }
+          cp_async_arrive_noinc(&ctrl->full[stage]);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+        }
+        continue;
+      }
       // per-row source pointers (pixel base) and coordinates of my RPT rows
       const T* rbase[RPT];
       int ry[RPT], rx[RPT];
@@ -462,7 +497,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
         ry[it] = pix < 0 ? -0x40000000 : (yx >> 16);        // invalid rows fail every bounds test
         rx[it] = yx & 0xffff;
       }
-      const long long lo_delta = SPLIT3 ? (state_lo - state) : 0;
       KCursor cur;
       cur.init(kb0 * C::BK + c * C::VEC, Cp, kW);
       // Gather = async 16-byte copies straight into the swizzled UMMA tile (zero-filled outside
@@ -470,26 +504,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&ctrl->empty[stage], phase ^ 1u);
         const uint32_t a_hi = smem_u32(smem + stage * C::STAGE_BYTES);
-        if (half_taps) {                                     // (always table-driven: K is tiny)
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            int2 e;
-            asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];"
-                         : "=r"(e.x), "=r"(e.y)
-                         : "r"(ktab_s + (uint32_t)(((kb * 8 + c) * 2 + h) * 8)));
-            const int dy = e.y >> 16, dx = (int)(short)(e.y & 0xffff);
-#pragma unroll
-            for (int it = 0; it < RPT; ++it) {
-              const bool ok = (unsigned)(ry[it] + dy) < (unsigned)H && (unsigned)(rx[it] + dx) < (unsigned)W;
-              const T* src = ok ? rbase[it] + e.x : state;
-              cp_async8(a_hi + soff[it] + 8 * h, src, ok ? 8u : 0u);
-              if (SPLIT3) cp_async8(a_hi + C::A_BYTES + soff[it] + 8 * h, src + lo_delta, ok ? 8u : 0u);
-            }
-          }
-          cp_async_arrive_noinc(&ctrl->full[stage]);
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
-          continue;
-        }
         int dy, dx;
         long long koff;
         bool kvalid;
