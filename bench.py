@@ -447,8 +447,8 @@ def main():
 
 
 def kernel_roofline(args, model, frames, dev, tdt, step_us):
-    """Per-kernel CUDA-event timing of the same frames (eager, one event pair per launch) and the
-    roofline of the dominant kernel.  Algorithmic bytes / FLOPs per launch: DESIGN.md section 4."""
+    """Per-kernel CUDA-event timing of one steady-state frame (graph replays of each recorded launch)
+    and the roofline of the dominant kernel.  Algorithmic bytes / FLOPs per launch: DESIGN.md 3."""
     import torch
     import cbinfer_b200 as cb
     from cbinfer_b200 import conv2d_cg as cg
@@ -461,52 +461,83 @@ def kernel_roofline(args, model, frames, dev, tdt, step_us):
     bf16 = float(peaks.get("bf16_tflops", 1590.0))
     src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
     es = 4 if args.dtype == "f32" else 2
-    rec = {}
+    # Steady-state time of every launch of one frame: the arguments of each C-ABI call of a real
+    # frame are recorded, then each call is replayed REP times inside one CUDA graph and timed with
+    # CUDA events on the launching stream (per-launch time incl. the dependent-launch gap; an event
+    # pair around a single eager launch would include the host's launch latency).  Replays run in
+    # reverse order so a producer's repetitions do not wipe its consumers' inputs.
+    REP = 20
     cur = {"layer": None}
-    orig = {n: getattr(cg, n) for n in ("detect", "detect_sparse", "dilate_compact", "pool_compact",
-                                        "conv_update", "maxPool2d", "maxPool2d_detect",
-                                        "detect_compact_sparse")}
+    calls = []
+    names = ("detect", "detect_sparse", "dilate_compact", "pool_compact", "conv_update", "maxPool2d",
+             "maxPool2d_detect", "detect_compact_sparse")
+    orig = {n: getattr(cg, n) for n in names}
 
-    def timed(name):
+    def recorder(name):
         fn = orig[name]
 
         def w(*a, **k):
-            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a0.record()
-            r = fn(*a, **k)
-            a1.record()
-            rec.setdefault((cur["layer"], name), []).append((a0, a1))
-            return r
+            if name == "dilate_compact":
+                k = dict(k, clear_raw=False)  # keep the raw bitmap: the replays must see the real input
+            calls.append((cur["layer"], name, a, k))
+            return fn(*a, **k)
         return w
 
     hooks = []
     for lname, m in model.named_children():
         hooks.append(m.register_forward_pre_hook(lambda mod, inp, lname=lname: cur.__setitem__("layer", lname)))
-    for n in orig:
-        setattr(cg, n, timed(n))
     try:
         cb.clearMemory(model)
         with torch.no_grad():
-            for i in range(0, 12):
+            for i in range(0, 4):
                 model(frames[i])
-                if i == 1:
-                    rec.clear()               # drop the all-changed first frames
+            for n in orig:
+                setattr(cg, n, recorder(n))
+            model(frames[4])
         torch.cuda.synchronize()
+        counts = {ln: int(m._scratch["count"].item()) for ln, m in model.named_children()
+                  if type(m) is cb.CBConv2d}
     finally:
         for n, f in orig.items():
             setattr(cg, n, f)
         for h in hooks:
             h.remove()
+    rec = {}
+    for lname, kname, a, k in reversed(calls):
+        k = dict(k)
+        if kname == "dilate_compact":
+            k["clear_raw"] = False           # keep the input bitmap intact across repetitions
+        if kname == "detect_sparse":
+            k["bits_are_clear"] = False
+        fn = orig[kname]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            fn(*a, **k)
+        torch.cuda.current_stream().wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(REP):
+                fn(*a, **k)
+        g.replay()
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(3):
+            g.replay()
+        a1.record()
+        torch.cuda.synchronize()
+        rec[(lname, kname)] = (a0.elapsed_time(a1) * 1e3 / (3 * REP), 3 * REP)
+        del g
     mods = dict(model.named_children())
     table = []
-    for (lname, kname), evs in rec.items():
-        us = sum(a.elapsed_time(b) for a, b in evs) / len(evs) * 1e3
+    for (lname, kname), (us, nl) in rec.items():
         m = mods[lname]
-        row = {"layer": lname, "kernel": kname, "us": round(us, 2), "launches": len(evs)}
+        row = {"layer": lname, "kernel": kname, "us": round(us, 2), "launches": nl}
         if type(m) is cb.CBConv2d:
             B, Cin, Hh, Ww = m.prevInput.shape
             P = B * Hh * Ww
-            n = int(m._scratch["count"].item())
+            n = counts[lname]
             k2 = m.kernel_size[0] * m.kernel_size[1]
             if kname == "detect_sparse":
                 row.update(bound="hbm")
@@ -528,6 +559,7 @@ def kernel_roofline(args, model, frames, dev, tdt, step_us):
             row["frac"] = row["achieved"] / row["peak"]
             row["achieved"] = round(row["achieved"], 2)
         table.append(row)
+    cb.clearMemory(model)                     # the recorded frame left raw bitmaps uncleared
     table.sort(key=lambda r: -r["us"])
     total = sum(r["us"] for r in table)
     top = next((r for r in table if "achieved" in r), None)

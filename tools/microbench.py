@@ -41,6 +41,8 @@ def main():
              for n, m in model.named_children()]
     for n in OPS:
         def w(*a, _n=n, **k):
+            if _n == "dilate_compact":
+                k = dict(k, clear_raw=False)   # keep the raw bitmap so the replays see the real input
             calls.append((cur["layer"], _n, a, k))
             return orig[_n](*a, **k)
         setattr(cg, n, w)
