@@ -91,9 +91,14 @@ class CBPoolMax2d(nn.Module):
             self.outputState, self._stateBuf = cg.pixel_major((B, nc, oh, ow), input.dtype,
                                                               input.device, _INF)
             self._scratch = None
+        # candidates handed downstream are complete only if neither the producer's output nor this
+        # pool's state was written from outside the kernels (see CBConv2d.forward_normal)
+        complete = getattr(changeIndexes, 'complete', True) and \
+            getattr(self, '_outVersion', None) == self.outputState._version
+        self._outVersion = self.outputState._version
         nxt = self._fusedNext[0] if getattr(self, '_fusedNext', None) else None
         tgt = None
-        if nxt is not None and changeIndexes.bits is not None and input.stride(1) == 1:
+        if nxt is not None and complete and changeIndexes.bits is not None and input.stride(1) == 1:
             tgt = nxt._fusedDetectTarget(tuple(self.outputState.shape), input.dtype, input.device)
         if tgt is not None:
             # pooling + the next layer's detection in one kernel (cb_maxpool2x2_detect)
@@ -112,8 +117,9 @@ class CBPoolMax2d(nn.Module):
             s = self._scratch
             cg.pool_compact(changeIndexes.bits, (B, h, w), (B, oh, ow), s["idx"], s["count"], s["ws"],
                             out_bits=s["dil_bits"])
-            return 'changeIndexes', output, ChangeIndexes(s["idx"], s["count"], (B, oh, ow),
-                                                          bits=s["dil_bits"])
+            pooled = ChangeIndexes(s["idx"], s["count"], (B, oh, ow), bits=s["dil_bits"])
+            pooled.complete = complete
+            return 'changeIndexes', output, pooled
         if self.propChangeIndexes:
             # reference behaviour: the *input-resolution* indices are forwarded (conv2d.py:75-76)
             return 'changeIndexes', output, changeIndexes
@@ -237,6 +243,7 @@ class CBConv2d(nn.Module):
         if not getattr(self, 'candidateDetect', False) or self.finegrained or self._fresh \
                 or self._inBuf is None or tuple(self.prevInput.shape) != tuple(shape) \
                 or self.prevInput.dtype != dtype or self._lastThr is None \
+                or getattr(self, '_inVersion', None) != self.prevInput._version \
                 or self.threshold < self._lastThr or self._scratch is None \
                 or not self._scratch.get("raw_clear", False):
             return None
@@ -306,6 +313,15 @@ class CBConv2d(nn.Module):
         outpSize = (B, self.out_channels, H, W)
         if tuple(self.prevOutput.size()) != outpSize or self.prevOutput.dtype != dt or self._outBuf is None:
             self.prevOutput, self._outBuf = cg.pixel_major(outpSize, dt, dev, _INF)    # :195-199
+        # State tensors written from outside this module's kernels (the reference's eval scripts
+        # snapshot and restore getStateTensors() with copy_, poseDetection/eval03.py:87-95): torch
+        # bumps the tensor version, our kernels do not.  A touched prevInput is treated as fresh
+        # (dense scan, operand planes rebuilt); a touched prevOutput makes this frame's index list
+        # an incomplete candidate set for the next layer.
+        if getattr(self, '_inVersion', None) != self.prevInput._version:
+            self._fresh = True
+            self._auxPlanes = None
+        ext_out = getattr(self, '_outVersion', None) != self.prevOutput._version
         if self._scratch is None:
             self._scratch = cg.alloc_scratch((B, H, W), dev, want_map=self.saveChangeMap)
         if self.saveChangeMap and "dil_map" not in self._scratch:
@@ -329,7 +345,7 @@ class CBConv2d(nn.Module):
             if not isinstance(candidates, ChangeIndexes):
                 candidates = ChangeIndexes.from_tensor(candidates.detach(), (B, H, W))
             if self._fresh or self._lastThr is None or self.threshold < self._lastThr \
-                    or tuple(candidates.shape) != (B, H, W):
+                    or tuple(candidates.shape) != (B, H, W) or not getattr(candidates, 'complete', True):
                 candidates = None          # exactness conditions not met: full scan
 
         if changeIndexes is None:
@@ -384,6 +400,12 @@ class CBConv2d(nn.Module):
                        lo_buf=aux[2] if aux is not None and aux[0] == 'tf32' else None,
                        planes16=aux[1:] if aux is not None and aux[0] == 'bf16' else None,
                        ws=self._workspace(dev))                                        # :242-251
+        self._inVersion = self.prevInput._version
+        self._outVersion = self.prevOutput._version
+        if ext_out and isinstance(changeIndexes, ChangeIndexes):
+            changeIndexes.complete = False
+        elif isinstance(changeIndexes, ChangeIndexes):
+            changeIndexes.complete = True
 
         if self.propChangeIndexes:
             return 'changeIndexes', self.prevOutput, changeIndexes

@@ -43,6 +43,9 @@ class ChangeIndexes(object):
         self.count = count            # int32 [1] on the device
         self.shape = shape            # (B, H, W) the indices refer to
         self.bits = bits              # optional dilated bitmap the list was compacted from
+        # False when the producer's output was also modified outside its own kernels (e.g. a state
+        # snapshot restored with copy_): the list is then not a complete candidate set downstream
+        self.complete = True
 
     @classmethod
     def from_tensor(cls, idx, shape):

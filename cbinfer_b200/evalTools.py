@@ -62,6 +62,33 @@ def inferFramesetBenchmark(model, frames, cuda=True, preprocessor=None, repeat=3
     return (min(times), min(state["ev"])) if cuda else (min(times), None)
 
 
+def inferNextFrameBenchmark(model, frame, numIter=3):
+    """reference poseDetection/eval03.py:87-106: time ONE next frame from the model's current state
+    - snapshot getStateTensors(), and before every repetition restore the snapshot with copy_.  The
+    modules notice state written from outside their kernels (tensor version) and fall back to the
+    dense scan / rebuild their operand planes for that frame, so every repetition does the same work
+    and gives the same result.  Returns (min wall seconds, min CUDA-event seconds)."""
+    from . import getStateTensors
+    snapshot = [t.clone() for t in getStateTensors(model)]
+    frame = frame.cuda()
+    torch.cuda.synchronize()
+    wall, dev = [], []
+    for _ in range(numIter):
+        for now, prev in zip(getStateTensors(model), snapshot):
+            now.copy_(prev)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = timeit.default_timer()
+        a.record()
+        with torch.no_grad():
+            model(frame)
+        b.record()
+        torch.cuda.synchronize()
+        wall.append(timeit.default_timer() - t0)
+        dev.append(a.elapsed_time(b) * 1e-3)
+    return min(wall), min(dev)
+
+
 def getCBconvLayers(model):
     """reference evalTools.py:85-103 in spirit: the CBConv2d modules in forward order."""
     return [m for m in model.modules() if type(m) is CBConv2d]

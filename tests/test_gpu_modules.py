@@ -495,3 +495,40 @@ def test_save_load_converted_model_roundtrip(tmp_path):
     assert repr(m2) == repr(m)
     for f, o in zip(frames, outs):
         assert torch.equal(m2(f), o)
+
+
+@pytest.mark.parametrize("cand", [True, False])
+def test_state_snapshot_restore_like_eval03(cand):
+    """the reference's per-frame timing restores getStateTensors() snapshots with copy_
+    (poseDetection/eval03.py:87-95): hidden operand planes and the candidate-detection shortcuts must
+    not go stale when the state is written from outside the kernels."""
+    import cbinfer_b200 as cb
+    from cbinfer_b200 import evalTools, models, video
+    base = models.sceneLabelingBaseline().cuda()
+    frames = [f.cuda() for f in video.sequence(2, 48, 72, 6, 0.1)]
+    ms = [models.sceneLabelingCBinfer(base, experimentIdx=6, threshold=0.02, candidateDetect=cand)
+          for _ in range(2)]
+    for f in frames[:3]:
+        for m in ms:
+            m(f)
+    snap = [t.clone() for t in cb.getStateTensors(ms[0])]
+    a = ms[0](frames[3]).clone()
+    ref3 = ms[1](frames[3]).clone()
+    assert torch.equal(a, ref3)
+    for now, prev in zip(cb.getStateTensors(ms[0]), snap):      # back to the state before frame 3
+        now.copy_(prev)
+    b = ms[0](frames[3]).clone()
+    assert torch.equal(b, ref3)
+    # and the sequence continues identically afterwards (candidate path re-armed)
+    for f in frames[4:]:
+        assert torch.equal(ms[0](f), ms[1](f))
+    # a restore to a much older state followed by a different frame: still equal to a model that
+    # really was in that state
+    m3 = models.sceneLabelingCBinfer(base, experimentIdx=6, threshold=0.02, candidateDetect=cand)
+    for f in frames[:3]:
+        m3(f)
+    for now, prev in zip(cb.getStateTensors(ms[0]), snap):
+        now.copy_(prev)
+    assert torch.equal(ms[0](frames[5]), m3(frames[5]))
+    wall, dev = evalTools.inferNextFrameBenchmark(ms[0], frames[4])
+    assert wall > 0 and dev > 0
