@@ -172,3 +172,47 @@ def poseModelCBinfer(pose, threshold=1e-1, feedbackLoop=True, pools=True):
             mm.feedbackLoop = feedbackLoop
             mm.copyInput = False
     return shareWorkspace(m).eval()
+
+
+def getCBModuleList(m):
+    """the CBConv2d layers of a (sub)model in forward order (poseDetection/modelConverter.py:76-83)"""
+    return [mm for mm in m.modules() if type(mm) is CBConv2d]
+
+
+def tuneHierarchical(modelTest, tuneModules, lossTolFirst=5e-5, lossTolDefault=2e-6):
+    """Block-wise threshold search of the reference's pose experiment 11
+    (poseDetection/modelConverter.py:107-168), generalised from T=2 to any number of stages:
+    all thresholds start at 0; the trunk ``model0`` is tuned together with ``model1_1``; then, stage
+    by stage, branch 1 is tuned, its thresholds are stashed and zeroed while branch 2 of the same
+    stage is tuned (so the two branches do not mask each other's loss), and restored afterwards.
+
+    ``tuneModules(cbModuleList, lossToleranceList)`` runs the greedy search on the given layers -
+    normally a closure over :func:`cbinfer_b200.tuneThresholdParameters` with the user's sequences
+    (exactly what the reference script does).  Returns {block name: thresholds}."""
+    allMods = getCBModuleList(modelTest)
+    for m in allMods:
+        m.threshold = 0
+    names = dict(modelTest.named_children())
+    out = {}
+    t = 1
+    while 'model%d_1' % t in names:
+        b1, b2 = names['model%d_1' % t], names.get('model%d_2' % t)
+        mods1 = getCBModuleList(b1)
+        if t == 1 and 'model0' in names:
+            mods = getCBModuleList(names['model0']) + mods1
+            tuneModules(mods, [lossTolFirst] + [lossTolDefault] * (len(mods) - 1))
+            out['model0'] = [m.threshold for m in getCBModuleList(names['model0'])]
+        else:
+            tuneModules(mods1, [lossTolDefault] * len(mods1))
+        stash = [m.threshold for m in mods1]
+        out['model%d_1' % t] = stash
+        if b2 is not None:
+            for m in mods1:
+                m.threshold = 0
+            mods2 = getCBModuleList(b2)
+            tuneModules(mods2, [lossTolDefault] * len(mods2))
+            out['model%d_2' % t] = [m.threshold for m in mods2]
+            for m, th in zip(mods1, stash):
+                m.threshold = th
+        t += 1
+    return out

@@ -106,3 +106,39 @@ def test_synthetic_video_change_rate():
         assert abs(rate - 0.05) < 0.01
     fr = video.sequence(1, 48, 64, 3, 0.2, mode="iid")
     assert 0.1 < (fr[1] != fr[0]).any(1).float().mean().item() < 0.3
+
+
+def test_hierarchical_tuner_and_pickle_roundtrip(tmp_path):
+    """host logic of the reference's pose experiment 11 (poseDetection/modelConverter.py:107-168):
+    trunk + first branch together, then per stage branch 1 / branch 2 with the stash-zero-restore
+    dance; and the deployment flow clearMemory + torch.save / torch.load of a converted model."""
+    import torch
+    import cbinfer_b200 as cb
+    from cbinfer_b200 import models
+    pose = models.poseModelCBinfer(models.PoseModel(T=3), threshold=0.5)
+    calls = []
+
+    def fake_tune(mods, tols):
+        assert len(mods) == len(tols)
+        # everything outside the modules being tuned is either untuned (0) or already restored
+        others = [m.threshold for m in models.getCBModuleList(pose) if m not in mods]
+        calls.append((len(mods), tols[0], sorted(set(others))))
+        for i, m in enumerate(mods):
+            m.threshold = 0.01 * (len(calls) + i / 100.0)
+
+    out = models.tuneHierarchical(pose, fake_tune)
+    assert list(out) == ['model0', 'model1_1', 'model1_2', 'model2_1', 'model2_2', 'model3_1', 'model3_2']
+    assert calls[0][1] == 5e-5 and all(c[1] == 2e-6 for c in calls[1:])
+    assert calls[0][2] == [0]                                  # first call: everything else at 0
+    # while model1_2 is tuned, model1_1 is zeroed: the only non-zero thresholds are model0's
+    kids = dict(pose.named_children())
+    n0 = len(models.getCBModuleList(kids['model0']))
+    assert all(m.threshold > 0 for m in models.getCBModuleList(pose))
+    assert len(calls) == 6 and calls[0][0] == n0 + len(models.getCBModuleList(kids['model1_1']))
+    cb.clearMemory(pose)
+    path = str(tmp_path / "pose.net")
+    torch.save(pose, path)
+    back = torch.load(path, weights_only=False)
+    assert [m.threshold for m in models.getCBModuleList(back)] == \
+        [m.threshold for m in models.getCBModuleList(pose)]
+    assert repr(back) == repr(pose)
