@@ -265,6 +265,8 @@ int cb_maxpool2x2(void* stream, int dtype, const void* x, long long x_sb, long l
     const int cpp = (int)(x_sx / vec);
     int glog = 0;
     while ((1 << glog) < cpp && glog < 5) ++glog;
+    glog = cb::glog_tuned(glog);
+  glog = cb::glog_tuned(glog);
     CB_DISPATCH_DTYPE(dtype, (cb::launch_pdl(maxpool2x2_vec_kernel<T, VEC>, grid, 256, 0, (cudaStream_t)stream, 
                                  (const T*)x, x_sb, x_sy, (int)x_sx, idx, count, dil_bits, (T*)out,
                                  o_sb, o_sy, (int)o_sx, cpp, glog, H, W, oH, oW)));
@@ -316,6 +318,7 @@ int cb_maxpool2x2_detect(void* stream, int dtype, const void* x, long long x_sb,
   const int cpp = x_pitch / vec;
   int glog = 0;
   while ((1 << glog) < cpp && glog < 5) ++glog;
+  glog = cb::glog_tuned(glog);
   const unsigned grid = (unsigned)(sm_count() * 16);
   cudaStream_t s = (cudaStream_t)stream;
 #define CB_MPD(U_)                                                                                \

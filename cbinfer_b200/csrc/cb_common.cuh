@@ -39,6 +39,19 @@ __device__ __forceinline__ void pdl_prologue() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
+// log2 of the lanes that share one pixel in the candidate-detection / pooling kernels.  One lane
+// per 16-byte chunk would be the obvious choice; two chunks per lane halves the number of warps
+// (one wave instead of two at 8 streams) and doubles the loads in flight per lane: measured
+// pool+detect 11.3 -> 8.3 us, sparse detect 7.7 -> 6.7 us.  CBINFER_GLOG_DELTA overrides (tuning).
+inline int glog_tuned(int glog) {
+  static const int delta = [] {
+    const char* e = getenv("CBINFER_GLOG_DELTA");
+    return e ? atoi(e) : 1;
+  }();
+  const int g = glog - delta;
+  return g < 0 ? 0 : g;
+}
+
 template <typename... KArgs, typename... Args>
 inline void launch_cluster(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
                            cudaStream_t s, unsigned cluster_x, Args&&... args) {

@@ -537,6 +537,7 @@ int launch_detect_sparse(cudaStream_t stream, const void* x, long long x_sb, lon
   const int cpv = (C + VEC - 1) / VEC;
   int glog = 0;
   while ((1 << glog) < cpv && glog < 5) ++glog;
+  glog = cb::glog_tuned(glog);
 #define CB_DETS(U_)                                                                              \
   if (vec_ok)                                                                                    \
     cb::launch_pdl(detect_sparse_vec_kernel<T, VEC, U_>, grid, 256, 0, stream,                               \
@@ -704,6 +705,7 @@ int launch_detect_compact_sparse(cudaStream_t stream, const void* x, long long x
   const int cpv = (C + VEC - 1) / VEC;
   int glog = 0;
   while ((1 << glog) < cpv && glog < 5) ++glog;
+  glog = cb::glog_tuned(glog);
   const unsigned grid = (unsigned)(sm_count() * 8);
   const int Wd = (W + 31) / 32;
   const T thr = thr_cast<T>(threshold);
