@@ -24,7 +24,7 @@ SYMBOLS = [
     "cb_version", "cb_last_error", "cb_device_info", "cb_bitmap_row_words", "cb_bitmap_words",
     "cb_compact_ws_bytes", "cb_channel_pitch", "cb_plane_pitch16", "cb_packed_weight_bytes", "cb_change_detect", "cb_change_detect_u8",
     "cb_dilate_compact", "cb_map_to_bits", "cb_change_detect_sparse", "cb_pool_compact", "cb_maxpool2x2_detect",
-    "cb_detect_compact_ws_bytes", "cb_detect_compact_sparse", "cb_pack_weights", "cb_conv_ws_bytes", "cb_conv_update", "cb_maxpool2x2",
+    "cb_detect_compact_ws_bytes", "cb_detect_compact_sparse", "cb_pack_weights", "cb_conv_ws_bytes", "cb_conv_update", "cb_conv_update_masked", "cb_maxpool2x2",
     "cb_gen_xmatrix", "cb_matrix_mult", "cb_update_output", "cb_fg_update",
 ]
 
@@ -69,6 +69,8 @@ def _load():
         "cb_conv_ws_bytes": (sz, []),
         "cb_conv_update": (i32, [vp, i32, i32, vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32,
                                  i32, i32, i32, i32, i32, vp, sz]),
+        "cb_conv_update_masked": (i32, [vp, i32, i32, vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32,
+                                        i32, i32, i32, i32, i32, vp, sz, vp, i32, vp, vp]),
         "cb_maxpool2x2": (i32, [vp, i32, vp, i64, i64, i64, i64, vp, vp, vp, vp, i64, i64, i64,
                                 i64, i32, i32, i32, i32, i32, i32]),
         "cb_maxpool2x2_detect": (i32, [vp, i32, vp, i64, i64, i32, vp, vp, vp, vp, i64, i64, i32,

@@ -180,6 +180,8 @@ class CBConv2d(nn.Module):
         self.fuse1x1 = False      # extension: detect+compact in one launch for 1x1 layers
         # extension: (divisor, bias) applied to uint8 input frames inside the detection kernel
         self.inputNorm = None
+        # extension: 1x1 layer on the candidate path without any compaction (see forward_normal)
+        self.maskedConv = False
         self._wsHolder = cg.ConvWorkspace()    # shared per model by pycbinfer.convert()
 
     # ---- state ---------------------------------------------------------------------------
@@ -336,6 +338,7 @@ class CBConv2d(nn.Module):
         aux_arg = None if aux is None else (aux[:2] if aux[0] == 'tf32' else aux)
 
         candidates = None
+        mask = None
         detected = isinstance(changeIndexes, DetectionDone)
         if detected:
             assert changeIndexes.owner is self
@@ -360,6 +363,12 @@ class CBConv2d(nn.Module):
             fused11 = (candidates is not None and tuple(self.kernel_size) == (1, 1)
                        and getattr(self, 'fuse1x1', False)
                        and not self.saveChangeMap and input.stride(1) == 1)
+            # extension: no compaction at all for a 1x1 layer on the candidate path - the
+            # contraction walks the candidate list and skips pixels whose raw bit is not set
+            # (cb_conv_update_masked); this layer's own index list is then never materialised
+            masked = (candidates is not None and not detected and tuple(self.kernel_size) == (1, 1)
+                      and getattr(self, 'maskedConv', False) and not fused11
+                      and not self.saveChangeMap and gemm != _lib.GEMM_SIMT_F32)
             if detected:
                 pass                     # the upstream pool kernel already did it
             elif fused11:
@@ -373,6 +382,10 @@ class CBConv2d(nn.Module):
                 cg.detect_sparse(input, self.prevInput, s["raw_bits"], self.threshold, mode,
                                  candidates, aux=aux_arg,
                                  bits_are_clear=s.get("raw_clear", False))
+                if masked:
+                    if "mask_sync" not in s:
+                        s["mask_sync"] = torch.zeros(2, dtype=torch.int32, device=dev)
+                    mask = dict(bits=s["raw_bits"], clear=True, count=s["count"], sync=s["mask_sync"])
             elif u8norm is not None:
                 cg.detect_u8(input, self.prevInput, s["raw_bits"], self.threshold, mode,
                              u8norm[0], u8norm[1], aux=aux_arg)
@@ -383,6 +396,10 @@ class CBConv2d(nn.Module):
             if not detected and fused11:
                 s["raw_clear"] = False
                 changeIndexes = ChangeIndexes(s["idx"], s["count"], (B, H, W), bits=None)
+            elif mask is not None:
+                s["raw_clear"] = True                # the masked contraction clears the bitmap
+                changeIndexes = ChangeIndexes(candidates.buffer, candidates.count, (B, H, W), bits=None)
+                changeIndexes.superset = True
             else:
                 changeIndexes = self._compact(s, B, H, W, sparse_next)
         else:
@@ -399,7 +416,7 @@ class CBConv2d(nn.Module):
                        self.out_channels, self.kernel_size, self.withReLU, gemm,
                        lo_buf=aux[2] if aux is not None and aux[0] == 'tf32' else None,
                        planes16=aux[1:] if aux is not None and aux[0] == 'bf16' else None,
-                       ws=self._workspace(dev))                                        # :242-251
+                       ws=self._workspace(dev), mask=mask)                             # :242-251
         self._inVersion = self.prevInput._version
         self._outVersion = self.prevOutput._version
         if ext_out and isinstance(changeIndexes, ChangeIndexes):
@@ -481,6 +498,7 @@ class CBConv2d(nn.Module):
         for name, val in (('saveChangeMap', False), ('propChangeIndexes', False),
                           ('gatherComputationStats', False), ('finegrained', False),
                           ('copyInput', True), ('feedbackLoop', False), ('gemmMode', 'auto'),
-                          ('candidateDetect', False), ('fuse1x1', False), ('inputNorm', None)):
+                          ('candidateDetect', False), ('fuse1x1', False), ('inputNorm', None),
+                          ('maskedConv', False)):
             if not(hasattr(self, name)):
                 setattr(self, name, val)

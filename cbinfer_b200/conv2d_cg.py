@@ -46,6 +46,9 @@ class ChangeIndexes(object):
         # False when the producer's output was also modified outside its own kernels (e.g. a state
         # snapshot restored with copy_): the list is then not a complete candidate set downstream
         self.complete = True
+        # True when the list is only a superset of the changed pixels (a masked 1x1 layer hands its
+        # own candidates on instead of compacting): fine as detection candidates, not an exact list
+        self.superset = False
 
     @classmethod
     def from_tensor(cls, idx, shape):
@@ -56,6 +59,9 @@ class ChangeIndexes(object):
         return cls(idx, count, shape)
 
     def tensor(self):
+        if self.superset:
+            raise _lib.CBinferError("this change list is a candidate superset (producer ran with "
+                                    "maskedConv=True); set maskedConv=False on it for exact lists")
         return self.buffer[: int(self.count.item())]
 
     # tensor-like conveniences (all synchronise)
@@ -263,7 +269,7 @@ class ConvWorkspace(object):
 
 
 def conv_update(state_buf, changes, packed_w, bias_f32, out_buf, Cin, Cout, filtSize, relu, gemm,
-                lo_buf=None, planes16=None, ws=None):
+                lo_buf=None, planes16=None, ws=None, mask=None):
     """cb_conv_update on pixel-major buffers [B,H,W,pitch].  GEMM_TC_3X (fp32) consumes the tf32
     remainder plane `lo_buf`, GEMM_TC_BF16X3 the bf16 hi/lo planes `planes16`; both are derived
     on the fly when the caller does not maintain them (cb_change_detect can)."""
@@ -278,6 +284,19 @@ def conv_update(state_buf, changes, packed_w, bias_f32, out_buf, Cin, Cout, filt
         pitch = src.shape[3]
     elif gemm == _lib.GEMM_TC_3X and state_buf.dtype == torch.float32 and lo_buf is None:
         src_lo = tf32_lo(state_buf)
+    if mask is not None:
+        # `changes` is a superset list; mask = dict(bits=raw bitmap, clear=bool, count=int32[1] out,
+        # sync=int32[2] zeroed once): only pixels whose bit is set are processed (cb_conv_update_masked)
+        check(C.cb_conv_update_masked(stream_ptr(state_buf.device), dtype_code(state_buf), gemm,
+                                      src.data_ptr(), src_lo.data_ptr() if src_lo is not None else None,
+                                      pitch, changes.buffer.data_ptr(), changes.count.data_ptr(),
+                                      packed_w.data_ptr(), bias_f32.data_ptr(), out_buf.data_ptr(),
+                                      out_buf.shape[3], B, H, W, Cin, Cout, filtSize[0], filtSize[1],
+                                      int(bool(relu)), ws.data_ptr() if ws is not None else None,
+                                      ws.numel() if ws is not None else 0,
+                                      mask['bits'].data_ptr(), int(bool(mask.get('clear', False))),
+                                      mask['count'].data_ptr(), mask['sync'].data_ptr()))
+        return
     check(C.cb_conv_update(stream_ptr(state_buf.device), dtype_code(state_buf), gemm,
                            src.data_ptr(), src_lo.data_ptr() if src_lo is not None else None,
                            pitch, changes.buffer.data_ptr(),

@@ -219,7 +219,7 @@ size_t cb_conv_ws_bytes(void) {
   return (size_t)cb::UM_SK_FLAG_BYTES + (size_t)sm_count() * 256 * 1024;
 }
 
-int cb_conv_update(void* stream, int dtype, int gemm, const void* state, const void* state_lo,
+static int conv_update_impl(const cb::RowMask& mk, void* stream, int dtype, int gemm, const void* state, const void* state_lo,
                    int pitch_in, const int32_t* idx, const int32_t* count, const void* packed_w,
                    const float* bias, void* out, int pitch_out, int B, int H, int W, int Cin,
                    int Cout, int kH, int kW, int relu, void* ws, size_t ws_bytes) {
@@ -232,6 +232,7 @@ int cb_conv_update(void* stream, int dtype, int gemm, const void* state, const v
   CB_CHECK_ARG((long long)B * H * W < (1ll << 31), "conv_update: more than 2^31 pixels");
   if (B == 0 || H == 0 || W == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
+  CB_CHECK_ARG(!(mk.bits && gemm == CB_GEMM_SIMT_F32), "conv_update_masked: tensor-core modes only");
   if (gemm == CB_GEMM_SIMT_F32) {
     const int CoutP = (Cout + 3) / 4 * 4;
     const unsigned grid = (unsigned)(sm_count() * 4);
@@ -242,7 +243,32 @@ int cb_conv_update(void* stream, int dtype, int gemm, const void* state, const v
     return 0;
   }
   return cb::umma_conv_update(s, dtype, gemm, state, state_lo, pitch_in, idx, count, packed_w, bias, out,
-                              pitch_out, B, H, W, Cin, Cout, kH, kW, relu, ws, ws_bytes);
+                              pitch_out, B, H, W, Cin, Cout, kH, kW, relu, ws, ws_bytes, mk);
+}
+
+int cb_conv_update(void* stream, int dtype, int gemm, const void* state, const void* state_lo,
+                   int pitch_in, const int32_t* idx, const int32_t* count, const void* packed_w,
+                   const float* bias, void* out, int pitch_out, int B, int H, int W, int Cin,
+                   int Cout, int kH, int kW, int relu, void* ws, size_t ws_bytes) {
+  return conv_update_impl(cb::RowMask{nullptr, nullptr, nullptr, nullptr, 0}, stream, dtype, gemm, state,
+                          state_lo, pitch_in, idx, count, packed_w, bias, out, pitch_out, B, H, W, Cin,
+                          Cout, kH, kW, relu, ws, ws_bytes);
+}
+
+int cb_conv_update_masked(void* stream, int dtype, int gemm, const void* state, const void* state_lo,
+                          int pitch_in, const int32_t* idx, const int32_t* count, const void* packed_w,
+                          const float* bias, void* out, int pitch_out, int B, int H, int W, int Cin,
+                          int Cout, int kH, int kW, int relu, void* ws, size_t ws_bytes,
+                          uint32_t* mask_bits, int clear_mask, int32_t* count_out, void* sync_ws) {
+  CB_CHECK_ARG(mask_bits && sync_ws, "conv_update_masked: null pointer");
+  cb::RowMask mk;
+  mk.bits = mask_bits;
+  mk.clear = clear_mask ? mask_bits : nullptr;
+  mk.count_out = count_out;
+  mk.sync = (unsigned*)sync_ws;
+  mk.nwords = (int)cb_bitmap_words(B, H, W);
+  return conv_update_impl(mk, stream, dtype, gemm, state, state_lo, pitch_in, idx, count, packed_w, bias,
+                          out, pitch_out, B, H, W, Cin, Cout, kH, kW, relu, ws, ws_bytes);
 }
 
 int cb_maxpool2x2(void* stream, int dtype, const void* x, long long x_sb, long long x_sc,

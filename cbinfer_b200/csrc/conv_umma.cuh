@@ -312,6 +312,40 @@ __device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// Row mask: `idx` may be a SUPERSET of the pixels to update (e.g. the previous layer's change list
+// handed to a 1x1 layer as detection candidates); a row is processed only if its pixel's bit is set
+// in `bits` (the raw change bitmap the detection just produced).  That removes the ordered
+// compaction between detection and contraction for layers that need no dilation.  The number of
+// processed pixels is written to *count_out; with `clear` the last CTA to finish zeroes the bitmap
+// (ready for the next frame's atomicOr-ing detection).  `sync` = {done counter, count accumulator},
+// zeroed once by the caller, left clean by the kernel.
+struct RowMask {
+  const uint32_t* bits;
+  uint32_t* clear;
+  int32_t* count_out;
+  unsigned* sync;
+  int nwords;
+};
+// (s_flag: one word of dynamic shared memory -- the kernel must not own static shared memory)
+__device__ __forceinline__ void rowmask_finish(const RowMask& mk, volatile unsigned* s_flag) {
+  // every CTA of the selected variant passes here exactly once, after its last read of the bitmap
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned prev = atomicAdd(mk.sync, 1u);
+    *s_flag = prev == gridDim.x - 1u;
+  }
+  __syncthreads();
+  if (!*s_flag) return;
+  __threadfence();
+  if (threadIdx.x == 0) {
+    if (mk.count_out) *mk.count_out = (int32_t)atomicExch(mk.sync + 1, 0u);
+    mk.sync[0] = 0u;
+  }
+  if (mk.clear)
+    for (int i = threadIdx.x; i < mk.nwords; i += blockDim.x) mk.clear[i] = 0u;
+}
+
 // packed weights: [NSPLIT][CoutPad][KpPad] elements of T (K-major); tensor map dims {KpPad, NSPLIT*CoutPad}
 // T = operand element type in the state planes / shared memory, TO = element type of `out`
 // (TO != T only for 3xBF16: bf16 hi/lo operand planes of an fp32 layer).
@@ -321,8 +355,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
                  const T* __restrict__ state_lo, int Cp, const int32_t* __restrict__ idx, const int32_t* __restrict__ count,
                  const float* __restrict__ bias, TO* __restrict__ out, int Op, int H, int W,
                  int Cout, int CoutPad, int kH, int kW, int Kp, int relu, int sel_lo, int sel_hi,
-                 uint32_t* __restrict__ sk_ws) {
+                 uint32_t* __restrict__ sk_ws, const RowMask mk) {
   pdl_prologue();
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   using C = UmmaCfg<T, SPLIT3, BN, DEEP>;
   constexpr int UM_EPI = um_epi(BN), UM_THREADS = um_threads(BN);
   constexpr int RPT = UM_BM * 8 / UM_PRODUCERS;            // 16-byte chunks per thread per stage
@@ -346,10 +381,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
   const bool sk = !DEEP && sk_ws != nullptr;              // stream-K (never together with clusters)
   if (!sk && tile0 >= total_tiles) {                      // group-uniform: before any barrier / alloc
     if (KSmax > 1) { cluster_sync_all(); cluster_sync_all(); }   // busy peers still sync twice
+    if (mk.bits) rowmask_finish(mk, reinterpret_cast<volatile unsigned*>(smem_raw));
     return;
   }
 
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if (smem_u32(smem) & 1023u) __trap();                   // SWIZZLE_128B tiles need 1024-byte alignment
   UmmaCtrl* ctrl = reinterpret_cast<UmmaCtrl*>(smem + C::STAGES * C::STAGE_BYTES);
@@ -446,9 +481,18 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
           const int p = pix % P;
           const int yy = p / W;
           yx = (yy << 16) | (p - yy * W);
+          if (mk.bits) {                                    // superset list: keep flagged pixels only
+            const int xx = p - yy * W;
+            const uint32_t wbits = mk.bits[((long long)(pix / P) * H + yy) * ((W + 31) >> 5) + (xx >> 5)];
+            if (!((wbits >> (xx & 31)) & 1u)) pix = -1;
+          }
         }
         ctrl->pix[buf][tid] = pix;
         ctrl->yx[buf][tid] = yx;
+        if (mk.bits && kb0 == 0 && tile - mt * ntiles == 0 && krank == 0) {   // once per M tile
+          const unsigned m = __ballot_sync(0xffffffffu, pix >= 0);
+          if ((tid & 31) == 0 && m) atomicAdd(mk.sync + 1, (unsigned)__popc(m));
+        }
       }
       asm volatile("bar.sync 1, %0;" ::"n"(UM_PRODUCERS) : "memory");   // producers only
       if (tid == 0) mbar_arrive(&ctrl->tab_full[buf]);      // release: the epilogue may read the table
@@ -774,6 +818,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
                  "r"((uint32_t)C::TMEM_COLS)
                  : "memory");
   }
+  if (mk.bits) rowmask_finish(mk, &ctrl->pad);
 }
 
 // ---- weight packing ----------------------------------------------------------------------------
@@ -893,7 +938,8 @@ int launch_conv_umma(cudaStream_t s, int dtype, const void* state, const void* s
                      const int32_t* idx,
                      const int32_t* count, const void* packed, const float* bias, void* out,
                      int Op, int B, int H, int W, int Cout, int CoutPad, int kH, int kW, int relu,
-                     int sel_lo, int sel_hi, int ksplit, void* ws, size_t ws_bytes) {
+                     int sel_lo, int sel_hi, int ksplit, void* ws, size_t ws_bytes,
+                     const RowMask& mk) {
   using C = UmmaCfg<T, SPLIT3, BN, DEEP>;
   const int Kp = kH * kW * Cp;
   const int KpPad = umma_kp_pad_es((int)sizeof(T), Cp, kH, kW);
@@ -990,7 +1036,7 @@ int launch_conv_umma(cudaStream_t s, int dtype, const void* state, const void* s
   cb::launch_cluster(kern, (unsigned)grid, um_threads(BN), (size_t)smem_bytes, s, (unsigned)ks, map, (const T*)state, (const T*)state_lo, Cp,
                                                         idx, count, bias,
                                                         (TO*)out, Op, H, W, Cout, CoutPad, kH, kW,
-                                                        Kp, relu, sel_lo, sel_hi, sk_ws);
+                                                        Kp, relu, sel_lo, sel_hi, sk_ws, mk);
   CB_CHECK_LAUNCH("conv_update(umma)");
   return 0;
 }
@@ -1000,12 +1046,12 @@ int dispatch_bn(int bn, cudaStream_t s, int dtype, const void* state, const void
                 const int32_t* idx,
                 const int32_t* count, const void* packed, const float* bias, void* out, int Op,
                 int B, int H, int W, int Cout, int CoutPad, int kH, int kW, int relu, int sel_lo,
-                int sel_hi, int ksplit, void* ws, size_t ws_bytes) {
+                int sel_hi, int ksplit, void* ws, size_t ws_bytes, const RowMask& mk) {
 #define CB_BN(N)                                                                              \
   case N:                                                                                     \
     return launch_conv_umma<T, TO, SPLIT3, N, DEEP>(s, dtype, state, state_lo, Cp, idx, count, packed, bias, out, \
                                           Op, B, H, W, Cout, CoutPad, kH, kW, relu, sel_lo,   \
-                                          sel_hi, ksplit, ws, ws_bytes);
+                                          sel_hi, ksplit, ws, ws_bytes, mk);
   if (DEEP) {                                  // the deep variant only exists for N tiles <= 64
     switch (bn) {
       CB_BN(16) CB_BN(32) CB_BN(64)
@@ -1022,7 +1068,8 @@ int dispatch_bn(int bn, cudaStream_t s, int dtype, const void* state, const void
 inline int umma_conv_update(cudaStream_t s, int dtype, int gemm, const void* state,
                             const void* state_lo, int Cp, const int32_t* idx, const int32_t* count, const void* packed,
                             const float* bias, void* out, int Op, int B, int H, int W, int Cin,
-                            int Cout, int kH, int kW, int relu, void* ws, size_t ws_bytes) {
+                            int Cout, int kH, int kW, int relu, void* ws, size_t ws_bytes,
+                            const RowMask& mk = RowMask{nullptr, nullptr, nullptr, nullptr, 0}) {
   (void)Cin;
   CB_CHECK_ARG(gemm == CB_GEMM_TC || gemm == CB_GEMM_TC_3X || gemm == CB_GEMM_TC_BF16X3,
                "conv_update: bad gemm mode %d", gemm);
@@ -1046,22 +1093,22 @@ inline int umma_conv_update(cudaStream_t s, int dtype, int gemm, const void* sta
     if (bf16x3)
       return dispatch_bn<__nv_bfloat16, float, true, DP>(tile_n, s, dtype, state, state_lo, Cp, idx,
                                                          count, packed, bias, out, Op, B, H, W,
-                                                         Cout, CoutPad, kH, kW, relu, lo, hi, ksplit, ws, ws_bytes);
+                                                         Cout, CoutPad, kH, kW, relu, lo, hi, ksplit, ws, ws_bytes, mk);
     switch (dtype) {
       case CB_F32:
         return split3 ? dispatch_bn<float, float, true, DP>(tile_n, s, dtype, state, state_lo, Cp, idx, count,
                                                  packed, bias, out, Op, B, H, W, Cout, CoutPad, kH,
-                                                 kW, relu, lo, hi, ksplit, ws, ws_bytes)
+                                                 kW, relu, lo, hi, ksplit, ws, ws_bytes, mk)
                       : dispatch_bn<float, float, false, DP>(tile_n, s, dtype, state, state_lo, Cp, idx, count,
                                                   packed, bias, out, Op, B, H, W, Cout, CoutPad,
-                                                  kH, kW, relu, lo, hi, ksplit, ws, ws_bytes);
+                                                  kH, kW, relu, lo, hi, ksplit, ws, ws_bytes, mk);
       case CB_F16:
         return dispatch_bn<__half, __half, false, DP>(tile_n, s, dtype, state, state_lo, Cp, idx, count, packed,
-                                          bias, out, Op, B, H, W, Cout, CoutPad, kH, kW, relu, lo, hi, ksplit, ws, ws_bytes);
+                                          bias, out, Op, B, H, W, Cout, CoutPad, kH, kW, relu, lo, hi, ksplit, ws, ws_bytes, mk);
       case CB_BF16:
         return dispatch_bn<__nv_bfloat16, __nv_bfloat16, false, DP>(tile_n, s, dtype, state, state_lo, Cp, idx, count,
                                                  packed, bias, out, Op, B, H, W, Cout, CoutPad, kH,
-                                                 kW, relu, lo, hi, ksplit, ws, ws_bytes);
+                                                 kW, relu, lo, hi, ksplit, ws, ws_bytes, mk);
       default: return fail(2, "conv_update: bad dtype %d", dtype);
     }
   };

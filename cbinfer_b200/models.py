@@ -31,7 +31,7 @@ def sceneLabelingBaseline(seed=0):
     return m
 
 
-def enableCandidateDetection(m, fusePool=True):
+def enableCandidateDetection(m, fusePool=True, maskedConv=True):
     """B200 extension (no reference counterpart): inside every nn.Sequential, let each CB layer
     hand its change set to a directly following CB layer as detection *candidates*, so that layer
     thresholds only the pixels that were just rewritten instead of re-scanning its whole input.
@@ -49,6 +49,16 @@ def enableCandidateDetection(m, fusePool=True):
                     b.candidateDetect = True
                     if fusePool:             # pooling + b's detection in one kernel
                         a._fusedNext = [b]
+        if maskedConv:
+            # a 1x1 layer fed by a CB conv whose own index list nobody needs as an exact list (it is
+            # last, or feeds another candidate-detecting conv) skips the compaction altogether
+            for i, b in enumerate(kids):
+                if type(b) is CBConv2d and tuple(b.kernel_size) == (1, 1) and b.candidateDetect \
+                        and i > 0 and type(kids[i - 1]) is CBConv2d:
+                    nxt = kids[i + 1] if i + 1 < len(kids) else None
+                    if nxt is None or (type(nxt) is CBConv2d and nxt.candidateDetect) \
+                            or (not b.propChangeIndexes and type(nxt) is not CBPoolMax2d):
+                        b.maskedConv = True
     return m
 
 

@@ -182,6 +182,19 @@ int cb_conv_update(void* stream, int dtype, int gemm, const void* state, const v
                    const float* bias, void* out, int pitch_out, int B, int H, int W, int Cin,
                    int Cout, int kH, int kW, int relu, void* ws, size_t ws_bytes);
 
+/* cb_conv_update over a SUPERSET index list: a listed pixel is processed only if its bit is set in
+ * `mask_bits` (a raw change bitmap, e.g. what cb_change_detect_sparse just wrote for a 1x1 layer
+ * whose candidates were idx/count).  Layers that need no dilation can then skip the ordered
+ * compaction between detection and contraction (no reference counterpart; the reference runs
+ * torch.nonzero there, conv2d_cg.py:200-213).  *count_out = number of processed pixels;
+ * clear_mask != 0: the bitmap is zeroed once every CTA has consumed it.  sync_ws: 8 bytes of
+ * device memory zeroed once by the caller (left clean).  Tensor-core modes only. */
+int cb_conv_update_masked(void* stream, int dtype, int gemm, const void* state, const void* state_lo,
+                          int pitch_in, const int32_t* idx, const int32_t* count, const void* packed_w,
+                          const float* bias, void* out, int pitch_out, int B, int H, int W, int Cin,
+                          int Cout, int kH, int kW, int relu, void* ws, size_t ws_bytes,
+                          uint32_t* mask_bits, int clear_mask, int32_t* count_out, void* sync_ws);
+
 /* ---- change-based 2x2/stride-2 max pooling ------------------------------------------------
  * replaces: maxPool2d (conv2d_cg.py:33-37 -> cbconv2d_cg_backend.cu:199-240, half :207-250).
  * For every changed input pixel idx[j] (j < *count) recompute the max of its 2x2 window over

@@ -229,7 +229,9 @@ def test_candidate_detection_equals_dense_scan(feedback, dt, save_maps):
             if type(c) is cb.CBConv2d:
                 c.feedbackLoop = feedback
                 c.saveChangeMap = save_maps
-                c.fuse1x1 = not save_maps       # also exercise the fused 1x1 detect+compact
+                # 1x1 layers: fused detect+compact (feedback, no maps), masked contraction without any
+                # compaction (no feedback, no maps), plain candidate path (maps saved)
+                c.fuse1x1 = (not save_maps) and feedback
         ms.append(m)
     for t, f in enumerate(frames):
         outs = [m(f) for m in ms]
@@ -245,7 +247,10 @@ def test_candidate_detection_equals_dense_scan(feedback, dt, save_maps):
                     assert torch.equal(a.changeMap, b.changeMap), t
                 assert torch.equal(a.prevInput, b.prevInput), t
                 na, nb = int(a._scratch["count"].item()), int(b._scratch["count"].item())
-                assert na == nb and torch.equal(a._scratch["idx"][:na], b._scratch["idx"][:nb]), t
+                assert na == nb, t
+                if not (b.maskedConv and not b.fuse1x1 and not save_maps and t > 0):
+                    # (a masked 1x1 layer never materialises its own list: counts only)
+                    assert torch.equal(a._scratch["idx"][:na], b._scratch["idx"][:nb]), t
             else:
                 assert torch.equal(a.outputState, b.outputState), t
 

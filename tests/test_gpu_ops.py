@@ -386,6 +386,49 @@ def test_conv_update_random_shapes(cbm, seed):
     assert int(ws.view(torch.int32)[:1024].abs().sum()) == 0
 
 
+@pytest.mark.parametrize("mode,dt", [("bf16x3", "f32"), ("tc", "bf16")])
+def test_conv_update_masked_superset_list(cbm, mode, dt):
+    """cb_conv_update_masked: the index list is a superset, the raw bitmap decides which pixels are
+    updated; equals cb_conv_update on the exact list, reports the count, clears the bitmap."""
+    cg, lib, cb = cbm["cg"], cbm["lib"], cbm["cb"]
+    tdt, gemm = TORCH_DT[dt], cb.CBConv2d.GEMM_MODES[mode]
+    for (B, Cin, Cout, H, W, fs, fm) in [(2, 64, 48, 30, 45, 0.5, 0.6), (8, 256, 64, 60, 80, 0.4, 0.9),
+                                          (1, 16, 8, 9, 70, 1.0, 0.0), (1, 32, 256, 40, 40, 0.7, 1.0)]:
+        g = torch.Generator().manual_seed(B * 7 + Cin)
+        state, sbuf = cg.pixel_major((B, Cin, H, W), tdt, "cuda", 0)
+        state.copy_((torch.rand(B, Cin, H, W, generator=g) - 0.5).to(tdt))
+        w = ((torch.rand(Cout, Cin, 1, 1, generator=g) - 0.5) * 2 * Cin ** -0.5).to(tdt).cuda()
+        bias = (torch.rand(Cout, generator=g) - 0.5).float().cuda()
+        sup = torch.rand(B * H * W, generator=g) < fs                      # superset (candidates)
+        keep = sup & (torch.rand(B * H * W, generator=g) < fm)             # flagged subset
+        sup_idx = torch.nonzero(sup).view(-1).int().cuda()
+        exact_idx = torch.nonzero(keep).view(-1).int().cuda()
+        bits = torch.zeros(lib.C.cb_bitmap_words(B, H, W), dtype=torch.int32, device="cuda")
+        lib.check(lib.C.cb_map_to_bits(lib.stream_ptr(torch.device("cuda")), keep.view(B, H, W).to(torch.int8).cuda().data_ptr(),
+                                       bits.data_ptr(), B, H, W))
+        packed = cg.pack_weights(w, gemm)
+        ws = torch.zeros(lib.C.cb_conv_ws_bytes(), dtype=torch.uint8, device="cuda")
+        outs = []
+        for masked in (False, True):
+            out, obuf = cg.pixel_major((B, Cout, H, W), tdt, "cuda", 0)
+            out.fill_(1.5)
+            if masked:
+                cnt = torch.full((1,), -1, dtype=torch.int32, device="cuda")
+                sync = torch.zeros(2, dtype=torch.int32, device="cuda")
+                cg.conv_update(sbuf, cg.ChangeIndexes.from_tensor(sup_idx, (B, H, W)), packed, bias, obuf,
+                               Cin, Cout, (1, 1), True, gemm, ws=ws,
+                               mask=dict(bits=bits, clear=True, count=cnt, sync=sync))
+                torch.cuda.synchronize()
+                assert int(cnt.item()) == int(exact_idx.numel())
+                assert int(bits.abs().sum()) == 0 and int(sync.abs().sum()) == 0
+            else:
+                cg.conv_update(sbuf, cg.ChangeIndexes.from_tensor(exact_idx, (B, H, W)), packed, bias, obuf,
+                               Cin, Cout, (1, 1), True, gemm, ws=ws)
+            torch.cuda.synchronize()
+            outs.append(out.clone())
+        assert torch.equal(outs[0], outs[1])
+
+
 def test_conv_update_zero_changes_is_noop(cbm):
     cg, lib = cbm["cg"], cbm["lib"]
     state, sbuf = cg.pixel_major((1, 16, 8, 8), torch.float32, "cuda", 1.0)
