@@ -302,7 +302,8 @@ class CBConv2d(nn.Module):
             if u8norm is None:
                 raise _lib.CBinferError("uint8 input needs CBConv2d.inputNorm = (divisor, bias), e.g. "
                                         "(255.0, 0.0) for the scene reader's frame/255")
-            if changeIndexes is not None or self.gatherComputationStats or self.in_channels > 4:
+            if (changeIndexes is not None and not isinstance(changeIndexes, DetectionDone)) \
+                    or self.gatherComputationStats or self.in_channels > 4:
                 input = input.float().div(u8norm[0]).add(u8norm[1])     # rare paths: plain fp32
                 u8norm = None
             dt = torch.float32
@@ -436,6 +437,39 @@ class CBConv2d(nn.Module):
 
     def _workspace(self, dev):
         return self._workspace_holder().get(dev)
+
+    def detectInput(self, input):
+        """Run only this layer's (dense) change detection on `input` and return the tuple that makes
+        the following ``forward`` skip it: ``model(first.detectInput(frame))``.  Lets a pipeline read
+        every frame where it lies (e.g. straight from a decoder's output buffer) while the rest of
+        the model replays as one CUDA graph captured on that tuple - no copy into a static input
+        tensor.  Needs a warmed-up layer (state allocated by an ordinary forward of this shape)."""
+        input = input.detach()
+        _lib.require_cuda(input)
+        B, _, H, W = input.shape
+        dt = torch.float32 if input.dtype == torch.uint8 else input.dtype
+        if self._inBuf is None or self._scratch is None or self.prevInput.size() != input.size() \
+                or self.prevInput.dtype != dt or self.finegrained or self.gatherComputationStats:
+            raise _lib.CBinferError("detectInput: run one ordinary forward of this input shape first")
+        if getattr(self, '_inVersion', None) != self.prevInput._version:
+            self._fresh = True
+            self._auxPlanes = None
+        gemm, _, _ = self._weights(dt, input.device)
+        aux = self._aux(gemm)
+        aux_arg = None if aux is None else (aux[:2] if aux[0] == 'tf32' else aux)
+        mode = _lib.UPDATE_CHANGED if self.feedbackLoop else _lib.UPDATE_ALL
+        if input.dtype == torch.uint8:
+            norm = getattr(self, 'inputNorm', None)
+            if norm is None or self.in_channels > 4:
+                raise _lib.CBinferError("detectInput: uint8 input needs inputNorm and <= 4 channels")
+            cg.detect_u8(input, self.prevInput, self._scratch["raw_bits"], self.threshold, mode,
+                         norm[0], norm[1], aux=aux_arg)
+        else:
+            cg.detect(input, self.prevInput, self._scratch["raw_bits"], self.threshold, mode, aux=aux_arg)
+        self._fresh = False
+        self._lastThr = self.threshold
+        self._inVersion = self.prevInput._version
+        return 'changeIndexes', input, DetectionDone(self)
 
     def _compact(self, s, B, H, W, sparse_next):
         """dilate the raw bitmap by the filter footprint and compact it to the index list."""

@@ -537,3 +537,28 @@ def test_state_snapshot_restore_like_eval03(cand):
     assert torch.equal(ms[0](frames[5]), m3(frames[5]))
     wall, dev = evalTools.inferNextFrameBenchmark(ms[0], frames[4])
     assert wall > 0 and dev > 0
+
+
+@pytest.mark.parametrize("u8", [False, True])
+def test_detect_input_then_forward_equals_forward(u8):
+    """CBConv2d.detectInput(frame) + model(token) == model(frame): the split that lets a pipeline
+    read frames in place and replay the rest of the model as one CUDA graph."""
+    import cbinfer_b200 as cb
+    from cbinfer_b200 import models, video
+    base = models.sceneLabelingBaseline().cuda()
+    frames = [f.cuda() for f in video.sequence(2, 40, 64, 6, 0.1)]
+    if u8:
+        frames = [f.mul(255).round().to(torch.uint8) for f in frames]
+    ms = [models.sceneLabelingCBinfer(base, experimentIdx=6, threshold=0.02, candidateDetect=True)
+          for _ in range(2)]
+    firsts = [[c for c in m.modules() if type(c) is cb.CBConv2d][0] for m in ms]
+    if u8:
+        for f in firsts:
+            f.inputNorm = (255.0, 0.0)
+    with pytest.raises(cb._lib.CBinferError):
+        firsts[1].detectInput(frames[0])                       # not warmed up yet
+    for t, f in enumerate(frames):
+        a = ms[0](f)
+        b = ms[1](f) if t < 2 else ms[1](firsts[1].detectInput(f))
+        assert torch.equal(a, b), t
+        assert torch.equal(firsts[0].prevInput, firsts[1].prevInput), t
