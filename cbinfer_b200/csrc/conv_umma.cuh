@@ -130,15 +130,8 @@ __device__ __forceinline__ void cp_async8(uint32_t dst, const void* src, uint32_
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes)
                : "memory");
 }
-#ifndef CB_GATHER_CA
-#define CB_GATHER_CA 0
-#endif
+// (.cg: L2 only; caching the gather in L1 with .ca measured no gain, profiles/r01_experiments.md)
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-#if CB_GATHER_CA
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes)
-               : "memory");
-  return;
-#endif
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes)
                : "memory");
 }
