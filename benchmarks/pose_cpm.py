@@ -26,8 +26,9 @@ def main():
            "convs": sum(1 for m in pose.modules() if isinstance(m, torch.nn.Conv2d))}
     ms, dense_out = time_frames(pose, [f.contiguous(memory_format=torch.channels_last) for f in fr], warm=3)
     res["dense_cudnn_ms"] = round(median(ms), 4)
-    for cand in (False, True):
+    for cand, par in ((False, False), (True, False), (True, True)):
         m = models.poseModelCBinfer(pose, threshold=0.0)
+        m.parallelBranches = par               # branch 2 of every stage on a side stream
         if cand:
             models.enableCandidateDetection(m)
         # fixed per-layer thresholds: factor * input range measured on frame 0 (dense hooks)
@@ -42,7 +43,7 @@ def main():
         for i, c in enumerate([mm for mm in m.modules() if type(mm) is cb.CBConv2d]):
             c.threshold = args.threshold_factor * feeds[i]
         ms, out = time_frames(m, fr, warm=3)
-        key = "cb_candidates" if cand else "cb_dense_scan"
+        key = ("cb_candidates_parallel_branches" if par else "cb_candidates") if cand else "cb_dense_scan"
         res[key + "_ms"] = round(median(ms), 4)
         with torch.no_grad():
             ref = pose(fr[-1])

@@ -156,12 +156,37 @@ class PoseModel(nn.Module):
         torch.random.set_rng_state(g)
         self.eval()
 
+    # The two branches of a stage are independent: with parallelBranches=True branch 2 runs on a
+    # side CUDA stream (fork / join around every stage), also inside a captured CUDA graph.  At batch
+    # 1 the model is launch-latency-bound (92 convs, ~3 dependent launches each), so overlapping the
+    # branches hides a good part of it.  (poseModelCBinfer gives the branches separate stream-K
+    # workspaces, which this needs.)
+    parallelBranches = False
+
+    def __getstate__(self):
+        d = self.__dict__.copy()
+        d['_side'] = None                      # CUDA streams are per process
+        return d
+
     def forward(self, x):
         feat = self.model0(x)
         tmp = feat
+        par = self.parallelBranches and x.is_cuda
+        if par and getattr(self, '_side', None) is None:
+            self._side = torch.cuda.Stream(x.device)
         for t in range(1, self.T + 1):
-            L = getattr(self, 'model%d_1' % t)(tmp)
-            S = getattr(self, 'model%d_2' % t)(tmp)
+            if par:
+                cur = torch.cuda.current_stream(x.device)
+                self._side.wait_stream(cur)
+                with torch.cuda.stream(self._side):
+                    S = getattr(self, 'model%d_2' % t)(tmp)
+                L = getattr(self, 'model%d_1' % t)(tmp)
+                cur.wait_stream(self._side)
+                S.record_stream(cur)
+                tmp.record_stream(self._side)
+            else:
+                L = getattr(self, 'model%d_1' % t)(tmp)
+                S = getattr(self, 'model%d_2' % t)(tmp)
             if t != self.T:
                 tmp = torch.cat([L, S, feat], 1)
         return L, S
@@ -181,7 +206,14 @@ def poseModelCBinfer(pose, threshold=1e-1, feedbackLoop=True, pools=True):
         if type(mm) is CBConv2d:
             mm.feedbackLoop = feedbackLoop
             mm.copyInput = False
-    return shareWorkspace(m).eval()
+    # one stream-K workspace per chain of layers that run in order: trunk + branch 1, and branch 2
+    # (the branches of a stage may overlap, PoseModel.parallelBranches)
+    chains = [nn.ModuleList(), nn.ModuleList()]
+    for name, child in m.named_children():
+        chains[1 if name.endswith('_2') else 0].append(child)
+    for ch in chains:
+        shareWorkspace(ch)
+    return m.eval()
 
 
 def getCBModuleList(m):

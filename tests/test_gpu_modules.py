@@ -562,3 +562,32 @@ def test_detect_input_then_forward_equals_forward(u8):
         b = ms[1](f) if t < 2 else ms[1](firsts[1].detectInput(f))
         assert torch.equal(a, b), t
         assert torch.equal(firsts[0].prevInput, firsts[1].prevInput), t
+
+
+def test_pose_model_cb_vs_dense_and_parallel_branches():
+    """CPM (T=2) converted: threshold 0 equals the dense model within the bf16 bar; running branch 2
+    of every stage on a side stream (also inside a CUDA graph) gives identical results."""
+    import cbinfer_b200 as cb
+    from cbinfer_b200 import models, video
+    from cbinfer_b200.runtime import FrameGraph
+    pose = models.PoseModel(T=2).cuda().to(torch.bfloat16)
+    frames = [f.cuda().to(torch.bfloat16) for f in video.sequence(1, 96, 128, 5, 0.1, lo=-0.5, hi=0.5)]
+    seq = models.enableCandidateDetection(models.poseModelCBinfer(pose, threshold=0.0))
+    par = models.enableCandidateDetection(models.poseModelCBinfer(pose, threshold=0.0))
+    par.parallelBranches = True
+    with torch.no_grad():
+        for f in frames[:3]:
+            a, b = seq(f), par(f)
+            for u, v in zip(a, b):
+                assert torch.equal(u, v)
+        ref = pose(frames[2])
+        for u, v in zip(a, ref):
+            assert _rel(to_val(u), to_val(v)) <= 1e-2
+        x = frames[3].clone()
+        g = FrameGraph(par, x)
+        for f in frames[3:]:
+            x.copy_(f)
+            got = g.replay()
+            exp = seq(f)
+            for u, v in zip(got, exp):
+                assert torch.equal(u, v)
