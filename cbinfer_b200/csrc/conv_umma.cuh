@@ -1108,7 +1108,11 @@ inline int umma_conv_update(cudaStream_t s, int dtype, int gemm, const void* sta
   const long long P = (long long)B * H * W;
   const int sms = sm_count();
   const long long exp_tiles = (P / 10 / UM_BM + 1) * (CoutPad / bn);
-  if (exp_tiles < sms / 2) {
+  // (short K - 1x1 layers, the RGB layer - gains nothing from the fine variant: a tile is only a
+  //  few stages long, and the second launch costs ~2 us; measured 8.5 -> 6.8 and 11.1 -> 9.1 us)
+  const int num_kb_all = umma_kp_pad_es(umma_operand_es(dtype, gemm), Cp, kH, kW) /
+                         (UM_ROW_BYTES / umma_operand_es(dtype, gemm));
+  if (exp_tiles < sms / 2 && num_kb_all >= 8) {
     // small-change regime: fewer tiles than SMs, so run ONE CTA per SM with a deep stage ring
     // (latency-bound otherwise) and, for wide layers, a 4x finer N tiling to spread the work
     int bn_small = bn > 64 ? (bn / 4 < 64 ? 64 : bn / 4) : bn;
