@@ -5,10 +5,12 @@ Workload (config.workload): BASELINE.json configs[1] -- the scene-labeling CBinf
 convs + both max-pools converted, feedback loop, fp32) on synthetic 640x480 video with 5 % block
 change per frame, `streams_per_gpu` independent video streams batched per GPU.
 
-A "step" is one frame of every resident stream through the whole model (one CUDA-graph replay).
+A "step" is one frame of every resident stream through the whole model: the first layer's change
+detection is launched on the frame where it lies in HBM, the other launches replay as one CUDA graph.
   value : frames/s with the frames already resident in HBM (device-timed, max over ranks)
   e2e   : frames/s through the public module call with HOST (pinned) frames: per step one H2D copy
           of the step's frames and one D2H read of the step's logits inside the timed region
+  e2e_u8_ingest : the same with uint8 host frames, normalised inside the detection kernel
   roofline      : dominant kernel vs its HBM / tensor roofline (per-kernel CUDA-event timing)
   cpu_baseline  : the reference's dense PyTorch CPU inference path on this box's host cores
 `--impl reference` times that CPU path alone on the same config.
