@@ -20,96 +20,98 @@ __all__ = ['CBConv2d', 'CBPoolMax2d', 'ChangeIndexes', 'subsitute', 'convertRecu
 verbose = False
 
 
-def _log(msg):
+def _log(fmt, *args):
     if verbose:
-        print(msg)
+        print(fmt % args if args else fmt)
+
+
+def _is(node, cls):
+    """exact-type test, as the reference does (subclasses of nn.Conv2d / nn.ReLU are left alone)"""
+    return type(node) is cls
 
 
 def subsitute(node, threshold=1e-1, finegrained=False):
-    if type(node) is torch.nn.modules.conv.Conv2d:
-        _log('replacing conv2d')
-        m = CBConv2d(node, threshold)
-        m.finegrained = finegrained
-        return m, True
-    else:
+    """(node, replaced?) - an exact nn.Conv2d becomes a CBConv2d sharing its parameters
+    (reference __init__.py:10-17; the misspelt name is the reference's)."""
+    if not _is(node, nn.Conv2d):
         return node, False
+    _log('replacing conv2d')
+    cb = CBConv2d(node, threshold)
+    cb.finegrained = finegrained
+    return cb, True
 
 
 def convertRecur(m, ignoreList=[], threshold=1e-1, finegrained=False):
-    changed = False
-
-    mout = nn.Sequential()
-    for i, (nodeName, node) in enumerate(m.named_children()):
-        if type(node) in [nn.Sequential]:
-            # handle nn.Sequential containers through recursion
-            # (the reference drops `finegrained` here, __init__.py:28; kept for parity)
-            msub, c = convertRecur(node, ignoreList, threshold)
-            mout.add_module(nodeName, msub)
-            changed |= c
-        elif type(node) in ignoreList + [nn.Dropout]:
-            # remove nodes not needed during inference (e.g. Dropout, and those in the ignoreList)
-            _log('removing node %s' % (type(node),))
+    """One conversion pass over the children of `m` (reference __init__.py:20-45): containers
+    recurse, Dropout and every type in `ignoreList` disappear, convolutions are substituted; the
+    result is a fresh nn.Sequential with the surviving child names.  Returns (model, changed?)."""
+    dropped = tuple(ignoreList) + (nn.Dropout,)
+    out, changed = nn.Sequential(), False
+    for name, child in m.named_children():
+        if _is(child, nn.Sequential):
+            # (like the reference, the recursion does not forward `finegrained`, __init__.py:28)
+            child, hit = convertRecur(child, ignoreList, threshold)
+        elif type(child) in dropped:
+            _log('removing node %s', type(child))
             changed = True
             continue
         else:
-            # handle simple substitutions (i.e. convert Conv2d to CBconv2d)
-            nodeOut, newNode = subsitute(node, threshold=threshold, finegrained=finegrained)
-            mout.add_module(nodeName, nodeOut)
-            changed |= newNode
-
-    # another round until convergence (a no-op apart from the ReLU merge, __init__.py:43-44)
+            child, hit = subsitute(child, threshold=threshold, finegrained=finegrained)
+        out.add_module(name, child)
+        changed = changed or hit
     if changed:
-        mout = convert(mout, ignoreList)
-    return mout, changed
+        # the reference converts again until nothing changes (__init__.py:43-44); the second
+        # pass only ever merges ReLUs
+        out = convert(out, ignoreList)
+    return out, changed
 
 
 def mergeReLURecur(m):
-    mout = nn.Sequential()
-    for i, (nodeName, node) in enumerate(m.named_children()):
-        # handle nn.Sequential containers through recursion
-        if type(node) in [nn.Sequential]:
-            mout.add_module(nodeName, mergeReLURecur(node))
+    """Fold an nn.ReLU that directly follows a CBConv2d into that layer's `withReLU` flag and drop
+    it from the container (reference __init__.py:47-66)."""
+    kids = list(m.named_children())
+    out = nn.Sequential()
+    for pos, (name, child) in enumerate(kids):
+        if _is(child, nn.Sequential):
+            out.add_module(name, mergeReLURecur(child))
             continue
-        # enable built-in ReLU of CBconv
-        elif type(node) in [CBConv2d]:
-            chldrn = list(m.children())
-            if len(chldrn) > i + 1 and type(chldrn[i + 1]) is torch.nn.modules.activation.ReLU:
-                node.withReLU = True
-        # remove ReLU if CBconv layer proceeded
-        elif type(node) is torch.nn.modules.activation.ReLU and i >= 1 and type(list(m.children())[i - 1]) is CBConv2d:
+        if _is(child, CBConv2d):
+            follower = kids[pos + 1][1] if pos + 1 < len(kids) else None
+            if _is(follower, nn.ReLU):
+                child.withReLU = True
+        elif _is(child, nn.ReLU) and pos > 0 and _is(kids[pos - 1][1], CBConv2d):
             _log('merging ReLU layer')
-            continue  # i.e. don't add the module!!
-
-        mout.add_module(nodeName, node)
-    return mout
+            continue
+        out.add_module(name, child)
+    return out
 
 
 def propChangeIndexesOf1x1(rootModule):
-    seqContainers = list(filter(lambda m: type(m) == torch.nn.Sequential, rootModule.modules()))
-    for seqCont in seqContainers:
-        mPrev = None
-        for m in seqCont:
-            # the reference compares kernel_size (a tuple) with the list [1,1] (__init__.py:73), so
-            # this branch never fires there; kept verbatim in behaviour.
-            if type(m) == CBConv2d and type(mPrev) == CBConv2d and m.kernel_size == [1, 1]:
+    """reference __init__.py:68-77.  Its test `m.kernel_size == [1,1]` compares a tuple with a list
+    and therefore never holds; the behaviour (nothing is enabled) is kept on purpose."""
+    for seq in [c for c in rootModule.modules() if _is(c, nn.Sequential)]:
+        before = None
+        for layer in seq:
+            if _is(layer, CBConv2d) and _is(before, CBConv2d) and layer.kernel_size == [1, 1]:
                 _log('enabling propagation of change indexes for 1x1')
-                mPrev.propChangeIndexes = True
-            mPrev = m
+                before.propChangeIndexes = True
+            before = layer
     return rootModule
 
 
+def _cb_layers(net):
+    return [c for c in net.modules() if type(c) in (CBConv2d, CBPoolMax2d)]
+
+
 def clearMemory(net):
-    for m in net.modules():
-        if type(m) == CBConv2d or type(m) == CBPoolMax2d:
-            m.clearMemory()
+    """drop the per-layer state of every CB layer (reference __init__.py:79-82)"""
+    for layer in _cb_layers(net):
+        layer.clearMemory()
 
 
 def getStateTensors(net):
-    state = []
-    for m in net.modules():
-        if type(m) == CBConv2d or type(m) == CBPoolMax2d:
-            state += m.getStateTensors()
-    return state
+    """all state tensors of the CB layers in forward order (reference __init__.py:84-89)"""
+    return [t for layer in _cb_layers(net) for t in layer.getStateTensors()]
 
 
 def shareWorkspace(net):
@@ -125,9 +127,10 @@ def shareWorkspace(net):
 
 
 def convert(m, ignoreList=[], threshold=1e-1):
-    m1, changed = convertRecur(m, ignoreList=ignoreList, threshold=threshold)
-    mout = mergeReLURecur(m1)
-    return shareWorkspace(mout)
+    """nn.Conv2d -> CBConv2d, Dropout removed, ReLUs folded (reference __init__.py:91-94); returns an
+    nn.Sequential with the original child names."""
+    converted, _ = convertRecur(m, ignoreList=ignoreList, threshold=threshold)
+    return shareWorkspace(mergeReLURecur(converted))
 
 
 def convertPools(m):
@@ -155,41 +158,38 @@ def tuneThresholdParameters(vidSeqReader, evalSequences, numFramesPerSeq,
                             targetGenerator, preprocessor,
                             modelBaseline, modelTest, evaluator,
                             cbModuleList, lossToleranceList, initThreshold=1e-2, thresholdIncrFactor=1.2):
-    """Greedy front-to-back threshold search (reference __init__.py:98-144): for each CB module
-    raise its threshold by `thresholdIncrFactor` while the loss increase stays within the module's
-    tolerance, then step back once."""
-    if type(lossToleranceList) is not list:
-        # if loss tolerance is given as a single value, apply it to all modules
-        lossToleranceList = [lossToleranceList] * len(cbModuleList)
-    assert(len(cbModuleList) == len(lossToleranceList))
+    """Greedy front-to-back threshold search (reference __init__.py:98-144).  Layer by layer: start
+    at `initThreshold`, multiply by `thresholdIncrFactor` for as long as the summed loss over the
+    evaluation sequences stays within that layer's tolerance of the loss before the layer was
+    touched, then undo the last step.  A scalar tolerance applies to every layer."""
+    tolerances = lossToleranceList if type(lossToleranceList) is list \
+        else [lossToleranceList] * len(cbModuleList)
+    assert len(tolerances) == len(cbModuleList)
 
-    def evaluateModel():
+    def summed_loss():
         clearMemory(modelTest)
-        totalLoss = 0
+        total = 0
         with torch.no_grad():
-            for seqName in evalSequences:
-                frames, target = vidSeqReader.getDataFrames(seqName=seqName, numFrames=numFramesPerSeq)
+            for seq in evalSequences:
+                frames, target = vidSeqReader.getDataFrames(seqName=seq, numFrames=numFramesPerSeq)
                 if target is None:
                     target = targetGenerator(frames[-1])
+                out = None
                 for frame in frames:
-                    feedData = preprocessor(frame)
-                    outTest = modelTest(feedData.cuda())
-                loss = evaluator(outTest, target)
-                totalLoss += loss
-        return totalLoss
+                    out = modelTest(preprocessor(frame).cuda())
+                total += evaluator(out, target)
+        return total
 
-    # greedy front-to-back threshold adjustment
-    prevLoss = evaluateModel()
-    for i, m in enumerate(cbModuleList):
-        _log('adjusting threshold for module %d of %d' % (i + 1, len(cbModuleList)))
-        m.threshold = initThreshold  # initialize threshold value
+    reference_loss = summed_loss()
+    for pos, layer in enumerate(cbModuleList):
+        _log('adjusting threshold for module %d of %d', pos + 1, len(cbModuleList))
+        layer.threshold = initThreshold
         while True:
-            # increase th while loss ok. Once insufficient, take 1 step back.
-            m.threshold *= thresholdIncrFactor
-            loss = evaluateModel()
-            _log('. (%f < %f + %f)' % (loss, prevLoss, lossToleranceList[i],))
-            if loss - prevLoss > lossToleranceList[i]:
-                m.threshold /= thresholdIncrFactor
+            layer.threshold *= thresholdIncrFactor
+            loss = summed_loss()
+            _log('. (%f < %f + %f)', loss, reference_loss, tolerances[pos])
+            if loss - reference_loss > tolerances[pos]:
+                layer.threshold /= thresholdIncrFactor
                 break
-        prevLoss = evaluateModel()
+        reference_loss = summed_loss()
     return modelTest
