@@ -15,7 +15,7 @@ from .conv2d_cg import ChangeIndexes
 
 __all__ = ['CBConv2d', 'CBPoolMax2d', 'ChangeIndexes', 'subsitute', 'convertRecur', 'mergeReLURecur',
            'propChangeIndexesOf1x1', 'clearMemory', 'getStateTensors', 'convert',
-           'tuneThresholdParameters', 'convertPools']
+           'tuneThresholdParameters', 'convertPools', 'shareWorkspace']
 
 verbose = False
 
