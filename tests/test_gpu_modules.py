@@ -591,3 +591,30 @@ def test_pose_model_cb_vs_dense_and_parallel_branches():
             exp = seq(f)
             for u, v in zip(got, exp):
                 assert torch.equal(u, v)
+
+
+def test_computation_stats():
+    """gatherComputationStats (reference conv2d.py:201-218): op counts of the CG / FG variants from
+    the thresholded difference and its un-padded per-channel dilation, recomputed here in numpy."""
+    import cbinfer_b200 as cb
+    Cin, Cout, k, H, W, thr = 5, 7, 3, 12, 17, 0.2
+    conv = nn.Conv2d(Cin, Cout, k, padding=1).cuda()
+    m = cb.CBConv2d(conv, thr)
+    m.gatherComputationStats = True
+    f0 = rand_tensor((1, Cin, H, W), "f32", 1).cuda()
+    f1 = perturb(f0.cpu(), 0.15, 2).cuda()
+    m(f0)
+    m(f1)
+    st = {kk: int(v) for kk, v in m.compStats.items()}
+    a, b = to_np(f0)[0], to_np(f1)[0]
+    chg = np.abs(b - a) > np.float32(thr)
+    ops = Cout * k * k * 2
+    prop = np.zeros((Cin, H - k + 1, W - k + 1), bool)
+    for dy in range(k):
+        for dx in range(k):
+            prop |= chg[:, dy:dy + H - k + 1, dx:dx + W - k + 1]
+    assert st["numInputChangesPerFeatureMap"] == int(chg.sum()) * ops
+    assert st["numInputChanges"] == int(chg.any(0).sum()) * Cin * ops
+    assert st["numInputPropedChangesPerFeatureMap"] == int(prop.sum()) * ops
+    assert st["numInputPropedChanges"] == int(prop.any(0).sum()) * Cin * ops
+    assert st["totalInputValues"] == W * H * Cin * ops
