@@ -16,6 +16,8 @@ What is different underneath (B200-first, not a translation):
   * batch > 1 = independent video streams (the reference is batch 1);
   * CUDA only: the reference's CPU branches (conv2d.py:225-227,244-245,252-253) do not exist.
 """
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -85,7 +87,8 @@ class CBPoolMax2d(nn.Module):
         else:
             oh, ow = h // 2, w // 2
         if list(self.outputState.shape) != [B, nc, oh, ow] or self.outputState.dtype != input.dtype \
-                or self.outputState.device != input.device:
+                or self.outputState.device != input.device or self._stateBuf is None \
+                or self.outputState.data_ptr() != self._stateBuf.data_ptr():
             # deviation (stated): the reference allocates only once a non-empty index list arrives
             # (conv2d.py:53-62); deciding that needs a host sync, so the state is allocated up front.
             self.outputState, self._stateBuf = cg.pixel_major((B, nc, oh, ow), input.dtype,
@@ -182,6 +185,10 @@ class CBConv2d(nn.Module):
         self.inputNorm = None
         # extension: 1x1 layer on the candidate path without any compaction (see forward_normal)
         self.maskedConv = False
+        # extension: contraction over dirty 8x16 output tiles (TMA-staged halo, implicit im2col)
+        # instead of the per-pixel gather: 'auto' = where the library recommends it
+        # (cb_conv_tiled_supported == 1; CBINFER_TILES=0 disables), 'on' = wherever supported, 'off'
+        self.tileMode = 'auto'
         self._wsHolder = cg.ConvWorkspace()    # shared per model by pycbinfer.convert()
 
     # ---- state ---------------------------------------------------------------------------
@@ -308,13 +315,21 @@ class CBConv2d(nn.Module):
                 u8norm = None
             dt = torch.float32
 
-        if self.prevInput.size() != input.size() or self.prevInput.dtype != dt or self._inBuf is None:
+        # (model.half() / .to(device) on a warm model replace the registered buffers with fresh
+        #  tensors that no longer alias the pixel-major storage: treat that as a reset)
+        outpSize = (B, self.out_channels, H, W)
+        need_out = tuple(self.prevOutput.size()) != outpSize or self.prevOutput.dtype != dt \
+            or self._outBuf is None or self.prevOutput.device != dev \
+            or self.prevOutput.data_ptr() != self._outBuf.data_ptr()
+        need_in = need_out or self.prevInput.size() != input.size() or self.prevInput.dtype != dt \
+            or self._inBuf is None or self.prevInput.device != dev \
+            or self.prevInput.data_ptr() != self._inBuf.data_ptr()
+        if need_in:       # (a fresh output map needs every pixel recomputed: the input state goes too)
             self.prevInput, self._inBuf = cg.pixel_major(input.shape, dt, dev, _INF)   # :192-194
             self._auxPlanes = None
             self._scratch = None
             self._fresh = True
-        outpSize = (B, self.out_channels, H, W)
-        if tuple(self.prevOutput.size()) != outpSize or self.prevOutput.dtype != dt or self._outBuf is None:
+        if need_out:
             self.prevOutput, self._outBuf = cg.pixel_major(outpSize, dt, dev, _INF)    # :195-199
         # State tensors written from outside this module's kernels (the reference's eval scripts
         # snapshot and restore getStateTensors() with copy_, poseDetection/eval03.py:87-95): torch
@@ -340,6 +355,8 @@ class CBConv2d(nn.Module):
 
         candidates = None
         mask = None
+        tiled = False             # this frame's contraction walks the dirty-tile list
+        use_tiles = self._useTiles(dt, gemm, (B, H, W))
         detected = isinstance(changeIndexes, DetectionDone)
         if detected:
             assert changeIndexes.owner is self
@@ -402,22 +419,36 @@ class CBConv2d(nn.Module):
                 changeIndexes = ChangeIndexes(candidates.buffer, candidates.count, (B, H, W), bits=None)
                 changeIndexes.superset = True
             else:
-                changeIndexes = self._compact(s, B, H, W, sparse_next)
+                changeIndexes = self._compact(s, B, H, W, sparse_next, tiles=use_tiles)
+                tiled = use_tiles
         else:
             if not isinstance(changeIndexes, ChangeIndexes):
                 assert(changeIndexes.dim() == 1)
                 changeIndexes = ChangeIndexes.from_tensor(changeIndexes.detach(), (B, H, W))
+            elif tuple(changeIndexes.shape) != (B, H, W):
+                # e.g. a CBPoolMax2d with the reference's propChangeIndexes forwards INPUT-resolution
+                # indices (conv2d.py:75-76): using them here would scatter out of bounds
+                raise _lib.CBinferError("change indexes refer to a %s grid, this layer's map is %s"
+                                        % (tuple(changeIndexes.shape), (B, H, W)))
             if not self.feedbackLoop:
                 self.prevInput.copy_(input)                                            # :234-236
                 self._auxPlanes = None
                 aux = self._aux(gemm)
             # (with feedbackLoop the reference never refreshes prevInput here either, :220,234)
 
-        cg.conv_update(self._inBuf, changeIndexes, packed, bias32, self._outBuf, self.in_channels,
-                       self.out_channels, self.kernel_size, self.withReLU, gemm,
-                       lo_buf=aux[2] if aux is not None and aux[0] == 'tf32' else None,
-                       planes16=aux[1:] if aux is not None and aux[0] == 'bf16' else None,
-                       ws=self._workspace(dev), mask=mask)                             # :242-251
+        lo_buf = aux[2] if aux is not None and aux[0] == 'tf32' else None
+        planes16 = aux[1:] if aux is not None and aux[0] == 'bf16' else None
+        if tiled:
+            # spatially clustered change sets: contraction over the dirty 8x16 tiles (TMA-staged
+            # halo, implicit im2col through the UMMA descriptors), rows masked by the dilated bitmap
+            cg.conv_update_tiled(self._inBuf, s["tile_ws"], s["dil_bits"], packed, bias32, self._outBuf,
+                                 self.in_channels, self.out_channels, self.kernel_size, self.withReLU,
+                                 gemm, lo_buf=lo_buf, planes16=planes16)                # :242-251
+        else:
+            cg.conv_update(self._inBuf, changeIndexes, packed, bias32, self._outBuf, self.in_channels,
+                           self.out_channels, self.kernel_size, self.withReLU, gemm,
+                           lo_buf=lo_buf, planes16=planes16,
+                           ws=self._workspace(dev), mask=mask)                         # :242-251
         self._inVersion = self.prevInput._version
         self._outVersion = self.prevOutput._version
         if ext_out and isinstance(changeIndexes, ChangeIndexes):
@@ -471,13 +502,28 @@ class CBConv2d(nn.Module):
         self._inVersion = self.prevInput._version
         return 'changeIndexes', input, DetectionDone(self)
 
-    def _compact(self, s, B, H, W, sparse_next):
+    def _useTiles(self, dt, gemm, shape):
+        """tile path for this layer / shape?  (tileMode 'auto': where the library recommends it)"""
+        mode = getattr(self, 'tileMode', 'auto')
+        if mode == 'off' or os.environ.get("CBINFER_TILES", "1") == "0" or gemm == _lib.GEMM_SIMT_F32:
+            return False
+        key = (dt, gemm, tuple(shape), mode)
+        cache = self.__dict__.setdefault('_tileOk', {})
+        if key not in cache:
+            sup = cg.tiled_supported(dt, gemm, shape, self.in_channels, self.out_channels, self.kernel_size)
+            cache[key] = sup >= 1 if mode == 'on' else sup == 1
+        return cache[key]
+
+    def _compact(self, s, B, H, W, sparse_next, tiles=False):
         """dilate the raw bitmap by the filter footprint and compact it to the index list."""
+        if tiles and "tile_ws" not in s:
+            s["tile_ws"] = cg.alloc_tile_ws((B, H, W), s["idx"].device)
         dil_map = s.get("dil_map") if self.saveChangeMap else None
         # a layer on the candidate path lets the compaction zero the raw bitmap once it has been
         # consumed, so the next frame's candidate detection needs no memset
         cg.dilate_compact(s["raw_bits"], (B, H, W), self.kernel_size, s["idx"], s["count"],
-                          s["ws"], dil_bits=s["dil_bits"], dil_map=dil_map, clear_raw=sparse_next)
+                          s["ws"], dil_bits=s["dil_bits"], dil_map=dil_map, clear_raw=sparse_next,
+                          tile_ws=s["tile_ws"] if tiles else None)
         s["raw_clear"] = sparse_next
         if self.saveChangeMap:
             self.changeMap = dil_map[0] if B == 1 else dil_map
@@ -533,6 +579,6 @@ class CBConv2d(nn.Module):
                           ('gatherComputationStats', False), ('finegrained', False),
                           ('copyInput', True), ('feedbackLoop', False), ('gemmMode', 'auto'),
                           ('candidateDetect', False), ('fuse1x1', False), ('inputNorm', None),
-                          ('maskedConv', False)):
+                          ('maskedConv', False), ('tileMode', 'auto')):
             if not(hasattr(self, name)):
                 setattr(self, name, val)

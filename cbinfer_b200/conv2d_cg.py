@@ -179,14 +179,36 @@ def pool_compact(in_bits, in_shape, out_shape, idx, count, ws, out_bits=None):
 
 
 def dilate_compact(raw_bits, shape, filtSize, idx, count, ws, dil_bits=None, dil_map=None,
-                   clear_raw=False):
-    """cb_dilate_compact: dilation by the filter footprint + ordered compaction."""
+                   clear_raw=False, tile_ws=None):
+    """cb_dilate_compact: dilation by the filter footprint + ordered compaction.  With `tile_ws`
+    (cb_tile_ws_bytes of zeroed int32 device memory) the dirty 8x16 output tiles are listed as well
+    (cb_dilate_compact_tiles), for :func:`conv_update_tiled`."""
     B, H, W = shape
+    if tile_ws is not None:
+        check(C.cb_dilate_compact_tiles(stream_ptr(raw_bits.device), raw_bits.data_ptr(),
+                                        dil_bits.data_ptr() if dil_bits is not None else None,
+                                        dil_map.data_ptr() if dil_map is not None else None,
+                                        idx.data_ptr(), count.data_ptr(), ws.data_ptr(),
+                                        tile_ws.data_ptr(), B, H, W, (filtSize[0] - 1) // 2,
+                                        (filtSize[1] - 1) // 2, int(bool(clear_raw))))
+        return
     check(C.cb_dilate_compact(stream_ptr(raw_bits.device), raw_bits.data_ptr(),
                               dil_bits.data_ptr() if dil_bits is not None else None,
                               dil_map.data_ptr() if dil_map is not None else None,
                               idx.data_ptr(), count.data_ptr(), ws.data_ptr(), B, H, W,
                               (filtSize[0] - 1) // 2, (filtSize[1] - 1) // 2, int(bool(clear_raw))))
+
+
+def alloc_tile_ws(shape, device):
+    """tile workspace of cb_dilate_compact_tiles / cb_conv_update_tiled for a [B,H,W] pixel grid."""
+    B, H, W = shape
+    return torch.zeros(C.cb_tile_ws_bytes(B, H, W) // 4, dtype=torch.int32, device=device)
+
+
+def tiled_supported(dtype, gemm, shape, Cin, Cout, filtSize):
+    """cb_conv_tiled_supported: 1 = run the tile path, 2 = possible but not recommended, 0 = no."""
+    B, H, W = shape
+    return C.cb_conv_tiled_supported(dtype_code(dtype), gemm, B, H, W, Cin, Cout, filtSize[0], filtSize[1])
 
 
 def alloc_scratch(shape, device, want_map=False):
@@ -305,6 +327,29 @@ def conv_update(state_buf, changes, packed_w, bias_f32, out_buf, Cin, Cout, filt
                            filtSize[0], filtSize[1], int(bool(relu)),
                            ws.data_ptr() if ws is not None else None,
                            ws.numel() if ws is not None else 0))
+
+
+def conv_update_tiled(state_buf, tile_ws, dil_bits, packed_w, bias_f32, out_buf, Cin, Cout, filtSize,
+                      relu, gemm, lo_buf=None, planes16=None):
+    """cb_conv_update_tiled on pixel-major buffers: the contraction over the dirty 8x16 tiles listed
+    in `tile_ws` (TMA-staged halo tiles, implicit im2col), writing the pixels set in `dil_bits`.
+    Operand conventions as :func:`conv_update`."""
+    B, H, W, Cp = state_buf.shape
+    assert out_buf.shape[:3] == state_buf.shape[:3]
+    src, src_lo, pitch = state_buf, lo_buf, Cp
+    if gemm == _lib.GEMM_TC_BF16X3:
+        assert state_buf.dtype == torch.float32
+        if planes16 is None:
+            planes16 = bf16_planes(state_buf, Cin)
+        src, src_lo = planes16
+        pitch = src.shape[3]
+    elif gemm == _lib.GEMM_TC_3X and state_buf.dtype == torch.float32 and lo_buf is None:
+        src_lo = tf32_lo(state_buf)
+    check(C.cb_conv_update_tiled(stream_ptr(state_buf.device), dtype_code(state_buf), gemm,
+                                 src.data_ptr(), src_lo.data_ptr() if src_lo is not None else None,
+                                 pitch, tile_ws.data_ptr(), dil_bits.data_ptr(), packed_w.data_ptr(),
+                                 bias_f32.data_ptr(), out_buf.data_ptr(), out_buf.shape[3], B, H, W,
+                                 Cin, Cout, filtSize[0], filtSize[1], int(bool(relu))))
 
 
 def pixel_major(shape, dtype, device, fill):

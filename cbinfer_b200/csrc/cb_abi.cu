@@ -8,6 +8,7 @@
 #include "compact.cuh"
 #include "conv_simt.cuh"
 #include "conv_umma.cuh"
+#include "conv_tile.cuh"
 #include "detect.cuh"
 #include "fg.cuh"
 #include "pool.cuh"
@@ -118,8 +119,18 @@ int cb_change_detect_u8(void* stream, const uint8_t* x, long long x_sb, long lon
                           threshold, update_mode);
 }
 
-int cb_dilate_compact(void* stream, const uint32_t* raw_bits, uint32_t* dil_bits, int8_t* dil_map,
-                      int32_t* idx, int32_t* count, void* ws, int B, int H, int W, int kHHalf,
+static bool compact_coop() {
+  static const bool v = [] {
+    const char* e = getenv("CBINFER_COMPACT_COOP");          // tuning knob: 0 = per-thread expansion
+    return !(e && e[0] == '0');
+  }();
+  return v;
+}
+
+size_t cb_tile_ws_bytes(int B, int H, int W) { return cb::tile_ws_words(B, H, W) * sizeof(int32_t); }
+
+static int dilate_compact_impl(void* stream, const uint32_t* raw_bits, uint32_t* dil_bits, int8_t* dil_map,
+                      int32_t* idx, int32_t* count, void* ws, void* tile_ws, int B, int H, int W, int kHHalf,
                       int kWHalf, int clear_raw) {
   CB_CHECK_ARG(raw_bits && idx && count && ws, "dilate_compact: null pointer");
   CB_CHECK_ARG(raw_bits != dil_bits, "dilate_compact: dil_bits must not alias raw_bits");
@@ -137,9 +148,27 @@ int cb_dilate_compact(void* stream, const uint32_t* raw_bits, uint32_t* dil_bits
   cb::launch_pdl(dilate_compact_kernel, ntiles, kCompactThreads, 0, s, raw_bits, dil_bits, dil_map, idx, count,
                                                           ws, B, H, W, (W + 31) / 32, kHHalf,
                                                           kWHalf, (int)nwords, ntiles, 0, 0,
-                                                          clear_raw ? const_cast<uint32_t*>(raw_bits) : nullptr);
+                                                          clear_raw ? const_cast<uint32_t*>(raw_bits) : nullptr,
+                                                          (int32_t*)tile_ws, cb::tile_grid_y(H), cb::tile_grid_xp(W),
+                                                          (int)compact_coop());
   CB_CHECK_LAUNCH("dilate_compact");
   return 0;
+}
+
+int cb_dilate_compact(void* stream, const uint32_t* raw_bits, uint32_t* dil_bits, int8_t* dil_map,
+                      int32_t* idx, int32_t* count, void* ws, int B, int H, int W, int kHHalf,
+                      int kWHalf, int clear_raw) {
+  return dilate_compact_impl(stream, raw_bits, dil_bits, dil_map, idx, count, ws, nullptr, B, H, W,
+                             kHHalf, kWHalf, clear_raw);
+}
+
+int cb_dilate_compact_tiles(void* stream, const uint32_t* raw_bits, uint32_t* dil_bits,
+                            int8_t* dil_map, int32_t* idx, int32_t* count, void* ws, void* tile_ws,
+                            int B, int H, int W, int kHHalf, int kWHalf, int clear_raw) {
+  CB_CHECK_ARG(tile_ws, "dilate_compact_tiles: null tile workspace");
+  if ((long long)cb_bitmap_words(B, H, W) == 0) cudaMemsetAsync((int32_t*)tile_ws + 1, 0, sizeof(int32_t), (cudaStream_t)stream);
+  return dilate_compact_impl(stream, raw_bits, dil_bits, dil_map, idx, count, ws, tile_ws, B, H, W,
+                             kHHalf, kWHalf, clear_raw);
 }
 
 int cb_pool_compact(void* stream, const uint32_t* in_bits, uint32_t* out_bits, int32_t* idx,
@@ -157,7 +186,8 @@ int cb_pool_compact(void* stream, const uint32_t* in_bits, uint32_t* out_bits, i
   const int ntiles = (int)((nwords + kCompactTile - 1) / kCompactTile);
   cb::launch_pdl(dilate_compact_kernel, ntiles, kCompactThreads, 0, s, in_bits, out_bits, nullptr, idx, count, ws,
                                                           B, oH, oW, (oW + 31) / 32, 0, 0,
-                                                          (int)nwords, ntiles, H, (W + 31) / 32, nullptr);
+                                                          (int)nwords, ntiles, H, (W + 31) / 32, nullptr,
+                                                          nullptr, 0, 0, (int)compact_coop());
   CB_CHECK_LAUNCH("pool_compact");
   return 0;
 }
@@ -255,6 +285,32 @@ int cb_conv_update(void* stream, int dtype, int gemm, const void* state, const v
                           Cout, kH, kW, relu, ws, ws_bytes);
 }
 
+int cb_conv_tiled_supported(int dtype, int gemm, int B, int H, int W, int Cin, int Cout, int kH, int kW) {
+  if (gemm == CB_GEMM_SIMT_F32) return 0;
+  const int Cp = gemm == CB_GEMM_TC_BF16X3 ? cb::pitch16_of(Cin) : cb_channel_pitch(dtype, Cin);
+  cb::TilePlan plan;
+  cb::umma_tile_plan(plan, dtype, gemm, Cp, B, H, W, Cout, cb_channel_pitch(dtype, Cout), kH, kW, 0);
+  if (!plan.ok) return 0;
+  return plan.mma_clk_per_tile <= cb::tile_clk_limit() ? 1 : 2;
+}
+
+int cb_conv_update_tiled(void* stream, int dtype, int gemm, const void* state, const void* state_lo,
+                         int pitch_in, const void* tile_ws, const uint32_t* dil_bits,
+                         const void* packed_w, const float* bias, void* out, int pitch_out, int B,
+                         int H, int W, int Cin, int Cout, int kH, int kW, int relu) {
+  CB_CHECK_ARG(state && tile_ws && dil_bits && packed_w && bias && out, "conv_update_tiled: null pointer");
+  CB_CHECK_ARG(gemm != CB_GEMM_SIMT_F32, "conv_update_tiled: tensor-core modes only");
+  const int want_pitch = gemm == CB_GEMM_TC_BF16X3 ? cb::pitch16_of(Cin) : cb_channel_pitch(dtype, Cin);
+  CB_CHECK_ARG(pitch_in == want_pitch, "conv_update_tiled: pitch_in %d != channel pitch %d", pitch_in,
+               want_pitch);
+  CB_CHECK_ARG(pitch_out >= Cout, "conv_update_tiled: pitch_out < Cout");
+  CB_CHECK_ARG(gemm != CB_GEMM_TC_BF16X3 || dtype == CB_F32, "conv_update_tiled: 3xBF16 is for fp32 data");
+  if (B == 0 || H == 0 || W == 0) return 0;
+  return cb::umma_conv_update_tiled((cudaStream_t)stream, dtype, gemm, state, state_lo, pitch_in,
+                                    (const int32_t*)tile_ws, dil_bits, packed_w, bias, out, pitch_out,
+                                    B, H, W, Cout, kH, kW, relu);
+}
+
 int cb_conv_update_masked(void* stream, int dtype, int gemm, const void* state, const void* state_lo,
                           int pitch_in, const int32_t* idx, const int32_t* count, const void* packed_w,
                           const float* bias, void* out, int pitch_out, int B, int H, int W, int Cin,
@@ -292,7 +348,6 @@ int cb_maxpool2x2(void* stream, int dtype, const void* x, long long x_sb, long l
     int glog = 0;
     while ((1 << glog) < cpp && glog < 5) ++glog;
     glog = cb::glog_tuned(glog);
-  glog = cb::glog_tuned(glog);
     CB_DISPATCH_DTYPE(dtype, (cb::launch_pdl(maxpool2x2_vec_kernel<T, VEC>, grid, 256, 0, (cudaStream_t)stream, 
                                  (const T*)x, x_sb, x_sy, (int)x_sx, idx, count, dil_bits, (T*)out,
                                  o_sb, o_sy, (int)o_sx, cpp, glog, H, W, oH, oW)));

@@ -92,9 +92,10 @@ template <> struct DType<CB_F16> { using T = __half; static constexpr int VEC = 
 template <> struct DType<CB_BF16> { using T = __nv_bfloat16; static constexpr int VEC = 8; };
 
 __host__ __device__ inline int esize(int dtype) { return dtype == CB_F32 ? 4 : 2; }
-// channel pitch of the bf16 operand planes of an fp32 layer: 8-byte pixels for <= 4 channels (RGB
-// input layers), otherwise a multiple of 16 bytes
-__host__ __device__ inline int pitch16_of(int C) { return C <= 4 ? 4 : (C + 7) / 8 * 8; }
+// channel pitch of the bf16 operand planes of an fp32 layer: a multiple of 16 bytes (an RGB input
+// layer gets 16-byte pixels: the smallest pixel the tiled contraction's shared-memory descriptors
+// can address, conv_tile.cuh)
+__host__ __device__ inline int pitch16_of(int C) { return (C + 7) / 8 * 8; }
 
 __device__ __forceinline__ float to_float(float v) { return v; }
 __device__ __forceinline__ float to_float(__half v) { return __half2float(v); }

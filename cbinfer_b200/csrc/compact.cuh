@@ -98,7 +98,8 @@ dilate_compact_kernel(const uint32_t* __restrict__ raw, uint32_t* __restrict__ d
                       int8_t* __restrict__ dil_map, int32_t* __restrict__ idx,
                       int32_t* __restrict__ count, void* ws, int B, int H, int W, int Wd, int kh,
                       int kw, int nwords, int ntiles, int pool_hin, int pool_wdin,
-                      uint32_t* __restrict__ clear_bits) {
+                      uint32_t* __restrict__ clear_bits, int32_t* __restrict__ tile_ws, int tile_ty,
+                      int tile_xp, int coop) {
   pdl_prologue();
   CompactHeader* hdr = reinterpret_cast<CompactHeader*>(ws);
   volatile unsigned long long* tstate =
@@ -143,6 +144,22 @@ dilate_compact_kernel(const uint32_t* __restrict__ raw, uint32_t* __restrict__ d
       d[i] = pool_hin ? pooled_word(raw, r / H, y, j, pool_hin, pool_wdin, W)
                       : dilated_word(win, win0, r, y, j, H, W, Wd, kh, kw);
       if (dil_bits) dil_bits[w] = d[i];
+      if (tile_ws && d[i]) {
+        // dirty 8 x 16 output tiles for the tiled contraction (conv_tile.cuh): a word covers four
+        // tiles of one tile row; the first word to stamp a tile with this launch's tag appends it
+        // (unordered list, every tile once)
+        uint32_t* stamp = reinterpret_cast<uint32_t*>(tile_ws) + 4;
+        const int t0 = ((r / H) * tile_ty + y / 16) * tile_xp + 4 * j;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (((d[i] >> (8 * q)) & 0xffu) && *reinterpret_cast<volatile uint32_t*>(stamp + t0 + q) != tag) {
+            if (atomicExch(stamp + t0 + q, tag) != tag) {
+              const int pos = atomicAdd(tile_ws, 1);
+              tile_ws[4 + B * tile_ty * tile_xp + pos] = t0 + q;
+            }
+          }
+        }
+      }
     }
     cnt += __popc(d[i]);
   }
@@ -200,6 +217,24 @@ dilate_compact_kernel(const uint32_t* __restrict__ raw, uint32_t* __restrict__ d
 
   // ---- expand set bits to ascending pixel indices ------------------------------------------
   int o = s_base + s_warp[wid] + (incl - cnt);
+  if (coop && kCompactWPT == 1 && !dil_map) {
+    // warp-cooperative expansion: the warp walks its non-empty words; lane i writes bit i of the
+    // current word at its rank -> the 32 stores of a dense word are one coalesced 128-byte line
+    // (per-thread expansion writes 32 lines per instruction when a block of pixels changed)
+    const int w = w0;
+    const bool have = w < nwords && d[0] != 0u;
+    const int jj = have ? w % Wd : 0, rr = have ? w / Wd : 0;
+    const int mypix0 = rr * W + jj * 32;
+    unsigned todo = __ballot_sync(0xffffffffu, have);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const unsigned dd = __shfl_sync(0xffffffffu, d[0], src);
+      const int oo = __shfl_sync(0xffffffffu, o, src);
+      const int pp = __shfl_sync(0xffffffffu, mypix0, src);
+      if ((dd >> lane) & 1u) idx[oo + __popc(dd & ((1u << lane) - 1u))] = pp + lane;
+    }
+  } else {
 #pragma unroll
   for (int i = 0; i < kCompactWPT; ++i) {
     const int w = w0 + i;
@@ -219,6 +254,7 @@ dilate_compact_kernel(const uint32_t* __restrict__ raw, uint32_t* __restrict__ d
       for (int q = 0; q < n; ++q) m[q] = (int8_t)((d[i] >> q) & 1u);
     }
   }
+  }
 
   // ---- leave the workspace clean for the next launch ---------------------------------------
   __shared__ unsigned s_last;
@@ -228,6 +264,10 @@ dilate_compact_kernel(const uint32_t* __restrict__ raw, uint32_t* __restrict__ d
     s_last = prev == (unsigned)ntiles - 1u;
     if (s_last) {
       hdr->done = 0;
+      if (tile_ws) {                            // every block appended before its done-increment
+        tile_ws[1] = *reinterpret_cast<volatile int32_t*>(tile_ws);
+        tile_ws[0] = 0;
+      }
       __threadfence();
       *reinterpret_cast<volatile unsigned*>(&hdr->epoch) = epoch + 1u;
     }

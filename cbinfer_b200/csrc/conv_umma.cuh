@@ -385,8 +385,17 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
   const int num_kb = (Kp + C::BK - 1) / C::BK;
   TileSeg seg0;
   const long long sk_units = (long long)total_tiles * num_kb;
+  // stream-K runs on the first sk_grid CTAs only: with fewer (tile, K block) units than CTAs the
+  // extra ones would own an empty range, never raise their flag, and the tile owner would wait
+  // for them forever
+  const long long sk_grid = sk ? (sk_units < (long long)gridDim.x ? (sk_units > 0 ? sk_units : 1)
+                                                                  : (long long)gridDim.x) : 1;
+  if (sk && (long long)blockIdx.x >= sk_grid) {            // CTA-uniform: before any barrier / alloc
+    if (mk.bits) rowmask_finish(mk, reinterpret_cast<volatile unsigned*>(smem_raw));
+    return;
+  }
   if (sk)
-    seg0.init_sk(sk_units * blockIdx.x / gridDim.x, sk_units * (blockIdx.x + 1) / gridDim.x, num_kb);
+    seg0.init_sk(sk_units * blockIdx.x / sk_grid, sk_units * (blockIdx.x + 1) / sk_grid, num_kb);
   else
     seg0.init_static(tile0, tile_step, total_tiles, (int)((long long)num_kb * krank / KS),
                      (int)((long long)num_kb * (krank + 1) / KS));
@@ -651,7 +660,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
         sk_c0 = (int)blockIdx.x + 1;
         sk_c1 = sk_c0;
         const long long tile_end = (long long)(tile + 1) * num_kb;
-        while (sk_c1 < (int)gridDim.x && sk_units * sk_c1 / gridDim.x < tile_end) ++sk_c1;
+        while (sk_c1 < (int)sk_grid && sk_units * sk_c1 / sk_grid < tile_end) ++sk_c1;
         if (etid == 0) {
           for (int cta = sk_c0; cta < sk_c1; ++cta) {
             long long t0 = 0;

@@ -116,6 +116,17 @@ int cb_dilate_compact(void* stream, const uint32_t* raw_bits, uint32_t* dil_bits
                       int32_t* idx, int32_t* count, void* ws, int B, int H, int W, int kHHalf,
                       int kWHalf, int clear_raw);
 
+/* cb_dilate_compact that also lists the dirty 8 x 16 output tiles (x 8 wide, y 16 tall, aligned to
+ * the image origin) for cb_conv_update_tiled: tile_ws = cb_tile_ws_bytes(B,H,W) of device memory,
+ * zeroed once at allocation, private to the stream; after the call word [1] holds the number of
+ * tiles that contain at least one set bit of the dilated map and the (unordered) tile list sits
+ * behind the stamps.  No reference counterpart (the reference gathers per changed pixel,
+ * cbconv2d_cg_backend.cu:138-161). */
+size_t cb_tile_ws_bytes(int B, int H, int W);
+int cb_dilate_compact_tiles(void* stream, const uint32_t* raw_bits, uint32_t* dil_bits,
+                            int8_t* dil_map, int32_t* idx, int32_t* count, void* ws, void* tile_ws,
+                            int B, int H, int W, int kHHalf, int kWHalf, int clear_raw);
+
 /* ---- candidate ("sparse") detection ---------------------------------------------------------
  * Same per-pixel test and state maintenance as cb_change_detect, evaluated only at the
  * `*n_candidates` pixels listed in `candidates` (indices b*H*W + y*W + x, any order); raw_bits is
@@ -181,6 +192,23 @@ int cb_conv_update(void* stream, int dtype, int gemm, const void* state, const v
                    int pitch_in, const int32_t* idx, const int32_t* count, const void* packed_w,
                    const float* bias, void* out, int pitch_out, int B, int H, int W, int Cin,
                    int Cout, int kH, int kW, int relu, void* ws, size_t ws_bytes);
+
+/* cb_conv_update for spatially clustered change sets (same result, same operands): the work unit
+ * is a dirty 8 x 16 output tile from cb_dilate_compact_tiles' tile_ws; the tile's receptive-field
+ * halo of `state` is staged ONCE in shared memory by TMA (cp.async.bulk.tensor, zero fill outside
+ * the image) and the tensor cores read the im2col rows straight out of it through their
+ * shared-memory descriptors; only pixels whose bit is set in dil_bits (the dilated change bitmap
+ * of the same cb_dilate_compact_tiles call) are written.  Replaces genXMatrix
+ * (cbconv2d_cg_backend.cu:138-161) + GEMM + updateOutput (:175-189) like cb_conv_update.
+ * cb_conv_tiled_supported: 1 if the layer shape can run on this path AND its per-tile tensor work
+ * is small enough for whole-tile granularity to pay (else use cb_conv_update), 2 if it can run
+ * but is not recommended, 0 if unsupported (1x1 filters, operand pixels that are not 16/32/64 or a
+ * multiple of 128 bytes).  Tensor-core gemm modes only. */
+int cb_conv_tiled_supported(int dtype, int gemm, int B, int H, int W, int Cin, int Cout, int kH, int kW);
+int cb_conv_update_tiled(void* stream, int dtype, int gemm, const void* state, const void* state_lo,
+                         int pitch_in, const void* tile_ws, const uint32_t* dil_bits,
+                         const void* packed_w, const float* bias, void* out, int pitch_out, int B,
+                         int H, int W, int Cin, int Cout, int kH, int kW, int relu);
 
 /* cb_conv_update over a SUPERSET index list: a listed pixel is processed only if its bit is set in
  * `mask_bits` (a raw change bitmap, e.g. what cb_change_detect_sparse just wrote for a 1x1 layer

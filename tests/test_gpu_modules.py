@@ -618,3 +618,46 @@ def test_computation_stats():
     assert st["numInputPropedChangesPerFeatureMap"] == int(prop.sum()) * ops
     assert st["numInputPropedChanges"] == int(prop.any(0).sum()) * Cin * ops
     assert st["totalInputValues"] == W * H * Cin * ops
+
+
+def test_warm_model_cast_resets_state():
+    """nn.Module._apply (model.half(), .to(...)) replaces the registered state buffers with tensors
+    that no longer alias the pixel-major storage the kernels write: the modules must notice and
+    start from fresh state instead of returning a stale prevOutput."""
+    import cbinfer_b200 as cb
+    torch.manual_seed(4)
+    base = nn.Sequential(nn.Conv2d(3, 8, 3, padding=1), nn.ReLU(), nn.MaxPool2d(2, 2),
+                         nn.Conv2d(8, 6, 3, padding=1)).cuda().eval()
+    m = cb.convertPools(cb.convert(base, threshold=0.0))
+    frames = _frames((1, 3, 16, 20), "f32", 3, 0.2, seed=1)
+    for f in frames[:2]:
+        m(f)
+    m.half()                                        # warm model, new dtype
+    base_h = base.half()
+    x = frames[2].half()
+    out = m(x)
+    ref = base_h(x)
+    assert out.dtype == torch.float16
+    assert _rel(to_val(out), to_val(ref)) <= 5e-3
+    m.float()                                       # and back (weights were rounded to fp16 meanwhile)
+    base.float()
+    out = m(frames[2])
+    assert _rel(to_val(out), to_val(base(frames[2]))) <= 1e-4
+    c0 = [c for c in m.modules() if type(c) is cb.CBConv2d][0]
+    assert c0.prevInput.data_ptr() == c0._inBuf.data_ptr()
+
+
+def test_change_indexes_of_wrong_grid_are_rejected():
+    """the reference's CBPoolMax2d(propChangeIndexes) forwards INPUT-resolution indices
+    (conv2d.py:75-76); a following CBConv2d must not scatter with them."""
+    import cbinfer_b200 as cb
+    from cbinfer_b200 import _lib
+    torch.manual_seed(5)
+    conv0 = cb.CBConv2d(nn.Conv2d(3, 4, 3, padding=1).cuda(), 0.1)
+    conv0.propChangeIndexes = True
+    pool = cb.CBPoolMax2d(nn.MaxPool2d(2, 2))
+    pool.propChangeIndexes = True
+    conv1 = cb.CBConv2d(nn.Conv2d(4, 4, 3, padding=1).cuda(), 0.1)
+    x = rand_tensor((1, 3, 12, 16), "f32", 1)
+    with pytest.raises(_lib.CBinferError):
+        conv1(pool(conv0(x)))

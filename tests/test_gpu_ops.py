@@ -513,3 +513,35 @@ def test_fg_random_vs_oracle(cbm, orc):
         e = to_np(out0[b:b + 1])
         orc.cbconvFG(to_np(x[b:b + 1]), to_np(prev[b:b + 1]), e, to_np(w), 0.25)
         np.testing.assert_allclose(out[b:b + 1].cpu().numpy(), e, rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize("n", [1, 100, 300, 5000])
+def test_conv_update_stream_k_tiny_change_set(cbm, n):
+    """A near-static frame on a large map with the stream-K workspace: fewer (tile, K block) units
+    than CTAs.  CTAs with an empty share must drop out (they would never raise their flag and the
+    tile owner would wait for them until the trap)."""
+    import torch.nn.functional as F
+    cg, lib, cb = cbm["cg"], cbm["lib"], cbm["cb"]
+    B, Cin, Cout, H, W, k = 8, 64, 256, 120, 160, 7
+    gemm = lib.GEMM_TC_BF16X3
+    torch.backends.cudnn.allow_tf32 = False
+    state, sbuf = cg.pixel_major((B, Cin, H, W), torch.float32, "cuda", 0)
+    state.copy_(rand_tensor((B, Cin, H, W), "f32", seed=3))
+    w = rand_tensor((Cout, Cin, k, k), "f32", seed=11, scale=(Cin * k * k) ** -0.5)
+    bias = rand_tensor((Cout,), "f32", seed=12)
+    g = torch.Generator().manual_seed(n)
+    sel = torch.randperm(B * H * W, generator=g)[:n].sort().values.int().cuda()
+    ci = cg.ChangeIndexes.from_tensor(sel, (B, H, W))
+    ws = torch.zeros(lib.C.cb_conv_ws_bytes(), dtype=torch.uint8, device="cuda")
+    out, obuf = cg.pixel_major((B, Cout, H, W), torch.float32, "cuda", 0)
+    out.fill_(3.0)
+    for _ in range(2):
+        cg.conv_update(sbuf, ci, cg.pack_weights(w, gemm), bias, obuf, Cin, Cout, (k, k), True, gemm, ws=ws)
+    torch.cuda.synchronize()
+    assert int(ws.view(torch.int32)[:1024].abs().sum()) == 0
+    ref = F.relu(F.conv2d(state, w, bias, padding=k // 2))
+    touched = torch.zeros(B * H * W, dtype=torch.bool, device="cuda")
+    touched[sel.long()] = True
+    tm = touched.view(B, 1, H, W).expand(B, Cout, H, W)
+    assert float((out[~tm] - 3.0).abs().max()) == 0.0
+    assert float((out[tm] - ref[tm]).abs().max()) / float(ref.abs().max()) <= CONV_TOL[("bf16x3", "f32")]
