@@ -131,12 +131,16 @@ dilate_compact_kernel(const uint32_t* __restrict__ raw, uint32_t* __restrict__ d
 
   // ---- dilated words (consecutive words per thread keep the index order) ------------------
   unsigned d[kCompactWPT];
+  unsigned twin[kCompactWPT];                                // tiles this thread stamped first
+  int tt0[kCompactWPT];
   int cnt = 0;
   const int w0 = tile * kCompactTile + tid * kCompactWPT;    // 32-bit index math: nwords < 2^31
 #pragma unroll
   for (int i = 0; i < kCompactWPT; ++i) {
     const int w = w0 + i;
     d[i] = 0;
+    twin[i] = 0;
+    tt0[i] = 0;
     if (w < nwords) {
       const int j = w % Wd;
       const int r = w / Wd;
@@ -144,22 +148,29 @@ dilate_compact_kernel(const uint32_t* __restrict__ raw, uint32_t* __restrict__ d
       d[i] = pool_hin ? pooled_word(raw, r / H, y, j, pool_hin, pool_wdin, W)
                       : dilated_word(win, win0, r, y, j, H, W, Wd, kh, kw);
       if (dil_bits) dil_bits[w] = d[i];
-      if (tile_ws && d[i]) {
-        // dirty 8 x 16 output tiles for the tiled contraction (conv_tile.cuh): a word covers four
-        // tiles of one tile row; the first word to stamp a tile with this launch's tag appends it
-        // (unordered list, every tile once)
-        uint32_t* stamp = reinterpret_cast<uint32_t*>(tile_ws) + 4;
-        const int t0 = ((r / H) * tile_ty + y / 16) * tile_xp + 4 * j;
+    }
+    if (tile_ws) {
+      // dirty 8 x 16 output tiles for the tiled contraction (conv_tile.cuh): a word covers four
+      // tiles of one tile row; the first word to stamp a tile with this launch's tag appends it
+      // (unordered list, every tile once).  The four exchanges of a word are independent; their
+      // results are only needed after the index expansion, where the append position is reserved
+      // once per warp.
+      uint32_t* stamp = reinterpret_cast<uint32_t*>(tile_ws) + 4;
+      int t0 = 0;
+      unsigned win = 0;
+      if (w < nwords && d[i]) {
+        const int j = w % Wd, r = w / Wd;
+        t0 = ((r / H) * tile_ty + (r % H) / 16) * tile_xp + 4 * j;
+        unsigned old[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if (((d[i] >> (8 * q)) & 0xffu) && *reinterpret_cast<volatile uint32_t*>(stamp + t0 + q) != tag) {
-            if (atomicExch(stamp + t0 + q, tag) != tag) {
-              const int pos = atomicAdd(tile_ws, 1);
-              tile_ws[4 + B * tile_ty * tile_xp + pos] = t0 + q;
-            }
-          }
-        }
+        for (int q = 0; q < 4; ++q)
+          old[q] = ((d[i] >> (8 * q)) & 0xffu) ? atomicExch(stamp + t0 + q, tag) : tag;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (old[q] != tag) win |= 1u << q;
       }
+      twin[i] = win;
+      tt0[i] = t0;
     }
     cnt += __popc(d[i]);
   }
@@ -254,6 +265,33 @@ dilate_compact_kernel(const uint32_t* __restrict__ raw, uint32_t* __restrict__ d
       for (int q = 0; q < n; ++q) m[q] = (int8_t)((d[i] >> q) & 1u);
     }
   }
+  }
+
+  // ---- append the tiles this warp stamped first ------------------------------------------------
+  if (tile_ws) {
+#pragma unroll
+    for (int i = 0; i < kCompactWPT; ++i) {
+      const unsigned win = twin[i];
+      const int t0 = tt0[i];
+      const int mine = __popc(win);
+      int incl_t = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl_t, o);
+        if (lane >= o) incl_t += v;
+      }
+      const int total_t = __shfl_sync(0xffffffffu, incl_t, 31);
+      int base_t = 0;
+      if (total_t) {
+        if (lane == 31) base_t = atomicAdd(tile_ws, total_t);
+        base_t = __shfl_sync(0xffffffffu, base_t, 31);
+        int pos = 4 + B * tile_ty * tile_xp + base_t + incl_t - mine;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if ((win >> q) & 1u) tile_ws[pos++] = t0 + q;
+      }
+    }
+    __syncthreads();                            // all appends of this block precede its done-increment
   }
 
   // ---- leave the workspace clean for the next launch ---------------------------------------

@@ -32,7 +32,6 @@ namespace cb {
 constexpr int TL_W = 8, TL_H = 16;             // output tile (pixels): 128 rows of the M dimension
 constexpr int TL_NHALO = 2;                    // halo buffers (tile i+1 loads while tile i computes; 1 if smem is tight)
 constexpr int TL_MAXB = 12;                    // weight ring slots
-constexpr int TL_MAXTAB = 1024;                // K-step table entries (8 KB)
 constexpr int TL_CTRL_BYTES = 512;
 
 __host__ __device__ inline int tile_grid_y(int H) { return (H + TL_H - 1) / TL_H; }
@@ -75,6 +74,12 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       : "memory");
 }
 
+__host__ __device__ constexpr bool tile_merge(bool split3, int bn) { return split3 && 4 * bn <= 512; }
+__host__ __device__ constexpr int tile_tmem_cols(bool split3, int bn) {
+  const int c = 2 * (tile_merge(split3, bn) ? 2 * bn : bn);
+  return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512;
+}
+
 // A-operand descriptor of a halo plane: start address filled in per K step
 __device__ __forceinline__ uint64_t tile_adesc_base(uint32_t sbo_bytes, int layout) {
   return ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | ((uint64_t)layout << 61);
@@ -91,49 +96,31 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap amap_hi, const __grid_const
   constexpr int ES = sizeof(T), BK = UM_ROW_BYTES / ES, UK = 32 / ES, KS = BK / UK;
   constexpr int NSPLIT = SPLIT3 ? 2 : 1;
   constexpr int B_BYTES = BN * UM_ROW_BYTES, B_STAGE = NSPLIT * B_BYTES;
-  constexpr int TMEM_COLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
+  // 3x split with N <= 128: the two products that share the `hi` state operand run as ONE
+  // instruction against the stacked [w_hi; w_lo] tile (N = 2*BN, columns BN.. hold a_hi*w_lo) and the
+  // epilogue adds the halves -- two instructions per K step instead of three (small-N instructions
+  // are issue-bound, not tensor-bound)
+  constexpr bool MERGE = tile_merge(SPLIT3, BN);
+  constexpr int ACC_COLS = MERGE ? 2 * BN : BN;                // TMEM columns of one accumulator
+  constexpr int TMEM_COLS = tile_tmem_cols(SPLIT3, BN);
   constexpr int EPI = um_epi(BN);
-  const int ntl = tile_ws[1];                               // dirty tiles (cb_dilate_compact_tiles)
+  // dirty tiles (cb_dilate_compact_tiles); the shuffle makes the value uniform for the compiler
+  const int ntl = __shfl_sync(0xffffffffu, tile_ws[1], 0);
   const int ntiles_n = g.CoutPad / BN;
   const long long total = (long long)ntl * ntiles_n;
   if ((long long)blockIdx.x >= total) return;               // CTA-uniform, before any barrier / alloc
   if (smem_u32(smem) & 1023u) __trap();
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);    // provably warp-uniform role index
   const int NT = g.B * g.TY * g.TXp;
   const int32_t* tiles = tile_ws + 4 + NT;
   const int halo_stage = NSPLIT * g.nblk * g.plane_bytes;
   uint8_t* bring = smem + g.nhalo * halo_stage;
   TileCtrl* ctrl = reinterpret_cast<TileCtrl*>(bring + g.nb * B_STAGE);
-  uint2* tab = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(ctrl) + TL_CTRL_BYTES);
-  const bool resident = ntiles_n == 1 && g.num_kb <= g.nb;
+  const bool fake = g.relu & 2;                              // TIMING EXPERIMENT ONLY (CBINFER_TILE_FAKE=1)
+  const bool resident = (ntiles_n == 1 && g.num_kb <= g.nb) || fake;
   const int ph = (g.kH - 1) / 2, pw = (g.kW - 1) / 2;
 
-  // ---- K-step table: per tcgen05.mma (32 bytes of K) the byte offset of its tap inside a halo
-  //      plane (+ channel block plane, + channel offset inside the pixel) and, for 16-byte pixels,
-  //      the distance to the second tap of the instruction (LBO) ---------------------------------
-  {
-    const int pixb = g.Cp * ES;
-    for (int e = tid; e < g.num_kb * KS; e += blockDim.x) {
-      const int k0 = e * UK;
-      uint2 v = make_uint2(0xffffffffu, 16u);                // beyond K: all-zero weights, skipped
-      if (k0 < g.Kp) {
-        const int tap = k0 / g.Cp, ci0 = k0 - tap * g.Cp;
-        const int ky = tap / g.kW, kx = tap - ky * g.kW;
-        if (pixb == 16) {
-          const int t1 = tap + 1, ky1 = t1 / g.kW, kx1 = t1 - ky1 * g.kW;
-          v.x = (uint32_t)((ky * g.HWX + kx) * 16);
-          // (a second tap beyond the filter meets zero weights; it re-reads the first tap so that no
-          //  uninitialised shared memory -- possibly NaN patterns -- enters the product)
-          v.y = t1 < g.kH * g.kW ? (uint32_t)(((ky1 * g.HWX + kx1) - (ky * g.HWX + kx)) * 16) : 0u;
-        } else {
-          const int byte = ci0 * ES;
-          const int blk = byte >> 7, within = byte & 127;    // (pixels <= 128 B: blk == 0)
-          v.x = (uint32_t)(blk * g.plane_bytes + (ky * g.HWX + kx) * g.pix_row + within);
-        }
-      }
-      tab[e] = v;
-    }
-  }
   if (tid == 0) {
     for (int s = 0; s < TL_MAXB; ++s) {
       mbar_init(&ctrl->b_full[s], 1);
@@ -169,103 +156,165 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap amap_hi, const __grid_const
 
   if (warp == 0) {
     // =============================== weight tiles (TMA ring) ================================
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      int it = 0;
-      for (long long w = blockIdx.x; w < total; w += gridDim.x, ++it) {
-        if (resident && it > 0) break;
-        const int nt = (int)(w % ntiles_n);
-        for (int kb = 0; kb < g.num_kb; ++kb) {
-          if (!resident) mbar_wait(&ctrl->b_empty[stage], phase ^ 1u);
-          uint8_t* b_hi = bring + stage * B_STAGE;
+    // (whole warp, uniform operands, one elected lane issues: see the MMA warp)
+    const bool leader = elect_one();
+    const int nb = g.nb, num_kb = g.num_kb, CoutPad = g.CoutPad;
+    uint32_t stage = 0, phase = 0;
+    int it = 0;
+    for (long long w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+      if (resident && it > 0) break;
+      const int nt = (int)(w % ntiles_n);
+      for (int kb = 0; kb < (fake && num_kb > nb ? nb : num_kb); ++kb) {
+        if (!resident) mbar_wait(&ctrl->b_empty[stage], phase ^ 1u);
+        if (leader) {
+          const uint32_t b_hi = smem_u32(bring + stage * B_STAGE);
           mbar_arrive_expect_tx(&ctrl->b_full[stage], (uint32_t)B_STAGE);
-          tma_load_2d(smem_u32(b_hi), &wmap, kb * BK, nt * BN, &ctrl->b_full[stage]);
-          if (SPLIT3)
-            tma_load_2d(smem_u32(b_hi + B_BYTES), &wmap, kb * BK, g.CoutPad + nt * BN, &ctrl->b_full[stage]);
-          if (++stage == (uint32_t)g.nb) { stage = 0; phase ^= 1u; }
+          tma_load_2d(b_hi, &wmap, kb * BK, nt * BN, &ctrl->b_full[stage]);
+          if (SPLIT3) tma_load_2d(b_hi + B_BYTES, &wmap, kb * BK, CoutPad + nt * BN, &ctrl->b_full[stage]);
         }
+        __syncwarp();
+        if (++stage == (uint32_t)nb) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
     // =============================== halo tiles (TMA, tile mode, zero fill) =================
-    if (lane == 0) {
-      const int BE = g.pix_row / ES;                         // channels per 128-byte block
-      const uint32_t box_bytes = (uint32_t)(g.HWX * g.HWY * g.pix_row);
-      int it = 0;
-      for (long long w = blockIdx.x; w < total; w += gridDim.x, ++it) {
-        const int tile = __ldg(tiles + (int)(w / ntiles_n));
-        const int b = tile / tiles_per_img, r = tile - b * tiles_per_img;
-        const int ty = r / g.TXp, tx = r - ty * g.TXp;
-        const int hb = it % g.nhalo;
-        mbar_wait(&ctrl->halo_empty[hb], (uint32_t)(((it / g.nhalo) & 1) ^ 1));
-        mbar_arrive_expect_tx(&ctrl->halo_full[hb], (uint32_t)(NSPLIT * g.nblk) * box_bytes);
+    const bool leader = elect_one();
+    const int BE = g.pix_row / ES;                           // channels per 128-byte block
+    const uint32_t box_bytes = (uint32_t)(g.HWX * g.HWY * g.pix_row);
+    const int nhalo = g.nhalo, nblk = g.nblk, plane_bytes = g.plane_bytes, TXp = g.TXp;
+    int it = 0;
+    for (long long w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+      const int tile = __shfl_sync(0xffffffffu, __ldg(tiles + (int)(w / ntiles_n)), 0);
+      const int b = tile / tiles_per_img, r = tile - b * tiles_per_img;
+      const int ty = r / TXp, tx = r - ty * TXp;
+      const int hb = it % nhalo;
+      mbar_wait(&ctrl->halo_empty[hb], (uint32_t)(((it / nhalo) & 1) ^ 1));
+      if (leader) {
+        mbar_arrive_expect_tx(&ctrl->halo_full[hb], (uint32_t)(NSPLIT * nblk) * box_bytes);
         const uint32_t dst = smem_u32(smem + hb * halo_stage);
-        for (int blk = 0; blk < g.nblk; ++blk) {
-          tma_load_4d(dst + blk * g.plane_bytes, &amap_hi, blk * BE, tx * TL_W - pw, ty * TL_H - ph, b,
+        for (int blk = 0; blk < nblk; ++blk) {
+          tma_load_4d(dst + blk * plane_bytes, &amap_hi, blk * BE, tx * TL_W - pw, ty * TL_H - ph, b,
                       &ctrl->halo_full[hb]);
           if (SPLIT3)
-            tma_load_4d(dst + (g.nblk + blk) * g.plane_bytes, &amap_lo, blk * BE, tx * TL_W - pw,
+            tma_load_4d(dst + (nblk + blk) * plane_bytes, &amap_lo, blk * BE, tx * TL_W - pw,
                         ty * TL_H - ph, b, &ctrl->halo_full[hb]);
         }
       }
+      __syncwarp();
     }
   } else if (warp == 2) {
     // =============================== MMA issuer ==============================================
-    if (lane == 0) {
-      constexpr int KIND = sizeof(T) == 4 ? 0 : 1;
-      const uint32_t idesc = umma_idesc(sizeof(T) == 4 ? 2 : (std::is_same<T, __half>::value ? 0 : 1), BN);
-      const uint64_t abase = tile_adesc_base((uint32_t)(g.HWX * g.pix_row), g.layout);
-      const uint32_t lo_plane = (uint32_t)(g.nblk * g.plane_bytes);
-      const uint32_t tab_s = smem_u32(tab);
-      uint32_t stage = 0, phase = 0;
-      int it = 0;
-      for (long long w = blockIdx.x; w < total; w += gridDim.x, ++it) {
-        const int hb = it % g.nhalo;
-        const uint32_t ab = (uint32_t)it & 1u, aph = ((uint32_t)it >> 1) & 1u;
-        mbar_wait(&ctrl->halo_full[hb], (uint32_t)((it / g.nhalo) & 1));
-        mbar_wait(&ctrl->tmem_empty[ab], aph ^ 1u);
-        tc_fence_after();
-        const uint32_t a_hi = smem_u32(smem + hb * halo_stage);
-        const uint32_t tmem_d = tmem_base + ab * (uint32_t)BN;
-        uint32_t acc = 0;
-        for (int kb = 0; kb < g.num_kb; ++kb) {
+    // The WHOLE warp runs this loop -- control flow, barrier waits and every descriptor are then
+    // warp-uniform, so they live in uniform registers and a tcgen05.mma costs a handful of
+    // uniform-ALU instructions; one elected lane issues.  (Under `if (lane == 0)` the compiler cannot
+    // prove uniformity and wraps every UTCHMMA in an ELECT / 5x R2UR / branch "waterfall" loop:
+    // ~150 cycles per instruction, measured -- more than the tensor time of an N <= 256 tile.)
+    // Descriptor offsets follow the K order (ky, kx, ci) incrementally; no table, no divisions.
+    constexpr int KIND = sizeof(T) == 4 ? 0 : 1;
+    constexpr int FMT = sizeof(T) == 4 ? 2 : (std::is_same<T, __half>::value ? 0 : 1);
+    const uint32_t idesc = umma_idesc(FMT, BN);
+    const uint32_t idesc2 = umma_idesc(FMT, MERGE ? 2 * BN : BN);
+    // descriptors as (hi word: SBO | version | layout, constant) + (lo word: start >> 4 | LBO >> 4 << 16,
+    // running): one uniform add per operand and K step (the uniform datapath executes in order at
+    // ~10 cycles per dependent instruction, so every instruction in this loop is on the issue path)
+    const uint32_t a_hi32 = (uint32_t)(tile_adesc_base((uint32_t)(g.HWX * g.pix_row), g.layout) >> 32);
+    const uint32_t b_hi32 = (uint32_t)(umma_desc(0) >> 32);
+    const bool leader = elect_one();
+    const int pixb = g.Cp * ES, kH = g.kH, kW = g.kW, nblk = g.nblk, nhalo = g.nhalo, nb = g.nb;
+    const int ntaps = kH * kW;
+    const uint32_t pix16 = (uint32_t)g.pix_row >> 4;          // one halo pixel, in 16-byte units
+    const uint32_t row16 = (uint32_t)g.HWX * pix16;          // one halo row
+    const uint32_t plane16 = (uint32_t)g.plane_bytes >> 4;   // one channel-block plane
+    const uint32_t lo16 = (uint32_t)nblk * plane16;          // hi plane(s) -> lo plane(s)
+    const int steps_in = g.pix_row >> 5;                     // K steps inside one 128-byte block of a pixel
+    const uint32_t bring16 = (smem_u32(bring) & 0x3FFFFu) >> 4;
+    uint32_t stage = 0, phase = 0;
+    int it = 0;
+    for (long long w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+      const int hb = it % nhalo;
+      const uint32_t ab = (uint32_t)it & 1u, aph = ((uint32_t)it >> 1) & 1u;
+      mbar_wait(&ctrl->halo_full[hb], (uint32_t)((it / nhalo) & 1));
+      mbar_wait(&ctrl->tmem_empty[ab], aph ^ 1u);
+      tc_fence_after();
+      const uint32_t a16 = (smem_u32(smem + hb * halo_stage) & 0x3FFFFu) >> 4;
+      const uint32_t tmem_d = tmem_base + ab * (uint32_t)ACC_COLS;
+      uint32_t acc = 0, b_run = 0;
+      int ks = 0, kbi = 0;
+      // one K step: 32 bytes of K from the halo (A lo word `alo`) against the running weight slice
+      auto step = [&](uint32_t alo) {
+        if (ks == 0) {                                       // next weight stage (KS K steps each)
           if (resident) {
-            stage = (uint32_t)kb;
-            if (it == 0) mbar_wait(&ctrl->b_full[stage], 0u);
+            stage = (uint32_t)(kbi % nb);
+            if (it == 0 && kbi < nb) mbar_wait(&ctrl->b_full[stage], 0u);
           } else {
             mbar_wait(&ctrl->b_full[stage], phase);
           }
           tc_fence_after();
-          const uint32_t b_hi = smem_u32(bring + stage * B_STAGE);
-          const uint32_t b_lo = b_hi + B_BYTES;
-#pragma unroll
-          for (int ks = 0; ks < KS; ++ks) {
-            uint32_t off, lbo;
-            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];"
-                         : "=r"(off), "=r"(lbo)
-                         : "r"(tab_s + (uint32_t)((kb * KS + ks) * 8)));
-            if (off == 0xffffffffu) continue;
-            const uint64_t ad = abase | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16);
-            const uint64_t ad_hi = ad | (uint64_t)(((a_hi + off) & 0x3FFFFu) >> 4);
-            const uint32_t adv = (uint32_t)(ks * 32);
-            if (SPLIT3) {
-              const uint64_t ad_lo = ad | (uint64_t)(((a_hi + lo_plane + off) & 0x3FFFFu) >> 4);
-              umma<KIND>(tmem_d, ad_lo, umma_desc(b_hi + adv), idesc, acc);
-              umma<KIND>(tmem_d, ad_hi, umma_desc(b_lo + adv), idesc, 1u);
-              umma<KIND>(tmem_d, ad_hi, umma_desc(b_hi + adv), idesc, 1u);
-            } else {
-              umma<KIND>(tmem_d, ad_hi, umma_desc(b_hi + adv), idesc, acc);
-            }
-            acc = 1u;
-          }
-          if (!resident) {
-            umma_commit(&ctrl->b_empty[stage]);
-            if (++stage == (uint32_t)g.nb) { stage = 0; phase ^= 1u; }
+          b_run = (bring16 + stage * (uint32_t)(B_STAGE >> 4)) | (1u << 16);
+        }
+        if (leader) {
+          const uint64_t ad_hi = ((uint64_t)a_hi32 << 32) | alo;
+          const uint64_t bd_hi = ((uint64_t)b_hi32 << 32) | b_run;
+          if (MERGE) {
+            const uint64_t ad_lo = ((uint64_t)a_hi32 << 32) | (alo + lo16);
+            umma<KIND>(tmem_d, ad_hi, bd_hi, idesc2, acc);   // a_hi * [w_hi | w_lo]  (w_lo tile follows w_hi)
+            umma<KIND>(tmem_d, ad_lo, bd_hi, idesc, 1u);     // a_lo * w_hi
+          } else if (SPLIT3) {
+            const uint64_t ad_lo = ((uint64_t)a_hi32 << 32) | (alo + lo16);
+            const uint64_t bd_lo = ((uint64_t)b_hi32 << 32) | (b_run + (uint32_t)(B_BYTES >> 4));
+            umma<KIND>(tmem_d, ad_lo, bd_hi, idesc, acc);
+            umma<KIND>(tmem_d, ad_hi, bd_lo, idesc, 1u);
+            umma<KIND>(tmem_d, ad_hi, bd_hi, idesc, 1u);
+          } else {
+            umma<KIND>(tmem_d, ad_hi, bd_hi, idesc, acc);
           }
         }
+        acc = 1u;
+        b_run += 2;
+        if (++ks == KS) {
+          ks = 0;
+          ++kbi;
+          if (!resident) {
+            if (leader) umma_commit(&ctrl->b_empty[stage]);  // frees the weight stage when done
+            if (++stage == (uint32_t)nb) { stage = 0; phase ^= 1u; }
+          }
+        }
+      };
+      if (pixb == 16) {
+        // 16-byte pixels: two taps per instruction, LBO = distance to the second tap (next pixel,
+        // or the first pixel of the next filter row: HWX - kW + 1 = TL_W pixels on)
+        uint32_t u = a16;
+        int kx = 0;
+        for (int tap = 0; tap < ntaps; tap += 2) {
+          const uint32_t u1 = u + (kx + 1 == kW ? (uint32_t)TL_W : 1u);
+          const int kx1 = kx + 1 == kW ? 0 : kx + 1;
+          // (a second tap beyond the filter meets zero weights: it re-reads the first one, so no
+          //  uninitialised shared memory enters the product)
+          const uint32_t lbo = tap + 1 < ntaps ? u1 - u : 0u;
+          step(u | (lbo << 16));
+          u = u1 + (kx1 + 1 == kW ? (uint32_t)TL_W : 1u);
+          kx = kx1 + 1 == kW ? 0 : kx1 + 1;
+        }
+      } else {
+        uint32_t arow = a16 | (1u << 16);
+        for (int ky = 0; ky < kH; ++ky, arow += row16) {
+          uint32_t atap = arow;
+          for (int kx = 0; kx < kW; ++kx, atap += pix16) {
+            uint32_t ablk = atap;
+            for (int blk = 0; blk < nblk; ++blk, ablk += plane16)
+              for (int j = 0; j < steps_in; ++j) step(ablk + 2u * (uint32_t)j);
+          }
+        }
+      }
+      if (ks != 0 && !resident) {                            // partial last weight stage
+        if (leader) umma_commit(&ctrl->b_empty[stage]);
+        if (++stage == (uint32_t)nb) { stage = 0; phase ^= 1u; }
+      }
+      if (leader) {
         umma_commit(&ctrl->tmem_full[ab]);                   // accumulator complete
         umma_commit(&ctrl->halo_empty[hb]);                  // halo buffer consumed
       }
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // =============================== epilogue: TMEM -> bias / ReLU -> changed rows only ======
@@ -289,14 +338,22 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap amap_hi, const __grid_const
       const uint32_t ab = (uint32_t)it & 1u, aph = ((uint32_t)it >> 1) & 1u;
       mbar_wait(&ctrl->tmem_full[ab], aph);
       tc_fence_after();
-      const uint32_t trow = tmem_base + ab * (uint32_t)BN + ((uint32_t)(q * 32) << 16);
+      const uint32_t trow = tmem_base + ab * (uint32_t)ACC_COLS + ((uint32_t)(q * 32) << 16);
       TO* orow = out + (((long long)b * g.H + (on ? y : 0)) * g.W + (on ? x : 0)) * g.Op;
       if (__any_sync(0xffffffffu, on)) {
 #pragma unroll 1
         for (int c0 = cbeg; c0 < cbeg + COLS && c0 < BN; c0 += 16) {
           uint32_t acc[16];
           tmem_ld16(trow + (uint32_t)c0, acc);
-          tmem_ld_wait();
+          if (MERGE) {
+            uint32_t acc2[16];
+            tmem_ld16(trow + (uint32_t)(BN + c0), acc2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = __float_as_uint(__uint_as_float(acc[i]) + __uint_as_float(acc2[i]));
+          } else {
+            tmem_ld_wait();
+          }
           const int co0 = nt * BN + c0;
           if (on && co0 < g.Cout) {
             float f[16];
@@ -304,7 +361,7 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap amap_hi, const __grid_const
             for (int i = 0; i < 16; ++i) {
               const int co = co0 + i;
               float t = __uint_as_float(acc[i]) + (co < g.Cout ? __ldg(bias + co) : 0.f);
-              if (g.relu && t <= 0.f) t = 0.f;
+              if ((g.relu & 1) && t <= 0.f) t = 0.f;
               f[i] = t;
             }
             if (co0 + 16 <= g.Cout && (g.Op % OVEC) == 0) {
@@ -375,17 +432,17 @@ inline TilePlan tile_plan(int es, bool split3, int bn, int Cp, int B, int H, int
   g.nblk = pixb > 128 ? pixb / 128 : 1;
   g.plane_bytes = (g.HWX * g.HWY * g.pix_row + 1023) / 1024 * 1024;
   g.layout = g.pix_row == 16 ? 0 : g.pix_row == 32 ? 6 : g.pix_row == 64 ? 4 : 2;
-  g.Cout = Cout; g.CoutPad = CoutPad; g.Op = Op; g.relu = relu;
-  if (g.num_kb * 4 > TL_MAXTAB) return p;
+  g.Cout = Cout; g.CoutPad = CoutPad; g.Op = Op; g.relu = relu ? 1 : 0;
+  if (getenv("CBINFER_TILE_FAKE")) g.relu |= 2;
   if ((long long)g.HWX * g.pix_row >= (1 << 18)) return p;
   const int b_stage = nsplit * bn * UM_ROW_BYTES;
-  const int tmem_cols = 2 * bn <= 32 ? 32 : 2 * bn <= 64 ? 64 : 2 * bn <= 128 ? 128 : 2 * bn <= 256 ? 256 : 512;
+  const int tmem_cols = tile_tmem_cols(split3, bn);
   const int budget2 = 112 * 1024, budget1 = 224 * 1024;
   const bool one_ntile = CoutPad == bn;
   int nb = 0, occ = 1, fixed = 0;
   g.nhalo = 0;
   for (int nh = TL_NHALO; nh >= 1 && !g.nhalo; --nh) {       // fewer halo buffers when smem is tight
-    fixed = nh * nsplit * g.nblk * g.plane_bytes + TL_CTRL_BYTES + g.num_kb * 4 * 8;
+    fixed = nh * nsplit * g.nblk * g.plane_bytes + TL_CTRL_BYTES;
     if (nh == TL_NHALO && one_ntile && g.num_kb <= TL_MAXB && fixed + g.num_kb * b_stage <= budget2 &&
         2 * tmem_cols <= 512) {
       nb = g.num_kb; occ = 2; g.nhalo = nh;                  // resident weights, two CTAs per SM
@@ -407,6 +464,15 @@ inline TilePlan tile_plan(int es, bool split3, int bn, int Cp, int B, int H, int
     nb = (budget1 - fixed) / b_stage;
     if (nb > TL_MAXB) nb = TL_MAXB;
     if (one_ntile && g.num_kb <= nb) nb = g.num_kb;
+  }
+  if (occ == 2) {
+    // small layers (e.g. the RGB input layer: 50 KB, 64 TMEM columns): up to four CTAs per SM -- their
+    // instructions are issue-bound, more issuing warps keep the tensor pipe busier
+    int o = (227 * 1024) / (fixed + nb * b_stage + 1024);
+    if (o > 512 / tmem_cols) o = 512 / tmem_cols;
+    if (o > 4) o = 4;
+    if (force_occ > 1 && o > force_occ) o = force_occ;
+    if (o > occ) occ = o;
   }
   g.nb = nb;
   p.occ = occ;

@@ -192,6 +192,13 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// one lane of a converged warp (the same one every time)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(p));
+  return p != 0;
+}
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 UMMA):
 // start>>4 [0,14) | LBO>>4 = 1 [16,30) | SBO>>4 = 64 (8 rows x 128 B) [32,46) | version 1 [46,48)
 // | layout SWIZZLE_128B = 2 [61,64).
@@ -355,7 +362,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
   constexpr int UM_EPI = um_epi(BN), UM_THREADS = um_threads(BN);
   constexpr int RPT = UM_BM * 8 / UM_PRODUCERS;            // 16-byte chunks per thread per stage
   constexpr int RSTEP = UM_PRODUCERS / 8;                  // row stride between a thread's chunks
-  const int n = *count;
+  const int n = __shfl_sync(0xffffffffu, *count, 0);        // (the shuffle makes the value uniform for the compiler)
   const int mtiles = (n + UM_BM - 1) / UM_BM;
   const int ntiles = CoutPad / BN;
   const int total_tiles = mtiles * ntiles;
@@ -381,7 +388,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
   uint8_t* smem = smem_raw;
   if (smem_u32(smem) & 1023u) __trap();                   // SWIZZLE_128B tiles need 1024-byte alignment
   UmmaCtrl* ctrl = reinterpret_cast<UmmaCtrl*>(smem + C::STAGES * C::STAGE_BYTES);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);    // provably warp-uniform role index
   const int num_kb = (Kp + C::BK - 1) / C::BK;
   TileSeg seg0;
   const long long sk_units = (long long)total_tiles * num_kb;
@@ -751,63 +759,77 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
     }
   } else if (warp == TMA_WARP) {
     // =============================== TMA producer: weight tiles ==============================
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      TileSeg sg = seg0;
-      while (sg.next()) {
-        const int nt = sg.tile % ntiles, kb0 = sg.kb0, kb1 = sg.kb1;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&ctrl->empty[stage], phase ^ 1u);
-          uint8_t* b_hi = smem + stage * C::STAGE_BYTES + C::NSPLIT * C::A_BYTES;
+    // (whole warp, uniform operands, one elected lane issues: see the MMA warp)
+    const bool leader = elect_one();
+    uint32_t stage = 0, phase = 0;
+    TileSeg sg = seg0;
+    while (sg.next()) {
+      const int nt = sg.tile % ntiles, kb0 = sg.kb0, kb1 = sg.kb1;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&ctrl->empty[stage], phase ^ 1u);
+        if (leader) {
+          const uint32_t b_hi = smem_u32(smem + stage * C::STAGE_BYTES + C::NSPLIT * C::A_BYTES);
           mbar_arrive_expect_tx(&ctrl->full[stage], (uint32_t)(C::NSPLIT * C::B_BYTES));
-          tma_load_2d(smem_u32(b_hi), &wmap, kb * C::BK, nt * BN, &ctrl->full[stage]);
-          if (SPLIT3)
-            tma_load_2d(smem_u32(b_hi + C::B_BYTES), &wmap, kb * C::BK, CoutPad + nt * BN,
-                        &ctrl->full[stage]);
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+          tma_load_2d(b_hi, &wmap, kb * C::BK, nt * BN, &ctrl->full[stage]);
+          if (SPLIT3) tma_load_2d(b_hi + C::B_BYTES, &wmap, kb * C::BK, CoutPad + nt * BN, &ctrl->full[stage]);
         }
+        __syncwarp();
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == MMA_WARP) {
     // =============================== MMA issuer ==============================================
-    if (lane == 0) {
-      constexpr int KIND = sizeof(T) == 4 ? 0 : 1;
-      const uint32_t idesc =
-          umma_idesc(sizeof(T) == 4 ? 2 : (std::is_same<T, __half>::value ? 0 : 1), BN);
-      uint32_t stage = 0, phase = 0, sidx = 0;
-      TileSeg sg = seg0;
-      while (sg.next()) {
-        const int kb0 = sg.kb0, kb1 = sg.kb1;
-        const uint32_t buf = sidx & 1u, use = sidx >> 1;
-        ++sidx;
-        const uint32_t tmem_d = tmem_base + buf * (uint32_t)BN;
-        mbar_wait(&ctrl->tmem_empty[buf], (use & 1u) ^ 1u);  // epilogue drained this accumulator
+    // The whole warp walks the segments (uniform control flow, descriptors in uniform registers);
+    // one elected lane issues.  Under `if (lane == 0)` the compiler cannot prove the descriptors
+    // uniform and wraps every UTCHMMA in an ELECT / R2UR / branch loop (~150 cycles each, more than
+    // the 128 cycles of tensor work of an N = 256 instruction).
+    constexpr int KIND = sizeof(T) == 4 ? 0 : 1;
+    const uint32_t idesc =
+        umma_idesc(sizeof(T) == 4 ? 2 : (std::is_same<T, __half>::value ? 0 : 1), BN);
+    const bool leader = elect_one();
+    const uint32_t d_hi32 = (uint32_t)(umma_desc(0) >> 32);  // SBO | version | SWIZZLE_128B
+    uint32_t stage = 0, phase = 0, sidx = 0;
+    TileSeg sg = seg0;
+    while (sg.next()) {
+      const int kb0 = sg.kb0, kb1 = sg.kb1;
+      const uint32_t buf = sidx & 1u, use = sidx >> 1;
+      ++sidx;
+      const uint32_t tmem_d = tmem_base + buf * (uint32_t)BN;
+      mbar_wait(&ctrl->tmem_empty[buf], (use & 1u) ^ 1u);    // epilogue drained this accumulator
+      tc_fence_after();
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&ctrl->full[stage], phase);
+        fence_proxy_async_smem();                            // cp.async writes -> async proxy (UMMA)
         tc_fence_after();
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&ctrl->full[stage], phase);
-          fence_proxy_async_smem();                          // cp.async writes -> async proxy (UMMA)
-          tc_fence_after();
-          const uint32_t a_hi = smem_u32(smem + stage * C::STAGE_BYTES);
-          const uint32_t a_lo = a_hi + C::A_BYTES;
-          const uint32_t b_hi = a_hi + C::NSPLIT * C::A_BYTES;
-          const uint32_t b_lo = b_hi + C::B_BYTES;
+        // running low words of the descriptors: start >> 4 | LBO (1) << 16
+        const uint32_t a_hi = ((smem_u32(smem + stage * C::STAGE_BYTES) & 0x3FFFFu) >> 4) | (1u << 16);
+        const uint32_t a_lo = a_hi + (uint32_t)(C::A_BYTES >> 4);
+        const uint32_t b_hi = a_hi + (uint32_t)((C::NSPLIT * C::A_BYTES) >> 4);
+        const uint32_t b_lo = b_hi + (uint32_t)(C::B_BYTES >> 4);
+        if (leader) {
 #pragma unroll
           for (int ks = 0; ks < C::BK / C::UK; ++ks) {
-            const uint32_t adv = (uint32_t)(ks * 32);        // 32 bytes of K per instruction
+            const uint32_t adv = (uint32_t)(ks * 2);         // 32 bytes of K per instruction
             const uint32_t first = (kb != kb0 || ks) ? 1u : 0u;
+            const uint64_t dA = ((uint64_t)d_hi32 << 32) | (a_hi + adv);
+            const uint64_t dB = ((uint64_t)d_hi32 << 32) | (b_hi + adv);
             if (SPLIT3) {
-              umma<KIND>(tmem_d, umma_desc(a_lo + adv), umma_desc(b_hi + adv), idesc, first);
-              umma<KIND>(tmem_d, umma_desc(a_hi + adv), umma_desc(b_lo + adv), idesc, 1u);
-              umma<KIND>(tmem_d, umma_desc(a_hi + adv), umma_desc(b_hi + adv), idesc, 1u);
+              const uint64_t dAl = ((uint64_t)d_hi32 << 32) | (a_lo + adv);
+              const uint64_t dBl = ((uint64_t)d_hi32 << 32) | (b_lo + adv);
+              umma<KIND>(tmem_d, dAl, dB, idesc, first);
+              umma<KIND>(tmem_d, dA, dBl, idesc, 1u);
+              umma<KIND>(tmem_d, dA, dB, idesc, 1u);
             } else {
-              umma<KIND>(tmem_d, umma_desc(a_hi + adv), umma_desc(b_hi + adv), idesc, first);
+              umma<KIND>(tmem_d, dA, dB, idesc, first);
             }
           }
           umma_commit(&ctrl->empty[stage]);                  // frees the smem stage when done
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&ctrl->tmem_full[buf]);                  // accumulator complete
+        __syncwarp();
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
       }
+      if (leader) umma_commit(&ctrl->tmem_full[buf]);        // accumulator complete
+      __syncwarp();
     }
   }
 
