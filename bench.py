@@ -3,17 +3,23 @@
 
 Workload (config.workload): BASELINE.json configs[1] -- the scene-labeling CBinfer model (all five
 convs + both max-pools converted, feedback loop, fp32) on synthetic 640x480 video with 5 % block
-change per frame, `streams_per_gpu` independent video streams batched per GPU.
+change per frame, `streams_per_gpu` independent video streams batched per GPU.  `--workload
+streams1080p` = configs[4] (64 x 1080p streams in total, sharded 64/N per GPU, strong scaling),
+`--workload split4k` = one 3840x2160 stream in N row bands; `--rate` sets the change rate.
 
 A "step" is one frame of every resident stream through the whole model: the first layer's change
 detection is launched on the frame where it lies in HBM, the other launches replay as one CUDA graph.
-  value : frames/s with the frames already resident in HBM (device-timed, max over ranks)
+  value : frames/s with the frames already resident in HBM: blocks of exactly K steps, each
+          bracketed by barrier + synchronize and device-timed (max over ranks), repeated until
+          --min-seconds of device time were measured; the median block is reported
   e2e   : frames/s through the public module call with HOST (pinned) frames: per step one H2D copy
           of the step's frames and one D2H read of the step's logits inside the timed region
   e2e_u8_ingest : the same with uint8 host frames, normalised inside the detection kernel
+  parity_max_rel: the benchmarked configuration against the reference flow (unmodified reference
+          CUDA kernels of oracle/_ref + fp32 torch.matmul, tests/ref_flow.py), outside the timed region
   roofline      : dominant kernel vs its HBM / tensor roofline (per-kernel CUDA-event timing)
   cpu_baseline  : the reference's dense PyTorch CPU inference path on this box's host cores
-`--impl reference` times that CPU path alone on the same config.
+`--impl reference` times that CPU path alone on the same config; it never imports the product.
 
 Launch: python bench.py --gpus N --steps K --warmup W      (N>1: via torch.distributed.run)
 """
@@ -28,18 +34,28 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
 
+WORKLOADS = {
+    # name: (height, width, streams per GPU at N GPUs, scaling)
+    "scene640": dict(h=480, w=640, streams=lambda n: 8, scaling="weak",
+                     note="BASELINE configs[1]: 8 independent 640x480 streams per GPU"),
+    "streams1080p": dict(h=1080, w=1920, streams=lambda n: max(1, 64 // n), scaling="strong",
+                         note="BASELINE configs[4]: 64 independent 1080p streams in total, sharded 64/N per GPU"),
+}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--streams", type=int, default=8, help="video streams per GPU")
-    ap.add_argument("--groups", type=int, default=1,
-                    help="independent stream groups per GPU run as parallel branches of one CUDA graph "
-                         "(each group = streams/groups videos batched through its own model replica)")
-    ap.add_argument("--height", type=int, default=480)
-    ap.add_argument("--width", type=int, default=640)
+    ap.add_argument("--workload", default="scene640", choices=list(WORKLOADS) + ["split4k"],
+                    help="scene640 (default, BASELINE configs[1]); streams1080p = 64 x 1080p streams sharded "
+                         "64/N per GPU (strong scaling); split4k = one 3840x2160 stream in N row bands "
+                         "(delegates to benchmarks/split_4k.py)")
+    ap.add_argument("--streams", type=int, default=0, help="video streams per GPU (0 = the workload's own)")
+    ap.add_argument("--height", type=int, default=0)
+    ap.add_argument("--width", type=int, default=0)
     ap.add_argument("--rate", type=float, default=0.05, help="fraction of pixels changed per frame")
     ap.add_argument("--mode", default="block", choices=["block", "iid"])
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16", "f16"])
@@ -47,9 +63,67 @@ def parse():
     ap.add_argument("--threshold-factor", type=float, default=0.02)
     ap.add_argument("--dense-scan", action="store_true",
                     help="re-scan every layer's whole input like the reference (default: candidate detection)")
-    ap.add_argument("--no-extras", action="store_true", help="skip dense/latency/kernel/cpu legs")
+    ap.add_argument("--no-extras", action="store_true", help="skip dense/latency/kernel/cpu/check legs")
+    ap.add_argument("--no-check", action="store_true", help="skip the parity leg against the reference flow")
+    ap.add_argument("--min-seconds", type=float, default=0.25,
+                    help="repeat the K-step timed block until this much device time was measured (median block reported)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.workload in WORKLOADS:
+        wl = WORKLOADS[args.workload]
+        args.height = args.height or wl["h"]
+        args.width = args.width or wl["w"]
+        args.streams = args.streams or wl["streams"](max(args.gpus, int(os.environ.get("WORLD_SIZE", "1"))))
+        args.scaling = wl["scaling"]
+    return args
+
+
+# ---------------------------------------------------------------------------------------------
+# pure-torch restatement of the dense model and the synthetic video for the REFERENCE arm: that arm
+# must not load anything of the product (importing cbinfer_b200 dlopens libcbinfer_sm100.so).
+# tests/test_boundary.py checks these against cbinfer_b200.models / .video bit for bit.
+# ---------------------------------------------------------------------------------------------
+def dense_scene_cnn(seed=0):
+    """the dense scene-labeling CNN (topology: sceneLabeling/modelLoader.py:9-10,47,72-78)"""
+    import torch
+    import torch.nn as nn
+    g = torch.random.get_rng_state()
+    torch.manual_seed(seed)
+    m = nn.Sequential(
+        nn.Conv2d(3, 16, 7, padding=3), nn.ReLU(), nn.MaxPool2d(2, 2),
+        nn.Conv2d(16, 64, 7, padding=3), nn.ReLU(), nn.MaxPool2d(2, 2),
+        nn.Conv2d(64, 256, 7, padding=3), nn.ReLU(),
+        nn.Conv2d(256, 64, 1), nn.ReLU(),
+        nn.Conv2d(64, 8, 1),
+    ).eval()
+    torch.random.set_rng_state(g)
+    return m
+
+
+def synth_sequence(B, H, W, n, rate, mode="block", seed=0):
+    """static-camera synthetic video: frame t = frame t-1 with one re-drawn
+    rectangle of area rate*H*W (block) or Bernoulli(rate) pixels (iid) per stream"""
+    import math
+    import torch
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    frames = [torch.rand(B, 3, H, W, generator=g)]
+    for t in range(1, n):
+        f = frames[-1].clone()
+        if rate > 0:
+            g = torch.Generator(device="cpu").manual_seed(1000 + t)
+            if mode == "block":
+                area = rate * H * W
+                bh = min(H, max(1, int(round(math.sqrt(area * 3.0 / 4.0)))))
+                bw = min(W, max(1, int(round(area / bh))))
+                for b in range(B):
+                    y0 = int(torch.randint(0, H - bh + 1, (1,), generator=g))
+                    x0 = int(torch.randint(0, W - bw + 1, (1,), generator=g))
+                    f[b, :, y0:y0 + bh, x0:x0 + bw] = torch.rand(3, bh, bw, generator=g)
+            else:
+                m = torch.rand(B, 1, H, W, generator=g) < rate
+                f = torch.where(m, torch.rand(B, 3, H, W, generator=g), f)
+        frames.append(f)
+    return frames
 
 
 # ---------------------------------------------------------------------------------------------
@@ -113,30 +187,34 @@ class ClockSampler(threading.Thread):
 # ---------------------------------------------------------------------------------------------
 # the reference arm / cpu baseline: dense PyTorch CPU inference (the reference's dense path)
 # ---------------------------------------------------------------------------------------------
-def cpu_dense_fps(args, seconds, warm=2):
+def cpu_dense_fps(args, seconds, warm=2, max_steps=200):
+    """the reference's dense inference path (evalTools.inferFrameset on the unconverted model) on
+    the host cores, on the SAME batch as our arm: one step = one frame of all `streams` streams."""
     import torch
-    from cbinfer_b200 import models, video
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)            # reference: sceneLabeling/modelConverter.py:4
-    base = models.sceneLabelingBaseline().float()
-    frames = video.sequence(1, args.height, args.width, 4, args.rate, args.mode)
+    base = dense_scene_cnn().float()
+    S = args.streams
+    frames = synth_sequence(S, args.height, args.width, 4, args.rate, args.mode)
     times = []
     with torch.no_grad():
         for i in range(warm):
             base(frames[i % 4])
         t_end = time.perf_counter() + seconds
         i = 0
-        while (time.perf_counter() < t_end and len(times) < 200) or len(times) < 3:
+        while (time.perf_counter() < t_end and len(times) < max_steps) or len(times) < 3:
             t0 = time.perf_counter()
             base(frames[i % 4])
             times.append(time.perf_counter() - t0)
             i += 1
     mean = sum(times) / len(times)
-    return {"value": 1.0 / mean, "best": 1.0 / min(times), "unit": "frames/s", "cores": cores,
-            "kind": "reference",
-            "sample": "%d frames %dx%d through the dense nn.Conv2d/ReLU/MaxPool2d scene CNN on torch CPU "
-                      "(the reference's dense inference path, evalTools.inferFrameset), fp32, "
-                      "%d threads" % (len(times), args.width, args.height, cores)}
+    return {"value": S / mean, "best": S / min(times), "unit": "frames/s", "cores": cores,
+            "kind": "reference", "steps": len(times), "ms_per_step": mean * 1e3,
+            "sample": "%d steps of %d frames %dx%d (one frame of each of the %d streams, batched) through the "
+                      "dense nn.Conv2d/ReLU/MaxPool2d scene CNN on torch CPU (the reference's dense inference "
+                      "path, evalTools.inferFrameset), fp32, %d threads; BASELINE configs[0] is the same model "
+                      "on a 10-frame 320x240 sequence, this is the bench workload's size"
+                      % (len(times), S, args.width, args.height, S, cores)}
 
 
 def cpu_cb_oracle_fps(args, frames_cpu, thresholds, base, max_seconds=10.0):
@@ -186,18 +264,21 @@ def cpu_cb_oracle_fps(args, frames_cpu, thresholds, base, max_seconds=10.0):
 
 
 def run_reference(args):
+    """--impl reference: the reference's own CPU inference path, same config, nothing of the product
+    loaded (no `import cbinfer_b200`).  Each step = one frame of every stream of one GPU's batch."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     t0 = time.perf_counter()
-    per_step_budget = 120.0 / max(args.steps + args.warmup, 1)
-    r = cpu_dense_fps(args, seconds=min(60.0, per_step_budget * args.steps), warm=max(args.warmup, 1))
+    budget = min(150.0, max(5.0, 0.6 * (args.steps + args.warmup)))
+    r = cpu_dense_fps(args, seconds=budget, warm=max(min(args.warmup, 3), 1), max_steps=max(args.steps, 3))
+    assert "cbinfer_b200" not in sys.modules
     out = {
         "impl": "reference", "metric": "frames/s", "value": r["value"], "unit": "frames/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1000.0 / r["value"], "higher_is_better": True, "scaling": "weak",
+        "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup,
+        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": getattr(args, "scaling", "weak"),
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, streams=1),
+        "config": workload_config(args, streams=args.streams),
         "cpu_baseline": r,
         "e2e": {"value": r["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
@@ -208,7 +289,8 @@ def run_reference(args):
 def workload_config(args, streams):
     return {"workload": "sceneLabeling CBinfer CNN (5 CBConv2d + 2 CBPoolMax2d, feedback loop) on synthetic "
                         "%dx%d video, %.0f%% %s change per frame" % (args.width, args.height, args.rate * 100, args.mode),
-            "streams_per_gpu": streams, "stream_groups": getattr(args, "groups", 1), "height": args.height, "width": args.width,
+            "workload_name": args.workload,
+            "streams_per_gpu": streams, "height": args.height, "width": args.width,
             "change_rate": args.rate, "change_mode": args.mode, "threshold_factor": args.threshold_factor,
             "gemm": args.gemm, "detection": "dense re-scan per layer" if args.dense_scan else
             "dense scan on the input frame, candidate detection on CB-fed layers", "parallelism": "independent video streams sharded per GPU, no collective"}
@@ -217,10 +299,116 @@ def workload_config(args, streams):
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
+class SceneStep(object):
+    """One step of the bench: the first layer's change detection runs eagerly on each frame WHERE
+    IT LIES in HBM (CBConv2d.detectInput); everything after it replays as one CUDA graph captured
+    on the "detection done" tuple -- no copy of the frame into a static graph input."""
+
+    def __init__(self, model, frame0, frame1):
+        import torch
+        import cbinfer_b200 as cb
+        from cbinfer_b200.conv2d import DetectionDone
+        self.model = model
+        self.first = [m for m in model.modules() if type(m) is cb.CBConv2d][0]
+        self.static_in = frame0.clone()
+        with torch.no_grad():
+            model(self.static_in)                 # first frame: everything changed
+            self.static_in.copy_(frame1)
+            model(self.static_in)
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            model(self.static_in)
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            self.out = model(('changeIndexes', self.static_in, DetectionDone(self.first)))
+
+    def __call__(self, frame):
+        import torch
+        with torch.no_grad():
+            self.first.detectInput(frame)
+        self.graph.replay()
+        return self.out
+
+
+def build_model(args, base, first_frame):
+    """the benchmarked model: scene CBinfer net, all convs + pools converted, feedback loop,
+    thresholds = threshold_factor * range of each layer's dense input on the first frame"""
+    import cbinfer_b200 as cb
+    from cbinfer_b200 import models
+    mdl = models.sceneLabelingCBinfer(base, experimentIdx=6, threshold=0.1, convertAll=True,
+                                      clonePoolOutput=False, candidateDetect=not args.dense_scan)
+    for m in mdl.modules():
+        if type(m) is cb.CBConv2d:
+            m.gemmMode = args.gemm
+    thresholds = models.calibrateThresholds(base, mdl, first_frame, factor=args.threshold_factor)
+    return mdl, thresholds
+
+
+def parity_check(args, base, thresholds, frames_cpu, dev, nstreams=2, nframes=6):
+    """--check leg (outside every timed region): the benchmarked configuration (candidate path,
+    masked 1x1 layers, detectInput + graph) against the reference FLOW -- the unmodified reference
+    CUDA kernels of oracle/_ref driven by tests/ref_flow.py with fp32 torch.matmul -- on the first
+    `nstreams` streams.  Returns None when oracle/_ref was not built."""
+    import torch
+    import cbinfer_b200 as cb
+    from tests import ref_flow
+    if ref_flow.libs() is None:
+        return None
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    S = min(nstreams, frames_cpu[0].shape[0])
+    fr = [f[:S].to(dev) for f in frames_cpu[:nframes]]
+    mdl, _ = build_model(args, base, fr[0])
+    for c, th in zip([m for m in mdl.modules() if type(m) is cb.CBConv2d], thresholds):
+        c.threshold = th
+    step = SceneStep(mdl, fr[0], fr[1])
+    refs = [ref_flow.convert_sequential(base, thresholds) for _ in range(S)]
+    for s_ in range(S):
+        for t in (0, 1, 1):                       # the same frames the warm-up of SceneStep saw
+            ref_flow.run(refs[s_], fr[t][s_:s_ + 1].contiguous())
+    worst, l1_equal, flips = 0.0, True, 0
+    convs = [m for m in mdl.modules() if type(m) is cb.CBConv2d]
+    for t in range(2, len(fr)):
+        out = step(fr[t])
+        torch.cuda.synchronize()
+        n1 = int(convs[0]._scratch["count"])
+        mine = convs[0]._scratch["idx"][:n1]
+        for s_ in range(S):
+            ro, _ = ref_flow.run(refs[s_], fr[t][s_:s_ + 1].contiguous())
+            scale = float(ro.abs().max()) + 1e-30
+            worst = max(worst, float((out[s_:s_ + 1].float() - ro).abs().max()) / scale)
+            P = fr[t].shape[2] * fr[t].shape[3]
+            sel = mine[(mine >= s_ * P) & (mine < (s_ + 1) * P)] - s_ * P
+            l1_equal &= bool(torch.equal(sel, refs[s_][0].changeIndexes))
+    for s_ in range(S):
+        for li, ci in ((2, 1), (4, 2)):           # deeper 7x7 layers: differing change pixels (threshold flips)
+            ref_idx = refs[s_][li].changeIndexes
+            c = convs[ci]
+            n = int(c._scratch["count"])
+            P = c.prevInput.shape[2] * c.prevInput.shape[3]
+            mi = c._scratch["idx"][:n]
+            sel = mi[(mi >= s_ * P) & (mi < (s_ + 1) * P)] - s_ * P
+            a = torch.zeros(P, dtype=torch.bool, device=dev)
+            b = torch.zeros(P, dtype=torch.bool, device=dev)
+            a[sel.long()] = True
+            b[ref_idx.long()] = True
+            flips += int((a ^ b).sum())
+    return {"parity_max_rel": worst, "layer1_index_lists_bit_exact": l1_equal,
+            "deeper_layer_mask_bits_differing_last_frame": flips, "streams": S, "frames": len(fr) - 2,
+            "against": "unmodified reference kernels (oracle/_ref) + fp32 torch.matmul, tests/ref_flow.py"}
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "split4k":
+        sys.argv = [sys.argv[0], "--rate", str(args.rate), "--check"]
+        from benchmarks import split_4k
+        return split_4k.main()
 
     import torch
     import torch.distributed as dist
@@ -241,25 +429,12 @@ def main():
     torch.backends.cudnn.benchmark = True
 
     # ---- model + synthetic video (each rank: its own streams, seeds offset by rank) ----------
-    G = max(1, min(args.groups, S))
-    assert S % G == 0, "--streams must be a multiple of --groups"
-    Sg = S // G
     base = models.sceneLabelingBaseline().to(dev).to(tdt)
-
-    def make_model():
-        mdl = models.sceneLabelingCBinfer(base, experimentIdx=6, threshold=0.1, convertAll=True,
-                                          clonePoolOutput=False, candidateDetect=not args.dense_scan)
-        for m in mdl.modules():
-            if type(m) is cb.CBConv2d:
-                m.gemmMode = args.gemm
-        return mdl
-
-    model = make_model()                      # eager / e2e / kernel-table model (all S streams)
-    replicas = [make_model() for _ in range(G)]
     # the video is played forwards and backwards over a window of <= 48 frames (walking back undoes
-    # the same block change, so every step still sees one 5 % block change): long timed regions
-    # without holding hundreds of frames
-    nframes = min(K + Wm + 2, 48)
+    # the same block change, so every step still sees one block change): long timed regions
+    # without holding hundreds of frames; large workloads keep the window under ~6 GB
+    frame_bytes = S * 3 * H * W * 4
+    nframes = max(4, min(K + Wm + 2, 48, int(6e9 // frame_bytes)))
 
     def fidx(t):
         period = 2 * (nframes - 1)
@@ -268,60 +443,18 @@ def main():
 
     my_streams = streams.shard_streams(S * world, world, rank)      # global stream ids of this rank
     frames_cpu = video.sequence(S, H, W, nframes, args.rate, args.mode, seed=my_streams[0])
-    thresholds = models.calibrateThresholds(base, model, frames_cpu[0].to(dev).to(tdt),
-                                            factor=args.threshold_factor)
-    for r in replicas:
-        for c, th in zip([m for m in r.modules() if type(m) is cb.CBConv2d], thresholds):
-            c.threshold = th
     pinned = [f.to(tdt).pin_memory() for f in frames_cpu]
     frames = [f.to(dev, non_blocking=True) for f in pinned]
     torch.cuda.synchronize()
-
-    # ---- warm-up + ONE CUDA graph of one step: G independent branches (stream groups) ------------
-    static_in = frames[0].clone()
-    ins = [static_in[g * Sg:(g + 1) * Sg] for g in range(G)]
-    with torch.no_grad():
-        for r, x in zip(replicas, ins):
-            r(x)                              # first frame: everything changed
-        static_in.copy_(frames[1])
-        for r, x in zip(replicas, ins):
-            r(x)
-    torch.cuda.synchronize()
-    graph = torch.cuda.CUDAGraph()
-    branches = [torch.cuda.Stream() for _ in range(G)]
-    side = torch.cuda.Stream()
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side), torch.no_grad():
-        for r, x in zip(replicas, ins):
-            r(x)
-    torch.cuda.current_stream().wait_stream(side)
-    # The first layer's change detection runs eagerly on each frame WHERE IT LIES in HBM
-    # (CBConv2d.detectInput); everything after it replays as one CUDA graph captured on the
-    # "detection done" tuple - no copy of the frame into a static graph input.
-    from cbinfer_b200.conv2d import DetectionDone
-    firsts = [[m for m in r.modules() if type(m) is cb.CBConv2d][0] for r in replicas]
-    outs = [None] * G
-    with torch.cuda.graph(graph), torch.no_grad():
-        main = torch.cuda.current_stream()
-        for g in range(G):
-            branches[g].wait_stream(main)
-            with torch.cuda.stream(branches[g]):
-                outs[g] = replicas[g](('changeIndexes', ins[g], DetectionDone(firsts[g])))
-        for g in range(G):
-            main.wait_stream(branches[g])
-    static_out = outs[0]
-    # my kernels per step and group: per CBConv2d detect + dilate/compact + conv; per pool 1 (+1
-    # pooled compaction when it hands candidates on)
-    # dense scan: 5 x (detect, compact, conv) + 2 pools = 17; candidate path: the two pools also run
-    # the next conv's detection (15 launches)
-    # (13: the two trailing 1x1 layers skip the compaction, their contraction masks the candidate list)
-    my_launches_per_step = G * (17 if args.dense_scan else 13)
+    model, thresholds = build_model(args, base, frames[0])          # the timed model
+    step_obj = SceneStep(model, frames[0], frames[1])
+    # my kernels per step: dense scan: 5 x (detect, compact, conv) + 2 pools = 17; candidate path: the two
+    # pools also run the next conv's detection (15) and the two trailing 1x1 layers skip the compaction,
+    # their contraction masks the candidate list (13)
+    my_launches_per_step = 17 if args.dense_scan else 13
 
     def step(t):
-        with torch.no_grad():
-            for g in range(G):
-                firsts[g].detectInput(frames[fidx(t)][g * Sg:(g + 1) * Sg])
-        graph.replay()
+        step_obj(frames[fidx(t)])
 
     def barrier():
         if world > 1:
@@ -332,112 +465,130 @@ def main():
     for _ in range(Wm):
         step(t)
         t += 1
-    # ---- timed region: K steps, device-timed -----------------------------------------------------
+    # ---- timed region: blocks of EXACTLY K steps, each bracketed by barrier + synchronize and timed
+    #      on the device (max over ranks); blocks repeat until >= min_seconds were measured, the median
+    #      block is reported ------------------------------------------------------------------------
     sampler = ClockSampler(local)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    blocks, fps_blocks = [], []
     barrier()
     sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(K):
-        step(t)
-        t += 1
-    e1.record()
-    barrier()
+    while True:
+        barrier()
+        e0.record()
+        for _ in range(K):
+            step(t)
+            t += 1
+        e1.record()
+        barrier()
+        # whole-job rate: frames of all ranks / slowest rank's device time
+        fps_b, ms_b = streams.whole_job_rate(S * K, e0.elapsed_time(e1), dev)
+        blocks.append(ms_b)
+        fps_blocks.append(fps_b)
+        if sum(blocks) >= args.min_seconds * 1e3 or len(blocks) >= 500:
+            break
     clocks = sampler.stop()
-    # whole-job rate: frames of all ranks / slowest rank's device time
-    fps, elapsed_ms = streams.whole_job_rate(S * K, e0.elapsed_time(e1), dev)
-    counts = [sum(int(m._scratch["count"].item()) for m in ms)
-              for ms in zip(*[[m for m in r.modules() if type(m) is cb.CBConv2d] for r in replicas])]
-    state_mb = sum(t.numel() * t.element_size() for r in replicas for t in cb.getStateTensors(r)) / 1e6
+    order = sorted(range(len(blocks)), key=lambda i: blocks[i])
+    mid = order[len(order) // 2]
+    fps, elapsed_ms = fps_blocks[mid], blocks[mid]
+    counts = [int(m._scratch["count"].item()) for m in model.modules() if type(m) is cb.CBConv2d]
+    state_mb = sum(x.numel() * x.element_size() for x in cb.getStateTensors(model)) / 1e6
 
     # ---- e2e: the public per-frame API with HOST frames: every step copies its frames from pinned
     #      host memory (H2D) and reads its logits back (D2H).  runtime.FramePipeline = one graph
     #      replay per frame with the copies of neighbouring frames overlapped on their own streams.
     from cbinfer_b200 import runtime
-    for r in replicas:
-        cb.clearMemory(r)
-    del graph
+    del step_obj
     cb.clearMemory(model)
-    pipe = runtime.FramePipeline(model, frames[0], depth=2)
+
+    def e2e_leg(pin, first_frame_dev):
+        pipe = runtime.FramePipeline(model, first_frame_dev, depth=2)
+        for i in range(1, Wm + 1):
+            pipe.submit(pin[fidx(i)])
+        pipe.drain()
+        i0, walls, last = Wm + 1, [], None
+        while True:
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(i0, i0 + K):
+                last = pipe.submit(pin[fidx(i)])
+            pipe.wait(last)
+            pipe.drain()
+            wall_ms = (time.perf_counter() - t0) * 1e3
+            barrier()
+            # host wall clock from first submit to last result on the host (a device event pair on
+            # the default stream does not see the side streams)
+            walls.append(streams.whole_job_rate(S * K, wall_ms, dev))
+            i0 += K
+            if sum(w[1] for w in walls) >= args.min_seconds * 1e3 or len(walls) >= 200:
+                break
+        walls.sort(key=lambda w: w[1])
+        f_, ms_ = walls[len(walls) // 2]
+        d2h_ = pipe.out_host[0].numel() * pipe.out_host[0].element_size()
+        chk = float(pipe.out_host[last].float().abs().sum())
+        del pipe
+        return f_, ms_, d2h_, chk, len(walls)
+
     h2d = pinned[0].numel() * pinned[0].element_size()
-    d2h = pipe.out_host[0].numel() * pipe.out_host[0].element_size()
-    slots = []
-    for i in range(1, Wm + 1):
-        slots.append(pipe.submit(pinned[fidx(i)]))
-    pipe.drain()
-    barrier()
-    t0 = time.perf_counter()
-    e0.record()
-    last = None
-    for i in range(Wm + 1, Wm + 1 + K):
-        last = pipe.submit(pinned[fidx(i)])
-    pipe.wait(last)
-    pipe.drain()
-    e2e_wall_ms = (time.perf_counter() - t0) * 1e3
-    e1.record()
-    barrier()
-    # host wall clock from first submit to last result on the host (the device event pair on the
-    # default stream does not see the side streams)
-    e2e_fps, e2e_ms = streams.whole_job_rate(S * K, e2e_wall_ms, dev)
-    e2e_checksum = float(pipe.out_host[last].float().abs().sum())
+    e2e_fps, e2e_ms, d2h, e2e_checksum, e2e_blocks = e2e_leg(pinned, frames[0])
 
     # ---- e2e with uint8 host frames (what a camera / decoder delivers): the first layer's detection
     #      kernel normalises u8/255 on the fly (cb_change_detect_u8), so a quarter of the bytes cross
     #      PCIe.  Same pipeline, same change pattern; reported beside `e2e`, never instead of it.
     e2e_u8 = None
     if args.dtype == "f32":
-        del pipe
         cb.clearMemory(model)
         first = [m for m in model.modules() if type(m) is cb.CBConv2d][0]
         first.inputNorm = (255.0, 0.0)
         pinned8 = [f.mul(255.0).round().to(torch.uint8).pin_memory() for f in frames_cpu]
-        pipe8 = runtime.FramePipeline(model, pinned8[0].to(dev), depth=2)
-        for i in range(1, Wm + 1):
-            pipe8.submit(pinned8[fidx(i)])
-        pipe8.drain()
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(Wm + 1, Wm + 1 + K):
-            last = pipe8.submit(pinned8[fidx(i)])
-        pipe8.wait(last)
-        pipe8.drain()
-        u8_wall_ms = (time.perf_counter() - t0) * 1e3
-        barrier()
-        u8_fps, u8_ms = streams.whole_job_rate(S * K, u8_wall_ms, dev)
+        u8_fps, u8_ms, _, u8_chk, _ = e2e_leg(pinned8, pinned8[0].to(dev))
         e2e_u8 = {"value": u8_fps, "unit": "frames/s", "ms_per_step": u8_ms / K,
                   "h2d_gbs": pinned8[0].numel() / (u8_ms / K * 1e-3) / 1e9,
                   "h2d_bytes_per_step": pinned8[0].numel(), "d2h_bytes_per_step": d2h,
-                  "checksum": float(pipe8.out_host[last].float().abs().sum()),
+                  "checksum": u8_chk,
                   "path": "as e2e, but the pinned host frames are uint8 and are normalised (u8/255) inside "
                           "the first layer's detection kernel (cb_change_detect_u8)"}
-        del pipe8
+        del pinned8
         first.inputNorm = None
         cb.clearMemory(model)
 
     result = {
         "metric": "frames/s", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
-        "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": args.dtype, "data": "synthetic",
         "config": dict(workload_config(args, S),
+                       note=WORKLOADS[args.workload]["note"],
                        l2="no flush: per-step working set = persistent state maps of %d streams = %.0f MB %s 126 MB L2"
                           % (S, state_mb, ">" if state_mb > 126 else "<= (L2-resident!)"),
                        launch="per step: first-layer detection launched eagerly on the frame where it lies in "
                               "HBM, the other launches replayed as one CUDA graph",
+                       timing="median of %d timed blocks of %d steps each (blocks repeat until %.2f s of device "
+                              "time); min %.4f / max %.4f ms per step" % (
+                                  len(blocks), K, args.min_seconds, min(blocks) / K, max(blocks) / K),
                        thresholds=[round(x, 5) for x in thresholds],
                        changed_pixels_last_frame=counts),
+        "timed_blocks": len(blocks), "timed_region_s": sum(blocks) * 1e-3,
         "clocks": clocks,
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms / K, "checksum": e2e_checksum,
+                "ms_per_step": e2e_ms / K, "checksum": e2e_checksum, "timed_blocks": e2e_blocks,
                 "h2d_gbs": h2d / (e2e_ms / K * 1e-3) / 1e9,     # PCIe roofline of this leg (Gen5 x16 ~ 55 GB/s)
                 "path": "runtime.FramePipeline: per step pinned H2D of the frames, one graph replay, D2H of the "
                         "logits; copies of neighbouring steps overlap compute (3 streams); host wall clock"},
-        "gpu_launches": my_launches_per_step * K,
+        "gpu_launches": my_launches_per_step * K * len(blocks),
     }
     if e2e_u8 is not None:
         result["e2e_u8_ingest"] = e2e_u8
 
-    # ---- extras on rank 0 at N=1: kernel table / roofline, dense cuDNN, single-stream latency, CPU ----
+    # ---- extras on rank 0: parity leg, kernel table / roofline, dense cuDNN, single-stream latency, CPU ----
     if rank == 0 and not args.no_extras:
+        if not args.no_check and args.dtype == "f32":
+            try:
+                chk = parity_check(args, base, thresholds, frames_cpu, dev)
+                if chk is not None:
+                    result["parity_max_rel"] = chk["parity_max_rel"]
+                    result["parity"] = chk
+            except Exception as e:
+                result["parity_error"] = repr(e)
         try:
             result.update(kernel_roofline(args, model, frames, dev, tdt, elapsed_ms / K * 1e3))
         except Exception as e:                                   # never lose the headline line
@@ -453,7 +604,7 @@ def main():
                 result["single_stream_error"] = repr(e)
             try:
                 result["cpu_baseline"] = cpu_dense_fps(args, seconds=args.cpu_seconds)
-                if args.dtype == "f32":
+                if args.dtype == "f32" and args.workload == "scene640":
                     r = cpu_cb_oracle_fps(args, [f[:1].float() for f in frames_cpu[:12]], thresholds, base.float().cpu())
                     base.to(dev)
                     if r:
@@ -490,8 +641,8 @@ def kernel_roofline(args, model, frames, dev, tdt, step_us):
     REP = 20
     cur = {"layer": None}
     calls = []
-    names = ("detect", "detect_sparse", "dilate_compact", "pool_compact", "conv_update", "maxPool2d",
-             "maxPool2d_detect", "detect_compact_sparse")
+    names = ("detect", "detect_sparse", "dilate_compact", "pool_compact", "conv_update", "conv_update_tiled",
+             "maxPool2d", "maxPool2d_detect", "detect_compact_sparse")
     orig = {n: getattr(cg, n) for n in names}
 
     def recorder(name):
@@ -568,12 +719,14 @@ def kernel_roofline(args, model, frames, dev, tdt, step_us):
             elif kname == "dilate_compact":
                 by = P // 8 + 4 * n
                 row.update(bound="hbm", bytes=by, achieved=by / (us * 1e-6) / 1e9, peak=hbm, unit="GB/s")
-            elif kname == "conv_update":
+            elif kname in ("conv_update", "conv_update_tiled"):
                 fl = 2.0 * n * Cin * k2 * m.out_channels
                 by = min(n * k2, P) * Cin * es + m.out_channels * Cin * k2 * es + 4 * n + n * m.out_channels * es
                 pk = bf16 / 2 if (args.dtype == "f32" and args.gemm in ("tc", "tc3x")) else bf16
                 row.update(bound="tensor", flops=fl, bytes=by, achieved=fl / (us * 1e-6) / 1e12, peak=pk,
                            unit="TFLOP/s", n=n, hbm_gbs=by / (us * 1e-6) / 1e9)
+                if kname == "conv_update_tiled":
+                    row["tiles"] = int(m._scratch["tile_ws"][1])
         else:
             row.update(bound="hbm")
         if "achieved" in row:
@@ -589,7 +742,7 @@ def kernel_roofline(args, model, frames, dev, tdt, step_us):
         key = "%s[%s]" % (top["kernel"], top["layer"])
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(REPO, "profiles", "r01_traffic.json"))).get(key, {}).get("bytes")
+            traffic = json.load(open(os.path.join(REPO, "profiles", "r02_traffic.json"))).get(key, {}).get("bytes")
         except Exception:
             pass
         out["roofline"] = {"kernel": key, "bound": top["bound"],

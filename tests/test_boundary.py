@@ -142,3 +142,30 @@ def test_hierarchical_tuner_and_pickle_roundtrip(tmp_path):
     assert [m.threshold for m in models.getCBModuleList(back)] == \
         [m.threshold for m in models.getCBModuleList(pose)]
     assert repr(back) == repr(pose)
+
+
+def test_bench_reference_arm_is_product_free():
+    """bench.py's reference arm rebuilds the dense model and the synthetic video in plain torch
+    (it must not load libcbinfer_sm100.so): both must equal the package's builders bit for bit, and
+    running the arm must not import the product."""
+    import subprocess
+    import sys
+    import torch
+    import bench
+    from cbinfer_b200 import models, video
+    a, b = bench.dense_scene_cnn(), models.sceneLabelingBaseline()
+    for pa, pb in zip(a.parameters(), b.parameters()):
+        assert torch.equal(pa, pb)
+    for mode in ("block", "iid"):
+        fa = bench.synth_sequence(2, 24, 32, 4, 0.1, mode, seed=3)
+        fb = video.sequence(2, 24, 32, 4, 0.1, mode, seed=3)
+        assert all(torch.equal(x, y) for x, y in zip(fa, fb))
+    code = ("import sys; sys.argv=['bench.py','--impl','reference','--steps','3','--warmup','1','--height','48',"
+            "'--width','64','--streams','2']; import bench; bench.main(); "
+            "assert 'cbinfer_b200' not in sys.modules; assert not any('libcbinfer' in l for l in open('/proc/self/maps'))")
+    r = subprocess.run([sys.executable, "-c", code], cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    import json
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["config"]["streams_per_gpu"] == 2 and line["gpu_launches"] == 0

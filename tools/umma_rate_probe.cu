@@ -51,13 +51,37 @@ __global__ void __launch_bounds__(128) rate_kernel(int pattern, int seq, int rep
     const long long t0 = clock64();
     if (pattern >= 10) {
       // minimal issue loop: running low words of the descriptors, one add each per K step
-      const uint32_t px = pattern == 11 ? 32u : 128u;
-      const uint64_t ab = pattern == 11 ? tile_adesc_base(HWX * px, 6) : (umma_desc(0) & ~0x3FFFull);
+      const uint32_t px = pattern >= 11 ? 32u : 128u;
+      const uint64_t ab = pattern >= 11 ? tile_adesc_base(HWX * px, 6) : (umma_desc(0) & ~0x3FFFull);
       const uint32_t ahi32 = (uint32_t)(ab >> 32), bhi32 = (uint32_t)(umma_desc(0) >> 32);
       const uint32_t lbo = 1u << 16;
       for (int r = 0; r < reps; ++r) {
         uint32_t alo = ((abuf & 0x3FFFFu) >> 4) | lbo, blo = ((bbuf & 0x3FFFFu) >> 4) | lbo;
-        const uint32_t astep = pattern == 11 ? px >> 4 : 2u;
+        const uint32_t astep = pattern >= 11 ? px >> 4 : 2u;
+        if (pattern == 12 || pattern == 13) {
+          // four K steps per elected region (pattern 13: no branch at all, predicated issue)
+#pragma unroll 1
+          for (int i = 0; i < 48; i += 4) {
+            uint32_t al[4], bl[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { al[j] = alo + (uint32_t)j * 2u; bl[j] = blo + (uint32_t)j * 2u; }
+            if (leader) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint64_t ad_hi = ((uint64_t)ahi32 << 32) | al[j];
+                const uint64_t ad_lo = ((uint64_t)ahi32 << 32) | (al[j] + 2560u);
+                const uint64_t bd_hi = ((uint64_t)bhi32 << 32) | bl[j];
+                if (seq == 3) {
+                  umma<1>(tmem, ad_hi, bd_hi, idesc, 1u);
+                  umma<1>(tmem, ad_lo, bd_hi, idesc, 1u);
+                } else {
+                  umma<1>(tmem, ad_hi, bd_hi, idesc, 1u);
+                }
+              }
+            }
+            alo += 8;
+          }
+        } else
 #pragma unroll 1
         for (int i = 0; i < 49; ++i) {
           const uint64_t ad_hi = ((uint64_t)ahi32 << 32) | alo;
@@ -131,7 +155,7 @@ void run(int pattern, int seq, int nacc, int ctas, unsigned long long* d) {
   if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); exit(1); }
   unsigned long long cy = 0;
   cudaMemcpy(&cy, d, 8, cudaMemcpyDeviceToHost);
-  const double n = 49.0 * seq * reps;
+  const double n = (pattern == 12 ? 48.0 * (seq == 3 ? 2 : 1) : 49.0 * seq) * reps;
   printf("N=%3d pattern %d seq %d accumulators %d ctas %3d: %7.1f cycles / MMA  (tensor floor %d)\n", N, pattern, seq, nacc,
          ctas, cy / n, N / 2);
 }
@@ -139,7 +163,7 @@ void run(int pattern, int seq, int nacc, int ctas, unsigned long long* d) {
 int main() {
   unsigned long long* d;
   cudaMalloc(&d, 8);
-  for (int pattern = 10; pattern <= 11; ++pattern)
+  for (int pattern = 10; pattern <= 12; ++pattern)
     for (int seq = 1; seq <= 3; seq += 2) {
       run<16>(pattern, seq, 1, 1, d);
       run<64>(pattern, seq, 1, 1, d);
