@@ -449,9 +449,11 @@ def main():
     model, thresholds = build_model(args, base, frames[0])          # the timed model
     step_obj = SceneStep(model, frames[0], frames[1])
     # my kernels per step: dense scan: 5 x (detect, compact, conv) + 2 pools = 17; candidate path: the two
-    # pools also run the next conv's detection (15) and the two trailing 1x1 layers skip the compaction,
-    # their contraction masks the candidate list (13)
-    my_launches_per_step = 17 if args.dense_scan else 13
+    # pools also run the next conv's detection (15), the two trailing 1x1 layers skip the compaction (their
+    # contraction masks the candidate list: 13) and the two tiled convs pool in their epilogue (11)
+    fused_pools = sum(1 for m in model.modules() if type(m) is cb.CBConv2d and getattr(m, '_fusedPool', None)
+                      and os.environ.get("CBINFER_FUSE_POOL", "1") != "0" and os.environ.get("CBINFER_TILES", "1") != "0")
+    my_launches_per_step = 17 if args.dense_scan else 13 - fused_pools
 
     def step(t):
         step_obj(frames[fidx(t)])

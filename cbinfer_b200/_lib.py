@@ -27,6 +27,7 @@ SYMBOLS = [
     "cb_detect_compact_ws_bytes", "cb_detect_compact_sparse", "cb_pack_weights", "cb_conv_ws_bytes", "cb_conv_update", "cb_conv_update_masked", "cb_maxpool2x2",
     "cb_gen_xmatrix", "cb_matrix_mult", "cb_update_output", "cb_fg_update",
     "cb_tile_ws_bytes", "cb_dilate_compact_tiles", "cb_conv_tiled_supported", "cb_conv_update_tiled",
+    "cb_conv_tiled_pool_supported", "cb_conv_update_tiled_pool",
 ]
 
 
@@ -64,6 +65,10 @@ def _load():
         "cb_conv_tiled_supported": (i32, [i32] * 9),
         "cb_conv_update_tiled": (i32, [vp, i32, i32, vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32,
                                        i32, i32, i32, i32, i32]),
+        "cb_conv_tiled_pool_supported": (i32, [i32, i32, i32]),
+        "cb_conv_update_tiled_pool": (i32, [vp, i32, i32, vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32,
+                                            i32, i32, i32, i32, i32,
+                                            vp, i64, i64, i32, i32, i32, vp, i64, i64, i32, i32, vp, vp, vp, f32, i32]),
         "cb_map_to_bits": (i32, [vp, vp, vp, i32, i32, i32]),
         "cb_change_detect_sparse": (i32, [vp, i32, vp, i64, i64, i64, i64, vp, i64, i64, i64, i64, i32,
                                           vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, i32, i32]),

@@ -72,12 +72,44 @@ class CBPoolMax2d(nn.Module):
     def getStateTensors(self):
         return [self.outputState] if hasattr(self, 'outputState') else []
 
+    def _pooled_size(self, h, w):
+        if self.ceil_mode:
+            return (h - 1) // 2 + 1, (w - 1) // 2 + 1
+        return h // 2, w // 2
+
+    def _fusedPoolTarget(self, input_shape, dtype, device):
+        """What an upstream CBConv2d on the tile path needs to pool inside its own epilogue and run the
+        next layer's detection there (cb_conv_update_tiled_pool), or None when this pool's state is
+        not allocated yet / was touched from outside, or the next layer's candidate-detection
+        conditions do not hold (then the ordinary path runs and sets everything up)."""
+        nxt = self._fusedNext[0] if getattr(self, '_fusedNext', None) else None
+        if nxt is None or self._stateBuf is None:
+            return None
+        B, nc, h, w = input_shape
+        oh, ow = self._pooled_size(h, w)
+        st = self.outputState
+        if list(st.shape) != [B, nc, oh, ow] or st.dtype != dtype or st.device != device \
+                or st.data_ptr() != self._stateBuf.data_ptr() \
+                or getattr(self, '_outVersion', None) != st._version:
+            return None
+        tgt = nxt._fusedDetectTarget(tuple(st.shape), dtype, device)
+        if tgt is None:
+            return None
+        return dict(out=st, next_state=tgt['state'], next_raw_bits=tgt['raw_bits'],
+                    threshold=tgt['threshold'], mode=tgt['mode'], aux=tgt['aux'])
+
     def forward(self, inp):
         assert(type(inp) == tuple and inp[0] == 'changeIndexes')
         input = inp[1].detach()
         changeIndexes = inp[2]
         assert input.dim() == 4
         _lib.require_cuda(input)
+        if getattr(changeIndexes, 'pooledBy', None) is self:
+            # the producing CBConv2d already pooled its tiles and ran the next layer's detection
+            # inside its epilogue (cb_conv_update_tiled_pool)
+            changeIndexes.pooledBy = None
+            output = self.outputState.clone() if self.cloneOutput else self.outputState
+            return 'changeIndexes', output, DetectionDone(self._fusedNext[0])
         B, nc, h, w = input.shape
         if not isinstance(changeIndexes, ChangeIndexes):
             assert(changeIndexes.dim() == 1)
@@ -440,10 +472,19 @@ class CBConv2d(nn.Module):
         planes16 = aux[1:] if aux is not None and aux[0] == 'bf16' else None
         if tiled:
             # spatially clustered change sets: contraction over the dirty 8x16 tiles (TMA-staged
-            # halo, implicit im2col through the UMMA descriptors), rows masked by the dilated bitmap
+            # halo, implicit im2col through the UMMA descriptors), rows masked by the dilated bitmap;
+            # a directly following CBPoolMax2d (+ the detection of the layer after it) rides along
+            # in the epilogue when everything is warmed up
+            pool_args = None
+            fp = getattr(self, '_fusedPool', None)
+            if fp and self.propChangeIndexes and not ext_out and os.environ.get("CBINFER_FUSE_POOL", "1") != "0" \
+                    and _lib.C.cb_conv_tiled_pool_supported(_lib.dtype_code(dt), gemm, self.out_channels):
+                pool_args = fp[0]._fusedPoolTarget(outpSize, dt, dev)
             cg.conv_update_tiled(self._inBuf, s["tile_ws"], s["dil_bits"], packed, bias32, self._outBuf,
                                  self.in_channels, self.out_channels, self.kernel_size, self.withReLU,
-                                 gemm, lo_buf=lo_buf, planes16=planes16)                # :242-251
+                                 gemm, lo_buf=lo_buf, planes16=planes16, pool=pool_args)  # :242-251
+            if pool_args is not None:
+                changeIndexes.pooledBy = fp[0]
         else:
             cg.conv_update(self._inBuf, changeIndexes, packed, bias32, self._outBuf, self.in_channels,
                            self.out_channels, self.kernel_size, self.withReLU, gemm,

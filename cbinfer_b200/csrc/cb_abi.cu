@@ -294,10 +294,10 @@ int cb_conv_tiled_supported(int dtype, int gemm, int B, int H, int W, int Cin, i
   return plan.mma_clk_per_tile <= cb::tile_clk_limit() ? 1 : 2;
 }
 
-int cb_conv_update_tiled(void* stream, int dtype, int gemm, const void* state, const void* state_lo,
+static int conv_update_tiled_impl(void* stream, int dtype, int gemm, const void* state, const void* state_lo,
                          int pitch_in, const void* tile_ws, const uint32_t* dil_bits,
                          const void* packed_w, const float* bias, void* out, int pitch_out, int B,
-                         int H, int W, int Cin, int Cout, int kH, int kW, int relu) {
+                         int H, int W, int Cin, int Cout, int kH, int kW, int relu, const cb::PoolFuse& pf) {
   CB_CHECK_ARG(state && tile_ws && dil_bits && packed_w && bias && out, "conv_update_tiled: null pointer");
   CB_CHECK_ARG(gemm != CB_GEMM_SIMT_F32, "conv_update_tiled: tensor-core modes only");
   const int want_pitch = gemm == CB_GEMM_TC_BF16X3 ? cb::pitch16_of(Cin) : cb_channel_pitch(dtype, Cin);
@@ -308,7 +308,52 @@ int cb_conv_update_tiled(void* stream, int dtype, int gemm, const void* state, c
   if (B == 0 || H == 0 || W == 0) return 0;
   return cb::umma_conv_update_tiled((cudaStream_t)stream, dtype, gemm, state, state_lo, pitch_in,
                                     (const int32_t*)tile_ws, dil_bits, packed_w, bias, out, pitch_out,
-                                    B, H, W, Cout, kH, kW, relu);
+                                    B, H, W, Cout, kH, kW, relu, pf);
+}
+
+int cb_conv_update_tiled(void* stream, int dtype, int gemm, const void* state, const void* state_lo,
+                         int pitch_in, const void* tile_ws, const uint32_t* dil_bits,
+                         const void* packed_w, const float* bias, void* out, int pitch_out, int B,
+                         int H, int W, int Cin, int Cout, int kH, int kW, int relu) {
+  cb::PoolFuse pf;
+  memset(&pf, 0, sizeof(pf));
+  return conv_update_tiled_impl(stream, dtype, gemm, state, state_lo, pitch_in, tile_ws, dil_bits, packed_w,
+                                bias, out, pitch_out, B, H, W, Cin, Cout, kH, kW, relu, pf);
+}
+
+int cb_conv_tiled_pool_supported(int dtype, int gemm, int Cout) {
+  (void)dtype;
+  return gemm != CB_GEMM_SIMT_F32 && cb::tile_pool_ok(gemm, Cout) ? 1 : 0;
+}
+
+int cb_conv_update_tiled_pool(void* stream, int dtype, int gemm, const void* state, const void* state_lo,
+                              int pitch_in, const void* tile_ws, const uint32_t* dil_bits,
+                              const void* packed_w, const float* bias, void* out, int pitch_out, int B,
+                              int H, int W, int Cin, int Cout, int kH, int kW, int relu,
+                              void* pool_out, long long o_sb, long long o_sy, int o_pitch, int oH, int oW,
+                              void* next_state, long long n_sb, long long n_sy, int n_pitch, int aux_mode,
+                              void* aux_hi, void* aux_lo, uint32_t* next_raw_bits, float threshold,
+                              int update_mode) {
+  CB_CHECK_ARG(pool_out && next_state && next_raw_bits, "conv_update_tiled_pool: null pointer");
+  CB_CHECK_ARG(update_mode == CB_UPDATE_NONE || update_mode == CB_UPDATE_CHANGED || update_mode == CB_UPDATE_ALL,
+               "conv_update_tiled_pool: bad update_mode %d", update_mode);
+  const size_t es = cb::esize(dtype);
+  const int vec = (int)(16 / es);
+  const bool ok = (o_pitch % vec) == 0 && o_pitch == n_pitch && o_pitch >= Cout && pitch_out == o_pitch &&
+                  ((o_sy * es) % 16) == 0 && ((n_sy * es) % 16) == 0 && ((o_sb * es) % 16) == 0 &&
+                  ((n_sb * es) % 16) == 0 && ((uintptr_t)pool_out % 16) == 0 && ((uintptr_t)next_state % 16) == 0 &&
+                  ((uintptr_t)out % 16) == 0;
+  CB_CHECK_ARG(ok, "conv_update_tiled_pool: needs pixel-major, 16-byte aligned maps of equal pitch");
+  cb::PoolFuse pf;
+  memset(&pf, 0, sizeof(pf));
+  pf.out = pool_out; pf.o_sb = o_sb; pf.o_sy = o_sy; pf.op = o_pitch; pf.oH = oH; pf.oW = oW;
+  pf.nst = next_state; pf.n_sb = n_sb; pf.n_sy = n_sy; pf.np = n_pitch;
+  pf.nbits = next_raw_bits; pf.thr = threshold; pf.update = update_mode;
+  int rc = 0;
+  CB_DISPATCH_DTYPE(dtype, rc = cb::make_aux<T>(pf.aux, aux_mode, aux_hi, aux_lo, next_state, Cout));
+  if (rc) return rc;
+  return conv_update_tiled_impl(stream, dtype, gemm, state, state_lo, pitch_in, tile_ws, dil_bits, packed_w,
+                                bias, out, pitch_out, B, H, W, Cin, Cout, kH, kW, relu, pf);
 }
 
 int cb_conv_update_masked(void* stream, int dtype, int gemm, const void* state, const void* state_lo,

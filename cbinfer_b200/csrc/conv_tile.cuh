@@ -26,6 +26,8 @@
 // Warp roles: 0 weight TMA, 1 halo TMA, 2 MMA issuer (+ TMEM alloc), 3 spare, 4.. epilogue.
 #pragma once
 #include "conv_umma.cuh"
+#include "detect.cuh"
+#include "pool.cuh"
 
 namespace cb {
 
@@ -65,6 +67,26 @@ struct TileGeom {
   int Cout, CoutPad, Op, relu;
 };
 
+// Optional fused tail of the epilogue: change-based 2x2 / stride-2 max pooling of the tile's output
+// (reference maxPool2d_kernel, cbconv2d_cg_backend.cu:199-227) + the NEXT layer's change detection on
+// the re-pooled pixels (the job of cb_maxpool2x2_detect, pool.cuh), so conv -> pool -> detect is one
+// launch.  An 8 x 16 tile holds 4 x 8 whole windows (tiles are aligned to even coordinates); the four
+// pixels of a window are lanes l, l^1, l^8, l^9 of one epilogue warp.  Pixels of a touched window
+// that were not recomputed are read back from the output map, so the pooled value is the maximum
+// of exactly the stored values.  out == nullptr: no fusion.
+struct PoolFuse {
+  void* out;                     // pooled map (pixel-major, element type = the conv's output type)
+  long long o_sb, o_sy;
+  int op, oH, oW;
+  void* nst;                     // next layer's previous-input state (same shape as the pooled map)
+  long long n_sb, n_sy;
+  int np;
+  AuxPlanes aux;                 // its operand planes (fp32 layers)
+  uint32_t* nbits;               // its raw change bitmap (kept clear by its compaction)
+  float thr;
+  int update;                    // CB_UPDATE_*
+};
+
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1,
                                             int c2, int c3, uint64_t* bar) {
   asm volatile(
@@ -90,7 +112,7 @@ __global__ void __launch_bounds__(128 + um_epi(BN))
 conv_tile_kernel(const __grid_constant__ CUtensorMap amap_hi, const __grid_constant__ CUtensorMap amap_lo,
                  const __grid_constant__ CUtensorMap wmap, const int32_t* __restrict__ tile_ws,
                  const uint32_t* __restrict__ dil_bits, const float* __restrict__ bias,
-                 TO* __restrict__ out, const TileGeom g) {
+                 TO* __restrict__ out, const TileGeom g, const PoolFuse pf) {
   pdl_prologue();
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int ES = sizeof(T), BK = UM_ROW_BYTES / ES, UK = 32 / ES, KS = BK / UK;
@@ -325,6 +347,8 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap amap_hi, const __grid_const
     constexpr int NGROUP = EPI / 128;
     constexpr int COLS = (BN / NGROUP) < 16 ? 16 : (BN / NGROUP);
     const int cbeg = ((warp - 4) >> 2) * COLS;
+    const bool pooling = pf.out != nullptr;                  // (host: BN <= 64, one N tile, Cout % 16 == 0)
+    const TO pthr = thr_cast<TO>(pf.thr);
     int it = 0;
     for (long long w = blockIdx.x; w < total; w += gridDim.x, ++it) {
       const int tile = __ldg(tiles + (int)(w / ntiles_n));
@@ -332,15 +356,26 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap amap_hi, const __grid_const
       const int b = tile / tiles_per_img, r = tile - b * tiles_per_img;
       const int ty = r / g.TXp, tx = r - ty * g.TXp;
       const int y = ty * TL_H + rty, x = tx * TL_W + rtx;
+      const bool inimg = y < g.H && x < g.W;
       bool on = false;
-      if (y < g.H && x < g.W)
+      if (inimg)
         on = (__ldg(dil_bits + ((long long)b * g.H + y) * g.Wd + (x >> 5)) >> (x & 31)) & 1u;
       const uint32_t ab = (uint32_t)it & 1u, aph = ((uint32_t)it >> 1) & 1u;
       mbar_wait(&ctrl->tmem_full[ab], aph);
       tc_fence_after();
       const uint32_t trow = tmem_base + ab * (uint32_t)ACC_COLS + ((uint32_t)(q * 32) << 16);
-      TO* orow = out + (((long long)b * g.H + (on ? y : 0)) * g.W + (on ? x : 0)) * g.Op;
-      if (__any_sync(0xffffffffu, on)) {
+      TO* orow = out + (((long long)b * g.H + (inimg ? y : 0)) * g.W + (inimg ? x : 0)) * g.Op;
+      const unsigned onmask = __ballot_sync(0xffffffffu, on);
+      // fused pooling: window = lanes (l & ~9) + {0, 1, 8, 9}; its top-left lane owns the pooled pixel
+      const unsigned wmask = 0x303u << (lane & 0x16);
+      const bool win_on = pooling && (onmask & wmask) != 0u;
+      const int yo = y >> 1, xo = x >> 1;
+      const bool owner = win_on && (lane & 9) == 0 && yo < pf.oH && xo < pf.oW;
+      TO* po = reinterpret_cast<TO*>(pf.out) + b * pf.o_sb + yo * pf.o_sy + (long long)xo * pf.op;
+      TO* ns = reinterpret_cast<TO*>(pf.nst) + b * pf.n_sb + yo * pf.n_sy + (long long)xo * pf.np;
+      const long long opix = ((long long)b * pf.oH + yo) * pf.oW + xo;
+      bool pchg = false;
+      if (onmask) {
 #pragma unroll 1
         for (int c0 = cbeg; c0 < cbeg + COLS && c0 < BN; c0 += 16) {
           uint32_t acc[16];
@@ -355,8 +390,10 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap amap_hi, const __grid_const
             tmem_ld_wait();
           }
           const int co0 = nt * BN + c0;
+          float f[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = -INFINITY;
           if (on && co0 < g.Cout) {
-            float f[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const int co = co0 + i;
@@ -375,7 +412,10 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap amap_hi, const __grid_const
                 for (int i = 0; i < 16; i += 8) {
                   TO h[8];
 #pragma unroll
-                  for (int e = 0; e < 8; ++e) h[e] = from_float<TO>(f[i + e]);
+                  for (int e = 0; e < 8; ++e) {
+                    h[e] = from_float<TO>(f[i + e]);
+                    f[i + e] = to_float(h[e]);               // the stored (rounded) value is what gets pooled
+                  }
                   *reinterpret_cast<uint4*>(orow + co0 + i) = *reinterpret_cast<uint4*>(h);
                 }
               }
@@ -384,11 +424,49 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap amap_hi, const __grid_const
               for (int i = 0; i < 16; ++i)
                 if (co0 + i < g.Cout) orow[co0 + i] = from_float<TO>(f[i]);
             }
+          } else if (win_on && inimg && co0 < g.Cout) {
+            // an untouched pixel of a touched window: its stored value takes part in the maximum
+#pragma unroll
+            for (int i = 0; i < 16; i += OVEC) {
+              const uint4 v = ld16(orow + co0 + i);
+              const TO* e = reinterpret_cast<const TO*>(&v);
+#pragma unroll
+              for (int k = 0; k < OVEC; ++k) f[i + k] = to_float(e[k]);
+            }
+          }
+          if (pooling) {
+            // 2x2 maximum across the window's lanes, then the owner re-pools, thresholds against the
+            // next layer's state and maintains it (cb_maxpool2x2_detect semantics)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              f[i] = fmaxf(f[i], __shfl_xor_sync(0xffffffffu, f[i], 1));
+              f[i] = fmaxf(f[i], __shfl_xor_sync(0xffffffffu, f[i], 8));
+            }
+            if (owner && co0 < g.Cout) {
+#pragma unroll
+              for (int i = 0; i < 16; i += OVEC) {
+                TO h[OVEC];
+#pragma unroll
+                for (int k = 0; k < OVEC; ++k) h[k] = from_float<TO>(f[i + k]);
+                const uint4 res = *reinterpret_cast<uint4*>(h);
+                st16(po + co0 + i, res);
+                const uint4 sv = ld16(ns + co0 + i);
+                pchg |= Chunk<TO>::changed(sv, res, pthr);
+                if (pf.update == CB_UPDATE_ALL) store_state<TO>(ns + co0 + i, res, pf.aux, opix, co0 + i);
+              }
+            }
           }
         }
       }
       tc_fence_before();
       mbar_arrive(&ctrl->tmem_empty[ab]);
+      if (owner && pchg) {
+        const int oWd = (pf.oW + 31) >> 5;
+        atomicOr(pf.nbits + ((long long)b * pf.oH + yo) * oWd + (xo >> 5), 1u << (xo & 31));
+        if (pf.update == CB_UPDATE_CHANGED)                  // feedback: accept the new pooled pixel
+          for (int c = 0; c < g.Cout; c += OVEC)
+            store_state<TO>(ns + c, ld16(po + c), pf.aux, opix, c);
+      }
     }
   }
 
@@ -495,7 +573,7 @@ inline CUtensorMapDataType tmap_dtype() {
 template <typename T, typename TO, bool SPLIT3, int BN>
 int launch_conv_tile(cudaStream_t s, const void* state, const void* state_lo, const int32_t* tile_ws,
                      const uint32_t* dil_bits, const void* packed, const float* bias, void* out,
-                     const TilePlan& plan) {
+                     const TilePlan& plan, const PoolFuse& pf) {
   const TileGeom& g = plan.g;
   auto enc = tensor_map_encoder();
   if (!enc) return fail(3, "conv_update_tiled: cuTensorMapEncodeTiled unavailable");
@@ -542,7 +620,7 @@ int launch_conv_tile(cudaStream_t s, const void* state, const void* state_lo, co
   if (grid > max_items) grid = max_items;
   if (grid < 1) grid = 1;
   cb::launch_pdl(kern, dim3((unsigned)grid), dim3(128 + um_epi(BN)), (size_t)plan.smem_bytes, s, amap[0],
-                 amap[1], wmap, tile_ws, dil_bits, bias, (TO*)out, g);
+                 amap[1], wmap, tile_ws, dil_bits, bias, (TO*)out, g, pf);
   CB_CHECK_LAUNCH("conv_update_tiled");
   return 0;
 }
@@ -557,6 +635,9 @@ inline long long tile_clk_limit() {
   return v;
 }
 
+// fused pooling: one epilogue warp per TMEM lane quarter owns all channels of its pixels
+inline bool tile_pool_ok(int gemm, int Cout) { return Cout <= 64 && (Cout % 16) == 0 && umma_bn(gemm, Cout) == umma_cout_pad(gemm, Cout); }
+
 inline int umma_tile_plan(TilePlan& plan, int dtype, int gemm, int Cp, int B, int H, int W, int Cout,
                           int Op, int kH, int kW, int relu) {
   if (!(gemm == CB_GEMM_TC || gemm == CB_GEMM_TC_3X || gemm == CB_GEMM_TC_BF16X3)) { plan.ok = false; return 0; }
@@ -570,7 +651,7 @@ inline int umma_conv_update_tiled(cudaStream_t s, int dtype, int gemm, const voi
                                   const void* state_lo, int Cp, const int32_t* tile_ws,
                                   const uint32_t* dil_bits, const void* packed, const float* bias,
                                   void* out, int Op, int B, int H, int W, int Cout, int kH, int kW,
-                                  int relu) {
+                                  int relu, const PoolFuse& pf) {
   TilePlan plan;
   umma_tile_plan(plan, dtype, gemm, Cp, B, H, W, Cout, Op, kH, kW, relu);
   CB_CHECK_ARG(plan.ok, "conv_update_tiled: layer shape not supported by the tile path");
@@ -580,13 +661,14 @@ inline int umma_conv_update_tiled(cudaStream_t s, int dtype, int gemm, const voi
   CB_CHECK_ARG(((uintptr_t)state % 16) == 0 && ((uintptr_t)packed % 128) == 0,
                "conv_update_tiled: state must be 16-byte and packed weights 128-byte aligned");
   const int bn = umma_bn(gemm, Cout);
+  CB_CHECK_ARG(!pf.out || tile_pool_ok(gemm, Cout), "conv_update_tiled: fused pooling needs Cout <= 64, a multiple of 16");
 #define CB_TBN(T_, TO_, S3_)                                                                       \
   switch (bn) {                                                                                    \
-    case 16: return launch_conv_tile<T_, TO_, S3_, 16>(s, state, state_lo, tile_ws, dil_bits, packed, bias, out, plan);   \
-    case 32: return launch_conv_tile<T_, TO_, S3_, 32>(s, state, state_lo, tile_ws, dil_bits, packed, bias, out, plan);   \
-    case 64: return launch_conv_tile<T_, TO_, S3_, 64>(s, state, state_lo, tile_ws, dil_bits, packed, bias, out, plan);   \
-    case 128: return launch_conv_tile<T_, TO_, S3_, 128>(s, state, state_lo, tile_ws, dil_bits, packed, bias, out, plan); \
-    case 256: return launch_conv_tile<T_, TO_, S3_, 256>(s, state, state_lo, tile_ws, dil_bits, packed, bias, out, plan); \
+    case 16: return launch_conv_tile<T_, TO_, S3_, 16>(s, state, state_lo, tile_ws, dil_bits, packed, bias, out, plan, pf);   \
+    case 32: return launch_conv_tile<T_, TO_, S3_, 32>(s, state, state_lo, tile_ws, dil_bits, packed, bias, out, plan, pf);   \
+    case 64: return launch_conv_tile<T_, TO_, S3_, 64>(s, state, state_lo, tile_ws, dil_bits, packed, bias, out, plan, pf);   \
+    case 128: return launch_conv_tile<T_, TO_, S3_, 128>(s, state, state_lo, tile_ws, dil_bits, packed, bias, out, plan, pf); \
+    case 256: return launch_conv_tile<T_, TO_, S3_, 256>(s, state, state_lo, tile_ws, dil_bits, packed, bias, out, plan, pf); \
     default: return fail(2, "conv_update_tiled: unsupported N tile %d", bn);                      \
   }
   if (bf16x3) { CB_TBN(__nv_bfloat16, float, true) }

@@ -49,6 +49,13 @@ def enableCandidateDetection(m, fusePool=True, maskedConv=True):
                     b.candidateDetect = True
                     if fusePool:             # pooling + b's detection in one kernel
                         a._fusedNext = [b]
+        if fusePool:
+            # conv -> pool -> conv: a conv on the tile path also pools in its epilogue (and runs the
+            # detection of the conv after the pool there), cb_conv_update_tiled_pool
+            for a, p, b in zip(kids[:-2], kids[1:-1], kids[2:]):
+                if type(a) is CBConv2d and type(p) is CBPoolMax2d and type(b) is CBConv2d \
+                        and getattr(p, '_fusedNext', None) and not a.finegrained:
+                    a._fusedPool = [p]
         if maskedConv:
             # a 1x1 layer fed by a CB conv whose own index list nobody needs as an exact list (it is
             # last, or feeds another candidate-detecting conv) skips the compaction altogether

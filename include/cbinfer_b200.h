@@ -210,6 +210,24 @@ int cb_conv_update_tiled(void* stream, int dtype, int gemm, const void* state, c
                          const void* packed_w, const float* bias, void* out, int pitch_out, int B,
                          int H, int W, int Cin, int Cout, int kH, int kW, int relu);
 
+/* cb_conv_update_tiled + the change-based 2x2 / stride-2 max pooling of its output (reference
+ * maxPool2d, conv2d_cg.py:58-82 -> cbconv2d_cg_backend.cu:199-227) + the NEXT layer's change detection
+ * on the re-pooled pixels, i.e. cb_conv_update_tiled followed by cb_maxpool2x2_detect, in ONE launch:
+ * the epilogue that scatters a tile's rows also takes the 2x2 maxima of its 4 x 8 windows (pixels
+ * of a touched window that were not recomputed are read back from `out`), writes pool_out,
+ * thresholds against next_state, ORs the change bits into next_raw_bits (kept clear by the caller)
+ * and maintains next_state / its operand planes per update_mode.  Needs Cout <= 64, Cout % 16 == 0
+ * (cb_conv_tiled_pool_supported) and pixel-major maps of equal pitch. */
+int cb_conv_tiled_pool_supported(int dtype, int gemm, int Cout);
+int cb_conv_update_tiled_pool(void* stream, int dtype, int gemm, const void* state, const void* state_lo,
+                              int pitch_in, const void* tile_ws, const uint32_t* dil_bits,
+                              const void* packed_w, const float* bias, void* out, int pitch_out, int B,
+                              int H, int W, int Cin, int Cout, int kH, int kW, int relu,
+                              void* pool_out, long long o_sb, long long o_sy, int o_pitch, int oH, int oW,
+                              void* next_state, long long n_sb, long long n_sy, int n_pitch, int aux_mode,
+                              void* aux_hi, void* aux_lo, uint32_t* next_raw_bits, float threshold,
+                              int update_mode);
+
 /* cb_conv_update over a SUPERSET index list: a listed pixel is processed only if its bit is set in
  * `mask_bits` (a raw change bitmap, e.g. what cb_change_detect_sparse just wrote for a 1x1 layer
  * whose candidates were idx/count).  Layers that need no dilation can then skip the ordered

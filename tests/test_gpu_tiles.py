@@ -210,3 +210,51 @@ def test_module_tile_path_equals_index_path(cbm, dt, monkeypatch):
             assert torch.equal(ca._scratch["dil_bits"], cbb._scratch["dil_bits"])
     assert all("tile_ws" in c._scratch for c in convs[0])
     assert not any("tile_ws" in c._scratch for c in convs[1])
+
+
+@pytest.mark.parametrize("dt,feedback", [("f32", True), ("f32", False), ("bf16", True), ("f16", True)])
+def test_fused_pool_in_tile_epilogue_is_bit_identical(cbm, dt, feedback, monkeypatch):
+    """conv (tile path) -> CBPoolMax2d -> conv on the candidate path: with the pooling and the next
+    layer's detection fused into the tile kernel's epilogue (cb_conv_update_tiled_pool) every
+    pooled map, state, change bitmap, index list and output is bit-identical to the three-kernel
+    sequence conv, cb_maxpool2x2_detect."""
+    import torch.nn as nn
+    cb = cbm["cb"]
+    from cbinfer_b200 import models, video
+    tdt = TORCH_DT[dt]
+    torch.manual_seed(7)
+    base = nn.Sequential(nn.Conv2d(3, 16, 7, padding=3), nn.ReLU(), nn.MaxPool2d(2, 2),
+                         nn.Conv2d(16, 64, 7, padding=3), nn.ReLU(), nn.MaxPool2d(2, 2),
+                         nn.Conv2d(64, 32, 3, padding=1)).cuda().to(tdt).eval()
+    frames = [f.cuda().to(tdt) for f in video.sequence(2, 100, 136, 7, 0.08, "block", seed=9)]
+    frames.insert(4, frames[3].clone())            # an unchanged frame
+    runs = []
+    for fuse in ("1", "0"):
+        monkeypatch.setenv("CBINFER_FUSE_POOL", fuse)
+        m = cb.convertPools(cb.convert(base, threshold=0.04))
+        for c in m.modules():
+            if type(c) is cb.CBConv2d:
+                c.feedbackLoop = feedback
+            if type(c) is cb.CBPoolMax2d:
+                c.cloneOutput = False
+        models.enableCandidateDetection(m)
+        outs = []
+        for f in frames:
+            o = m(f)
+            torch.cuda.synchronize()
+            convs = [c for c in m.modules() if type(c) is cb.CBConv2d]
+            pools = [c for c in m.modules() if type(c) is cb.CBPoolMax2d]
+            outs.append(dict(out=o.clone(), counts=[int(c._scratch["count"]) for c in convs],
+                             dil=[c._scratch["dil_bits"].clone() for c in convs],
+                             states=[c.prevInput.clone() for c in convs],
+                             pooled=[p.outputState.clone() for p in pools]))
+        runs.append(outs)
+        if fuse == "1":
+            assert all(getattr(c, '_fusedPool', None) for c in convs[:2])
+    for t, (a, b) in enumerate(zip(*runs)):
+        assert a["counts"] == b["counts"], t
+        assert torch.equal(a["out"], b["out"]), t
+        for k in ("dil", "states", "pooled"):
+            for x, y in zip(a[k], b[k]):
+                assert torch.equal(x, y), (t, k)
+    assert sum(runs[0][-1]["counts"]) > 0
