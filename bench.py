@@ -374,8 +374,7 @@ def parity_check(args, base, thresholds, frames_cpu, dev, nstreams=2, nframes=6)
     for t in range(2, len(fr)):
         out = step(fr[t])
         torch.cuda.synchronize()
-        n1 = int(convs[0]._scratch["count"])
-        mine = convs[0]._scratch["idx"][:n1]
+        mine = convs[0].lastChangeIndexes()
         for s_ in range(S):
             ro, _ = ref_flow.run(refs[s_], fr[t][s_:s_ + 1].contiguous())
             scale = float(ro.abs().max()) + 1e-30
@@ -387,9 +386,8 @@ def parity_check(args, base, thresholds, frames_cpu, dev, nstreams=2, nframes=6)
         for li, ci in ((2, 1), (4, 2)):           # deeper 7x7 layers: differing change pixels (threshold flips)
             ref_idx = refs[s_][li].changeIndexes
             c = convs[ci]
-            n = int(c._scratch["count"])
             P = c.prevInput.shape[2] * c.prevInput.shape[3]
-            mi = c._scratch["idx"][:n]
+            mi = c.lastChangeIndexes()
             sel = mi[(mi >= s_ * P) & (mi < (s_ + 1) * P)] - s_ * P
             a = torch.zeros(P, dtype=torch.bool, device=dev)
             b = torch.zeros(P, dtype=torch.bool, device=dev)
@@ -643,7 +641,7 @@ def kernel_roofline(args, model, frames, dev, tdt, step_us):
     REP = 20
     cur = {"layer": None}
     calls = []
-    names = ("detect", "detect_sparse", "dilate_compact", "pool_compact", "conv_update", "conv_update_tiled",
+    names = ("detect", "detect_sparse", "dilate_compact", "dilate_tiles", "pool_compact", "conv_update", "conv_update_tiled",
              "maxPool2d", "maxPool2d_detect", "detect_compact_sparse")
     orig = {n: getattr(cg, n) for n in names}
 
@@ -651,7 +649,7 @@ def kernel_roofline(args, model, frames, dev, tdt, step_us):
         fn = orig[name]
 
         def w(*a, **k):
-            if name == "dilate_compact":
+            if name in ("dilate_compact", "dilate_tiles"):
                 k = dict(k, clear_raw=False)  # keep the raw bitmap: the replays must see the real input
             calls.append((cur["layer"], name, a, k))
             return fn(*a, **k)
@@ -679,7 +677,7 @@ def kernel_roofline(args, model, frames, dev, tdt, step_us):
     rec = {}
     for lname, kname, a, k in reversed(calls):
         k = dict(k)
-        if kname == "dilate_compact":
+        if kname in ("dilate_compact", "dilate_tiles"):
             k["clear_raw"] = False           # keep the input bitmap intact across repetitions
         if kname == "detect_sparse":
             k["bits_are_clear"] = False
@@ -718,8 +716,8 @@ def kernel_roofline(args, model, frames, dev, tdt, step_us):
             elif kname == "detect":
                 by = 2 * Cin * P * es + P // 8
                 row.update(bound="hbm", bytes=by, achieved=by / (us * 1e-6) / 1e9, peak=hbm, unit="GB/s")
-            elif kname == "dilate_compact":
-                by = P // 8 + 4 * n
+            elif kname in ("dilate_compact", "dilate_tiles"):
+                by = P // 8 + (4 * n if kname == "dilate_compact" else P // 8)
                 row.update(bound="hbm", bytes=by, achieved=by / (us * 1e-6) / 1e9, peak=hbm, unit="GB/s")
             elif kname in ("conv_update", "conv_update_tiled"):
                 fl = 2.0 * n * Cin * k2 * m.out_channels

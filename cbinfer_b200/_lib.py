@@ -27,7 +27,7 @@ SYMBOLS = [
     "cb_detect_compact_ws_bytes", "cb_detect_compact_sparse", "cb_pack_weights", "cb_conv_ws_bytes", "cb_conv_update", "cb_conv_update_masked", "cb_maxpool2x2",
     "cb_gen_xmatrix", "cb_matrix_mult", "cb_update_output", "cb_fg_update",
     "cb_tile_ws_bytes", "cb_dilate_compact_tiles", "cb_conv_tiled_supported", "cb_conv_update_tiled",
-    "cb_conv_tiled_pool_supported", "cb_conv_update_tiled_pool",
+    "cb_conv_tiled_pool_supported", "cb_conv_update_tiled_pool", "cb_dilate_tiles",
 ]
 
 
@@ -65,6 +65,7 @@ def _load():
         "cb_conv_tiled_supported": (i32, [i32] * 9),
         "cb_conv_update_tiled": (i32, [vp, i32, i32, vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32,
                                        i32, i32, i32, i32, i32]),
+        "cb_dilate_tiles": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32]),
         "cb_conv_tiled_pool_supported": (i32, [i32, i32, i32]),
         "cb_conv_update_tiled_pool": (i32, [vp, i32, i32, vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32,
                                             i32, i32, i32, i32, i32,

@@ -235,6 +235,7 @@ class CBConv2d(nn.Module):
         self._packed = None       # (key, packed weights, fp32 bias)
         self._fresh = True        # state holds +inf: the next detection must be a full scan
         self._lastThr = None
+        self._lastChanges = None
         self.changeMap = None
         if getattr(self, '_wsHolder', None) is not None:
             self._wsHolder.clear()
@@ -389,6 +390,15 @@ class CBConv2d(nn.Module):
         mask = None
         tiled = False             # this frame's contraction walks the dirty-tile list
         use_tiles = self._useTiles(dt, gemm, (B, H, W))
+        # a directly following CBPoolMax2d (+ the detection of the layer after it) rides along in the
+        # tile kernel's epilogue when everything is warmed up (cb_conv_update_tiled_pool); nobody
+        # then needs this layer's ordered index list, so it is only compacted on demand
+        pool_args = None
+        fp = getattr(self, '_fusedPool', None)
+        if use_tiles and fp and self.propChangeIndexes and not ext_out \
+                and os.environ.get("CBINFER_FUSE_POOL", "1") != "0" \
+                and _lib.C.cb_conv_tiled_pool_supported(_lib.dtype_code(dt), gemm, self.out_channels):
+            pool_args = fp[0]._fusedPoolTarget(outpSize, dt, dev)
         detected = isinstance(changeIndexes, DetectionDone)
         if detected:
             assert changeIndexes.owner is self
@@ -451,7 +461,9 @@ class CBConv2d(nn.Module):
                 changeIndexes = ChangeIndexes(candidates.buffer, candidates.count, (B, H, W), bits=None)
                 changeIndexes.superset = True
             else:
-                changeIndexes = self._compact(s, B, H, W, sparse_next, tiles=use_tiles)
+                changeIndexes = self._compact(s, B, H, W, sparse_next, tiles=use_tiles,
+                                              lazy=pool_args is not None and not self.saveChangeMap
+                                              and os.environ.get("CBINFER_LAZY_LIST", "1") != "0")
                 tiled = use_tiles
         else:
             if not isinstance(changeIndexes, ChangeIndexes):
@@ -472,14 +484,7 @@ class CBConv2d(nn.Module):
         planes16 = aux[1:] if aux is not None and aux[0] == 'bf16' else None
         if tiled:
             # spatially clustered change sets: contraction over the dirty 8x16 tiles (TMA-staged
-            # halo, implicit im2col through the UMMA descriptors), rows masked by the dilated bitmap;
-            # a directly following CBPoolMax2d (+ the detection of the layer after it) rides along
-            # in the epilogue when everything is warmed up
-            pool_args = None
-            fp = getattr(self, '_fusedPool', None)
-            if fp and self.propChangeIndexes and not ext_out and os.environ.get("CBINFER_FUSE_POOL", "1") != "0" \
-                    and _lib.C.cb_conv_tiled_pool_supported(_lib.dtype_code(dt), gemm, self.out_channels):
-                pool_args = fp[0]._fusedPoolTarget(outpSize, dt, dev)
+            # halo, implicit im2col through the UMMA descriptors), rows masked by the dilated bitmap
             cg.conv_update_tiled(self._inBuf, s["tile_ws"], s["dil_bits"], packed, bias32, self._outBuf,
                                  self.in_channels, self.out_channels, self.kernel_size, self.withReLU,
                                  gemm, lo_buf=lo_buf, planes16=planes16, pool=pool_args)  # :242-251
@@ -492,6 +497,7 @@ class CBConv2d(nn.Module):
                            ws=self._workspace(dev), mask=mask)                         # :242-251
         self._inVersion = self.prevInput._version
         self._outVersion = self.prevOutput._version
+        self._lastChanges = changeIndexes
         if ext_out and isinstance(changeIndexes, ChangeIndexes):
             changeIndexes.complete = False
         elif isinstance(changeIndexes, ChangeIndexes):
@@ -501,6 +507,15 @@ class CBConv2d(nn.Module):
             return 'changeIndexes', self.prevOutput, changeIndexes
         else:
             return self.prevOutput
+
+    def lastChangeIndexes(self):
+        """This frame's change indexes as an int32 tensor (ascending b*H*W + y*W + x): what the
+        reference hands on as ``changeIndexes`` (conv2d.py:256-257).  The list of a layer on the
+        tile path is compacted only now, on demand."""
+        ci = getattr(self, '_lastChanges', None)
+        if ci is None:
+            raise _lib.CBinferError("no frame processed yet")
+        return ci.tensor() if isinstance(ci, ChangeIndexes) else ci
 
     def _workspace_holder(self):
         if getattr(self, '_wsHolder', None) is None:
@@ -555,10 +570,16 @@ class CBConv2d(nn.Module):
             cache[key] = sup >= 1 if mode == 'on' else sup == 1
         return cache[key]
 
-    def _compact(self, s, B, H, W, sparse_next, tiles=False):
+    def _compact(self, s, B, H, W, sparse_next, tiles=False, lazy=False):
         """dilate the raw bitmap by the filter footprint and compact it to the index list."""
         if tiles and "tile_ws" not in s:
             s["tile_ws"] = cg.alloc_tile_ws((B, H, W), s["idx"].device)
+        if tiles and lazy:
+            # tiles + dilated bitmap + count only; the ordered list is compacted if somebody asks
+            cg.dilate_tiles(s["raw_bits"], (B, H, W), self.kernel_size, s["count"], s["ws"], s["dil_bits"],
+                            s["tile_ws"], clear_raw=sparse_next)
+            s["raw_clear"] = sparse_next
+            return ChangeIndexes(s["idx"], s["count"], (B, H, W), bits=s["dil_bits"], ws=s["ws"], listed=False)
         dil_map = s.get("dil_map") if self.saveChangeMap else None
         # a layer on the candidate path lets the compaction zero the raw bitmap once it has been
         # consumed, so the next frame's candidate detection needs no memset

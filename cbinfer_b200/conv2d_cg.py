@@ -38,8 +38,12 @@ class ChangeIndexes(object):
     (conv2d_cg.py:202): consumers in this package read ``count`` on the device; anything that
     needs a real tensor (``len``, ``.tensor()``, indexing) synchronises on demand."""
 
-    def __init__(self, buffer, count, shape, bits=None):
-        self.buffer = buffer          # int32 [capacity]
+    def __init__(self, buffer, count, shape, bits=None, ws=None, listed=True):
+        self._buffer = buffer         # int32 [capacity]
+        # listed=False: only the dilated bitmap, the tile list and the count exist so far (cb_dilate_tiles);
+        # the ordered list is compacted from `bits` the first time somebody asks for it
+        self.listed = listed
+        self._ws = ws                 # compaction workspace for that
         self.count = count            # int32 [1] on the device
         self.shape = shape            # (B, H, W) the indices refer to
         self.bits = bits              # optional dilated bitmap the list was compacted from
@@ -49,6 +53,15 @@ class ChangeIndexes(object):
         # True when the list is only a superset of the changed pixels (a masked 1x1 layer hands its
         # own candidates on instead of compacting): fine as detection candidates, not an exact list
         self.superset = False
+
+    @property
+    def buffer(self):
+        if not self.listed:
+            # compacted on every access, never cached: under CUDA-graph replay this python object
+            # outlives the frame it was created for, while `bits` always holds the current frame
+            assert self.bits is not None and self._ws is not None
+            dilate_compact(self.bits, self.shape, (1, 1), self._buffer, self.count, self._ws)
+        return self._buffer
 
     @classmethod
     def from_tensor(cls, idx, shape):
@@ -62,7 +75,8 @@ class ChangeIndexes(object):
         if self.superset:
             raise _lib.CBinferError("this change list is a candidate superset (producer ran with "
                                     "maskedConv=True); set maskedConv=False on it for exact lists")
-        return self.buffer[: int(self.count.item())]
+        buf = self.buffer
+        return buf[: int(self.count.item())]
 
     # tensor-like conveniences (all synchronise)
     def __len__(self):
@@ -86,7 +100,7 @@ class ChangeIndexes(object):
 
     @property
     def is_cuda(self):
-        return self.buffer.is_cuda
+        return self._buffer.is_cuda
 
     def cpu(self):
         return self.tensor().cpu()
@@ -176,6 +190,14 @@ def pool_compact(in_bits, in_shape, out_shape, idx, count, ws, out_bits=None):
     check(C.cb_pool_compact(stream_ptr(in_bits.device), in_bits.data_ptr(),
                             out_bits.data_ptr() if out_bits is not None else None,
                             idx.data_ptr(), count.data_ptr(), ws.data_ptr(), B, H, W, oH, oW))
+
+
+def dilate_tiles(raw_bits, shape, filtSize, count, ws, dil_bits, tile_ws, clear_raw=False):
+    """cb_dilate_tiles: dilation + dirty-tile list + change count, no ordered index list."""
+    B, H, W = shape
+    check(C.cb_dilate_tiles(stream_ptr(raw_bits.device), raw_bits.data_ptr(), dil_bits.data_ptr(),
+                            count.data_ptr(), ws.data_ptr(), tile_ws.data_ptr(), B, H, W,
+                            (filtSize[0] - 1) // 2, (filtSize[1] - 1) // 2, int(bool(clear_raw))))
 
 
 def dilate_compact(raw_bits, shape, filtSize, idx, count, ws, dil_bits=None, dil_map=None,

@@ -131,8 +131,8 @@ size_t cb_tile_ws_bytes(int B, int H, int W) { return cb::tile_ws_words(B, H, W)
 
 static int dilate_compact_impl(void* stream, const uint32_t* raw_bits, uint32_t* dil_bits, int8_t* dil_map,
                       int32_t* idx, int32_t* count, void* ws, void* tile_ws, int B, int H, int W, int kHHalf,
-                      int kWHalf, int clear_raw) {
-  CB_CHECK_ARG(raw_bits && idx && count && ws, "dilate_compact: null pointer");
+                      int kWHalf, int clear_raw, int no_list = 0) {
+  CB_CHECK_ARG(raw_bits && (idx || no_list) && count && ws, "dilate_compact: null pointer");
   CB_CHECK_ARG(raw_bits != dil_bits, "dilate_compact: dil_bits must not alias raw_bits");
   CB_CHECK_ARG(kHHalf >= 0 && kWHalf >= 0 && kWHalf <= 31, "dilate_compact: kWHalf must be <= 31");
   CB_CHECK_ARG((long long)B * H * W < (1ll << 31), "dilate_compact: more than 2^31 pixels");
@@ -150,7 +150,7 @@ static int dilate_compact_impl(void* stream, const uint32_t* raw_bits, uint32_t*
                                                           kWHalf, (int)nwords, ntiles, 0, 0,
                                                           clear_raw ? const_cast<uint32_t*>(raw_bits) : nullptr,
                                                           (int32_t*)tile_ws, cb::tile_grid_y(H), cb::tile_grid_xp(W),
-                                                          (int)compact_coop());
+                                                          (int)compact_coop(), no_list);
   CB_CHECK_LAUNCH("dilate_compact");
   return 0;
 }
@@ -171,6 +171,14 @@ int cb_dilate_compact_tiles(void* stream, const uint32_t* raw_bits, uint32_t* di
                              kHHalf, kWHalf, clear_raw);
 }
 
+int cb_dilate_tiles(void* stream, const uint32_t* raw_bits, uint32_t* dil_bits, int32_t* count, void* ws,
+                    void* tile_ws, int B, int H, int W, int kHHalf, int kWHalf, int clear_raw) {
+  CB_CHECK_ARG(tile_ws && dil_bits, "dilate_tiles: null pointer");
+  if ((long long)cb_bitmap_words(B, H, W) == 0) cudaMemsetAsync((int32_t*)tile_ws + 1, 0, sizeof(int32_t), (cudaStream_t)stream);
+  return dilate_compact_impl(stream, raw_bits, dil_bits, nullptr, nullptr, count, ws, tile_ws, B, H, W,
+                             kHHalf, kWHalf, clear_raw, 1);
+}
+
 int cb_pool_compact(void* stream, const uint32_t* in_bits, uint32_t* out_bits, int32_t* idx,
                     int32_t* count, void* ws, int B, int H, int W, int oH, int oW) {
   CB_CHECK_ARG(in_bits && idx && count && ws, "pool_compact: null pointer");
@@ -187,7 +195,7 @@ int cb_pool_compact(void* stream, const uint32_t* in_bits, uint32_t* out_bits, i
   cb::launch_pdl(dilate_compact_kernel, ntiles, kCompactThreads, 0, s, in_bits, out_bits, nullptr, idx, count, ws,
                                                           B, oH, oW, (oW + 31) / 32, 0, 0,
                                                           (int)nwords, ntiles, H, (W + 31) / 32, nullptr,
-                                                          nullptr, 0, 0, (int)compact_coop());
+                                                          nullptr, 0, 0, (int)compact_coop(), 0);
   CB_CHECK_LAUNCH("pool_compact");
   return 0;
 }

@@ -99,7 +99,7 @@ dilate_compact_kernel(const uint32_t* __restrict__ raw, uint32_t* __restrict__ d
                       int32_t* __restrict__ count, void* ws, int B, int H, int W, int Wd, int kh,
                       int kw, int nwords, int ntiles, int pool_hin, int pool_wdin,
                       uint32_t* __restrict__ clear_bits, int32_t* __restrict__ tile_ws, int tile_ty,
-                      int tile_xp, int coop) {
+                      int tile_xp, int coop, int no_list) {
   pdl_prologue();
   CompactHeader* hdr = reinterpret_cast<CompactHeader*>(ws);
   volatile unsigned long long* tstate =
@@ -175,6 +175,14 @@ dilate_compact_kernel(const uint32_t* __restrict__ raw, uint32_t* __restrict__ d
     cnt += __popc(d[i]);
   }
 
+  if (no_list) {
+    // tiles only (the consumer walks the tile list and masks rows with dil_bits): no ordered index
+    // list, hence no scan across tiles -- the change count is a plain sum (hdr->reserved)
+    int tot = cnt;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    if (lane == 0 && tot) atomicAdd(&hdr->reserved, (unsigned)tot);
+  } else {
   // ---- block scan of popcounts -----------------------------------------------------------
   int incl = cnt;
 #pragma unroll
@@ -267,6 +275,8 @@ dilate_compact_kernel(const uint32_t* __restrict__ raw, uint32_t* __restrict__ d
   }
   }
 
+  }   // !no_list
+
   // ---- append the tiles this warp stamped first ------------------------------------------------
   if (tile_ws) {
 #pragma unroll
@@ -302,6 +312,10 @@ dilate_compact_kernel(const uint32_t* __restrict__ raw, uint32_t* __restrict__ d
     s_last = prev == (unsigned)ntiles - 1u;
     if (s_last) {
       hdr->done = 0;
+      if (no_list) {                            // every block added its popcounts before its done-increment
+        *count = (int32_t)*reinterpret_cast<volatile unsigned*>(&hdr->reserved);
+        hdr->reserved = 0;
+      }
       if (tile_ws) {                            // every block appended before its done-increment
         tile_ws[1] = *reinterpret_cast<volatile int32_t*>(tile_ws);
         tile_ws[0] = 0;

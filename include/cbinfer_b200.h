@@ -127,6 +127,13 @@ int cb_dilate_compact_tiles(void* stream, const uint32_t* raw_bits, uint32_t* di
                             int8_t* dil_map, int32_t* idx, int32_t* count, void* ws, void* tile_ws,
                             int B, int H, int W, int kHHalf, int kWHalf, int clear_raw);
 
+/* cb_dilate_compact_tiles without the ordered index list: dilated bitmap (dil_bits, required), dirty
+ * tile list (tile_ws) and *count = number of dilated pixels.  For layers whose only consumers walk
+ * tiles (cb_conv_update_tiled[_pool]): no scan across the bitmap, no index expansion.  An ordered
+ * list can still be produced later from dil_bits with cb_dilate_compact(kHHalf = kWHalf = 0). */
+int cb_dilate_tiles(void* stream, const uint32_t* raw_bits, uint32_t* dil_bits, int32_t* count, void* ws,
+                    void* tile_ws, int B, int H, int W, int kHHalf, int kWHalf, int clear_raw);
+
 /* ---- candidate ("sparse") detection ---------------------------------------------------------
  * Same per-pixel test and state maintenance as cb_change_detect, evaluated only at the
  * `*n_candidates` pixels listed in `candidates` (indices b*H*W + y*W + x, any order); raw_bits is

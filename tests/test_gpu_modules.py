@@ -250,7 +250,7 @@ def test_candidate_detection_equals_dense_scan(feedback, dt, save_maps):
                 assert na == nb, t
                 if not (b.maskedConv and not b.fuse1x1 and not save_maps and t > 0):
                     # (a masked 1x1 layer never materialises its own list: counts only)
-                    assert torch.equal(a._scratch["idx"][:na], b._scratch["idx"][:nb]), t
+                    assert torch.equal(a.lastChangeIndexes(), b.lastChangeIndexes()), t
             else:
                 assert torch.equal(a.outputState, b.outputState), t
 
@@ -313,7 +313,7 @@ def test_full_size_properties(res):
     convs = [mm for mm in m.modules() if type(mm) is cb.CBConv2d]
     n1 = int(convs[0]._scratch["count"].item())
     assert 0.05 * H * W <= n1 <= 0.08 * H * W          # 5 % block + 3-pixel dilation ring
-    idx = convs[0]._scratch["idx"][:n1]
+    idx = convs[0].lastChangeIndexes()
     assert bool((idx[1:] > idx[:-1]).all())
     bits = convs[0]._scratch["dil_bits"].cpu().numpy().view(np.uint32)
     assert int(np.unpackbits(bits.view(np.uint8)).sum()) == n1

@@ -66,7 +66,7 @@ def _teacher_forced(base, thresholds, frames, tol, tdt=torch.float32):
                 y_t = y[1] if type(y) == tuple else y
                 yr_t = y_ref[1] if type(y_ref) == tuple else y_ref
                 n = int(o._scratch["count"])
-                assert torch.equal(o._scratch["idx"][:n], r.changeIndexes), (t, li, n, r.changeIndexes.numel())
+                assert torch.equal(o.lastChangeIndexes(), r.changeIndexes), (t, li, n, r.changeIndexes.numel())
                 assert torch.equal(o.prevInput, r.prevInput), (t, li)
                 scale = float(yr_t.float().abs().max()) + 1e-30
                 err = float((y_t.float() - yr_t.float()).abs().max()) / scale
@@ -183,7 +183,7 @@ def test_cpm_368_fp16_teacher_forced_vs_reference_flow():
                 y_t = y[1] if type(y) == tuple else y
                 yr_t = yr[1] if type(yr) == tuple else yr
                 n = int(o._scratch["count"])
-                assert torch.equal(o._scratch["idx"][:n], r.changeIndexes), (b, t, li)
+                assert torch.equal(o.lastChangeIndexes(), r.changeIndexes), (b, t, li)
                 assert torch.equal(o.prevInput, r.prevInput), (b, t, li)
                 scale = float(yr_t.float().abs().max()) + 1e-30
                 assert float((y_t.float() - yr_t.float()).abs().max()) / scale <= 2e-3, (b, t, li)

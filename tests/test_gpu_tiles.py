@@ -258,3 +258,31 @@ def test_fused_pool_in_tile_epilogue_is_bit_identical(cbm, dt, feedback, monkeyp
             for x, y in zip(a[k], b[k]):
                 assert torch.equal(x, y), (t, k)
     assert sum(runs[0][-1]["counts"]) > 0
+
+
+@pytest.mark.parametrize("shape,k,frac", [((2, 97, 131), 7, 0.02), ((1, 480, 640), 7, 0.3), ((3, 16, 8), 3, 1.0),
+                                          ((1, 40, 40), 5, 0.0)])
+def test_dilate_tiles_equals_dilate_compact(cbm, shape, k, frac):
+    """cb_dilate_tiles (no ordered list) yields the same dilated bitmap, change count and tile set as
+    cb_dilate_compact_tiles; the list compacted on demand from the bitmap equals the eager one."""
+    cg = cbm["cg"]
+    B, H, W = shape
+    g = torch.Generator().manual_seed(H + k)
+    raw = (torch.rand(B, H, W, generator=g) < frac).to(torch.int8).cuda()
+    raw_bits, _ = cg._map_to_bits(raw)
+    s1, s2 = cg.alloc_scratch(shape, "cuda"), cg.alloc_scratch(shape, "cuda")
+    t1, t2 = cg.alloc_tile_ws(shape, "cuda"), cg.alloc_tile_ws(shape, "cuda")
+    for _ in range(2):
+        cg.dilate_compact(raw_bits, shape, (k, k), s1["idx"], s1["count"], s1["ws"], dil_bits=s1["dil_bits"], tile_ws=t1)
+        cg.dilate_tiles(raw_bits, shape, (k, k), s2["count"], s2["ws"], s2["dil_bits"], t2)
+    torch.cuda.synchronize()
+    n = int(s1["count"])
+    assert int(s2["count"]) == n
+    assert torch.equal(s1["dil_bits"], s2["dil_bits"])
+    assert int(t1[1]) == int(t2[1])
+    NT = (t1.numel() - 4) // 2
+    assert sorted(t1[4 + NT: 4 + NT + int(t1[1])].tolist()) == sorted(t2[4 + NT: 4 + NT + int(t2[1])].tolist())
+    assert int(t2[0]) == 0
+    lazy = cg.ChangeIndexes(s2["idx"], s2["count"], shape, bits=s2["dil_bits"], ws=s2["ws"], listed=False)
+    assert len(lazy) == n
+    assert torch.equal(lazy.tensor(), s1["idx"][:n])
