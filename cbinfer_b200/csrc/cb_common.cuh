@@ -52,16 +52,24 @@ inline int glog_tuned(int glog) {
   return g < 0 ? 0 : g;
 }
 
+// cooperative != 0: the grid is launched only when ALL its CTAs can be resident at once (kernels whose
+// CTAs wait for each other, e.g. the stream-K finisher spinning on its contributors' flags, must not
+// be half-resident next to another grid on a concurrent stream)
 template <typename... KArgs, typename... Args>
 inline void launch_cluster(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
-                           cudaStream_t s, unsigned cluster_x, Args&&... args) {
+                           cudaStream_t s, unsigned cluster_x, int cooperative, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[3];
   unsigned na = 0;
+  if (cooperative) {
+    attr[na].id = cudaLaunchAttributeCooperative;
+    attr[na].val.cooperative = 1;
+    ++na;
+  }
   if (pdl_enabled()) {
     attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[na].val.programmaticStreamSerializationAllowed = 1;
@@ -82,7 +90,7 @@ inline void launch_cluster(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t
 template <typename... KArgs, typename... Args>
 inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
                        Args&&... args) {
-  launch_cluster(kern, grid, block, smem, s, 1u, static_cast<Args&&>(args)...);
+  launch_cluster(kern, grid, block, smem, s, 1u, 0, static_cast<Args&&>(args)...);
 }
 
 // ---- dtype traits --------------------------------------------------------------------------

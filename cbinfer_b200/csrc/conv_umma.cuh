@@ -1002,11 +1002,11 @@ int launch_conv_umma(cudaStream_t s, int dtype, const void* state, const void* s
   const int smem_bytes = DEEP ? C::STAGES * C::STAGE_BYTES + UM_CTRL_BYTES + C::TABLE_MAX * 8 + C::RED_BYTES
                               : C::STAGES * C::STAGE_BYTES + UM_CTRL_BYTES + table_entries * 8;
   int occ = C::CTAS_PER_SM;
+  int occ_real = 0;                                          // what the runtime says fits (cooperative launches need it exact)
   if (!DEEP) {
-    int q = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, um_threads(BN), smem_bytes) == cudaSuccess &&
-        q > occ)
-      occ = q > 4 ? 4 : q;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_real, kern, um_threads(BN), smem_bytes) == cudaSuccess &&
+        occ_real > occ)
+      occ = occ_real > 4 ? 4 : occ_real;
   }
   if (occ > 512 / C::TMEM_COLS) occ = 512 / C::TMEM_COLS;     // two accumulators per CTA must fit TMEM
   const long long max_tiles = (((long long)B * H * W + UM_BM - 1) / UM_BM) * (CoutPad / BN);
@@ -1051,13 +1051,21 @@ int launch_conv_umma(cudaStream_t s, int dtype, const void* state, const void* s
     if (slots >= sm_count() / 2) {                           // enough partial-tile slots to be useful
       if (grid > slots) grid = slots;
       if (grid * (long long)sizeof(uint32_t) > UM_SK_FLAG_BYTES) grid = UM_SK_FLAG_BYTES / sizeof(uint32_t);
+      if (occ_real > 0 && grid > (long long)sm_count() * occ_real) grid = (long long)sm_count() * occ_real;
       sk_ws = (uint32_t*)ws;
     }
   }
   if (!sk_ws && grid > max_tiles) grid = max_tiles;
   if (grid < 1) grid = 1;
   grid *= ks;
-  cb::launch_cluster(kern, (unsigned)grid, um_threads(BN), (size_t)smem_bytes, s, (unsigned)ks, map, (const T*)state, (const T*)state_lo, Cp,
+  // stream-K CTAs wait for each other's partial tiles: cooperative launch = all of them resident, also
+  // next to another stream-K grid on a concurrent stream (PoseModel.parallelBranches)
+  static const bool coop_sk = [] {
+    const char* e = getenv("CBINFER_SK_COOP");               // tuning knob: 0 = plain launch
+    return !(e && e[0] == '0');
+  }();
+  cb::launch_cluster(kern, (unsigned)grid, um_threads(BN), (size_t)smem_bytes, s, (unsigned)ks,
+                     (sk_ws && coop_sk) ? 1 : 0, map, (const T*)state, (const T*)state_lo, Cp,
                                                         idx, count, bias,
                                                         (TO*)out, Op, H, W, Cout, CoutPad, kH, kW,
                                                         Kp, relu, sel_lo, sel_hi, sk_ws, mk);

@@ -545,3 +545,41 @@ def test_conv_update_stream_k_tiny_change_set(cbm, n):
     tm = touched.view(B, 1, H, W).expand(B, Cout, H, W)
     assert float((out[~tm] - 3.0).abs().max()) == 0.0
     assert float((out[tm] - ref[tm]).abs().max()) / float(ref.abs().max()) <= CONV_TOL[("bf16x3", "f32")]
+
+
+def test_stream_k_grids_on_concurrent_streams(cbm):
+    """Two stream-K contractions (each with its own workspace) on two CUDA streams, 200 rounds: the
+    finisher CTAs spin on their contributors' flags, so every grid must be resident as a whole
+    (cooperative launch) -- two half-resident grids would wait for each other until the trap."""
+    import torch.nn.functional as F
+    cg, lib = cbm["cg"], cbm["lib"]
+    gemm = lib.GEMM_TC_BF16X3
+    torch.backends.cudnn.allow_tf32 = False
+    B, Cin, Cout, H, W, k = 4, 64, 256, 120, 160, 7
+    jobs = []
+    for j in range(2):
+        state, sbuf = cg.pixel_major((B, Cin, H, W), torch.float32, "cuda", 0)
+        state.copy_(rand_tensor((B, Cin, H, W), "f32", seed=3 + j))
+        w = rand_tensor((Cout, Cin, k, k), "f32", seed=11 + j, scale=(Cin * k * k) ** -0.5)
+        bias = rand_tensor((Cout,), "f32", seed=12 + j)
+        g = torch.Generator().manual_seed(j)
+        sel = torch.nonzero(torch.rand(B * H * W, generator=g) < 0.4).view(-1).int().cuda()
+        out, obuf = cg.pixel_major((B, Cout, H, W), torch.float32, "cuda", 0)
+        jobs.append(dict(state=state, sbuf=sbuf, w=w, bias=bias, sel=sel, out=out, obuf=obuf,
+                         ci=cg.ChangeIndexes.from_tensor(sel, (B, H, W)), packed=cg.pack_weights(w, gemm),
+                         ws=torch.zeros(lib.C.cb_conv_ws_bytes(), dtype=torch.uint8, device="cuda"),
+                         stream=torch.cuda.Stream()))
+    torch.cuda.synchronize()
+    for _ in range(200):
+        for jb in jobs:
+            with torch.cuda.stream(jb["stream"]):
+                cg.conv_update(jb["sbuf"], jb["ci"], jb["packed"], jb["bias"], jb["obuf"], Cin, Cout, (k, k), True,
+                               gemm, ws=jb["ws"])
+    torch.cuda.synchronize()
+    for jb in jobs:
+        ref = F.relu(F.conv2d(jb["state"], jb["w"], jb["bias"], padding=k // 2))
+        touched = torch.zeros(B * H * W, dtype=torch.bool, device="cuda")
+        touched[jb["sel"].long()] = True
+        tm = touched.view(B, 1, H, W).expand(B, Cout, H, W)
+        assert float((jb["out"][tm] - ref[tm]).abs().max()) / float(ref.abs().max()) <= CONV_TOL[("bf16x3", "f32")]
+        assert int(jb["ws"].view(torch.int32)[:1024].abs().sum()) == 0

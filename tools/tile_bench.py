@@ -73,6 +73,13 @@ if __name__ == "__main__":
         one(8, 16, 64, 240, 320, 7, 0.05, "bf16x3", f32, kind="iid")
         one(1, 3, 16, 480, 640, 7, 0.05, "bf16x3", f32)
         one(1, 16, 64, 240, 320, 7, 0.05, "bf16x3", f32)
+    elif a.set == "dense":
+        for rate in (0.5, 1.0):
+            one(8, 64, 256, 120, 160, 7, rate, "tc", bf)
+            one(8, 64, 256, 120, 160, 7, rate, "bf16x3", f32)
+            one(8, 64, 64, 368, 368, 3, rate, "tc", bf)
+            one(8, 512, 512, 46, 46, 3, rate, "tc", bf)
+            one(8, 128, 128, 46, 46, 7, rate, "tc", bf)
     else:
         for rate in (0.05, 1.0):
             one(8, 64, 64, 368, 368, 3, rate, "tc", bf)
