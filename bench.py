@@ -451,7 +451,9 @@ def main():
     # contraction masks the candidate list: 13) and the two tiled convs pool in their epilogue (11)
     fused_pools = sum(1 for m in model.modules() if type(m) is cb.CBConv2d and getattr(m, '_fusedPool', None)
                       and os.environ.get("CBINFER_FUSE_POOL", "1") != "0" and os.environ.get("CBINFER_TILES", "1") != "0")
-    my_launches_per_step = 17 if args.dense_scan else 13 - fused_pools
+    fused_tail = sum(1 for m in model.modules() if type(m) is cb.CBConv2d and getattr(m, '_fusedTail', None)
+                     and os.environ.get("CBINFER_FUSE_TAIL", "1") != "0")
+    my_launches_per_step = 17 if args.dense_scan else 13 - fused_pools - 3 * fused_tail
 
     def step(t):
         step_obj(frames[fidx(t)])
@@ -641,7 +643,7 @@ def kernel_roofline(args, model, frames, dev, tdt, step_us):
     REP = 20
     cur = {"layer": None}
     calls = []
-    names = ("detect", "detect_sparse", "dilate_compact", "dilate_tiles", "pool_compact", "conv_update", "conv_update_tiled",
+    names = ("detect", "detect_sparse", "dilate_compact", "dilate_tiles", "pool_compact", "conv_update", "conv_update_tiled", "tail_update",
              "maxPool2d", "maxPool2d_detect", "detect_compact_sparse")
     orig = {n: getattr(cg, n) for n in names}
 
@@ -681,6 +683,8 @@ def kernel_roofline(args, model, frames, dev, tdt, step_us):
             k["clear_raw"] = False           # keep the input bitmap intact across repetitions
         if kname == "detect_sparse":
             k["bits_are_clear"] = False
+        if kname == "tail_update":
+            a = a[:17] + (0,) + a[18:]       # update_mode NONE: every repetition sees the same changes
         fn = orig[kname]
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())

@@ -28,6 +28,7 @@ SYMBOLS = [
     "cb_gen_xmatrix", "cb_matrix_mult", "cb_update_output", "cb_fg_update",
     "cb_tile_ws_bytes", "cb_dilate_compact_tiles", "cb_conv_tiled_supported", "cb_conv_update_tiled",
     "cb_conv_tiled_pool_supported", "cb_conv_update_tiled_pool", "cb_dilate_tiles",
+    "cb_tail_supported", "cb_tail_update",
 ]
 
 
@@ -65,6 +66,9 @@ def _load():
         "cb_conv_tiled_supported": (i32, [i32] * 9),
         "cb_conv_update_tiled": (i32, [vp, i32, i32, vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32,
                                        i32, i32, i32, i32, i32]),
+        "cb_tail_supported": (i32, [i32] * 5),
+        "cb_tail_update": (i32, [vp, vp, vp, vp, vp, vp, i32, f32, vp, vp, vp, vp, i32, i32, f32, vp, vp, i32, i32, i32,
+                                 i32, vp, vp, vp]),
         "cb_dilate_tiles": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32]),
         "cb_conv_tiled_pool_supported": (i32, [i32, i32, i32]),
         "cb_conv_update_tiled_pool": (i32, [vp, i32, i32, vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32,

@@ -39,6 +39,16 @@ class DetectionDone(object):
         self.owner = owner
 
 
+class TailDone(object):
+    """Marker in the index slot of the tuple: the upstream 1x1 CBConv2d already ran this layer's
+    detection AND contraction inside its own kernel (cb_tail_update); this layer's state and output
+    are up to date.  `candidates` is the superset list both layers walked."""
+
+    def __init__(self, owner, candidates):
+        self.owner = owner
+        self.candidates = candidates
+
+
 def _parse_input(inp):
     """tensor, or ('changeIndexes', tensor, indices) from an upstream CB layer (conv2d.py:180-187)."""
     if type(inp) == tuple:
@@ -383,6 +393,18 @@ class CBConv2d(nn.Module):
             self._gatherStats(input)
 
         gemm, packed, bias32 = self._weights(dt, dev)
+        if isinstance(changeIndexes, TailDone):
+            # the upstream 1x1 layer's kernel already did this layer's frame (cb_tail_update)
+            assert changeIndexes.owner is self
+            self._lastChanges = changeIndexes.candidates
+            self._inVersion = self.prevInput._version
+            self._outVersion = self.prevOutput._version
+            if self.propChangeIndexes:
+                return 'changeIndexes', self.prevOutput, changeIndexes.candidates
+            return self.prevOutput
+        tail = self._tryTail(input, changeIndexes, gemm, packed, bias32, s, outpSize, ext_out)
+        if tail is not None:
+            return tail
         aux = self._aux(gemm)
         aux_arg = None if aux is None else (aux[:2] if aux[0] == 'tf32' else aux)
 
@@ -507,6 +529,73 @@ class CBConv2d(nn.Module):
             return 'changeIndexes', self.prevOutput, changeIndexes
         else:
             return self.prevOutput
+
+    # ---- two chained 1x1 layers in one launch (extension) ------------------------------------------
+    def _tailTarget(self, shape, dt, dev, feedback):
+        """What the 1x1 layer feeding this one needs to run this layer's frame inside its own kernel
+        (cb_tail_update), or None while the exactness conditions of candidate detection do not hold
+        for this layer (fresh state, lowered threshold, state touched from outside, ...)."""
+        if not (getattr(self, 'candidateDetect', False) and getattr(self, 'maskedConv', False)) \
+                or self.finegrained or self.saveChangeMap or self.gatherComputationStats \
+                or getattr(self, 'fuse1x1', False) \
+                or tuple(self.kernel_size) != (1, 1) or self.feedbackLoop != feedback \
+                or self._fresh or self._inBuf is None or self._outBuf is None or self._scratch is None \
+                or tuple(self.prevInput.shape) != tuple(shape) or self.prevInput.dtype != dt \
+                or self.prevInput.device != dev or self._lastThr is None or self.threshold < self._lastThr \
+                or getattr(self, '_inVersion', None) != self.prevInput._version \
+                or getattr(self, '_outVersion', None) != self.prevOutput._version \
+                or self.prevInput.data_ptr() != self._inBuf.data_ptr() \
+                or self.prevOutput.data_ptr() != self._outBuf.data_ptr() \
+                or not self._scratch.get("raw_clear", False):
+            return None
+        gemm, packed, bias32 = self._weights(dt, dev)
+        return dict(gemm=gemm, packed=packed, bias=bias32, state=self._inBuf, out=self._outBuf,
+                    thr=self.threshold, relu=self.withReLU, count=self._scratch["count"])
+
+    def _tryTail(self, input, changeIndexes, gemm, packed, bias32, s, outpSize, ext_out):
+        ft = getattr(self, '_fusedTail', None)
+        if not ft or os.environ.get("CBINFER_FUSE_TAIL", "1") == "0":
+            return None
+        B, C0, H, W = input.shape
+        if not isinstance(changeIndexes, ChangeIndexes) or not getattr(self, 'candidateDetect', False) \
+                or not getattr(self, 'maskedConv', False) or tuple(self.kernel_size) != (1, 1) \
+                or getattr(self, 'fuse1x1', False) \
+                or self.saveChangeMap or self.gatherComputationStats or ext_out or input.dtype != torch.float32 \
+                or self._fresh or self._lastThr is None or self.threshold < self._lastThr \
+                or tuple(changeIndexes.shape) != (B, H, W) or not getattr(changeIndexes, 'complete', True) \
+                or not s.get("raw_clear", False):
+            return None
+        nxt = ft[0]
+        C1, C2 = self.out_channels, nxt.out_channels
+        if not _lib.C.cb_tail_supported(_lib.dtype_code(input.dtype), gemm, C0, C1, C2):
+            return None
+        # the input must be the upstream layer's pixel-major map itself (pitch == channels)
+        if input.stride() != (H * W * C0, 1, W * C0, C0) or self._inBuf.shape[3] != C0 \
+                or self._outBuf.shape[3] != C1:
+            return None
+        tgt = nxt._tailTarget(outpSize, input.dtype, input.device, self.feedbackLoop)
+        if tgt is None or tgt['gemm'] != gemm:
+            return None
+        if "tail_sync" not in s:
+            s["tail_sync"] = torch.zeros(4, dtype=torch.int32, device=input.device)
+        x_buf = input.permute(0, 2, 3, 1)
+        cg.tail_update(x_buf, self._inBuf, packed, bias32, self._outBuf, self.withReLU, self.threshold,
+                       tgt['state'], tgt['packed'], tgt['bias'], tgt['out'], tgt['relu'], tgt['thr'],
+                       changeIndexes, C0, C1, C2,
+                       _lib.UPDATE_CHANGED if self.feedbackLoop else _lib.UPDATE_ALL,
+                       s["count"], tgt['count'], s["tail_sync"])
+        # the kernel splits its operands on the fly: the layers' operand planes are stale now
+        self._auxPlanes = None
+        nxt._auxPlanes = None
+        self._lastThr = self.threshold
+        nxt._lastThr = nxt.threshold
+        self._inVersion = self.prevInput._version
+        self._outVersion = self.prevOutput._version
+        sup = ChangeIndexes(changeIndexes._buffer, changeIndexes.count, (B, H, W), bits=changeIndexes.bits,
+                            ws=changeIndexes._ws, listed=changeIndexes.listed)
+        sup.superset = True
+        self._lastChanges = sup
+        return 'changeIndexes', self.prevOutput, TailDone(nxt, sup)
 
     def lastChangeIndexes(self):
         """This frame's change indexes as an int32 tensor (ascending b*H*W + y*W + x): what the

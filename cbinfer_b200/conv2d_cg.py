@@ -390,6 +390,20 @@ def conv_update_tiled(state_buf, tile_ws, dil_bits, packed_w, bias_f32, out_buf,
                                  Cin, Cout, filtSize[0], filtSize[1], int(bool(relu))))
 
 
+def tail_update(x_buf, state1_buf, packed1, bias1, out1_buf, relu1, thr1, state2_buf, packed2, bias2,
+                out2_buf, relu2, thr2, candidates, C0, C1, C2, update_mode, count1, count2, sync):
+    """cb_tail_update: two chained 1x1 change-based layers (detect, contraction, detect,
+    contraction) for the candidate pixels in one launch; pixel-major fp32 buffers [B,H,W,pitch]."""
+    assert x_buf.dtype == torch.float32 and x_buf.shape[3] == C0 and state1_buf.shape == x_buf.shape
+    assert out1_buf.shape[3] == C1 and state2_buf.shape == out1_buf.shape
+    check(C.cb_tail_update(stream_ptr(x_buf.device), x_buf.data_ptr(), state1_buf.data_ptr(),
+                           packed1.data_ptr(), bias1.data_ptr(), out1_buf.data_ptr(), int(bool(relu1)),
+                           float(thr1), state2_buf.data_ptr(), packed2.data_ptr(), bias2.data_ptr(),
+                           out2_buf.data_ptr(), out2_buf.shape[3], int(bool(relu2)), float(thr2),
+                           candidates.buffer.data_ptr(), candidates.count.data_ptr(), C0, C1, C2,
+                           int(update_mode), count1.data_ptr(), count2.data_ptr(), sync.data_ptr()))
+
+
 def pixel_major(shape, dtype, device, fill):
     """Allocate a [B,C,H,W]-shaped *view* over a pixel-major [B,H,W,pitch] buffer whose pitch is
     C rounded up to 16 bytes.  Real channels are set to `fill`, pad channels to 0 (they meet zero

@@ -13,6 +13,7 @@
 #include "fg.cuh"
 #include "pool.cuh"
 #include "staged.cuh"
+#include "tail.cuh"
 
 namespace cb {
 
@@ -378,6 +379,32 @@ int cb_conv_update_masked(void* stream, int dtype, int gemm, const void* state, 
   mk.nwords = (int)cb_bitmap_words(B, H, W);
   return conv_update_impl(mk, stream, dtype, gemm, state, state_lo, pitch_in, idx, count, packed_w, bias,
                           out, pitch_out, B, H, W, Cin, Cout, kH, kW, relu, ws, ws_bytes);
+}
+
+int cb_tail_supported(int dtype, int gemm, int C0, int C1, int C2) {
+  return dtype == CB_F32 && gemm == CB_GEMM_TC_BF16X3 && cb::tail_supported(C0, C1, C2) ? 1 : 0;
+}
+
+int cb_tail_update(void* stream, const float* x, float* state1, const void* packed_w1, const float* bias1,
+                   float* out1, int relu1, float thr1, float* state2, const void* packed_w2,
+                   const float* bias2, float* out2, int pitch_out2, int relu2, float thr2,
+                   const int32_t* candidates, const int32_t* n_candidates, int C0, int C1, int C2,
+                   int update_mode, int32_t* count1, int32_t* count2, void* sync_ws) {
+  CB_CHECK_ARG(x && state1 && packed_w1 && bias1 && out1 && state2 && packed_w2 && bias2 && out2 && candidates &&
+                   n_candidates && count1 && count2 && sync_ws, "tail_update: null pointer");
+  CB_CHECK_ARG(update_mode == CB_UPDATE_NONE || update_mode == CB_UPDATE_CHANGED || update_mode == CB_UPDATE_ALL,
+               "tail_update: bad update_mode %d", update_mode);
+  CB_CHECK_ARG(((uintptr_t)x % 16) == 0 && ((uintptr_t)state1 % 16) == 0 && ((uintptr_t)out1 % 16) == 0 &&
+                   ((uintptr_t)state2 % 16) == 0 && ((uintptr_t)out2 % 16) == 0 &&
+                   ((uintptr_t)packed_w1 % 128) == 0 && ((uintptr_t)packed_w2 % 128) == 0,
+               "tail_update: maps must be 16-byte, packed weights 128-byte aligned");
+  cb::TailArgs a;
+  a.x = x; a.st1 = state1; a.out1 = out1; a.st2 = state2; a.out2 = out2;
+  a.cand = candidates; a.ncand = n_candidates; a.bias1 = bias1; a.bias2 = bias2;
+  a.count1 = count1; a.count2 = count2; a.sync = (unsigned*)sync_ws;
+  a.xp = C0; a.p1 = C1; a.p2 = pitch_out2; a.C0 = C0; a.C1 = C1; a.C2 = C2;
+  a.relu1 = relu1; a.relu2 = relu2; a.update = update_mode; a.thr1 = thr1; a.thr2 = thr2;
+  return cb::tail_update((cudaStream_t)stream, a, packed_w1, packed_w2);
 }
 
 int cb_maxpool2x2(void* stream, int dtype, const void* x, long long x_sb, long long x_sc,

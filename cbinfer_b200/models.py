@@ -66,6 +66,12 @@ def enableCandidateDetection(m, fusePool=True, maskedConv=True):
                     if nxt is None or (type(nxt) is CBConv2d and nxt.candidateDetect) \
                             or (not b.propChangeIndexes and type(nxt) is not CBPoolMax2d):
                         b.maskedConv = True
+        # two trailing masked 1x1 layers: one kernel runs detect + contraction of both (cb_tail_update)
+        if maskedConv and len(kids) >= 2:
+            b, c = kids[-2], kids[-1]
+            if type(b) is CBConv2d and type(c) is CBConv2d and b.maskedConv and c.maskedConv \
+                    and not c.propChangeIndexes:
+                b._fusedTail = [c]
     return m
 
 

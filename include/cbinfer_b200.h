@@ -248,6 +248,27 @@ int cb_conv_update_masked(void* stream, int dtype, int gemm, const void* state, 
                           int Cout, int kH, int kW, int relu, void* ws, size_t ws_bytes,
                           uint32_t* mask_bits, int clear_mask, int32_t* count_out, void* sync_ws);
 
+/* ---- two chained 1x1 layers in one launch ---------------------------------------------------
+ * The trailing pointwise layers of a network on the candidate path (e.g. 256 -> 64 (+ReLU) -> 8):
+ * per candidate pixel (the pixels the upstream layer just rewrote, `candidates`/`n_candidates`)
+ *   layer 1: threshold x against state1 (cb_change_detect_sparse semantics, strict >), accept
+ *            changed pixels into state1 (update_mode CB_UPDATE_CHANGED = feedback, CB_UPDATE_ALL =
+ *            copy), out1[p] = act(bias1 + W1 . x[p]) for the changed ones;
+ *   layer 2: threshold out1[p] against state2 for those pixels, accept, out2[p] = act(bias2 + W2 . out1[p]).
+ * Replaces, per layer, changeDetection + nonzero + genXMatrix + GEMM + updateOutput
+ * (pycbinfer/conv2d.py:222-251) -- here: cb_change_detect_sparse + cb_conv_update_masked twice --
+ * with bit-identical results (same K order and 3xBF16 split).  fp32 pixel-major maps whose pitch
+ * equals the channel count (C0 % 64 == 0, C0 <= 256; C1 in {16,32,64}; C2 <= 16, pitch_out2 % 4 == 0);
+ * packed weights from cb_pack_weights(CB_F32, CB_GEMM_TC_BF16X3, ...).  *count1 / *count2 = pixels
+ * each layer updated.  sync_ws: 12 bytes zeroed once (left clean).  The layers' operand planes
+ * (CB_AUX_BF16_PAIR) are NOT maintained: rebuild them before using cb_conv_update on these layers. */
+int cb_tail_supported(int dtype, int gemm, int C0, int C1, int C2);
+int cb_tail_update(void* stream, const float* x, float* state1, const void* packed_w1, const float* bias1,
+                   float* out1, int relu1, float thr1, float* state2, const void* packed_w2,
+                   const float* bias2, float* out2, int pitch_out2, int relu2, float thr2,
+                   const int32_t* candidates, const int32_t* n_candidates, int C0, int C1, int C2,
+                   int update_mode, int32_t* count1, int32_t* count2, void* sync_ws);
+
 /* ---- change-based 2x2/stride-2 max pooling ------------------------------------------------
  * replaces: maxPool2d (conv2d_cg.py:33-37 -> cbconv2d_cg_backend.cu:199-240, half :207-250).
  * For every changed input pixel idx[j] (j < *count) recompute the max of its 2x2 window over

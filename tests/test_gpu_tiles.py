@@ -286,3 +286,57 @@ def test_dilate_tiles_equals_dilate_compact(cbm, shape, k, frac):
     lazy = cg.ChangeIndexes(s2["idx"], s2["count"], shape, bits=s2["dil_bits"], ws=s2["ws"], listed=False)
     assert len(lazy) == n
     assert torch.equal(lazy.tensor(), s1["idx"][:n])
+
+
+@pytest.mark.parametrize("feedback", [True, False])
+def test_fused_tail_is_bit_identical(cbm, feedback, monkeypatch):
+    """conv 7x7 -> 1x1 (ReLU) -> 1x1 on the candidate path: the two trailing 1x1 layers as ONE
+    launch (cb_tail_update) against sparse detect + masked contraction twice: outputs, states and
+    change counts bit-identical on every frame (same K order, same 3xBF16 split)."""
+    import torch.nn as nn
+    cb = cbm["cb"]
+    from cbinfer_b200 import models, video
+    torch.manual_seed(11)
+    base = nn.Sequential(nn.Conv2d(3, 64, 7, padding=3), nn.ReLU(), nn.Conv2d(64, 64, 1), nn.ReLU(),
+                         nn.Conv2d(64, 8, 1)).cuda().eval()
+    base2 = nn.Sequential(nn.Conv2d(16, 256, 3, padding=1), nn.ReLU(), nn.Conv2d(256, 32, 1), nn.ReLU(),
+                          nn.Conv2d(32, 16, 1), nn.ReLU()).cuda().eval()
+    for net, cin in ((base, 3), (base2, 16)):
+        g = torch.Generator().manual_seed(3)
+        f0 = torch.rand(2, cin, 60, 88, generator=g)
+        frames = [f0]
+        for t in range(1, 7):
+            f = frames[-1].clone()
+            y0, x0 = 5 * t, 9 * t
+            f[:, :, y0:y0 + 20, x0:x0 + 30] = torch.rand(2, cin, 20, 30, generator=g)
+            frames.append(f)
+        frames.insert(3, frames[2].clone())          # an unchanged frame
+        frames = [f.cuda() for f in frames]
+        runs = []
+        for fuse in ("1", "0"):
+            monkeypatch.setenv("CBINFER_FUSE_TAIL", fuse)
+            m = cb.convert(net, threshold=0.05)
+            for c in m.modules():
+                if type(c) is cb.CBConv2d:
+                    c.feedbackLoop = feedback
+            models.enableCandidateDetection(m)
+            convs = [c for c in m.modules() if type(c) is cb.CBConv2d]
+            assert getattr(convs[1], '_fusedTail', None)
+            outs = []
+            for f in frames:
+                o = m(f)
+                torch.cuda.synchronize()
+                outs.append(dict(out=o.clone(), counts=[int(c._scratch["count"]) for c in convs],
+                                 states=[c.prevInput.clone() for c in convs],
+                                 outs=[c.prevOutput.clone() for c in convs]))
+            runs.append(outs)
+        for t, (a, b) in enumerate(zip(*runs)):
+            assert a["counts"] == b["counts"], (t, a["counts"], b["counts"])
+            assert torch.equal(a["out"], b["out"]), t
+            for k in ("states", "outs"):
+                for x, y in zip(a[k], b[k]):
+                    assert torch.equal(x, y), (t, k)
+        assert sum(runs[0][-1]["counts"]) > 0
+        # and against the dense model at the end (thresholded, so only loosely)
+        ref = net(frames[-1])
+        assert float((runs[0][-1]["out"] - ref).abs().max()) <= 0.2 * float(ref.abs().max()) + 0.05
