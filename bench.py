@@ -63,6 +63,12 @@ def parse():
     ap.add_argument("--threshold-factor", type=float, default=0.02)
     ap.add_argument("--dense-scan", action="store_true",
                     help="re-scan every layer's whole input like the reference (default: candidate detection)")
+    ap.add_argument("--eager-detect", action="store_true",
+                    help="first-layer detection launched eagerly per frame + one graph for the rest (default: one "
+                         "graph per input slot of the frame ring, detection included)")
+    ap.add_argument("--profile", type=int, default=0, metavar="N",
+                    help="profiling aid: after the warm-up run N steps between cudaProfilerStart/Stop and exit "
+                         "(ncu --profile-from-start off); prints no bench line")
     ap.add_argument("--no-extras", action="store_true", help="skip dense/latency/kernel/cpu/check legs")
     ap.add_argument("--no-check", action="store_true", help="skip the parity leg against the reference flow")
     ap.add_argument("--min-seconds", type=float, default=0.25,
@@ -332,6 +338,19 @@ class SceneStep(object):
         self.graph.replay()
         return self.out
 
+    def capture_slot(self, frame):
+        """A graph of the WHOLE step for one input slot (a frame buffer at a fixed address, as in a
+        decoder's surface pool): first-layer detection on that slot + the rest of the model.  One
+        graph launch per step instead of an eager launch + a graph launch."""
+        import torch
+        from cbinfer_b200.conv2d import DetectionDone
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g), torch.no_grad():
+            tup = self.first.detectInput(frame)
+            out = self.model(tup)
+        assert out.data_ptr() == self.out.data_ptr()
+        return g
+
 
 def build_model(args, base, first_frame):
     """the benchmarked model: scene CBinfer net, all convs + pools converted, feedback loop,
@@ -455,8 +474,19 @@ def main():
                      and os.environ.get("CBINFER_FUSE_TAIL", "1") != "0")
     my_launches_per_step = 17 if args.dense_scan else 13 - fused_pools - 3 * fused_tail
 
+    # one captured graph per input slot of the frame ring (the bench cycles over `nframes` device
+    # buffers): a step is ONE graph launch -- first-layer detection on the slot where the frame lies
+    # + the rest of the model.  --eager-detect: detection launched eagerly on arbitrary frame addresses
+    # + one graph for the rest (what CBConv2d.detectInput offers to callers without a fixed ring).
+    slot_graphs = None
+    if not args.eager_detect:
+        slot_graphs = [step_obj.capture_slot(f) for f in frames]
+
     def step(t):
-        step_obj(frames[fidx(t)])
+        if slot_graphs is not None:
+            slot_graphs[fidx(t)].replay()
+        else:
+            step_obj(frames[fidx(t)])
 
     def barrier():
         if world > 1:
@@ -467,6 +497,16 @@ def main():
     for _ in range(Wm):
         step(t)
         t += 1
+    if args.profile:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        for _ in range(args.profile):
+            step(t)
+            t += 1
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print(json.dumps({"profiled_steps": args.profile, "launches_per_step": my_launches_per_step}))
+        return
     # ---- timed region: blocks of EXACTLY K steps, each bracketed by barrier + synchronize and timed
     #      on the device (max over ranks); blocks repeat until >= min_seconds were measured, the median
     #      block is reported ------------------------------------------------------------------------
@@ -500,7 +540,7 @@ def main():
     #      host memory (H2D) and reads its logits back (D2H).  runtime.FramePipeline = one graph
     #      replay per frame with the copies of neighbouring frames overlapped on their own streams.
     from cbinfer_b200 import runtime
-    del step_obj
+    del step_obj, slot_graphs
     cb.clearMemory(model)
 
     def e2e_leg(pin, first_frame_dev):
@@ -562,8 +602,10 @@ def main():
                        note=WORKLOADS[args.workload]["note"],
                        l2="no flush: per-step working set = persistent state maps of %d streams = %.0f MB %s 126 MB L2"
                           % (S, state_mb, ">" if state_mb > 126 else "<= (L2-resident!)"),
-                       launch="per step: first-layer detection launched eagerly on the frame where it lies in "
-                              "HBM, the other launches replayed as one CUDA graph",
+                       launch=("per step: first-layer detection launched eagerly on the frame where it lies in "
+                               "HBM, the other launches replayed as one CUDA graph") if args.eager_detect else
+                              ("per step ONE CUDA-graph launch: a graph per input slot of the %d-frame ring holds the "
+                               "first-layer detection on that slot (read in place) and the rest of the model" % nframes),
                        timing="median of %d timed blocks of %d steps each (blocks repeat until %.2f s of device "
                               "time); min %.4f / max %.4f ms per step" % (
                                   len(blocks), K, args.min_seconds, min(blocks) / K, max(blocks) / K),
