@@ -54,8 +54,6 @@ def main():
                 row = {"layer": name, "shape": [Cin, Cout, k, H, W], "dtype": dtn, "rate": rate, "batch": args.batch}
                 modes = [("cg", "auto")] + ([("cg_tf32", "tc"), ("fg", None)] if dtn == "f32" else [])
                 for label, gm in modes:
-                    if label == "fg" and (rate > 0.2 or Cin * Cout * k * k > 600000):
-                        continue                 # FG atomics: only meaningful at low change rates
                     m = cb.CBConv2d(conv, 0.0)
                     m.withReLU = True
                     if label == "fg":
@@ -63,7 +61,7 @@ def main():
                     else:
                         m.feedbackLoop = True
                         m.gemmMode = gm
-                    ms, _ = time_frames(m, fr, warm=3, graph=(label != "fg"))
+                    ms, _ = time_frames(m, fr, warm=3, graph=True)
                     row[label + "_ms"] = round(median(ms), 4)
                 for tf32 in ((False, True) if dtn == "f32" else (True,)):
                     torch.backends.cudnn.allow_tf32 = tf32

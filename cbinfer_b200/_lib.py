@@ -26,6 +26,7 @@ SYMBOLS = [
     "cb_dilate_compact", "cb_map_to_bits", "cb_change_detect_sparse", "cb_pool_compact", "cb_maxpool2x2_detect",
     "cb_detect_compact_ws_bytes", "cb_detect_compact_sparse", "cb_pack_weights", "cb_conv_ws_bytes", "cb_conv_update", "cb_conv_update_masked", "cb_maxpool2x2",
     "cb_gen_xmatrix", "cb_matrix_mult", "cb_update_output", "cb_fg_update",
+    "cb_fg_detect", "cb_conv_accumulate",
     "cb_tile_ws_bytes", "cb_dilate_compact_tiles", "cb_conv_tiled_supported", "cb_conv_update_tiled",
     "cb_conv_tiled_pool_supported", "cb_conv_update_tiled_pool", "cb_dilate_tiles",
     "cb_tail_supported", "cb_tail_update",
@@ -96,6 +97,10 @@ def _load():
         "cb_matrix_mult": (i32, [vp, i32, vp, vp, vp, vp, i32, i32, i32]),
         "cb_update_output": (i32, [vp, i32, vp, vp, vp, i32, i32, i32, i32]),
         "cb_fg_update": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, f32]),
+        "cb_fg_detect": (i32, [vp, vp, i64, i64, i64, i64, vp, i64, i64, i32, vp, vp, vp, vp, i32, i32, i32,
+                               i32, f32]),
+        "cb_conv_accumulate": (i32, [vp, i32, i32, vp, vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32,
+                                     i32, i32, i32, vp, sz]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -319,14 +319,65 @@ class CBConv2d(nn.Module):
 
     # ---- fine-grained path (conv2d.py:160-176) ---------------------------------------------
     def forward_fg(self, inp):
-        input = inp.detach().contiguous()
+        """Reference flow: the first frame is a dense convolution (:163-167); afterwards every input
+        VALUE whose change exceeds the threshold pushes W*delta into (a clone of) prevOutput
+        (cbconvFG, :169-170) and prevInput = input (:175).  Here: per-value thresholded delta planes
+        (cb_fg_detect) -> touched output pixels (cb_dilate_compact) -> accumulating tcgen05
+        contraction over them (cb_conv_accumulate); gemmMode='simt' keeps the scattered
+        red.global.add kernel on planar tensors (cb_fg_update, exact fp32 products)."""
+        input = inp.detach()
         _lib.require_cuda(input)
-        if self.prevInput.size() != input.size():
+        if input.dtype != torch.float32:
+            raise _lib.CBinferError("the fine-grained path is fp32 only (as in the reference)")
+        if getattr(self, 'gemmMode', 'auto') == 'simt':
+            return self._forward_fg_planar(input.contiguous())
+        B, _, H, W = input.shape
+        dev = input.device
+        outpSize = (B, self.out_channels, H, W)
+        gemm = _lib.GEMM_TC_BF16X3
+        key = (self.weight.data_ptr(), self.weight._version, 'fg', str(dev))
+        if self._packed is None or self._packed[0] != key:
+            self._packed = (key, cg.pack_weights(self.weight.detach().to(device=dev, dtype=torch.float32), gemm),
+                            None)
+        fresh = self.prevInput.size() != input.size() or self._inBuf is None or self._outBuf is None \
+            or self.prevInput.device != dev or self.prevInput.data_ptr() != self._inBuf.data_ptr() \
+            or tuple(self.prevOutput.size()) != outpSize or self.prevOutput.data_ptr() != self._outBuf.data_ptr() \
+            or self._auxPlanes is None or self._auxPlanes[0] != 'fg'
+        if fresh:
+            self.prevOutput, self._outBuf = cg.pixel_major(outpSize, torch.float32, dev, 0)
+            self.prevOutput.copy_(F.conv2d(input, self.weight.detach(),
+                                           padding=tuple(s // 2 for s in self.weight.size()[2:]),
+                                           bias=self.bias.detach()))
+            self.prevInput, self._inBuf = cg.pixel_major(input.shape, torch.float32, dev, 0)
+            self.prevInput.copy_(input)
+            p16 = _lib.C.cb_plane_pitch16(self.in_channels)
+            self._auxPlanes = ('fg', torch.zeros(B, H, W, p16, dtype=torch.bfloat16, device=dev),
+                               torch.zeros(B, H, W, p16, dtype=torch.bfloat16, device=dev))
+            self._scratch = cg.alloc_scratch((B, H, W), dev)
+            self._scratch["nvalues"] = torch.zeros(1, dtype=torch.int32, device=dev)
+        else:
+            s = self._scratch
+            planes = self._auxPlanes[1:]
+            cg.fg_detect(input, self.prevInput, self._inBuf, planes, s["raw_bits"], self.threshold,
+                         count=s["nvalues"])
+            cg.dilate_compact(s["raw_bits"], (B, H, W), self.kernel_size, s["idx"], s["count"], s["ws"],
+                              dil_bits=s["dil_bits"])
+            changes = ChangeIndexes(s["idx"], s["count"], (B, H, W), bits=s["dil_bits"])
+            cg.conv_accumulate(planes, changes, self._packed[1], self._outBuf, self.in_channels,
+                               self.out_channels, self.kernel_size, gemm, ws=self._workspace(dev))
+            self._lastChanges = changes
+        # the reference updates a clone (:169), so outputs handed out earlier stay as they were
+        return F.relu(self.prevOutput) if self.withReLU else self.prevOutput.clone()
+
+    def _forward_fg_planar(self, input):
+        if self.prevInput.size() != input.size() or not self.prevInput.is_contiguous() \
+                or not self.prevOutput.is_contiguous():
             # init prevOutput with a dense convolution, as the reference does (conv2d.py:163-167)
             self.prevOutput = F.conv2d(input, self.weight.detach(),
                                        padding=tuple(s // 2 for s in self.weight.size()[2:]),
                                        bias=self.bias.detach()).contiguous()
             self.prevInput = input.clone()
+            self._inBuf = self._outBuf = None
         else:
             po = self.prevOutput.clone()                     # conv2d.py:169
             # also performs prevInput = input (conv2d.py:175) in the same pass

@@ -351,6 +351,37 @@ def conv_update(state_buf, changes, packed_w, bias_f32, out_buf, Cin, Cout, filt
                            ws.numel() if ws is not None else 0))
 
 
+def fg_detect(x, prev_view, prev_buf, planes16, raw_bits, threshold, count=None):
+    """cb_fg_detect: per-VALUE thresholded delta of x against the pixel-major fp32 state (`prev_view` =
+    the [B,C,H,W] view of `prev_buf` [B,H,W,pitch]) -> bf16 hi/lo delta planes `planes16`, raw pixel
+    bitmap, changed-value count; the state is overwritten with x."""
+    require_cuda(x, prev_buf, raw_bits)
+    B, Cc, H, W = x.shape
+    assert x.dtype == torch.float32 and prev_buf.dtype == torch.float32
+    assert tuple(prev_view.shape) == tuple(x.shape) and prev_view.stride(1) == 1
+    hi, lo = planes16
+    assert hi.dtype == torch.bfloat16 and hi.shape == (B, H, W, C.cb_plane_pitch16(Cc)) and lo.shape == hi.shape
+    check(C.cb_fg_detect(stream_ptr(x.device), x.data_ptr(), *_strides4(x), prev_view.data_ptr(),
+                         prev_view.stride(0), prev_view.stride(2), prev_view.stride(3),
+                         hi.data_ptr(), lo.data_ptr(), raw_bits.data_ptr(),
+                         count.data_ptr() if count is not None else None, B, Cc, H, W, float(threshold)))
+
+
+def conv_accumulate(planes16, changes, packed_w, out_buf, Cin, Cout, filtSize, gemm, ws=None):
+    """cb_conv_accumulate: out_buf[pix, :] += contraction of the operand planes around pix with the
+    packed weights, for the listed pixels (no bias, no ReLU) - the fine-grained update."""
+    src, src_lo = planes16
+    B, H, W, pitch = src.shape
+    assert gemm == _lib.GEMM_TC_BF16X3 and out_buf.dtype == torch.float32
+    assert out_buf.shape[:3] == src.shape[:3]
+    check(C.cb_conv_accumulate(stream_ptr(src.device), _lib.F32, gemm, src.data_ptr(), src_lo.data_ptr(),
+                               pitch, changes.buffer.data_ptr(), changes.count.data_ptr(),
+                               packed_w.data_ptr(), out_buf.data_ptr(), out_buf.shape[3], B, H, W, Cin,
+                               Cout, filtSize[0], filtSize[1],
+                               ws.data_ptr() if ws is not None else None,
+                               ws.numel() if ws is not None else 0))
+
+
 def conv_update_tiled(state_buf, tile_ws, dil_bits, packed_w, bias_f32, out_buf, Cin, Cout, filtSize,
                       relu, gemm, lo_buf=None, planes16=None, pool=None):
     """cb_conv_update_tiled on pixel-major buffers: the contraction over the dirty 8x16 tiles listed

@@ -291,7 +291,28 @@ int cb_conv_update(void* stream, int dtype, int gemm, const void* state, const v
                    int Cout, int kH, int kW, int relu, void* ws, size_t ws_bytes) {
   return conv_update_impl(cb::RowMask{nullptr, nullptr, nullptr, nullptr, 0}, stream, dtype, gemm, state,
                           state_lo, pitch_in, idx, count, packed_w, bias, out, pitch_out, B, H, W, Cin,
-                          Cout, kH, kW, relu, ws, ws_bytes);
+                          Cout, kH, kW, relu ? 1 : 0, ws, ws_bytes);
+}
+
+int cb_conv_accumulate(void* stream, int dtype, int gemm, const void* state, const void* state_lo,
+                       int pitch_in, const int32_t* idx, const int32_t* count, const void* packed_w,
+                       void* out, int pitch_out, int B, int H, int W, int Cin, int Cout, int kH, int kW,
+                       void* ws, size_t ws_bytes) {
+  CB_CHECK_ARG(gemm != CB_GEMM_SIMT_F32, "conv_accumulate: tensor-core modes only");
+  // flag bit 1 of the epilogue: out += contraction, bias unused (any valid pointer satisfies the checks)
+  return conv_update_impl(cb::RowMask{nullptr, nullptr, nullptr, nullptr, 0}, stream, dtype, gemm, state,
+                          state_lo, pitch_in, idx, count, packed_w, (const float*)packed_w, out, pitch_out,
+                          B, H, W, Cin, Cout, kH, kW, 2, ws, ws_bytes);
+}
+
+int cb_fg_detect(void* stream, const float* x, long long x_sb, long long x_sc, long long x_sy,
+                 long long x_sx, float* prev, long long p_sb, long long p_sy, int p_pitch, void* delta_hi,
+                 void* delta_lo, uint32_t* raw_bits, int32_t* count, int B, int C, int H, int W,
+                 float threshold) {
+  CB_CHECK_ARG(x && prev && delta_hi && delta_lo && raw_bits, "fg_detect: null pointer");
+  CB_CHECK_ARG(B >= 0 && C > 0 && H >= 0 && W >= 0, "fg_detect: bad shape");
+  return cb::launch_fg_detect((cudaStream_t)stream, x, x_sb, x_sc, x_sy, x_sx, prev, p_sb, p_sy, p_pitch,
+                              delta_hi, delta_lo, raw_bits, count, B, C, H, W, threshold);
 }
 
 int cb_conv_tiled_supported(int dtype, int gemm, int B, int H, int W, int Cin, int Cout, int kH, int kW) {
@@ -378,7 +399,7 @@ int cb_conv_update_masked(void* stream, int dtype, int gemm, const void* state, 
   mk.sync = (unsigned*)sync_ws;
   mk.nwords = (int)cb_bitmap_words(B, H, W);
   return conv_update_impl(mk, stream, dtype, gemm, state, state_lo, pitch_in, idx, count, packed_w, bias,
-                          out, pitch_out, B, H, W, Cin, Cout, kH, kW, relu, ws, ws_bytes);
+                          out, pitch_out, B, H, W, Cin, Cout, kH, kW, relu ? 1 : 0, ws, ws_bytes);
 }
 
 int cb_tail_supported(int dtype, int gemm, int C0, int C1, int C2) {

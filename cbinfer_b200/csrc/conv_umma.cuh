@@ -719,8 +719,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap wmap, const T* __restrict__
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const int co = co0 + i;
-            float t = __uint_as_float(acc[i]) + (co < Cout ? __ldg(bias + co) : 0.f);
-            if (relu && t <= 0.f) t = 0.f;
+            // relu bit 1 (cb_conv_accumulate): out += contraction, no bias (fine-grained delta update)
+            float t = __uint_as_float(acc[i]) +
+                      (co < Cout ? ((relu & 2) ? to_float(orow[co]) : __ldg(bias + co)) : 0.f);
+            if ((relu & 1) && t <= 0.f) t = 0.f;
             f[i] = t;
           }
           if (co0 + 16 <= Cout && (Op % OVEC) == 0) {        // full, 16-byte aligned run

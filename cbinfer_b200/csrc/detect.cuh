@@ -224,6 +224,139 @@ detect_narrow_kernel(const T* __restrict__ x, long long x_sb, long long x_sc, lo
   if (lane == 0) bits[warp] = word;
 }
 
+// Planar x (NCHW: the pixels of a row are contiguous, any channel stride -- what a dense layer or the
+// user hands in) against a pixel-major state of more than one 16-byte chunk per pixel.  The two
+// layouts want opposite lane mappings (x coalesces across pixels, the state across channels), so a
+// block of 8 warps transposes `nw` bitmap words (32 pixels each) through shared memory:
+//   phase 1: lane = pixel, warp = (word, channel chunk): VEC coalesced row loads per chunk -> one
+//            16-byte shared-memory store at [pixel][chunk] (odd chunk pitch: conflict-free);
+//   phase 2: thread = (pixel, chunk) in state order: 16-byte state load (coalesced), compare, state
+//            / operand-plane store, pixel flags OR-ed into the word.
+// nw is chosen so that every warp has >= 2 (word, chunk) pairs: 2*VEC row loads in flight per lane.
+// Both sides stream at full sector efficiency; the generic kernel reads the state at a stride of one
+// pixel per lane (measured 1 TB/s at C = 64).
+constexpr int kPlanarMaxWords = 8;
+struct PlanarWord {
+  long long xoff, soff, pix;     // element offsets of the word's first pixel in x / the state, global pixel index
+  int npx;                       // valid pixels (0: word beyond the map)
+};
+
+__device__ __forceinline__ void planar_words_setup(PlanarWord* wi, unsigned* s_word, int word0, int nw,
+                                                   long long nwords, int H, int W, int Wd, long long x_sb,
+                                                   long long x_sy, long long x_sx, long long s_sb,
+                                                   long long s_sy, int sp) {
+  if (threadIdx.x < (unsigned)nw) {
+    const long long word = (long long)word0 + threadIdx.x;
+    PlanarWord w = {0, 0, 0, 0};
+    if (word < nwords) {
+      const int j = (int)(word % Wd);
+      const long long r = word / Wd;
+      const int y = (int)(r % H);
+      const long long b = r / H;
+      const int x0 = j * 32;
+      w.npx = min(32, W - x0);
+      w.xoff = b * x_sb + y * x_sy + x0 * x_sx;
+      w.soff = b * s_sb + y * s_sy + (long long)x0 * sp;
+      w.pix = (b * H + y) * W + x0;
+    }
+    wi[threadIdx.x] = w;
+    s_word[threadIdx.x] = 0u;
+  }
+  __syncthreads();
+}
+
+// phase 1: x -> xs[(w*32 + px) * cps + cc]; chunks beyond C are zero-filled
+template <typename T, int VEC>
+__device__ __forceinline__ void planar_load_tile(uint4* xs, const PlanarWord* wi, const T* __restrict__ x,
+                                                 long long x_sc, long long x_sx, int nw, int cpv, int cps,
+                                                 int C, unsigned cpv_magic) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll 2
+  for (int p = wid; p < nw * cpv; p += 8) {
+    const int w = cpv == 1 ? p : (int)__umulhi((unsigned)p, cpv_magic), cc = p - w * cpv;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    T* ve = reinterpret_cast<T*>(&v);
+    if (lane < wi[w].npx) {
+      const T* xp = x + wi[w].xoff + lane * x_sx;
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        const int c = cc * VEC + e;
+        if (c < C) ve[e] = __ldg(xp + c * x_sc);
+      }
+    }
+    xs[(w * 32 + lane) * cps + cc] = v;
+  }
+}
+
+// OR the pixel flag of this thread into its word's accumulator (warp-reduced when the warp's 32
+// chunks belong to one word, which is the common case)
+__device__ __forceinline__ void planar_flag(unsigned* s_word, int w, unsigned m) {
+  const int w0 = __shfl_sync(0xffffffffu, w, 0), w1 = __shfl_sync(0xffffffffu, w, 31);
+  if (w0 == w1) {
+    m = __reduce_or_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0 && m) atomicOr(&s_word[w0], m);
+  } else if (m) {
+    atomicOr(&s_word[w], m);
+  }
+}
+
+template <typename T, int VEC, int UPDATE>
+__global__ void __launch_bounds__(256)
+detect_planar_kernel(const T* __restrict__ x, long long x_sb, long long x_sc, long long x_sy,
+                     T* __restrict__ st, long long s_sb, long long s_sy, int sp, AuxPlanes aux,
+                     uint32_t* __restrict__ bits, int B, int H, int W, int C, int Wd, T thr,
+                     unsigned cpv_magic, int cps, int nw) {
+  pdl_prologue();
+  extern __shared__ __align__(16) unsigned char dp_smem[];
+  uint4* xs = reinterpret_cast<uint4*>(dp_smem);                 // [nw*32][cps]
+  __shared__ unsigned s_word[kPlanarMaxWords];
+  __shared__ PlanarWord wi[kPlanarMaxWords];
+  const long long nwords = (long long)B * H * Wd;
+  const int word0 = blockIdx.x * nw;
+  planar_words_setup(wi, s_word, word0, nw, nwords, H, W, Wd, x_sb, x_sy, 1, s_sb, s_sy, sp);
+  const int cpv = (C + VEC - 1) / VEC, tail = C % VEC;
+  planar_load_tile<T, VEC>(xs, wi, x, x_sc, 1, nw, cpv, cps, C, cpv_magic);
+  __syncthreads();
+  const int nq = nw * 32 * cpv;
+  for (int q0 = 0; q0 < nq; q0 += 256) {
+    const int q = min(q0 + (int)threadIdx.x, nq - 1);            // (clamped lanes take no part below)
+    const bool in = q0 + (int)threadIdx.x < nq;
+    const int t = cpv == 1 ? q : (int)__umulhi((unsigned)q, cpv_magic), cc = q - t * cpv;
+    const int w = t >> 5, px = t & 31;
+    unsigned m = 0u;
+    if (in && px < wi[w].npx) {
+      uint4 xv = xs[t * cps + cc];
+      T* sptr = st + wi[w].soff + (long long)px * sp + cc * VEC;
+      const uint4 sv = ld16(sptr);
+      if (tail && cc == cpv - 1) xv = merge_tail<T, VEC>(xv, sv, tail);
+      if (Chunk<T>::changed(sv, xv, thr)) m = 1u << px;
+      if (UPDATE == CB_UPDATE_ALL) store_state<T>(sptr, xv, aux, wi[w].pix + px, cc * VEC);
+    }
+    planar_flag(s_word, w, m);
+  }
+  __syncthreads();
+  if (threadIdx.x < (unsigned)nw && wi[threadIdx.x].npx > 0) bits[word0 + threadIdx.x] = s_word[threadIdx.x];
+  if (UPDATE == CB_UPDATE_CHANGED) {              // feedback: accept the new value at changed pixels
+    for (int q = threadIdx.x; q < nq; q += 256) {
+      const int t = cpv == 1 ? q : (int)__umulhi((unsigned)q, cpv_magic), cc = q - t * cpv;
+      const int w = t >> 5, px = t & 31;
+      if ((s_word[w] >> px) & 1u) {
+        uint4 xv = xs[t * cps + cc];
+        T* sptr = st + wi[w].soff + (long long)px * sp + cc * VEC;
+        if (tail && cc == cpv - 1) xv = merge_tail<T, VEC>(xv, ld16(sptr), tail);
+        store_state<T>(sptr, xv, aux, wi[w].pix + px, cc * VEC);
+      }
+    }
+  }
+}
+
+// words per block of the planar kernels: every warp gets >= 2 (word, chunk) pairs, within 64 KB
+inline int planar_words_per_block(int cpv, int cps) {
+  int nw = 1;
+  while (nw < kPlanarMaxWords && nw * cpv < 16 && (size_t)(2 * nw) * 32 * cps * 16 <= 64 * 1024) nw *= 2;
+  return nw;
+}
+
 template <typename T, int UPDATE>
 __global__ void __launch_bounds__(256)
 detect_generic_kernel(const T* __restrict__ x, long long x_sb, long long x_sc, long long x_sy,
@@ -348,6 +481,13 @@ int launch_detect(cudaStream_t stream, const void* x, long long x_sb, long long 
                          ((uintptr_t)state % 16) == 0;
   const int cpv = (C + VEC - 1) / VEC;
   const unsigned magic = cpv > 1 ? (unsigned)((0x100000000ull + cpv - 1) / cpv) : 0u;
+  // planar x, pixel-major multi-chunk state: transposed through shared memory (detect_planar_kernel)
+  const int cps = cpv | 1;
+  const int planar_nw = planar_words_per_block(cpv, cps);
+  const size_t planar_smem = (size_t)planar_nw * 32 * cps * 16;
+  const bool planar_ok = !vec_ok && !narrow_ok && x_sx == 1 && s_sc == 1 && (s_sx % VEC) == 0 && s_sx >= C &&
+                         ((s_sy * es) % 16) == 0 && ((s_sb * es) % 16) == 0 && ((uintptr_t)state % 16) == 0 &&
+                         s_sx < (1ll << 30) && planar_smem <= 200 * 1024;
   // warps per word: keep >= 4 load batches (of U*32 chunks) per warp, at most one block per word
   int wlog = 0;
   while (wlog < 3 && (32 * cpv) / (1 << (wlog + 1)) >= 4 * 4 * 32) ++wlog;
@@ -369,6 +509,14 @@ int launch_detect(cudaStream_t stream, const void* x, long long x_sb, long long 
     cb::launch_pdl(detect_narrow_kernel<T, VEC, U_>, grid, block, 0, stream,                               \
         (const T*)x, x_sb, x_sc, x_sy, x_sx, (T*)state, s_sb, s_sy, aux, bits, B, H, W, C,  \
         Wd, thr);                                                                              \
+  } else if (planar_ok) {                                                                      \
+    if (planar_smem > 48 * 1024)                                                               \
+      cudaFuncSetAttribute(detect_planar_kernel<T, VEC, U_>,                                   \
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)planar_smem);     \
+    cb::launch_pdl(detect_planar_kernel<T, VEC, U_>, dim3((unsigned)((words + planar_nw - 1) / planar_nw)), \
+        block, planar_smem, stream,                                                            \
+        (const T*)x, x_sb, x_sc, x_sy, (T*)state, s_sb, s_sy, (int)s_sx, aux, bits, B, H, W, C, \
+        Wd, thr, magic, cps, planar_nw);                                                       \
   } else {                                                                                     \
     cb::launch_pdl(detect_generic_kernel<T, U_>, grid, block, 0, stream,                                   \
         (const T*)x, x_sb, x_sc, x_sy, x_sx, (T*)state, s_sb, s_sc, s_sy, s_sx, aux, bits,  \

@@ -318,6 +318,31 @@ int cb_fg_update(void* stream, const float* x, float* prev, const float* weight,
                  int32_t* count, int B, int Cin, int Cout, int H, int W, int kH, int kW,
                  float threshold);
 
+
+/* Fine-grained update on the tensor cores (B200 path of the same stage; the module uses it, the
+ * planar op above stays as the reference-layout drop-in).  The sum over the changed values of
+ * W[co,ci,ky,kx]*d (updateOutputFG_kernel, cbconv2d_fg_backend.cu:37-66) equals conv(D, W) with
+ * D = the thresholded delta map, so:
+ *   cb_fg_detect      replaces changeDetectionFG (cbconv2d_fg_backend.cu:7-23) + torch.nonzero
+ *                     (conv2d_fg.py:82): per value d = x - prev, D = d if |d| > thr else 0, written as
+ *                     bf16 hi/lo operand planes [B,H,W,cb_plane_pitch16(C)] (zero-initialised by the
+ *                     caller once; pad channels are never written); raw_bits = pixels with any changed
+ *                     value; *count (optional) = number of changed values; prev <- x (conv2d.py:175).
+ *                     x: any strides (fast paths: planar rows, or pixel-major like the state);
+ *                     prev: pixel-major fp32 [B,H,W,p_pitch].
+ *   cb_dilate_compact lists the output pixels inside the filter footprint of a changed value;
+ *   cb_conv_accumulate = cb_conv_update over that list with an accumulating epilogue:
+ *                     out[pix, :] += sum_taps D[pix+tap, :] . W  (no bias, no ReLU).  state/state_lo
+ *                     are the delta planes for CB_GEMM_TC_BF16X3. */
+int cb_fg_detect(void* stream, const float* x, long long x_sb, long long x_sc, long long x_sy,
+                 long long x_sx, float* prev, long long p_sb, long long p_sy, int p_pitch, void* delta_hi,
+                 void* delta_lo, uint32_t* raw_bits, int32_t* count, int B, int C, int H, int W,
+                 float threshold);
+int cb_conv_accumulate(void* stream, int dtype, int gemm, const void* state, const void* state_lo,
+                       int pitch_in, const int32_t* idx, const int32_t* count, const void* packed_w,
+                       void* out, int pitch_out, int B, int H, int W, int Cin, int Cout, int kH, int kW,
+                       void* ws, size_t ws_bytes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -166,18 +166,27 @@ def test_user_supplied_index_tensor(orc):
     assert y2.data_ptr() != pool.outputState.data_ptr()       # clone, conv2d.py:73
 
 
-def test_fine_grained_module(orc):
+@pytest.mark.parametrize("mode", ["auto", "simt"])
+@pytest.mark.parametrize("shape", [(1, 4, 11, 13, 6, 3), (2, 16, 24, 40, 24, 7), (1, 5, 9, 70, 8, 5)])
+def test_fine_grained_module(orc, mode, shape):
+    """finegrained=True (conv2d.py:160-176): 'auto' = thresholded delta planes + accumulating tcgen05
+    contraction, 'simt' = scattered red.global.add on planar tensors; both against the oracle's FG flow."""
     import cbinfer_b200 as cb
+    B, Cin, H, W, Cout, k = shape
     torch.manual_seed(4)
-    conv = nn.Conv2d(4, 6, 3, padding=1).cuda()
+    conv = nn.Conv2d(Cin, Cout, k, padding=k // 2).cuda()
     m = cb.CBConv2d(conv, 0.2)
     m.finegrained = True
     m.withReLU = True
-    o = orc.OracleCBConv2d(to_np(conv.weight), to_np(conv.bias), 0.2, withReLU=True, finegrained=True)
-    for f in _frames((1, 4, 11, 13), "f32", 4, 0.1, seed=2):
+    m.gemmMode = mode
+    os_ = [orc.OracleCBConv2d(to_np(conv.weight), to_np(conv.bias), 0.2, withReLU=True, finegrained=True)
+           for _ in range(B)]
+    for f in _frames((B, Cin, H, W), "f32", 4, 0.1, seed=2):
         out = m(f)
-        exp = o.forward(to_np(f))
+        exp = np.concatenate([o.forward(to_np(f[b:b + 1])) for b, o in enumerate(os_)])
         np.testing.assert_allclose(out.cpu().numpy(), exp, rtol=1e-4, atol=1e-4)
+        assert torch.equal(m.prevInput, f)                      # conv2d.py:175
+    assert len(m.getStateTensors()) == 2 and tuple(m.getStateTensors()[1].shape) == (B, Cout, H, W)
 
 
 def test_scene_model_small_vs_dense_and_oracle(orc):

@@ -110,11 +110,13 @@ DET_CASES = [  # B, C, H, W, kH, kW, thr
 
 
 @pytest.mark.parametrize("dt", ["f32", "f16", "bf16"])
-@pytest.mark.parametrize("layout", ["planar", "pixel"])
+@pytest.mark.parametrize("layout", ["planar", "pixel", "mixed"])
 @pytest.mark.parametrize("case", DET_CASES)
 def test_detect_dilate_compact(cbm, orc, dt, layout, case):
     """bit-exact mask, feedback-updated state and index list; planar = generic-stride kernel,
-    pixel = vectorised pixel-major kernel (incl. padded pitch for C % vec != 0)."""
+    pixel = vectorised pixel-major kernel (incl. padded pitch for C % vec != 0), mixed = planar NCHW
+    frame against a pixel-major state (narrow kernel for one-chunk pixels, shared-memory transposing
+    kernel for wide ones)."""
     cg, lib = cbm["cg"], cbm["lib"]
     B, C, H, W, kH, kW, thr = case
     prev = rand_tensor((B, C, H, W), dt, seed=sum(case[:4]) + 1)
@@ -124,6 +126,8 @@ def test_detect_dilate_compact(cbm, orc, dt, layout, case):
         xv.copy_(x)
         sv, _ = cg.pixel_major((B, C, H, W), TORCH_DT[dt], "cuda", 0)
         sv.copy_(prev)
+    elif layout == "mixed":
+        xv, sv = x.contiguous(), None
     else:
         xv, sv = x.contiguous(), prev.clone().contiguous()
     for update in (False, True):
@@ -170,7 +174,8 @@ def test_detect_update_all_and_special_values(cbm, orc):
     assert bits_to_map(s["raw_bits"], 2, 5, 37).all()
     assert torch.equal(view, xx)
     # tf32 remainder plane: written wherever the state is written, lo = v - trunc_tf32(v), exact
-    for shape, layout in (((2, 6, 5, 37), "pixel"), ((1, 3, 9, 40), "narrow"), ((1, 5, 7, 33), "planar")):
+    for shape, layout in (((2, 6, 5, 37), "pixel"), ((1, 3, 9, 40), "narrow"), ((1, 5, 7, 33), "planar"),
+                          ((2, 19, 6, 45), "narrow"), ((1, 64, 5, 70), "narrow")):
         x0, x1 = rand_tensor(shape, "f32", 5), None
         x1 = perturb(x0, 0.2, 6)
         if layout == "planar":
@@ -497,6 +502,53 @@ def test_fg_golden(cbm, golden, tag):
     assert torch.equal(prev, x)
     d = np.abs(golden[f"{tag}_in"] - golden[f"{tag}_prev"])
     assert int(cnt.item()) == int((d > float(golden[f"{tag}_thr"])).sum())
+
+
+@pytest.mark.parametrize("layout", ["planar", "pixel"])
+@pytest.mark.parametrize("case", [(2, 6, 10, 17, 23, 7, 3), (1, 16, 64, 20, 70, 7, 7), (3, 4, 5, 9, 33, 3, 3),
+                                  (1, 3, 16, 31, 40, 5, 5), (1, 64, 32, 6, 37, 3, 3)])
+def test_fg_tensor_core_path_vs_oracle(cbm, orc, golden, layout, case):
+    """cb_fg_detect + cb_dilate_compact + cb_conv_accumulate == the per-value scatter of the
+    reference (oracle cbconvFG, pinned to conv2d_fg_cpu by the golden vectors): delta planes, bitmap,
+    changed-value count and state exact, output within 1e-4 of max|out| (3xBF16 products)."""
+    cg, lib = cbm["cg"], cbm["lib"]
+    B, Cin, Cout, H, W, kH, kW = case
+    thr = 0.25
+    prev = rand_tensor((B, Cin, H, W), "f32", 31 + Cin)
+    x = perturb(prev, 0.1, 32 + Cout)
+    w = rand_tensor((Cout, Cin, kH, kW), "f32", 33, scale=0.2)
+    out0 = rand_tensor((B, Cout, H, W), "f32", 34)
+    pv, pbuf = cg.pixel_major((B, Cin, H, W), torch.float32, "cuda", 0)
+    pv.copy_(prev)
+    ov, obuf = cg.pixel_major((B, Cout, H, W), torch.float32, "cuda", 0)
+    ov.copy_(out0)
+    xin = x.contiguous() if layout == "planar" else cg.pixel_major((B, Cin, H, W), torch.float32, "cuda", 0)[0].copy_(x)
+    p16 = lib.C.cb_plane_pitch16(Cin)
+    hi = torch.zeros(B, H, W, p16, dtype=torch.bfloat16, device="cuda")
+    lo = torch.zeros_like(hi)
+    s = cg.alloc_scratch((B, H, W), "cuda")
+    nval = torch.zeros(1, dtype=torch.int32, device="cuda")
+    packed = cg.pack_weights(w, lib.GEMM_TC_BF16X3)
+    for rep in range(2):                 # second pass: nothing changes any more, planes go back to zero
+        cg.fg_detect(xin, pv, pbuf, (hi, lo), s["raw_bits"], thr, count=nval)
+        d = (x - prev) if rep == 0 else torch.zeros_like(x)
+        chg = d.abs() > thr
+        dm = torch.where(chg, d, torch.zeros_like(d)).permute(0, 2, 3, 1)
+        eh, el = cg.bf16_pair(dm)
+        assert torch.equal(hi[..., :Cin], eh) and torch.equal(lo[..., :Cin], el)
+        assert float(hi[..., Cin:].abs().sum()) == 0.0
+        assert int(nval.item()) == int(chg.sum())
+        assert np.array_equal(bits_to_map(s["raw_bits"], B, H, W), chg.any(1).cpu().numpy().astype(np.uint8))
+        assert torch.equal(pv, x)
+        cg.dilate_compact(s["raw_bits"], (B, H, W), (kH, kW), s["idx"], s["count"], s["ws"], dil_bits=s["dil_bits"])
+        ch = cg.ChangeIndexes(s["idx"], s["count"], (B, H, W), bits=s["dil_bits"])
+        ws = torch.zeros(lib.C.cb_conv_ws_bytes(), dtype=torch.uint8, device="cuda")
+        cg.conv_accumulate((hi, lo), ch, packed, obuf, Cin, Cout, (kH, kW), lib.GEMM_TC_BF16X3, ws=ws)
+    for b in range(B):
+        e = to_np(out0[b:b + 1])
+        orc.cbconvFG(to_np(x[b:b + 1]), to_np(prev[b:b + 1]), e, to_np(w), thr)
+        got = ov[b:b + 1].cpu().numpy()
+        assert np.abs(got - e).max() <= 1e-4 * max(1.0, np.abs(e).max())
 
 
 def test_fg_random_vs_oracle(cbm, orc):
