@@ -35,7 +35,9 @@ bool pdl_enabled();
 // ~20 dependent kernels of a frame; also inside CUDA graphs).  Experimental, enabled only with
 // CBINFER_PDL=1 (see pdl_enabled()); without the launch attribute both instructions are no-ops.
 __device__ __forceinline__ void pdl_prologue() {
+#ifndef CB_PDL_LATE          // -DCB_PDL_LATE: no early trigger (dependents are released when this grid's CTAs exit)
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
   asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 

@@ -99,3 +99,50 @@ class FramePipeline(object):
         self.h2d.synchronize()
         self.compute.synchronize()
         self.d2h.synchronize()
+
+
+def _cpulist(text):
+    cpus = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus += list(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_host_cores(local_rank, local_world, min_cores=2):
+    """Pin this feeder process to its own slice of the host cores, taken from the NUMA node its GPU
+    hangs off when the box exposes one (sysfs), so that the pinned frame buffers it allocates
+    afterwards are node-local and N feeders do not migrate over each other's cores.  Returns the
+    cores chosen (or None when the host gives every rank fewer than `min_cores`).  Call before the
+    first CUDA / pinned allocation."""
+    import os
+    try:
+        allowed = sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        return None
+    def node_of(i):
+        try:
+            p = torch.cuda.get_device_properties(i)
+            bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+            return int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        except Exception:                          # noqa: BLE001 - no sysfs / no such attribute
+            return -1
+
+    cpus, index, peers = allowed, local_rank, max(local_world, 1)
+    node = node_of(local_rank)
+    if node >= 0:
+        try:
+            local = set(_cpulist(open("/sys/devices/system/node/node%d/cpulist" % node).read())) & set(allowed)
+        except OSError:
+            local = set()
+        same = [i for i in range(peers) if node_of(i) == node]     # the feeders sharing this node
+        if len(local) >= min_cores * max(len(same), 1) and local_rank in same:
+            cpus, index, peers = sorted(local), same.index(local_rank), len(same)
+    per = len(cpus) // peers
+    if per < min_cores:
+        return None
+    mine = cpus[index * per:(index + 1) * per]
+    os.sched_setaffinity(0, mine)
+    return mine
