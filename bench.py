@@ -543,8 +543,24 @@ def main():
     del step_obj, slot_graphs
     cb.clearMemory(model)
 
-    def e2e_leg(pin, first_frame_dev):
-        pipe = runtime.FramePipeline(model, first_frame_dev, depth=2)
+    def copy_only_gbs(pin, first_frame_dev, n=60):
+        """host-side ceiling of the e2e legs: the same pinned buffers copied H2D on ALL ranks at once,
+        no compute (PCIe + host memory fabric of the box; per GPU, GB/s)"""
+        dst = torch.empty_like(first_frame_dev)
+        wall = 0.0
+        for _ in range(2):
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(n):
+                dst.copy_(pin[fidx(i)], non_blocking=True)
+            torch.cuda.synchronize()
+            wall = time.perf_counter() - t0
+            barrier()
+        worst = streams.max_over_ranks(wall, dev)
+        return pin[0].numel() * pin[0].element_size() * n / worst / 1e9
+
+    def e2e_leg(pin, first_frame_dev, mdl=None):
+        pipe = runtime.FramePipeline(mdl if mdl is not None else model, first_frame_dev, depth=2)
         for i in range(1, Wm + 1):
             pipe.submit(pin[fidx(i)])
         pipe.drain()
@@ -572,6 +588,7 @@ def main():
         return f_, ms_, d2h_, chk, len(walls)
 
     h2d = pinned[0].numel() * pinned[0].element_size()
+    ceiling_gbs = copy_only_gbs(pinned, frames[0])
     e2e_fps, e2e_ms, d2h, e2e_checksum, e2e_blocks = e2e_leg(pinned, frames[0])
 
     # ---- e2e with uint8 host frames (what a camera / decoder delivers): the first layer's detection
@@ -590,6 +607,25 @@ def main():
                   "checksum": u8_chk,
                   "path": "as e2e, but the pinned host frames are uint8 and are normalised (u8/255) inside "
                           "the first layer's detection kernel (cb_change_detect_u8)"}
+        # ... and with the task's result instead of the logits coming back: the label map (argmax over the
+        # classes, one byte per pixel) is computed on the device inside the same graph, so 1/32 of the
+        # D2H bytes cross the host fabric -- what bounds the multi-GPU e2e rate (see host_h2d_copy_only_gbs)
+        cb.clearMemory(model)
+
+        class LabelHead(torch.nn.Module):
+            def __init__(self, m):
+                super().__init__()
+                self.m = m
+
+            def forward(self, x):
+                return self.m(x).argmax(1).to(torch.uint8)
+
+        lb_fps, lb_ms, lb_d2h, lb_chk, _ = e2e_leg(pinned8, pinned8[0].to(dev), LabelHead(model))
+        e2e_u8["labels_out"] = {"value": lb_fps, "unit": "frames/s", "ms_per_step": lb_ms / K,
+                                "h2d_bytes_per_step": pinned8[0].numel(), "d2h_bytes_per_step": lb_d2h,
+                                "checksum": lb_chk,
+                                "path": "as e2e_u8_ingest, D2H = uint8 label map (argmax over the 8 classes on the "
+                                        "device) instead of the fp32 logits"}
         del pinned8
         first.inputNorm = None
         cb.clearMemory(model)
@@ -616,6 +652,9 @@ def main():
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / K, "checksum": e2e_checksum, "timed_blocks": e2e_blocks,
                 "h2d_gbs": h2d / (e2e_ms / K * 1e-3) / 1e9,     # PCIe roofline of this leg (Gen5 x16 ~ 55 GB/s)
+                # the box's host-side ceiling at this N: the same pinned frames copied H2D by all ranks
+                # at once without any compute (one GPU alone ~55 GB/s; 8 GPUs share ~190 GB/s)
+                "host_h2d_copy_only_gbs_per_gpu": ceiling_gbs,
                 "path": "runtime.FramePipeline: per step pinned H2D of the frames, one graph replay, D2H of the "
                         "logits; copies of neighbouring steps overlap compute (3 streams); host wall clock"},
         "gpu_launches": my_launches_per_step * K * len(blocks),

@@ -35,8 +35,9 @@ class DetectionDone(object):
     already ran this layer's change detection (fused into its pooling kernel); the layer's raw
     bitmap, state and operand planes are up to date."""
 
-    def __init__(self, owner):
+    def __init__(self, owner, dense=False):
         self.owner = owner
+        self.dense = dense        # True: a dense scan wrote every bitmap word (CBConv2d.detectInput)
 
 
 class TailDone(object):
@@ -392,6 +393,10 @@ class CBConv2d(nn.Module):
         input, changeIndexes = _parse_input(inp)
         assert(input.dim() == 4)
         assert(input.size(-3) == self.in_channels)
+        # a layer fed with plain frames re-scans them densely every frame, which rewrites every word of
+        # its raw bitmap: nothing ever ORs bits into it, so its compaction need not zero it afterwards
+        plain_input = changeIndexes is None or (isinstance(changeIndexes, DetectionDone)
+                                                and getattr(changeIndexes, 'dense', False))
         _lib.require_cuda(input)
         B, _, H, W = input.shape
         dev, dt = input.device, input.dtype
@@ -490,7 +495,7 @@ class CBConv2d(nn.Module):
             # copy is part of the detection pass; copyInput=False (alias the input as state) is
             # honoured as a copy -- the state always owns its memory.
             mode = _lib.UPDATE_CHANGED if self.feedbackLoop else _lib.UPDATE_ALL
-            sparse_next = bool(getattr(self, 'candidateDetect', False))
+            sparse_next = bool(getattr(self, 'candidateDetect', False)) and not plain_input
             # (measured: one launch fewer, but its serial compaction tail makes it slower than the
             #  two-kernel path once there are >~10k candidates, so it is opt-in: fuse1x1=True)
             fused11 = (candidates is not None and tuple(self.kernel_size) == (1, 1)
@@ -696,7 +701,7 @@ class CBConv2d(nn.Module):
         self._fresh = False
         self._lastThr = self.threshold
         self._inVersion = self.prevInput._version
-        return 'changeIndexes', input, DetectionDone(self)
+        return 'changeIndexes', input, DetectionDone(self, dense=True)
 
     def _useTiles(self, dt, gemm, shape):
         """tile path for this layer / shape?  (tileMode 'auto': where the library recommends it)"""

@@ -61,6 +61,7 @@ static inline unsigned grid_for(long long total, int threads, int per_sm = 8) {
 }  // namespace cb
 
 using namespace cb;
+static_assert(cb::kDtRows == cb::TL_H && cb::TL_W == 8, "dilate_tiles_kernel lists 8 x 16 tiles, four per bitmap word");
 
 #define CB_DISPATCH_DTYPE(dtype, ...)                                               \
   switch (dtype) {                                                                  \
@@ -176,6 +177,26 @@ int cb_dilate_tiles(void* stream, const uint32_t* raw_bits, uint32_t* dil_bits, 
                     void* tile_ws, int B, int H, int W, int kHHalf, int kWHalf, int clear_raw) {
   CB_CHECK_ARG(tile_ws && dil_bits, "dilate_tiles: null pointer");
   if ((long long)cb_bitmap_words(B, H, W) == 0) cudaMemsetAsync((int32_t*)tile_ws + 1, 0, sizeof(int32_t), (cudaStream_t)stream);
+  // CBINFER_DILATE_TILES=1: dilate_tiles_kernel (one block per tile row, one packed atomic per block).
+  // Faster alone (L1 bitmap of the bench: 4.7 vs 5.7 us back to back) but the whole step measured 1.5 %
+  // SLOWER with it on two boxes (0.193 vs 0.190 ms), so dilate_compact_kernel's tile mode stays the default.
+  static const bool lean = [] {
+    const char* e = getenv("CBINFER_DILATE_TILES");
+    return e && e[0] == '1';
+  }();
+  const int ty = cb::tile_grid_y(H), xp = cb::tile_grid_xp(W);
+  if (lean && (long long)cb_bitmap_words(B, H, W) > 0 && cb::dilate_tiles_ok(B, H, W, kHHalf, ty, xp) &&
+      kWHalf <= 31 && kHHalf >= 0 && kWHalf >= 0 && ((uintptr_t)ws % 8) == 0) {
+    CB_CHECK_ARG(raw_bits && count && ws && raw_bits != dil_bits, "dilate_tiles: bad pointers");
+    const int Wd = (W + 31) / 32;
+    // the packed counter is the first 8 bytes of the compaction workspace (CompactHeader.reserved/done,
+    // both zero at rest, so the two kernels can share one workspace)
+    cb::launch_pdl(dilate_tiles_kernel, dim3((unsigned)(B * ty)), dim3(kDtThreads), cb::dilate_tiles_smem(Wd, kHHalf),
+                   (cudaStream_t)stream, raw_bits, dil_bits, count, (unsigned long long*)ws, B, H, W, Wd, kHHalf,
+                   kWHalf, clear_raw ? const_cast<uint32_t*>(raw_bits) : nullptr, (int32_t*)tile_ws, ty, xp);
+    CB_CHECK_LAUNCH("dilate_tiles");
+    return 0;
+  }
   return dilate_compact_impl(stream, raw_bits, dil_bits, nullptr, nullptr, count, ws, tile_ws, B, H, W,
                              kHHalf, kWHalf, clear_raw, 1);
 }
@@ -321,7 +342,7 @@ int cb_conv_tiled_supported(int dtype, int gemm, int B, int H, int W, int Cin, i
   cb::TilePlan plan;
   cb::umma_tile_plan(plan, dtype, gemm, Cp, B, H, W, Cout, cb_channel_pitch(dtype, Cout), kH, kW, 0);
   if (!plan.ok) return 0;
-  return plan.mma_clk_per_tile <= cb::tile_clk_limit() ? 1 : 2;
+  return (plan.mma_clk_per_tile <= cb::tile_clk_limit() || plan.short_k) ? 1 : 2;
 }
 
 static int conv_update_tiled_impl(void* stream, int dtype, int gemm, const void* state, const void* state_lo,

@@ -136,6 +136,13 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap amap_hi, const __grid_const
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);    // provably warp-uniform role index
   const int NT = g.B * g.TY * g.TXp;
   const int32_t* tiles = tile_ws + 4 + NT;
+  // EXPERIMENT (CBINFER_TILE_SCRAMBLE=1): walk the tile list in a pseudo-random order (x 7919 mod n), so
+  // that the tiles in flight at any time are spread over the maps instead of being neighbours
+  const bool scramble = (g.relu & 4) && (ntl % 7919) != 0;
+  auto tile_at = [&](long long w) {
+    const int ti = (int)(w / ntiles_n);
+    return __ldg(tiles + (scramble ? (int)(((long long)ti * 7919ll) % ntl) : ti));
+  };
   const int halo_stage = NSPLIT * g.nblk * g.plane_bytes;
   uint8_t* bring = smem + g.nhalo * halo_stage;
   TileCtrl* ctrl = reinterpret_cast<TileCtrl*>(bring + g.nb * B_STAGE);
@@ -206,7 +213,7 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap amap_hi, const __grid_const
     const int nhalo = g.nhalo, nblk = g.nblk, plane_bytes = g.plane_bytes, TXp = g.TXp;
     int it = 0;
     for (long long w = blockIdx.x; w < total; w += gridDim.x, ++it) {
-      const int tile = __shfl_sync(0xffffffffu, __ldg(tiles + (int)(w / ntiles_n)), 0);
+      const int tile = __shfl_sync(0xffffffffu, tile_at(w), 0);
       const int b = tile / tiles_per_img, r = tile - b * tiles_per_img;
       const int ty = r / TXp, tx = r - ty * TXp;
       const int hb = it % nhalo;
@@ -351,7 +358,7 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap amap_hi, const __grid_const
     const TO pthr = thr_cast<TO>(pf.thr);
     int it = 0;
     for (long long w = blockIdx.x; w < total; w += gridDim.x, ++it) {
-      const int tile = __ldg(tiles + (int)(w / ntiles_n));
+      const int tile = tile_at(w);
       const int nt = (int)(w % ntiles_n);
       const int b = tile / tiles_per_img, r = tile - b * tiles_per_img;
       const int ty = r / g.TXp, tx = r - ty * g.TXp;
@@ -486,6 +493,7 @@ struct TilePlan {
   TileGeom g;
   int smem_bytes, occ;
   long long mma_clk_per_tile;    // rough tensor-pipe time of one tile (policy: cheap tiles only)
+  bool short_k;                  // policy: short single-pass K loop, one N tile
 };
 
 // Can (and should) this layer run on the tile path?  es = operand element bytes, Cp = operand channel
@@ -494,6 +502,7 @@ inline TilePlan tile_plan(int es, bool split3, int bn, int Cp, int B, int H, int
                           int CoutPad, int Op, int kH, int kW, int relu) {
   TilePlan p;
   p.ok = false;
+  p.short_k = false;
   TileGeom& g = p.g;
   const int pixb = Cp * es;
   if (!(pixb == 16 || pixb == 32 || pixb == 64 || (pixb % 128) == 0)) return p;
@@ -512,6 +521,7 @@ inline TilePlan tile_plan(int es, bool split3, int bn, int Cp, int B, int H, int
   g.layout = g.pix_row == 16 ? 0 : g.pix_row == 32 ? 6 : g.pix_row == 64 ? 4 : 2;
   g.Cout = Cout; g.CoutPad = CoutPad; g.Op = Op; g.relu = relu ? 1 : 0;
   if (getenv("CBINFER_TILE_FAKE")) g.relu |= 2;
+  if (getenv("CBINFER_TILE_SCRAMBLE")) g.relu |= 4;
   if ((long long)g.HWX * g.pix_row >= (1 << 18)) return p;
   const int b_stage = nsplit * bn * UM_ROW_BYTES;
   const int tmem_cols = tile_tmem_cols(split3, bn);
@@ -559,6 +569,11 @@ inline TilePlan tile_plan(int es, bool split3, int bn, int Cp, int B, int H, int
   const long long ksteps = (g.Kp + uk - 1) / uk;
   const long long per = bn / 2 < 32 ? 32 : bn / 2;           // cycles per instruction (N/2, smem floor ~32)
   p.mma_clk_per_tile = ksteps * (split3 ? 3 : 1) * per * (CoutPad / bn);
+  // single-pass layers whose K loop is short (<= 224 K steps, e.g. 64 channels x 7x7 in 16-bit data) and
+  // that need one N tile: a tile is then cheaper than the index-list kernel's split-K round trip at every
+  // change rate (measured, tools/tile_bench.py --set policy: 64->256 7x7 bf16 28 vs 39 us at 1 %, 29 vs 37
+  // at 5 %, 180 vs 239 at 100 %), while 128 channels x 7x7 (392 K steps) only wins when everything changed
+  p.short_k = !split3 && ksteps <= 224 && CoutPad == bn;
   p.ok = true;
   return p;
 }

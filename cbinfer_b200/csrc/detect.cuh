@@ -232,7 +232,7 @@ detect_narrow_kernel(const T* __restrict__ x, long long x_sb, long long x_sc, lo
 //            16-byte shared-memory store at [pixel][chunk] (odd chunk pitch: conflict-free);
 //   phase 2: thread = (pixel, chunk) in state order: 16-byte state load (coalesced), compare, state
 //            / operand-plane store, pixel flags OR-ed into the word.
-// nw is chosen so that every warp has >= 2 (word, chunk) pairs: 2*VEC row loads in flight per lane.
+// nw is chosen so that every warp has ~4 (word, chunk) pairs: 4*VEC row loads in flight per lane.
 // Both sides stream at full sector efficiency; the generic kernel reads the state at a stride of one
 // pixel per lane (measured 1 TB/s at C = 64).
 constexpr int kPlanarMaxWords = 8;
@@ -352,8 +352,17 @@ detect_planar_kernel(const T* __restrict__ x, long long x_sb, long long x_sc, lo
 
 // words per block of the planar kernels: every warp gets >= 2 (word, chunk) pairs, within 64 KB
 inline int planar_words_per_block(int cpv, int cps) {
+  static const int forced = [] {
+    const char* e = getenv("CBINFER_PLANAR_NW");               // tuning knob: 1, 2, 4 or 8
+    return e ? atoi(e) : 0;
+  }();
+  if (forced > 0 && forced <= kPlanarMaxWords && (forced & (forced - 1)) == 0 &&
+      (size_t)forced * 32 * cps * 16 <= 96 * 1024)
+    return forced;
+  // measured (tools/planar_bench.py, L2 flushed): 4 (word, chunk) pairs per warp, at most 4 words --
+  // C=64 fp32 153 -> 135 us at nw=2, bf16 100 -> 94 us at nw=4; 8 words lose again (fewer, fatter blocks)
   int nw = 1;
-  while (nw < kPlanarMaxWords && nw * cpv < 16 && (size_t)(2 * nw) * 32 * cps * 16 <= 64 * 1024) nw *= 2;
+  while (nw < 4 && nw * cpv < 32 && (size_t)(2 * nw) * 32 * cps * 16 <= 64 * 1024) nw *= 2;
   return nw;
 }
 

@@ -16,7 +16,11 @@ pytestmark = pytest.mark.gpu
 
 
 def _torchrun(script_args, nproc=2, timeout=600):
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    # order-fixed contraction: whole K ranges per CTA (no stream-K / cluster split-K, whose partial-sum
+    # order depends on the change count of the map a rank holds), so the band result can be compared
+    # bit for bit with the full frame; with the default settings the two differ by fp32 summation
+    # order (~1e-7 relative) plus the threshold decisions that flips
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", CBINFER_STREAMK="0", CBINFER_KSPLIT="1")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
            "--master-addr", "127.0.0.1", "--master-port", "29531"] + script_args
     p = subprocess.run(cmd, cwd=REPO, env=env, capture_output=True, text=True, timeout=timeout)

@@ -261,8 +261,30 @@ def test_fused_pool_in_tile_epilogue_is_bit_identical(cbm, dt, feedback, monkeyp
 
 
 @pytest.mark.parametrize("shape,k,frac", [((2, 97, 131), 7, 0.02), ((1, 480, 640), 7, 0.3), ((3, 16, 8), 3, 1.0),
-                                          ((1, 40, 40), 5, 0.0)])
+                                          ((1, 40, 40), 5, 0.0), ((2, 33, 65), 17, 0.01), ((1, 50, 300), 19, 0.01),
+                                          ((8, 240, 320), 7, 0.05), ((1, 7, 9000), 3, 0.05), ((2, 31, 70), 1, 0.2)])
 def test_dilate_tiles_equals_dilate_compact(cbm, shape, k, frac):
+    _dilate_tiles_check(cbm, shape, k, frac)
+
+
+def test_lean_dilate_tiles_kernel_subprocess():
+    """the opt-in one-block-per-tile-row kernel (CBINFER_DILATE_TILES=1, read once per process) gives the
+    same bitmap, count, tile set and cleared raw bitmap: the same checks in a child process"""
+    import os, subprocess, sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from tests import test_gpu_tiles as t\n"
+            "from cbinfer_b200 import conv2d_cg as cg, _lib\n"
+            "for shape, k, frac in (((2, 97, 131), 7, 0.02), ((1, 480, 640), 7, 0.3), ((3, 16, 8), 3, 1.0),\n"
+            "                       ((2, 33, 65), 17, 0.01), ((8, 240, 320), 7, 0.05), ((1, 7, 9000), 3, 0.05)):\n"
+            "    t._dilate_tiles_check(dict(cg=cg, lib=_lib), shape, k, frac)\n"
+            "print('lean ok')\n" % repo)
+    p = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, CBINFER_DILATE_TILES="1"),
+                       capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and "lean ok" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
+
+
+def _dilate_tiles_check(cbm, shape, k, frac):
     """cb_dilate_tiles (no ordered list) yields the same dilated bitmap, change count and tile set as
     cb_dilate_compact_tiles; the list compacted on demand from the bitmap equals the eager one."""
     cg = cbm["cg"]
@@ -286,6 +308,14 @@ def test_dilate_tiles_equals_dilate_compact(cbm, shape, k, frac):
     lazy = cg.ChangeIndexes(s2["idx"], s2["count"], shape, bits=s2["dil_bits"], ws=s2["ws"], listed=False)
     assert len(lazy) == n
     assert torch.equal(lazy.tensor(), s1["idx"][:n])
+    # clear_raw: same results, and the raw bitmap comes back zeroed (own rows by each block, the rows two
+    # tile rows share by the last block); the workspace is left clean for either kernel
+    rb = raw_bits.clone()
+    cg.dilate_tiles(rb, shape, (k, k), s2["count"], s2["ws"], s2["dil_bits"], t2, clear_raw=True)
+    assert int(s2["count"]) == n and torch.equal(s1["dil_bits"], s2["dil_bits"]) and int(t2[1]) == int(t1[1])
+    assert int(rb.abs().sum()) == 0
+    cg.dilate_compact(raw_bits, shape, (k, k), s2["idx"], s2["count"], s2["ws"], dil_bits=s2["dil_bits"], tile_ws=t2)
+    assert int(s2["count"]) == n and torch.equal(s2["idx"][:n], s1["idx"][:n])
 
 
 @pytest.mark.parametrize("feedback", [True, False])

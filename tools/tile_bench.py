@@ -80,6 +80,13 @@ if __name__ == "__main__":
             one(8, 64, 64, 368, 368, 3, rate, "tc", bf)
             one(8, 512, 512, 46, 46, 3, rate, "tc", bf)
             one(8, 128, 128, 46, 46, 7, rate, "tc", bf)
+    elif a.set == "policy":
+        # long-K layers the static policy keeps on the index-list kernel: where does the tile kernel win?
+        for rate in (0.01, 0.05, 0.2, 1.0):
+            one(8, 64, 256, 120, 160, 7, rate, "tc", bf)
+            one(8, 128, 128, 46, 46, 7, rate, "tc", bf)
+            one(8, 128, 128, 46, 46, 7, rate, "bf16x3", f32)
+            one(1, 128, 128, 46, 46, 7, rate, "tc", bf)
     else:
         for rate in (0.05, 1.0):
             one(8, 64, 64, 368, 368, 3, rate, "tc", bf)
