@@ -271,7 +271,7 @@ __device__ __forceinline__ void planar_load_tile(uint4* xs, const PlanarWord* wi
                                                  long long x_sc, long long x_sx, int nw, int cpv, int cps,
                                                  int C, unsigned cpv_magic) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#pragma unroll 2
+#pragma unroll 4
   for (int p = wid; p < nw * cpv; p += 8) {
     const int w = cpv == 1 ? p : (int)__umulhi((unsigned)p, cpv_magic), cc = p - w * cpv;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
@@ -318,21 +318,39 @@ detect_planar_kernel(const T* __restrict__ x, long long x_sb, long long x_sc, lo
   planar_load_tile<T, VEC>(xs, wi, x, x_sc, 1, nw, cpv, cps, C, cpv_magic);
   __syncthreads();
   const int nq = nw * 32 * cpv;
-  for (int q0 = 0; q0 < nq; q0 += 256) {
-    const int q = min(q0 + (int)threadIdx.x, nq - 1);            // (clamped lanes take no part below)
-    const bool in = q0 + (int)threadIdx.x < nq;
-    const int t = cpv == 1 ? q : (int)__umulhi((unsigned)q, cpv_magic), cc = q - t * cpv;
-    const int w = t >> 5, px = t & 31;
-    unsigned m = 0u;
-    if (in && px < wi[w].npx) {
-      uint4 xv = xs[t * cps + cc];
-      T* sptr = st + wi[w].soff + (long long)px * sp + cc * VEC;
-      const uint4 sv = ld16(sptr);
-      if (tail && cc == cpv - 1) xv = merge_tail<T, VEC>(xv, sv, tail);
-      if (Chunk<T>::changed(sv, xv, thr)) m = 1u << px;
-      if (UPDATE == CB_UPDATE_ALL) store_state<T>(sptr, xv, aux, wi[w].pix + px, cc * VEC);
+  // U chunk-iterations are batched: all U state loads of a batch are issued before the first
+  // warp-wide flag reduction (the shuffles would otherwise serialise them, one DRAM latency each)
+  constexpr int U = 4;
+  for (int q0 = 0; q0 < nq; q0 += 256 * U) {
+    uint4 xv[U], sv[U];
+    T* sptr[U];
+    int ws_[U], pxs[U], ccs[U];
+    bool act[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int qi = q0 + u * 256 + (int)threadIdx.x;
+      const int q = min(qi, nq - 1);                             // (clamped lanes take no part below)
+      const int t = cpv == 1 ? q : (int)__umulhi((unsigned)q, cpv_magic), cc = q - t * cpv;
+      const int w = t >> 5, px = t & 31;
+      ws_[u] = w; pxs[u] = px; ccs[u] = cc;
+      act[u] = qi < nq && px < wi[w].npx;
+      sptr[u] = st + wi[w].soff + (long long)px * sp + cc * VEC;
+      if (act[u]) {
+        sv[u] = ld16(sptr[u]);
+        xv[u] = xs[t * cps + cc];
+      }
     }
-    planar_flag(s_word, w, m);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (q0 + u * 256 >= nq) break;                             // block-uniform
+      unsigned m = 0u;
+      if (act[u]) {
+        if (tail && ccs[u] == cpv - 1) xv[u] = merge_tail<T, VEC>(xv[u], sv[u], tail);
+        if (Chunk<T>::changed(sv[u], xv[u], thr)) m = 1u << pxs[u];
+        if (UPDATE == CB_UPDATE_ALL) store_state<T>(sptr[u], xv[u], aux, wi[ws_[u]].pix + pxs[u], ccs[u] * VEC);
+      }
+      planar_flag(s_word, ws_[u], m);
+    }
   }
   __syncthreads();
   if (threadIdx.x < (unsigned)nw && wi[threadIdx.x].npx > 0) bits[word0 + threadIdx.x] = s_word[threadIdx.x];

@@ -169,3 +169,18 @@ def test_bench_reference_arm_is_product_free():
     import json
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["config"]["streams_per_gpu"] == 2 and line["gpu_launches"] == 0
+
+
+def test_compat_shim_exports_the_reference_symbols():
+    """the three libraries the unmodified reference dlopens (pycbinfer/conv2d_cg.py:44,50,
+    conv2d_fg.py:31), built from csrc/compat_shim.cu: every symbol of the reference's cdef headers
+    (conv2d_cg.py:6-38, conv2d_fg.py:13-24; conv2d_fg_cpu is the reference's CPU path: not built) resolves"""
+    import ctypes
+    from cbinfer_b200 import build
+    libs = build.build_compat()
+    cg = ["changeDetection", "changePropagation", "genXMatrix", "updateOutput", "maxPool2d"]
+    for name, syms in (("cbconv2d_cg_backend", cg), ("cbconv2d_cg_half_backend", cg),
+                       ("cbconv2d_fg_backend", ["changeDetectionFG", "updateOutputFG"])):
+        lib = ctypes.CDLL(libs[name])
+        for sname in syms:
+            assert getattr(lib, sname) is not None
