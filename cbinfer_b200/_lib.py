@@ -26,7 +26,7 @@ SYMBOLS = [
     "cb_dilate_compact", "cb_map_to_bits", "cb_change_detect_sparse", "cb_pool_compact", "cb_maxpool2x2_detect",
     "cb_detect_compact_ws_bytes", "cb_detect_compact_sparse", "cb_pack_weights", "cb_conv_ws_bytes", "cb_conv_update", "cb_conv_update_masked", "cb_maxpool2x2",
     "cb_gen_xmatrix", "cb_matrix_mult", "cb_update_output", "cb_fg_update",
-    "cb_fg_detect", "cb_conv_accumulate",
+    "cb_fg_detect", "cb_conv_accumulate", "cb_compact_small_max_words", "cb_change_detect_sparse_compact",
     "cb_tile_ws_bytes", "cb_dilate_compact_tiles", "cb_conv_tiled_supported", "cb_conv_update_tiled",
     "cb_conv_tiled_pool_supported", "cb_conv_update_tiled_pool", "cb_dilate_tiles",
     "cb_tail_supported", "cb_tail_update",
@@ -78,6 +78,10 @@ def _load():
         "cb_map_to_bits": (i32, [vp, vp, vp, i32, i32, i32]),
         "cb_change_detect_sparse": (i32, [vp, i32, vp, i64, i64, i64, i64, vp, i64, i64, i64, i64, i32,
                                           vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, i32, i32]),
+        "cb_compact_small_max_words": (i32, []),
+        "cb_change_detect_sparse_compact": (i32, [vp, i32, vp, i64, i64, i64, i64, vp, i64, i64, i64, i64, i32,
+                                                  vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, i32, i32,
+                                                  vp, vp, vp, vp, i32, i32, i32]),
         "cb_detect_compact_ws_bytes": (sz, [i32, i32, i32]),
         "cb_detect_compact_sparse": (i32, [vp, i32, vp, i64, i64, i64, i64, vp, i64, i64, i64, i64, i32,
                                            vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, i32]),

@@ -507,6 +507,7 @@ class CBConv2d(nn.Module):
             masked = (candidates is not None and not detected and tuple(self.kernel_size) == (1, 1)
                       and getattr(self, 'maskedConv', False) and not fused11
                       and not self.saveChangeMap and gemm != _lib.GEMM_SIMT_F32)
+            fusedSmall = False
             if detected:
                 pass                     # the upstream pool kernel already did it
             elif fused11:
@@ -516,6 +517,17 @@ class CBConv2d(nn.Module):
                                               dtype=torch.uint8, device=dev)
                 cg.detect_compact_sparse(input, self.prevInput, self.threshold, mode, candidates,
                                          s["idx"], s["count"], s["dcs_ws"], aux=aux_arg)
+            elif candidates is not None and not masked and not use_tiles and not self.saveChangeMap \
+                    and input.stride(1) == 1 and self._smallMap(B, H, W):
+                # small map: candidate detection + dilation + ordered compaction in ONE launch (the
+                # last block of the detection kernel compacts), cb_change_detect_sparse_compact
+                if "sdc_sync" not in s:
+                    s["sdc_sync"] = torch.zeros(1, dtype=torch.int32, device=dev)
+                cg.detect_sparse_compact(input, self.prevInput, s["raw_bits"], self.threshold, mode, candidates,
+                                         self.kernel_size, s["idx"], s["count"], s["sdc_sync"], aux=aux_arg,
+                                         bits_are_clear=s.get("raw_clear", False), dil_bits=s["dil_bits"],
+                                         clear_raw=sparse_next)
+                fusedSmall = True
             elif candidates is not None:
                 cg.detect_sparse(input, self.prevInput, s["raw_bits"], self.threshold, mode,
                                  candidates, aux=aux_arg,
@@ -534,6 +546,9 @@ class CBConv2d(nn.Module):
             if not detected and fused11:
                 s["raw_clear"] = False
                 changeIndexes = ChangeIndexes(s["idx"], s["count"], (B, H, W), bits=None)
+            elif fusedSmall:
+                s["raw_clear"] = sparse_next
+                changeIndexes = ChangeIndexes(s["idx"], s["count"], (B, H, W), bits=s["dil_bits"])
             elif mask is not None:
                 s["raw_clear"] = True                # the masked contraction clears the bitmap
                 changeIndexes = ChangeIndexes(candidates.buffer, candidates.count, (B, H, W), bits=None)
@@ -702,6 +717,12 @@ class CBConv2d(nn.Module):
         self._lastThr = self.threshold
         self._inVersion = self.prevInput._version
         return 'changeIndexes', input, DetectionDone(self, dense=True)
+
+    def _smallMap(self, B, H, W):
+        """bitmap small enough for the one-launch detection + compaction (cb_change_detect_sparse_compact)?"""
+        if os.environ.get("CBINFER_FUSE_SMALL", "1") == "0":
+            return False
+        return 0 < _lib.C.cb_bitmap_words(B, H, W) <= _lib.C.cb_compact_small_max_words()
 
     def _useTiles(self, dt, gemm, shape):
         """tile path for this layer / shape?  (tileMode 'auto': where the library recommends it)"""

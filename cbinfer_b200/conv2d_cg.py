@@ -166,6 +166,23 @@ def detect_sparse(x, state, raw_bits, threshold, update_mode, candidates, aux=No
                                     int(update_mode), int(bool(bits_are_clear))))
 
 
+def detect_sparse_compact(x, state, raw_bits, threshold, update_mode, candidates, filtSize, idx, count, sync,
+                          aux=None, bits_are_clear=False, dil_bits=None, clear_raw=False):
+    """cb_change_detect_sparse_compact: candidate detection + dilation + ordered compaction in one launch
+    (small maps: at most cb_compact_small_max_words() bitmap words).  `sync` = int32[1], zeroed once."""
+    require_cuda(x, state, raw_bits)
+    B, Cc, H, W = x.shape
+    assert state.shape == x.shape and state.dtype == x.dtype
+    assert tuple(candidates.shape) == (B, H, W)
+    mode, hi, lo = _aux_args(aux, state)
+    check(C.cb_change_detect_sparse_compact(
+        stream_ptr(x.device), dtype_code(x), x.data_ptr(), *_strides4(x), state.data_ptr(), *_strides4(state),
+        mode, hi, lo, candidates.buffer.data_ptr(), candidates.count.data_ptr(), raw_bits.data_ptr(), B, Cc, H, W,
+        float(threshold), int(update_mode), int(bool(bits_are_clear)),
+        dil_bits.data_ptr() if dil_bits is not None else None, idx.data_ptr(), count.data_ptr(), sync.data_ptr(),
+        (filtSize[0] - 1) // 2, (filtSize[1] - 1) // 2, int(bool(clear_raw))))
+
+
 def detect_compact_sparse(x, state, threshold, update_mode, candidates, idx, count, ws, aux=None,
                           bits=None):
     """cb_detect_compact_sparse: candidate detection + ordered compaction in one launch (layers

@@ -238,6 +238,36 @@ int cb_change_detect_sparse(void* stream, int dtype, const void* x, long long x_
   return 0;
 }
 
+int cb_compact_small_max_words(void) { return cb::kCompactWin; }
+
+int cb_change_detect_sparse_compact(void* stream, int dtype, const void* x, long long x_sb, long long x_sc,
+                                    long long x_sy, long long x_sx, void* state, long long s_sb,
+                                    long long s_sc, long long s_sy, long long s_sx, int aux_mode,
+                                    void* aux_hi, void* aux_lo, const int32_t* candidates,
+                                    const int32_t* n_candidates, uint32_t* raw_bits, int B, int C, int H,
+                                    int W, float threshold, int update_mode, int bits_are_clear,
+                                    uint32_t* dil_bits, int32_t* idx, int32_t* count, void* sync_ws,
+                                    int kHHalf, int kWHalf, int clear_raw) {
+  CB_CHECK_ARG(x && state && raw_bits && candidates && n_candidates && idx && count && sync_ws,
+               "change_detect_sparse_compact: null pointer");
+  CB_CHECK_ARG(B >= 0 && C > 0 && H >= 0 && W >= 0, "change_detect_sparse_compact: bad shape");
+  CB_CHECK_ARG(kHHalf >= 0 && kWHalf >= 0 && kWHalf <= 31, "change_detect_sparse_compact: kWHalf must be <= 31");
+  CB_CHECK_ARG(raw_bits != dil_bits, "change_detect_sparse_compact: dil_bits must not alias raw_bits");
+  const long long nwords = (long long)cb_bitmap_words(B, H, W);
+  if (nwords == 0) {
+    cudaMemsetAsync(count, 0, sizeof(int32_t), (cudaStream_t)stream);
+    return 0;
+  }
+  CB_CHECK_ARG(nwords <= cb::kCompactWin, "change_detect_sparse_compact: bitmap of %lld words > %d", nwords,
+               cb::kCompactWin);
+  cb::FusedCompact fc{dil_bits, idx, count, (unsigned*)sync_ws, kHHalf, kWHalf, (int)nwords, clear_raw};
+  CB_DISPATCH_DTYPE(dtype, return (launch_detect_sparse<T, VEC>(
+                               (cudaStream_t)stream, x, x_sb, x_sc, x_sy, x_sx, state, s_sb, s_sc,
+                               s_sy, s_sx, aux_mode, aux_hi, aux_lo, candidates, n_candidates, raw_bits,
+                               B, C, H, W, threshold, update_mode, bits_are_clear, &fc)));
+  return 0;
+}
+
 int cb_map_to_bits(void* stream, const int8_t* map, uint32_t* bits, int B, int H, int W) {
   CB_CHECK_ARG(map && bits, "map_to_bits: null pointer");
   const long long nwords = (long long)cb_bitmap_words(B, H, W);

@@ -26,7 +26,7 @@ constexpr int kCompactTile = kCompactThreads * kCompactWPT;  // words per tile (
 constexpr int kCompactWin = 6144;                            // staged raw window (words, 24 KB)
 
 struct CompactHeader {                         // first 16 bytes of the workspace
-  unsigned reserved, done, epoch, pad;
+  unsigned reserved, done, epoch, ticket;
 };
 
 __host__ __device__ inline size_t compact_ws_bytes(size_t nwords) {
@@ -91,8 +91,10 @@ __device__ __forceinline__ unsigned pooled_word(const uint32_t* __restrict__ raw
   return d;
 }
 
-// Tiles are taken in blockIdx order (blocks are dispatched in index order, so every predecessor of
-// a running tile is running or finished and the look-back cannot starve).
+// List mode: tiles are taken by ticket (atomicAdd on the header's `ticket`), not by blockIdx -- every
+// predecessor of a running tile then holds an earlier ticket, i.e. is running or finished, whatever
+// order the hardware dispatches blocks in, so the look-back cannot starve (as in CUB's single-pass
+// scan).  Tile-only mode has no scan across tiles and keeps blockIdx.
 __global__ void __launch_bounds__(kCompactThreads)
 dilate_compact_kernel(const uint32_t* __restrict__ raw, uint32_t* __restrict__ dil_bits,
                       int8_t* __restrict__ dil_map, int32_t* __restrict__ idx,
@@ -110,7 +112,13 @@ dilate_compact_kernel(const uint32_t* __restrict__ raw, uint32_t* __restrict__ d
   __shared__ uint32_t s_win[kCompactWin];
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int tile = blockIdx.x;
+  int tile = blockIdx.x;
+  if (!no_list && ntiles > 1) {
+    if (tid == 0) s_base = (int)atomicAdd(&hdr->ticket, 1u);
+    __syncthreads();
+    tile = s_base;
+    __syncthreads();
+  }
   const unsigned epoch = *reinterpret_cast<volatile unsigned*>(&hdr->epoch);
   const unsigned tag = epoch % 0x3ffffffeu + 1u;
 
@@ -312,6 +320,7 @@ dilate_compact_kernel(const uint32_t* __restrict__ raw, uint32_t* __restrict__ d
     s_last = prev == (unsigned)ntiles - 1u;
     if (s_last) {
       hdr->done = 0;
+      hdr->ticket = 0;
       if (no_list) {                            // every block added its popcounts before its done-increment
         *count = (int32_t)*reinterpret_cast<volatile unsigned*>(&hdr->reserved);
         hdr->reserved = 0;
@@ -331,6 +340,60 @@ dilate_compact_kernel(const uint32_t* __restrict__ raw, uint32_t* __restrict__ d
     if (s_last)
       for (int i = tid; i < nwords; i += kCompactThreads) clear_bits[i] = 0u;
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// block_dilate_compact -- dilation + ordered compaction of a SMALL bitmap (<= kCompactWin words, e.g. one
+// 368 x 368 map or eight 46 x 46 maps) by ONE thread block, called by the last block of the kernel that
+// produced the raw bitmap (detect_sparse_vec_kernel<.., FUSE>): a layer on a small map then needs two
+// launches per frame (detect + compact, contraction) instead of three -- such layers are bound by the
+// dependent-launch chain, not by bytes (pose network: 92 layers of <= 4416 bitmap words at batch 1).
+// Same results as dilate_compact_kernel: dilated bitmap, ascending index list, count; optional
+// zeroing of the raw bitmap.  All threads of the block must call it; `s_win` holds kCompactWin words.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void block_dilate_compact(uint32_t* __restrict__ raw, uint32_t* __restrict__ dil_bits,
+                                                     int32_t* __restrict__ idx, int32_t* __restrict__ count,
+                                                     uint32_t* s_win, int* s_warp, int H, int W, int Wd,
+                                                     int kh, int kw, int nwords, bool clear) {
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, wid = tid >> 5, nwarp = nthr >> 5;
+  for (int i = tid; i < nwords; i += nthr) s_win[i] = __ldcg(raw + i);     // (written by other blocks: L2)
+  __syncthreads();
+  const int wpt = (nwords + nthr - 1) / nthr;                              // consecutive words per thread
+  const int w0 = tid * wpt, w1 = min(nwords, w0 + wpt);
+  int cnt = 0;
+  for (int w = w0; w < w1; ++w) {
+    const int j = w % Wd, r = w / Wd;
+    const unsigned d = dilated_word(s_win, 0, r, r % H, j, H, W, Wd, kh, kw);
+    if (dil_bits) dil_bits[w] = d;
+    cnt += __popc(d);
+  }
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) s_warp[wid] = incl;
+  __syncthreads();
+  int woff = 0, total = 0;
+  for (int q = 0; q < nwarp; ++q) {
+    const int v = s_warp[q];
+    if (q < wid) woff += v;
+    total += v;
+  }
+  int o = woff + incl - cnt;
+  for (int w = w0; w < w1; ++w) {
+    const int j = w % Wd, r = w / Wd;
+    unsigned d = dilated_word(s_win, 0, r, r % H, j, H, W, Wd, kh, kw);
+    const int pix0 = r * W + j * 32;
+    while (d) {
+      idx[o++] = pix0 + __ffs(d) - 1;
+      d &= d - 1;
+    }
+  }
+  if (tid == 0) *count = total;
+  if (clear)
+    for (int i = tid; i < nwords; i += nthr) raw[i] = 0u;
 }
 
 // ------------------------------------------------------------------------------------------------

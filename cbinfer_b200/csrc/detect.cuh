@@ -13,6 +13,7 @@
 // HBM-bound: algorithmic bytes = 2*C*P*s read (+ P/8 bitmap, + feedback writes).
 #pragma once
 #include "cb_common.cuh"
+#include "compact.cuh"
 
 namespace cb {
 
@@ -271,7 +272,7 @@ __device__ __forceinline__ void planar_load_tile(uint4* xs, const PlanarWord* wi
                                                  long long x_sc, long long x_sx, int nw, int cpv, int cps,
                                                  int C, unsigned cpv_magic) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#pragma unroll 4
+#pragma unroll 2
   for (int p = wid; p < nw * cpv; p += 8) {
     const int w = cpv == 1 ? p : (int)__umulhi((unsigned)p, cpv_magic), cc = p - w * cpv;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
@@ -318,39 +319,21 @@ detect_planar_kernel(const T* __restrict__ x, long long x_sb, long long x_sc, lo
   planar_load_tile<T, VEC>(xs, wi, x, x_sc, 1, nw, cpv, cps, C, cpv_magic);
   __syncthreads();
   const int nq = nw * 32 * cpv;
-  // U chunk-iterations are batched: all U state loads of a batch are issued before the first
-  // warp-wide flag reduction (the shuffles would otherwise serialise them, one DRAM latency each)
-  constexpr int U = 4;
-  for (int q0 = 0; q0 < nq; q0 += 256 * U) {
-    uint4 xv[U], sv[U];
-    T* sptr[U];
-    int ws_[U], pxs[U], ccs[U];
-    bool act[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int qi = q0 + u * 256 + (int)threadIdx.x;
-      const int q = min(qi, nq - 1);                             // (clamped lanes take no part below)
-      const int t = cpv == 1 ? q : (int)__umulhi((unsigned)q, cpv_magic), cc = q - t * cpv;
-      const int w = t >> 5, px = t & 31;
-      ws_[u] = w; pxs[u] = px; ccs[u] = cc;
-      act[u] = qi < nq && px < wi[w].npx;
-      sptr[u] = st + wi[w].soff + (long long)px * sp + cc * VEC;
-      if (act[u]) {
-        sv[u] = ld16(sptr[u]);
-        xv[u] = xs[t * cps + cc];
-      }
+  for (int q0 = 0; q0 < nq; q0 += 256) {
+    const int q = min(q0 + (int)threadIdx.x, nq - 1);            // (clamped lanes take no part below)
+    const bool in = q0 + (int)threadIdx.x < nq;
+    const int t = cpv == 1 ? q : (int)__umulhi((unsigned)q, cpv_magic), cc = q - t * cpv;
+    const int w = t >> 5, px = t & 31;
+    unsigned m = 0u;
+    if (in && px < wi[w].npx) {
+      uint4 xv = xs[t * cps + cc];
+      T* sptr = st + wi[w].soff + (long long)px * sp + cc * VEC;
+      const uint4 sv = ld16(sptr);
+      if (tail && cc == cpv - 1) xv = merge_tail<T, VEC>(xv, sv, tail);
+      if (Chunk<T>::changed(sv, xv, thr)) m = 1u << px;
+      if (UPDATE == CB_UPDATE_ALL) store_state<T>(sptr, xv, aux, wi[w].pix + px, cc * VEC);
     }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (q0 + u * 256 >= nq) break;                             // block-uniform
-      unsigned m = 0u;
-      if (act[u]) {
-        if (tail && ccs[u] == cpv - 1) xv[u] = merge_tail<T, VEC>(xv[u], sv[u], tail);
-        if (Chunk<T>::changed(sv[u], xv[u], thr)) m = 1u << pxs[u];
-        if (UPDATE == CB_UPDATE_ALL) store_state<T>(sptr[u], xv[u], aux, wi[ws_[u]].pix + pxs[u], ccs[u] * VEC);
-      }
-      planar_flag(s_word, ws_[u], m);
-    }
+    planar_flag(s_word, w, m);
   }
   __syncthreads();
   if (threadIdx.x < (unsigned)nw && wi[threadIdx.x].npx > 0) bits[word0 + threadIdx.x] = s_word[threadIdx.x];
@@ -602,13 +585,22 @@ inline int launch_detect_u8(cudaStream_t stream, const void* x, long long x_sb, 
 // A group of 1 << glog lanes owns one candidate (16-byte chunks, pixel-major); set bits are
 // OR-ed into the pre-zeroed bitmap.
 // ------------------------------------------------------------------------------------------------
-template <typename T, int VEC, int UPDATE>
+// FUSE: the last block to finish also dilates and compacts the (small) bitmap, see block_dilate_compact
+struct FusedCompact {
+  uint32_t* dil_bits;
+  int32_t* idx;
+  int32_t* count;
+  unsigned* sync;                // one word, zero at rest: blocks done
+  int kh, kw, nwords, clear;
+};
+
+template <typename T, int VEC, int UPDATE, bool FUSE = false>
 __global__ void __launch_bounds__(256)
 detect_sparse_vec_kernel(const T* __restrict__ x, long long x_sb, long long x_sy, int xp,
                          T* __restrict__ st, long long s_sb, long long s_sy, int sp,
                          AuxPlanes aux, const int32_t* __restrict__ cand,
                          const int32_t* __restrict__ ncand, uint32_t* __restrict__ bits, int H,
-                         int W, int C, int Wd, T thr, int glog) {
+                         int W, int C, int Wd, T thr, int glog, FusedCompact fc) {
   pdl_prologue();
   const int n = *ncand;
   const int lane = threadIdx.x & 31;
@@ -655,6 +647,22 @@ detect_sparse_vec_kernel(const T* __restrict__ x, long long x_sb, long long x_sy
       }
     }
   }
+  if (FUSE) {
+    __shared__ uint32_t s_win[kCompactWin];
+    __shared__ int s_warp[8];
+    __shared__ unsigned s_last;
+    __threadfence();                                          // my bitmap bits precede my done-increment
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      s_last = atomicAdd(fc.sync, 1u) == gridDim.x - 1u;
+      if (s_last) *fc.sync = 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    block_dilate_compact(bits, fc.dil_bits, fc.idx, fc.count, s_win, s_warp, H, W, Wd, fc.kh, fc.kw, fc.nwords,
+                         fc.clear != 0);
+  }
 }
 
 template <typename T, int UPDATE>
@@ -693,7 +701,8 @@ int launch_detect_sparse(cudaStream_t stream, const void* x, long long x_sb, lon
                          long long x_sy, long long x_sx, void* state, long long s_sb,
                          long long s_sc, long long s_sy, long long s_sx, int aux_mode,
                          void* aux_hi, void* aux_lo, const int32_t* cand, const int32_t* ncand, uint32_t* bits, int B, int C,
-                         int H, int W, float threshold, int update, int bits_are_clear) {
+                         int H, int W, float threshold, int update, int bits_are_clear,
+                         const FusedCompact* fuse = nullptr) {
   const int Wd = (W + 31) / 32;
   const long long words = (long long)B * H * Wd;
   if (words == 0) return 0;
@@ -708,16 +717,30 @@ int launch_detect_sparse(cudaStream_t stream, const void* x, long long x_sb, lon
                       ((x_sb * es) % 16) == 0 && ((s_sb * es) % 16) == 0 &&
                       ((uintptr_t)x % 16) == 0 && ((uintptr_t)state % 16) == 0 &&
                       x_sx < (1ll << 30) && s_sx < (1ll << 30);
-  const unsigned grid = (unsigned)(sm_count() * 16);
+  unsigned grid = (unsigned)(sm_count() * 16);
   const int cpv = (C + VEC - 1) / VEC;
   int glog = 0;
   while ((1 << glog) < cpv && glog < 5) ++glog;
   glog = cb::glog_tuned(glog);
+  {
+    // small maps: no more blocks than there are pixels to look at (every block of the fused variant
+    // passes through one atomic)
+    const long long ppb = (long long)(32 >> glog) * 8;         // candidates per block and round
+    const long long need = ((long long)B * H * W + ppb - 1) / ppb;
+    if (need < (long long)grid) grid = (unsigned)(need < 1 ? 1 : need);
+  }
+  CB_CHECK_ARG(!fuse || (vec_ok && words <= kCompactWin), "change_detect_sparse_compact: needs pixel-major "
+               "tensors and a bitmap of at most %d words", kCompactWin);
+  FusedCompact fc = fuse ? *fuse : FusedCompact{nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0};
 #define CB_DETS(U_)                                                                              \
-  if (vec_ok)                                                                                    \
-    cb::launch_pdl(detect_sparse_vec_kernel<T, VEC, U_>, grid, 256, 0, stream,                               \
+  if (vec_ok && fuse)                                                                            \
+    cb::launch_pdl(detect_sparse_vec_kernel<T, VEC, U_, true>, grid, 256, 0, stream,                         \
         (const T*)x, x_sb, x_sy, (int)x_sx, (T*)state, s_sb, s_sy, (int)s_sx, aux, cand,      \
-        ncand, bits, H, W, C, Wd, thr, glog);                                                    \
+        ncand, bits, H, W, C, Wd, thr, glog, fc);                                                \
+  else if (vec_ok)                                                                               \
+    cb::launch_pdl(detect_sparse_vec_kernel<T, VEC, U_, false>, grid, 256, 0, stream,                        \
+        (const T*)x, x_sb, x_sy, (int)x_sx, (T*)state, s_sb, s_sy, (int)s_sx, aux, cand,      \
+        ncand, bits, H, W, C, Wd, thr, glog, fc);                                                \
   else                                                                                           \
     cb::launch_pdl(detect_sparse_generic_kernel<T, U_>, grid, 256, 0, stream,                                \
         (const T*)x, x_sb, x_sc, x_sy, x_sx, (T*)state, s_sb, s_sc, s_sy, s_sx, aux, cand,    \

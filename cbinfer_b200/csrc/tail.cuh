@@ -132,14 +132,20 @@ tail_kernel(const __grid_constant__ CUtensorMap w1map, const __grid_constant__ C
     {
       constexpr int RPW = TAIL_ROWS / (TAIL_THREADS / 32);   // 8 rows per warp
       constexpr int RB = 4;                                  // rows in flight per batch
+      // the warp's 8 candidate indices in one load (lane i holds row i's): the row loads of both
+      // batches then depend on ONE index round trip instead of one per batch
+      int mypix = -1;
+      {
+        const int j = tile * TAIL_ROWS + warp * RPW + lane;
+        if (lane < RPW && j < n) mypix = __ldg(a.cand + j);
+      }
 #pragma unroll 1
       for (int r0 = 0; r0 < RPW; r0 += RB) {
         uint4 xv[RB][2], sv[RB][2];
         int pix[RB];
 #pragma unroll
         for (int i = 0; i < RB; ++i) {
-          const int j = tile * TAIL_ROWS + warp * RPW + r0 + i;
-          pix[i] = j < n ? __ldg(a.cand + j) : -1;
+          pix[i] = __shfl_sync(0xffffffffu, mypix, r0 + i);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int c = lane + 32 * h;
@@ -213,12 +219,18 @@ tail_kernel(const __grid_constant__ CUtensorMap w1map, const __grid_constant__ C
     if (warp < 4) {
       const int row = warp * 32 + lane;
       pix1 = ctrl->flag1[row];
+      float* o1 = a.out1 + (long long)(pix1 < 0 ? 0 : pix1) * a.p1;
+      float* s2 = a.st2 + (long long)(pix1 < 0 ? 0 : pix1) * a.p1;
+      // layer 2's state row (<= 64 channels) is fetched while layer 1's MMAs run: one memory round trip
+      // for the whole row instead of one per 16-column slice of the accumulator
+      uint4 s2v[N1 / 4];
+#pragma unroll
+      for (int i = 0; i < N1 / 4; ++i)
+        s2v[i] = (pix1 >= 0 && 4 * i < a.C1) ? ld16(s2 + 4 * i) : make_uint4(0, 0, 0, 0);
       mbar_wait(&ctrl->mma1, par);
       tc_fence_after();
       const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-      float* o1 = a.out1 + (long long)(pix1 < 0 ? 0 : pix1) * a.p1;
-      float* s2 = a.st2 + (long long)(pix1 < 0 ? 0 : pix1) * a.p1;
-#pragma unroll 1
+#pragma unroll
       for (int c0 = 0; c0 < N1; c0 += 16) {
         uint32_t acc[16];
         tmem_ld16(trow + (uint32_t)c0, acc);
@@ -236,7 +248,7 @@ tail_kernel(const __grid_constant__ CUtensorMap w1map, const __grid_constant__ C
             const uint4 v = make_uint4(__float_as_uint(f[i]), __float_as_uint(f[i + 1]), __float_as_uint(f[i + 2]),
                                        __float_as_uint(f[i + 3]));
             st16(o1 + c0 + i, v);
-            const uint4 sv = ld16(s2 + c0 + i);
+            const uint4 sv = s2v[(c0 + i) >> 2];
             f2 |= Chunk<float>::changed(sv, v, a.thr2);
             if (a.update == CB_UPDATE_ALL) st16(s2 + c0 + i, v);
           }

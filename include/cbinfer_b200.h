@@ -149,6 +149,22 @@ int cb_change_detect_sparse(void* stream, int dtype,
                             uint32_t* raw_bits, int B, int C, int H, int W, float threshold,
                             int update_mode, int bits_are_clear);
 
+/* Small maps (bitmap of at most cb_compact_small_max_words() words, e.g. one 368 x 368 map or eight
+ * 46 x 46 maps): cb_change_detect_sparse and cb_dilate_compact in ONE launch -- the last block of the
+ * detection kernel dilates and compacts the bitmap (dil_bits optional, idx / count as cb_dilate_compact,
+ * sync_ws = 4 bytes of zeroed device memory, left zero).  Same results as the two calls; a layer on a
+ * small map is bound by its dependent-launch chain (reference: ~10 launches + a host sync per layer,
+ * conv2d.py:222-251), so this takes it from three launches per frame to two.  Pixel-major tensors. */
+int cb_compact_small_max_words(void);
+int cb_change_detect_sparse_compact(void* stream, int dtype, const void* x, long long x_sb, long long x_sc,
+                                    long long x_sy, long long x_sx, void* state, long long s_sb,
+                                    long long s_sc, long long s_sy, long long s_sx, int aux_mode,
+                                    void* aux_hi, void* aux_lo, const int32_t* candidates,
+                                    const int32_t* n_candidates, uint32_t* raw_bits, int B, int C, int H,
+                                    int W, float threshold, int update_mode, int bits_are_clear,
+                                    uint32_t* dil_bits, int32_t* idx, int32_t* count, void* sync_ws,
+                                    int kHHalf, int kWHalf, int clear_raw);
+
 /* cb_change_detect_sparse + ordered compaction in ONE launch, for layers whose change set needs no
  * dilation (1x1 kernels): idx[0..n) = the candidates that exceed the threshold, in candidate
  * order, *count = n; state / planes maintained as usual; `bits` (optional, pre-cleared) receives

@@ -264,6 +264,53 @@ def test_candidate_detection_equals_dense_scan(feedback, dt, save_maps):
                 assert torch.equal(a.outputState, b.outputState), t
 
 
+@pytest.mark.parametrize("dt", ["f32", "f16"])
+@pytest.mark.parametrize("case", [(2, 40, 13, 37, 3), (1, 128, 46, 46, 7), (8, 16, 46, 46, 7), (1, 8, 368, 368, 3),
+                                  (3, 5, 9, 70, 1), (1, 4, 1, 1, 3)])
+def test_fused_small_map_detect_compact_equals_two_launches(dt, case):
+    """cb_change_detect_sparse_compact (the last block of the candidate detection dilates and compacts a
+    small bitmap) == cb_change_detect_sparse + cb_dilate_compact: raw / dilated bitmaps, ascending index
+    list, count, feedback state; with and without clearing the raw bitmap; repeated calls (self-cleaning)."""
+    from cbinfer_b200 import _lib, conv2d_cg as cg
+    B, C, H, W, k = case
+    shape = (B, C, H, W)
+    prev = rand_tensor(shape, dt, 1)
+    x = perturb(prev, 0.1, 2)
+    g = torch.Generator().manual_seed(4)
+    cmask = (torch.rand(B, H, W, generator=g) < 0.4).to(torch.int8).cuda()      # candidates: a subset of the pixels
+    for update in (_lib.UPDATE_CHANGED, _lib.UPDATE_ALL, _lib.UPDATE_NONE):
+        for clear in (False, True):
+            res = []
+            for fused in (False, True):
+                st, _ = cg.pixel_major(shape, TORCH_DT[dt], "cuda", 0)
+                st.copy_(prev)
+                xv, _ = cg.pixel_major(shape, TORCH_DT[dt], "cuda", 0)
+                xv.copy_(x)
+                s = cg.alloc_scratch((B, H, W), "cuda")
+                cand = cg.changeIndexesExtr(cmask, lazy=True)
+                sync = torch.zeros(1, dtype=torch.int32, device="cuda")
+                for rep in range(2):
+                    if rep == 1 and update != _lib.UPDATE_NONE:
+                        break                                   # (the state moved: a second pass differs by design)
+                    if fused:
+                        cg.detect_sparse_compact(xv, st, s["raw_bits"], 0.3, update, cand, (k, k), s["idx"], s["count"],
+                                                 sync, bits_are_clear=(rep == 0 or clear), dil_bits=s["dil_bits"],
+                                                 clear_raw=clear)
+                    else:
+                        cg.detect_sparse(xv, st, s["raw_bits"], 0.3, update, cand, bits_are_clear=(rep == 0 or clear))
+                        cg.dilate_compact(s["raw_bits"], (B, H, W), (k, k), s["idx"], s["count"], s["ws"],
+                                          dil_bits=s["dil_bits"], clear_raw=clear)
+                n = int(s["count"].item())
+                res.append((n, s["idx"][:n].clone(), s["dil_bits"].clone(), s["raw_bits"].clone(), st.clone()))
+                assert int(sync.item()) == 0
+            assert res[0][0] == res[1][0], (update, clear)
+            for a, b in zip(res[0][1:], res[1][1:]):
+                assert torch.equal(a, b), (update, clear)
+            assert res[0][0] > 0 or H * W == 1
+            if clear:
+                assert int(res[1][3].abs().sum()) == 0
+
+
 def test_pool_compact_and_sparse_detect_ops():
     from cbinfer_b200 import _lib, conv2d_cg as cg
     g = torch.Generator().manual_seed(3)
