@@ -677,6 +677,22 @@ def main():
         except Exception as e:                                   # never lose the headline line
             result["roofline_error"] = repr(e)
         try:
+            ins = kernels_in_step(args, model, frames)
+            result["kernels_in_step"] = ins
+            rf = result.get("roofline")
+            if rf and rf.get("bound") == "tensor":
+                # the dominant kernel as it runs INSIDE a step (cold data), next to the warm replay figure
+                us = next((r["us"] for r in ins["launches"] if "%s[%s]" % (r["kernel"], r["layer"]) == rf["kernel"]), None)
+                if us:
+                    flops = next(r["flops"] for r in result["kernels"]
+                                 if "%s[%s]" % (r["kernel"], r["layer"]) == rf["kernel"])
+                    rf["in_step"] = {"us": us, "achieved": round(flops / (us * 1e-6) / 1e12, 2),
+                                     "frac": flops / (us * 1e-6) / 1e12 / rf["peak"],
+                                     "note": "timed by external event nodes inside the step's graph; includes ~%.0f us of "
+                                             "event-node overhead per launch" % ins["event_overhead_us_per_launch"]}
+        except Exception as e:
+            result["kernels_in_step_error"] = repr(e)
+        try:
             result["dense_cudnn"] = dense_gpu(args, base, frames, dev)
         except Exception as e:
             result["dense_cudnn_error"] = repr(e)
@@ -699,6 +715,96 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def kernels_in_step(args, model, frames, reps=40):
+    """Every launch of a step timed INSIDE the step: the step's CUDA graph is captured with external
+    timing events recorded as graph nodes around each C-ABI call, so each kernel runs on the inputs and in
+    the cache state it really sees (the back-to-back replays of kernel_roofline run warm).  The event nodes
+    cost a few microseconds per launch: the instrumented step is reported next to the plain one."""
+    import torch
+    import cbinfer_b200 as cb
+    from cbinfer_b200 import conv2d_cg as cg
+    cb.clearMemory(model)
+    fr = frames[:8]
+    so = SceneStep(model, fr[0], fr[1])
+    plain = [so.capture_slot(f) for f in fr]
+    names = ("detect", "detect_u8", "detect_sparse", "detect_sparse_compact", "dilate_compact", "dilate_tiles",
+             "pool_compact", "conv_update", "conv_update_tiled", "tail_update", "maxPool2d", "maxPool2d_detect",
+             "detect_compact_sparse")
+    orig = {n: getattr(cg, n) for n in names}
+    cur = {"layer": None, "log": None}
+
+    def wrap(name):
+        fn = orig[name]
+
+        def w(*a, **k):
+            e0 = torch.cuda.Event(enable_timing=True, external=True)
+            e1 = torch.cuda.Event(enable_timing=True, external=True)
+            e0.record()
+            r = fn(*a, **k)
+            e1.record()
+            cur["log"].append((cur["layer"], name, e0, e1))
+            return r
+        return w
+
+    hooks = [m.register_forward_pre_hook(lambda mod, inp, ln=ln: cur.__setitem__("layer", ln))
+             for ln, m in model.named_children()]
+    inst = []
+    try:
+        for n in names:
+            setattr(cg, n, wrap(n))
+        for f in fr:
+            cur["log"] = []
+            cur["layer"] = next(iter(dict(model.named_children())))
+            inst.append((so.capture_slot(f), cur["log"]))
+    finally:
+        for n, f in orig.items():
+            setattr(cg, n, f)
+        for h in hooks:
+            h.remove()
+    nf = len(fr)
+    period = 2 * (nf - 1)
+
+    def fidx(t):
+        r = t % period
+        return r if r < nf else period - r
+
+    def run(graphs):
+        t = 2
+        for _ in range(20):
+            graphs[fidx(t)].replay()
+            t += 1
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps * period):
+            graphs[fidx(t)].replay()
+            t += 1
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e3 / (reps * period)
+
+    plain_us = run(plain)
+    inst_us = run([g for g, _ in inst])
+    acc = {}
+    t = 2
+    for _ in range(reps):
+        g, lg = inst[fidx(t)]
+        g.replay()
+        torch.cuda.synchronize()
+        for i, (ln, name, e0, e1) in enumerate(lg):
+            acc.setdefault((i, ln, name), []).append(e0.elapsed_time(e1) * 1e3)
+        t += 1
+    rows = []
+    for (i, ln, name), v in sorted(acc.items()):
+        v.sort()
+        rows.append({"layer": ln, "kernel": name, "us": round(v[len(v) // 2], 2)})
+    del plain, inst, so
+    cb.clearMemory(model)
+    n = max(len(rows), 1)
+    return {"launches": rows, "plain_step_us": round(plain_us, 1), "instrumented_step_us": round(inst_us, 1),
+            "event_overhead_us_per_launch": round((inst_us - plain_us) / n, 1)}
 
 
 def kernel_roofline(args, model, frames, dev, tdt, step_us):

@@ -18,4 +18,4 @@ ncu -i gpurun_out/r02_full.ncu-rep --page details --csv > gpurun_out/r02_full_de
 ls -la gpurun_out/r02_full.ncu-rep
 SZ=$(stat -c %s gpurun_out/r02_full.ncu-rep 2>/dev/null || echo 0)
 if [ "$SZ" -gt 45000000 ]; then rm -f gpurun_out/r02_full.ncu-rep; echo "report too large, csv pages kept"; fi
-tail -3 gpurun_out/ncu_list.log gpurun_out/ncu_full.log
+tail -n 3 gpurun_out/ncu_list.log; tail -n 3 gpurun_out/ncu_full.log
