@@ -83,6 +83,20 @@ __device__ __forceinline__ void store_state_scalar(T* sptr, T v, const AuxPlanes
   *sptr = v;
 }
 
+// streaming (evict-first) loads for data a frame scan reads exactly once per step: the input frame and
+// the first layer's state (70 MB per step at 8 streams) should not push the small control structures
+// and the maps the following kernels reuse out of L2
+__device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
+__device__ __forceinline__ __half ld_stream(const __half* p) {
+  const unsigned short v = __ldcs(reinterpret_cast<const unsigned short*>(p));
+  return __ushort_as_half(v);
+}
+__device__ __forceinline__ __nv_bfloat16 ld_stream(const __nv_bfloat16* p) {
+  const unsigned short v = __ldcs(reinterpret_cast<const unsigned short*>(p));
+  return __ushort_as_bfloat16(v);
+}
+__device__ __forceinline__ uint4 ld16_stream(const void* p) { return __ldcs(reinterpret_cast<const uint4*>(p)); }
+
 constexpr int kDetWarps = 8;                   // warps per block
 
 // x: pixel-major, pitch xp (elements); state: pixel-major, pitch sp.  Rows may be strided (sy).
@@ -213,12 +227,12 @@ detect_narrow_kernel(const T* __restrict__ x, long long x_sb, long long x_sc, lo
   if (xx < W) {
     const T* xp = x + b * x_sb + y * x_sy + xx * x_sx;
     T* sp = st + b * s_sb + y * s_sy + (long long)xx * VEC;
-    uint4 sv = ld16(sp);
+    uint4 sv = ld16_stream(sp);
     uint4 nv = sv;                             // pad lanes keep the state's (zero) value
     T* ne = reinterpret_cast<T*>(&nv);
 #pragma unroll
     for (int c = 0; c < VEC; ++c)
-      if (c < C) ne[c] = xp[c * x_sc];
+      if (c < C) ne[c] = ld_stream(xp + c * x_sc);
     f = Chunk<T>::changed(sv, nv, thr);
     if (UPDATE == CB_UPDATE_ALL || (UPDATE == CB_UPDATE_CHANGED && f))
       store_state<T>(sp, nv, aux, ((long long)b * H + y) * W + xx, 0);
@@ -431,12 +445,12 @@ detect_u8_kernel(const uint8_t* __restrict__ x, long long x_sb, long long x_sc, 
   if (xx < W) {
     const uint8_t* xp = x + b * x_sb + y * x_sy + xx * x_sx;
     float* sp = st + b * s_sb + y * s_sy + (long long)xx * 4;
-    const uint4 sv = ld16(sp);
+    const uint4 sv = ld16_stream(sp);
     uint4 nv = sv;                             // pad lanes keep the state's (zero) value
     float* ne = reinterpret_cast<float*>(&nv);
 #pragma unroll
     for (int c = 0; c < 4; ++c)
-      if (c < C) ne[c] = __fadd_rn(__fdiv_rn((float)xp[c * x_sc], divisor), bias);
+      if (c < C) ne[c] = __fadd_rn(__fdiv_rn((float)__ldcs(xp + c * x_sc), divisor), bias);
     f = Chunk<float>::changed(sv, nv, thr);
     if (UPDATE == CB_UPDATE_ALL || (UPDATE == CB_UPDATE_CHANGED && f))
       store_state<float>(sp, nv, aux, ((long long)b * H + y) * W + xx, 0);
