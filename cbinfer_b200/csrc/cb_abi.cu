@@ -402,6 +402,18 @@ int cb_conv_update_tiled(void* stream, int dtype, int gemm, const void* state, c
                                 bias, out, pitch_out, B, H, W, Cin, Cout, kH, kW, relu, pf);
 }
 
+#ifdef CB_TILE_TRACE
+/* debugging aid of trace builds only (tools/tile_trace.py): copy the tile kernel's per-CTA timeline out and clear it */
+int cb_debug_tile_trace(long long* dst, int n_ctas) {
+  if (n_ctas > 2048) n_ctas = 2048;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(dst, cb::cb_tile_trace, (size_t)n_ctas * cb::TL_TRACE_EV * sizeof(long long));
+  static long long zeros[2048 * cb::TL_TRACE_EV];
+  cudaMemcpyToSymbol(cb::cb_tile_trace, zeros, sizeof(zeros));
+  return cb::TL_TRACE_EV;
+}
+#endif
+
 int cb_conv_tiled_pool_supported(int dtype, int gemm, int Cout) {
   (void)dtype;
   return gemm != CB_GEMM_SIMT_F32 && cb::tile_pool_ok(gemm, Cout) ? 1 : 0;

@@ -46,6 +46,20 @@ __host__ __device__ inline size_t tile_ws_words(int B, int H, int W) {
   return 4 + 2 * (size_t)B * tile_grid_y(H) * tile_grid_xp(W);
 }
 
+// -DCB_TILE_TRACE: per-CTA timeline of the tile kernel (clock64 relative to kernel entry) for
+// tools/tile_trace.py; not compiled into the product library
+#ifdef CB_TILE_TRACE
+constexpr int TL_TRACE_EV = 32;
+__device__ long long cb_tile_trace[2048 * TL_TRACE_EV];
+#define TL_TRACE(ev)                                                                              \
+  do {                                                                                            \
+    if ((ev) < TL_TRACE_EV && blockIdx.x < 2048)                                                  \
+      cb_tile_trace[blockIdx.x * TL_TRACE_EV + (ev)] = clock64() - trace_t0;                      \
+  } while (0)
+#else
+#define TL_TRACE(ev) do { } while (0)
+#endif
+
 struct TileCtrl {
   uint64_t b_full[TL_MAXB], b_empty[TL_MAXB];
   uint64_t halo_full[TL_NHALO], halo_empty[TL_NHALO];
@@ -114,6 +128,14 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap amap_hi, const __grid_const
                  const uint32_t* __restrict__ dil_bits, const float* __restrict__ bias,
                  TO* __restrict__ out, const TileGeom g, const PoolFuse pf) {
   pdl_prologue();
+#ifdef CB_TILE_TRACE
+  const long long trace_t0 = clock64();
+  if (threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    if (blockIdx.x < 2048) cb_tile_trace[blockIdx.x * TL_TRACE_EV + 31] = (long long)gt;
+  }
+#endif
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int ES = sizeof(T), BK = UM_ROW_BYTES / ES, UK = 32 / ES, KS = BK / UK;
   constexpr int NSPLIT = SPLIT3 ? 2 : 1;
@@ -180,6 +202,7 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap amap_hi, const __grid_const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (tid == 0) TL_TRACE(0);                                 // prologue done
   const uint32_t tmem_base = ctrl->tmem_base;
   const int tiles_per_img = g.TY * g.TXp;
 
@@ -219,6 +242,7 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap amap_hi, const __grid_const
       const int hb = it % nhalo;
       mbar_wait(&ctrl->halo_empty[hb], (uint32_t)(((it / nhalo) & 1) ^ 1));
       if (leader) {
+        TL_TRACE(1 + it * 6 + 0);                            // halo TMA issued
         mbar_arrive_expect_tx(&ctrl->halo_full[hb], (uint32_t)(NSPLIT * nblk) * box_bytes);
         const uint32_t dst = smem_u32(smem + hb * halo_stage);
         for (int blk = 0; blk < nblk; ++blk) {
@@ -263,6 +287,7 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap amap_hi, const __grid_const
       const int hb = it % nhalo;
       const uint32_t ab = (uint32_t)it & 1u, aph = ((uint32_t)it >> 1) & 1u;
       mbar_wait(&ctrl->halo_full[hb], (uint32_t)((it / nhalo) & 1));
+      if (leader) TL_TRACE(1 + it * 6 + 1);                  // halo landed
       mbar_wait(&ctrl->tmem_empty[ab], aph ^ 1u);
       tc_fence_after();
       const uint32_t a16 = (smem_u32(smem + hb * halo_stage) & 0x3FFFFu) >> 4;
@@ -279,6 +304,7 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap amap_hi, const __grid_const
             mbar_wait(&ctrl->b_full[stage], phase);
           }
           tc_fence_after();
+          if (leader && kbi == 0) TL_TRACE(1 + it * 6 + 5);  // first weight stage landed
           b_run = (bring16 + stage * (uint32_t)(B_STAGE >> 4)) | (1u << 16);
         }
         if (leader) {
@@ -342,6 +368,7 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap amap_hi, const __grid_const
       if (leader) {
         umma_commit(&ctrl->tmem_full[ab]);                   // accumulator complete
         umma_commit(&ctrl->halo_empty[hb]);                  // halo buffer consumed
+        TL_TRACE(1 + it * 6 + 2);                            // all MMAs of the tile issued
       }
       __syncwarp();
     }
@@ -370,6 +397,7 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap amap_hi, const __grid_const
       const uint32_t ab = (uint32_t)it & 1u, aph = ((uint32_t)it >> 1) & 1u;
       mbar_wait(&ctrl->tmem_full[ab], aph);
       tc_fence_after();
+      if (warp == 4 && lane == 0) TL_TRACE(1 + it * 6 + 3);  // accumulator complete (epilogue starts)
       const uint32_t trow = tmem_base + ab * (uint32_t)ACC_COLS + ((uint32_t)(q * 32) << 16);
       TO* orow = out + (((long long)b * g.H + (inimg ? y : 0)) * g.W + (inimg ? x : 0)) * g.Op;
       const unsigned onmask = __ballot_sync(0xffffffffu, on);
@@ -474,11 +502,13 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap amap_hi, const __grid_const
           for (int c = 0; c < g.Cout; c += OVEC)
             store_state<TO>(ns + c, ld16(po + c), pf.aux, opix, c);
       }
+      if (warp == 4 && lane == 0) TL_TRACE(1 + it * 6 + 4);  // epilogue of the tile done
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (tid == 0) TL_TRACE(30);                                // all roles done
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),

@@ -431,6 +431,11 @@ detect_u8_kernel(const uint8_t* __restrict__ x, long long x_sb, long long x_sc, 
                  AuxPlanes aux, uint32_t* __restrict__ bits, int B, int H, int W, int C, int Wd,
                  float divisor, float bias, float thr) {
   pdl_prologue();
+  // the 256 possible normalised values, computed once per block with the IEEE division and addition the
+  // host would use (bit-identical by construction): a table lookup per channel instead of a division
+  __shared__ float lut[256];
+  lut[threadIdx.x] = __fadd_rn(__fdiv_rn((float)threadIdx.x, divisor), bias);
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   // 32-bit index math (the host checks words < 2^31): two 64-bit divisions per warp were most of this
   // kernel's instructions (ncu: 173 warp instructions per 32 pixels, SM 54 % busy on an HBM-bound scan)
@@ -450,7 +455,7 @@ detect_u8_kernel(const uint8_t* __restrict__ x, long long x_sb, long long x_sc, 
     float* ne = reinterpret_cast<float*>(&nv);
 #pragma unroll
     for (int c = 0; c < 4; ++c)
-      if (c < C) ne[c] = __fadd_rn(__fdiv_rn((float)__ldcs(xp + c * x_sc), divisor), bias);
+      if (c < C) ne[c] = lut[__ldcs(xp + c * x_sc)];
     f = Chunk<float>::changed(sv, nv, thr);
     if (UPDATE == CB_UPDATE_ALL || (UPDATE == CB_UPDATE_CHANGED && f))
       store_state<float>(sp, nv, aux, ((long long)b * H + y) * W + xx, 0);
