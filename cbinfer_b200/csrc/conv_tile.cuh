@@ -122,7 +122,7 @@ __device__ __forceinline__ uint64_t tile_adesc_base(uint32_t sbo_bytes, int layo
 }
 
 template <typename T, typename TO, bool SPLIT3, int BN>
-__global__ void __launch_bounds__(128 + um_epi(BN))
+__global__ void __launch_bounds__(128 + um_epi(BN), BN <= 16 ? 4 : BN <= 64 ? 2 : 1)
 conv_tile_kernel(const __grid_constant__ CUtensorMap amap_hi, const __grid_constant__ CUtensorMap amap_lo,
                  const __grid_constant__ CUtensorMap wmap, const int32_t* __restrict__ tile_ws,
                  const uint32_t* __restrict__ dil_bits, const float* __restrict__ bias,
@@ -395,10 +395,6 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap amap_hi, const __grid_const
       if (inimg)
         on = (__ldg(dil_bits + ((long long)b * g.H + y) * g.Wd + (x >> 5)) >> (x & 31)) & 1u;
       const uint32_t ab = (uint32_t)it & 1u, aph = ((uint32_t)it >> 1) & 1u;
-      mbar_wait(&ctrl->tmem_full[ab], aph);
-      tc_fence_after();
-      if (warp == 4 && lane == 0) TL_TRACE(1 + it * 6 + 3);  // accumulator complete (epilogue starts)
-      const uint32_t trow = tmem_base + ab * (uint32_t)ACC_COLS + ((uint32_t)(q * 32) << 16);
       TO* orow = out + (((long long)b * g.H + (inimg ? y : 0)) * g.W + (inimg ? x : 0)) * g.Op;
       const unsigned onmask = __ballot_sync(0xffffffffu, on);
       // fused pooling: window = lanes (l & ~9) + {0, 1, 8, 9}; its top-left lane owns the pooled pixel
@@ -409,10 +405,39 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap amap_hi, const __grid_const
       TO* po = reinterpret_cast<TO*>(pf.out) + b * pf.o_sb + yo * pf.o_sy + (long long)xo * pf.op;
       TO* ns = reinterpret_cast<TO*>(pf.nst) + b * pf.n_sb + yo * pf.n_sy + (long long)xo * pf.np;
       const long long opix = ((long long)b * pf.oH + yo) * pf.oW + xo;
+      // What the pooling tail reads from global memory -- the stored values of a touched window's
+      // untouched pixels, the next layer's state row of the window's owner -- has not been seen for a
+      // frame: with the loads inside the column loop a tile's epilogue was a chain of 8 dependent
+      // DRAM round trips (trace, cold: 6-8 us per tile for 64 channels).  The first 16-column slice is
+      // fetched BEFORE waiting for the accumulator (hidden behind the tile's MMAs), every further slice
+      // one iteration ahead.
+      // (one-slice layers, BN <= 16, keep their loads inside the loop: they run four CTAs per SM on 64
+      //  registers per thread, and 8 more vector registers across the wait would halve that)
+      constexpr bool EARLY = BN > 16;
+      constexpr int NV = 16 / OVEC;
+      uint4 orv[NV], nsv[NV];
+      auto fetch = [&](int c0, uint4* o, uint4* n) {
+        const int co0 = nt * BN + c0;
+        const bool need_o = win_on && inimg && !on && co0 < g.Cout;
+        const bool need_n = owner && co0 < g.Cout;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          o[i] = need_o ? ld16(orow + co0 + i * OVEC) : make_uint4(0u, 0u, 0u, 0u);
+          n[i] = need_n ? ld16(ns + co0 + i * OVEC) : make_uint4(0u, 0u, 0u, 0u);
+        }
+      };
+      if (EARLY && pooling && onmask) fetch(cbeg, orv, nsv);
+      mbar_wait(&ctrl->tmem_full[ab], aph);
+      tc_fence_after();
+      if (warp == 4 && lane == 0) TL_TRACE(1 + it * 6 + 3);  // accumulator complete (epilogue starts)
+      const uint32_t trow = tmem_base + ab * (uint32_t)ACC_COLS + ((uint32_t)(q * 32) << 16);
       bool pchg = false;
       if (onmask) {
 #pragma unroll 1
         for (int c0 = cbeg; c0 < cbeg + COLS && c0 < BN; c0 += 16) {
+          uint4 orn[NV], nsn[NV];
+          const bool more = EARLY && pooling && c0 + 16 < cbeg + COLS && c0 + 16 < BN;
+          if (more) fetch(c0 + 16, orn, nsn);
           uint32_t acc[16];
           tmem_ld16(trow + (uint32_t)c0, acc);
           if (MERGE) {
@@ -463,7 +488,7 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap amap_hi, const __grid_const
             // an untouched pixel of a touched window: its stored value takes part in the maximum
 #pragma unroll
             for (int i = 0; i < 16; i += OVEC) {
-              const uint4 v = ld16(orow + co0 + i);
+              const uint4 v = EARLY ? orv[i / OVEC] : ld16(orow + co0 + i);
               const TO* e = reinterpret_cast<const TO*>(&v);
 #pragma unroll
               for (int k = 0; k < OVEC; ++k) f[i + k] = to_float(e[k]);
@@ -485,10 +510,17 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap amap_hi, const __grid_const
                 for (int k = 0; k < OVEC; ++k) h[k] = from_float<TO>(f[i + k]);
                 const uint4 res = *reinterpret_cast<uint4*>(h);
                 st16(po + co0 + i, res);
-                const uint4 sv = ld16(ns + co0 + i);
+                const uint4 sv = EARLY ? nsv[i / OVEC] : ld16(ns + co0 + i);
                 pchg |= Chunk<TO>::changed(sv, res, pthr);
                 if (pf.update == CB_UPDATE_ALL) store_state<TO>(ns + co0 + i, res, pf.aux, opix, co0 + i);
               }
+            }
+          }
+          if (more) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+              orv[i] = orn[i];
+              nsv[i] = nsn[i];
             }
           }
         }
@@ -589,6 +621,7 @@ inline TilePlan tile_plan(int es, bool split3, int bn, int Cp, int B, int H, int
     int o = (227 * 1024) / (fixed + nb * b_stage + 1024);
     if (o > 512 / tmem_cols) o = 512 / tmem_cols;
     if (o > 4) o = 4;
+    if (bn > 16 && o > 2) o = 2;                             // register side: __launch_bounds__ of the kernel
     if (force_occ > 1 && o > force_occ) o = force_occ;
     if (o > occ) occ = o;
   }
@@ -661,6 +694,8 @@ int launch_conv_tile(cudaStream_t s, const void* state, const void* state_lo, co
     attr_dev = dev;
   }
   const long long max_items = (long long)g.B * g.TY * tile_grid_x(g.W) * (g.CoutPad / BN);
+  // (the plan counts shared memory and TMEM columns; the register side is pinned by the kernel's
+  //  __launch_bounds__: 4 CTAs per SM for N <= 16, 2 for N <= 64)
   long long grid = (long long)sm_count() * plan.occ;
   if (grid > max_items) grid = max_items;
   if (grid < 1) grid = 1;

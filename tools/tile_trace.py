@@ -17,7 +17,7 @@ C.cb_debug_tile_trace.argtypes = [ctypes.c_void_p, ctypes.c_int]
 MHZ = 1965.0
 
 
-def run(B, Cin, Cout, H, W, k, rate, cold):
+def run(B, Cin, Cout, H, W, k, rate, cold, pool=False):
     gemm = _lib.GEMM_TC_BF16X3
     torch.manual_seed(0)
     state, sbuf = cg.pixel_major((B, Cin, H, W), torch.float32, "cuda", 0)
@@ -36,8 +36,17 @@ def run(B, Cin, Cout, H, W, k, rate, cold):
     cg.dilate_compact(raw_bits, shape, (k, k), s["idx"], s["count"], s["ws"], dil_bits=s["dil_bits"], tile_ws=tws)
     ntl = int(tws[1])
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    pargs = None
+    if pool:                                               # conv -> 2x2 pool -> next layer's detection in the epilogue
+        pv, _ = cg.pixel_major((B, Cout, H // 2, W // 2), torch.float32, "cuda", 0)
+        nv, nbuf = cg.pixel_major((B, Cout, H // 2, W // 2), torch.float32, "cuda", 0)
+        s2 = cg.alloc_scratch((B, H // 2, W // 2), "cuda")
+        nh, nl = cg.bf16_planes(nbuf, Cout)
+        pargs = dict(out=pv, next_state=nv, next_raw_bits=s2["raw_bits"], threshold=0.05, mode=_lib.UPDATE_CHANGED,
+                     aux=('bf16', nh, nl))
     for _ in range(3):
-        cg.conv_update_tiled(sbuf, tws, s["dil_bits"], packed, bias, obuf, Cin, Cout, (k, k), True, gemm, planes16=planes)
+        cg.conv_update_tiled(sbuf, tws, s["dil_bits"], packed, bias, obuf, Cin, Cout, (k, k), True, gemm, planes16=planes,
+                             pool=pargs)
     torch.cuda.synchronize()
     buf = (ctypes.c_longlong * (2048 * 32))()
     C.cb_debug_tile_trace(buf, 2048)                       # clear
@@ -46,12 +55,14 @@ def run(B, Cin, Cout, H, W, k, rate, cold):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    cg.conv_update_tiled(sbuf, tws, s["dil_bits"], packed, bias, obuf, Cin, Cout, (k, k), True, gemm, planes16=planes)
+    cg.conv_update_tiled(sbuf, tws, s["dil_bits"], packed, bias, obuf, Cin, Cout, (k, k), True, gemm, planes16=planes,
+                         pool=pargs)
     e1.record()
     torch.cuda.synchronize()
     nev = C.cb_debug_tile_trace(buf, 2048)
-    print("\n== %d->%d %dx%d k%d B%d %.0f%%: %d tiles, %s caches, kernel %.1f us (event pair, incl. launch)"
-          % (Cin, Cout, H, W, k, B, rate * 100, ntl, "COLD" if cold else "warm", e0.elapsed_time(e1) * 1e3))
+    print("\n== %d->%d %dx%d k%d B%d %.0f%%%s: %d tiles, %s caches, kernel %.1f us (event pair, incl. launch)"
+          % (Cin, Cout, H, W, k, B, rate * 100, " + fused pool/detect" if pool else "", ntl, "COLD" if cold else "warm",
+             e0.elapsed_time(e1) * 1e3))
     rows = []
     for cta in range(2048):
         ev = [buf[cta * nev + i] for i in range(nev)]
@@ -78,5 +89,6 @@ def run(B, Cin, Cout, H, W, k, rate, cold):
 
 
 for cold in (False, True):
-    run(8, 16, 64, 240, 320, 7, 0.05, cold)
-    run(8, 3, 16, 480, 640, 7, 0.05, cold)
+    for pool in (False, True):
+        run(8, 16, 64, 240, 320, 7, 0.05, cold, pool)
+        run(8, 3, 16, 480, 640, 7, 0.05, cold, pool)
