@@ -8,3 +8,6 @@ echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 
 echo "== bench (default)"; ( time python bench.py ) > gpurun_out/r02_bench_full.json 2> gpurun_out/bench_full.err; echo "exit $?"; grep real gpurun_out/bench_full.err
 echo "== bench --impl reference"; ( time python bench.py --impl reference ) > gpurun_out/r02_bench_reference.json 2> gpurun_out/bench_ref.err; echo "exit $?"; grep real gpurun_out/bench_ref.err
 bash tools/gpu_profile.sh
+if [ -f build/libcbinfer_trace.so ]; then
+  echo "== tile trace"; CBINFER_LIB=$PWD/build/libcbinfer_trace.so timeout 300 python tools/tile_trace.py > gpurun_out/r02_tile_trace.txt 2>&1; echo "exit $?"
+fi
