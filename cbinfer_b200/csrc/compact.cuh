@@ -25,6 +25,7 @@ constexpr int kCompactWPT = CB_COMPACT_WPT;                  // words per thread
 constexpr int kCompactTile = kCompactThreads * kCompactWPT;  // words per tile (16384 pixels; measured best of 256..2048)
 constexpr int kCompactWin = 6144;                            // staged raw window (words, 24 KB)
 
+constexpr int kCompactResidentTiles = 2 * 132;  // blocks that are co-resident on any B200 (>= 132 SMs, >= 2 per SM)
 struct CompactHeader {                         // first 16 bytes of the workspace
   unsigned reserved, done, epoch, ticket;
 };
@@ -94,7 +95,8 @@ __device__ __forceinline__ unsigned pooled_word(const uint32_t* __restrict__ raw
 // List mode: tiles are taken by ticket (atomicAdd on the header's `ticket`), not by blockIdx -- every
 // predecessor of a running tile then holds an earlier ticket, i.e. is running or finished, whatever
 // order the hardware dispatches blocks in, so the look-back cannot starve (as in CUB's single-pass
-// scan).  Tile-only mode has no scan across tiles and keeps blockIdx.
+// scan).  Tile-only mode has no scan across tiles and keeps blockIdx, and so do grids small enough to
+// be resident as a whole.
 __global__ void __launch_bounds__(kCompactThreads)
 dilate_compact_kernel(const uint32_t* __restrict__ raw, uint32_t* __restrict__ dil_bits,
                       int8_t* __restrict__ dil_map, int32_t* __restrict__ idx,
@@ -113,7 +115,9 @@ dilate_compact_kernel(const uint32_t* __restrict__ raw, uint32_t* __restrict__ d
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   int tile = blockIdx.x;
-  if (!no_list && ntiles > 1) {
+  // (up to 2 blocks per SM the whole grid is resident at once and no order can starve anybody: those
+  //  launches skip the ticket -- one more dependent global round trip, 2 us inside a step)
+  if (!no_list && ntiles > kCompactResidentTiles) {
     if (tid == 0) s_base = (int)atomicAdd(&hdr->ticket, 1u);
     __syncthreads();
     tile = s_base;
