@@ -183,6 +183,7 @@ def test_module_tile_path_equals_index_path(cbm, dt, monkeypatch):
     cb = cbm["cb"]
     from cbinfer_b200 import models, video
     monkeypatch.setenv("CBINFER_STREAMK", "0")
+    monkeypatch.setenv("CBINFER_TILES", "1")             # (the test is about the tile path: ignore an outer knob)
     tdt = TORCH_DT[dt]
     torch.manual_seed(3)
     base = nn.Sequential(nn.Conv2d(3, 16, 7, padding=3), nn.ReLU(), nn.MaxPool2d(2, 2),
