@@ -8,6 +8,7 @@
 #include "compact.cuh"
 #include "conv_simt.cuh"
 #include "conv_umma.cuh"
+#include "conv_pair.cuh"
 #include "conv_tile.cuh"
 #include "detect.cuh"
 #include "fg.cuh"

@@ -1099,6 +1099,13 @@ int dispatch_bn(int bn, cudaStream_t s, int dtype, const void* state, const void
 #undef CB_BN
 }
 
+// conv_pair.cuh: the same contraction on CTA pairs (cta_group::2), for wide layers with many changed pixels
+inline bool pair_supported(int es, int Cp, int CoutPad, int kH, int kW);
+template <typename T, typename TO, bool SPLIT3>
+int launch_conv_pair(cudaStream_t s, const void* state, const void* state_lo, int Cp, const int32_t* idx,
+                     const int32_t* count, const void* packed, const float* bias, void* out, int Op, int H, int W,
+                     int Cout, int CoutPad, int kH, int kW, int relu, int sel_lo, int sel_hi);
+
 inline int umma_conv_update(cudaStream_t s, int dtype, int gemm, const void* state,
                             const void* state_lo, int Cp, const int32_t* idx, const int32_t* count, const void* packed,
                             const float* bias, void* out, int Op, int B, int H, int W, int Cin,
@@ -1184,6 +1191,29 @@ inline int umma_conv_update(cudaStream_t s, int dtype, int gemm, const void* sta
     const int rc = run_t(std::true_type{}, bn_small, 0, m_switch, ksplit);
     if (rc) return rc;
     return run_t(std::false_type{}, bn, m_switch, 0x7fffffff);
+  }
+  // Opt-in (CBINFER_PAIR_MIN=n, read per call): wide layers (N tile 256, 16-bit operands) run on CTA pairs
+  // (conv_pair.cuh: tcgen05.mma.cta_group::2, M = 256 per instruction, each CTA loads half of the weight tile)
+  // from n M tiles on; the index-list kernel keeps the smaller counts; both are launched, the count decides on
+  // the device.  Bit-identical results.  OFF by default: measured on the 64 -> 256 7x7 layer it buys 1-5 % from
+  // 20 % change on and loses 10-25 % below (no stream-K, an extra launch) -- profiles/r02_experiments.md.
+  const char* pm_env = getenv("CBINFER_PAIR_MIN");
+  const int pair_min = pm_env ? atoi(pm_env) : 0;
+  const int es_op = umma_operand_es(dtype, gemm);
+  const long long max_mtiles = (P + UM_BM - 1) / UM_BM;
+  if (pair_min > 0 && bn == 256 && !mk.bits && !(relu & 2) && (bf16x3 || dtype == CB_F16 || dtype == CB_BF16) &&
+      pair_supported(es_op, Cp, CoutPad, kH, kW) && max_mtiles >= pair_min && sms >= 2) {
+    const int rc = run_t(std::false_type{}, bn, 0, pair_min);
+    if (rc) return rc;
+    if (bf16x3)
+      return launch_conv_pair<__nv_bfloat16, float, true>(s, state, state_lo, Cp, idx, count, packed, bias, out, Op, H,
+                                                          W, Cout, CoutPad, kH, kW, relu, pair_min, 0x7fffffff);
+    if (dtype == CB_F16)
+      return launch_conv_pair<__half, __half, false>(s, state, state_lo, Cp, idx, count, packed, bias, out, Op, H, W,
+                                                     Cout, CoutPad, kH, kW, relu, pair_min, 0x7fffffff);
+    return launch_conv_pair<__nv_bfloat16, __nv_bfloat16, false>(s, state, state_lo, Cp, idx, count, packed, bias, out,
+                                                                 Op, H, W, Cout, CoutPad, kH, kW, relu, pair_min,
+                                                                 0x7fffffff);
   }
   return run_t(std::false_type{}, bn, 0, 0x7fffffff);
 }

@@ -7,6 +7,7 @@ stated tolerances for the contraction.
 import numpy as np
 import pytest
 import torch
+import torch.nn.functional as F
 
 from tests.util import (ORC_DT, TORCH_DT, bits_to_map, perturb, rand_tensor, to_np, to_val)
 
@@ -432,6 +433,51 @@ def test_conv_update_masked_superset_list(cbm, mode, dt):
             torch.cuda.synchronize()
             outs.append(out.clone())
         assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("case", [("bf16x3", "f32", 2, 64, 256, 80, 96, 3, 0.9, True), ("bf16x3", "f32", 1, 64, 256, 120, 160, 7, 0.55, True),
+                                  ("tc", "bf16", 2, 64, 256, 72, 80, 3, 1.0, False), ("tc", "f16", 1, 128, 512, 90, 100, 3, 0.8, True),
+                                  ("bf16x3", "f32", 1, 32, 200, 96, 96, 5, 0.75, False)])
+def test_conv_update_cta_pair_kernel_equals_index_list_kernel(cbm, case, monkeypatch):
+    """wide layers with many changed pixels run on CTA pairs (tcgen05.mma.cta_group::2, conv_pair.cuh): the
+    same products in the same K order as the index-list kernel, so the two must agree BIT FOR BIT
+    (CBINFER_PAIR_MIN=0 keeps the index-list kernel; odd tile counts, ragged Cout, two N tiles included);
+    both within the contraction tolerance of the dense convolution."""
+    cg, cb, lib = cbm["cg"], cbm["cb"], cbm["lib"]
+    mode, dt, B, Cin, Cout, H, W, k, frac, relu = case
+    tdt, gemm = TORCH_DT[dt], cb.CBConv2d.GEMM_MODES[mode]
+    g = torch.Generator().manual_seed(Cin + H)
+    state, sbuf = cg.pixel_major((B, Cin, H, W), tdt, "cuda", 0)
+    state.copy_((torch.rand(B, Cin, H, W, generator=g) - 0.5).to(tdt))
+    w = ((torch.rand(Cout, Cin, k, k, generator=g) - 0.5) * 2 * (Cin * k * k) ** -0.5).to(tdt).cuda()
+    bias = (torch.rand(Cout, generator=g) - 0.5).cuda()
+    idx = torch.nonzero(torch.rand(B * H * W, generator=g) < frac).view(-1).int().cuda()
+    n = idx.numel()
+    assert n > 1000
+    ci = cg.ChangeIndexes.from_tensor(idx, (B, H, W))
+    packed = cg.pack_weights(w, gemm)
+    planes = cg.bf16_planes(sbuf, Cin) if gemm == lib.GEMM_TC_BF16X3 else None
+    outs = []
+    for pair_min in ("0", "1"):          # (no stream-K workspace: whole K ranges per CTA on both sides)
+        monkeypatch.setenv("CBINFER_PAIR_MIN", pair_min)
+        out, obuf = cg.pixel_major((B, Cout, H, W), tdt, "cuda", 0)
+        out.fill_(2.0)
+        for _ in range(2):
+            cg.conv_update(sbuf, ci, packed, bias, obuf, Cin, Cout, (k, k), relu, gemm, planes16=planes)
+        torch.cuda.synchronize()
+        outs.append(out.clone())
+    assert torch.equal(outs[0], outs[1])
+    ref = F.conv2d(state.double(), w.double(), bias.double(), padding=k // 2).float()      # (fp64: no TF32 in the reference)
+    if relu:
+        ref = F.relu(ref)
+    m = torch.zeros(B * H * W, dtype=torch.bool, device="cuda")
+    m[idx.long()] = True
+    tm = m.view(B, 1, H, W).expand(B, Cout, H, W)
+    scale = float(ref.abs().max()) + 1e-30
+    tol = {"f32": 1e-4, "bf16": 1e-2, "f16": 2e-3}[dt]
+    assert float((outs[1].float()[tm] - ref[tm]).abs().max()) / scale <= tol
+    if not bool(tm.all()):
+        assert float((outs[1].float()[~tm] - 2.0).abs().max()) == 0.0
 
 
 def test_conv_update_zero_changes_is_noop(cbm):
