@@ -29,7 +29,7 @@ SYMBOLS = [
     "cb_fg_detect", "cb_conv_accumulate", "cb_compact_small_max_words", "cb_change_detect_sparse_compact",
     "cb_tile_ws_bytes", "cb_dilate_compact_tiles", "cb_conv_tiled_supported", "cb_conv_update_tiled",
     "cb_conv_tiled_pool_supported", "cb_conv_update_tiled_pool", "cb_dilate_tiles",
-    "cb_tail_supported", "cb_tail_update",
+    "cb_tail_supported", "cb_tail_update", "cb_dilate_compact_hinted",
 ]
 
 
@@ -71,6 +71,8 @@ def _load():
         "cb_tail_update": (i32, [vp, vp, vp, vp, vp, vp, i32, f32, vp, vp, vp, vp, i32, i32, f32, vp, vp, i32, i32, i32,
                                  i32, vp, vp, vp]),
         "cb_dilate_tiles": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32]),
+        "cb_dilate_compact_hinted": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32,
+                                           vp, vp, vp, vp, vp]),
         "cb_conv_tiled_pool_supported": (i32, [i32, i32, i32]),
         "cb_conv_update_tiled_pool": (i32, [vp, i32, i32, vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32,
                                             i32, i32, i32, i32, i32,

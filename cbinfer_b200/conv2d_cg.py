@@ -209,20 +209,63 @@ def pool_compact(in_bits, in_shape, out_shape, idx, count, ws, out_bits=None):
                             idx.data_ptr(), count.data_ptr(), ws.data_ptr(), B, H, W, oH, oW))
 
 
-def dilate_tiles(raw_bits, shape, filtSize, count, ws, dil_bits, tile_ws, clear_raw=False):
-    """cb_dilate_tiles: dilation + dirty-tile list + change count, no ordered index list."""
+class PrefetchHints(object):
+    """L2 prefetch hints of cb_dilate_compact_hinted: pixel-major maps ``[B, tH, tW, pitch]`` (contiguous)
+    whose rows at the changed pixels a later kernel will read -- ``(buffer, shift)`` pairs, shift 1 for a
+    map at the 2x2-pooled resolution.  Holds the ctypes argument arrays (and the buffers alive)."""
+    MAX = 3
+
+    def __init__(self, targets):
+        import ctypes
+        targets = [(t, int(sh)) for t, sh in targets
+                   if t is not None and t.dim() == 4 and t.is_contiguous() and t.data_ptr() % 16 == 0
+                   and (t.shape[3] * t.element_size()) % 16 == 0 and t.numel() > 0][:self.MAX]
+        self.targets = targets
+        self.n = len(targets)
+        self.key = tuple((t.data_ptr(), tuple(t.shape), sh) for t, sh in targets)
+        self.base = (ctypes.c_void_p * max(self.n, 1))(*[t.data_ptr() for t, _ in targets])
+        ia = ctypes.c_int * max(self.n, 1)
+        self.row_bytes = ia(*[t.shape[3] * t.element_size() for t, _ in targets])
+        self.shift = ia(*[sh for _, sh in targets])
+        self.h = ia(*[t.shape[1] for t, _ in targets])
+        self.w = ia(*[t.shape[2] for t, _ in targets])
+
+
+def _dilate_hinted(raw_bits, shape, filtSize, idx, count, ws, dil_bits, dil_map, tile_ws, clear_raw, no_list,
+                   hints):
     B, H, W = shape
+    check(C.cb_dilate_compact_hinted(stream_ptr(raw_bits.device), raw_bits.data_ptr(),
+                                     dil_bits.data_ptr() if dil_bits is not None else None,
+                                     dil_map.data_ptr() if dil_map is not None else None,
+                                     idx.data_ptr() if idx is not None else None, count.data_ptr(),
+                                     ws.data_ptr(), tile_ws.data_ptr() if tile_ws is not None else None,
+                                     B, H, W, (filtSize[0] - 1) // 2, (filtSize[1] - 1) // 2,
+                                     int(bool(clear_raw)), int(bool(no_list)), hints.n, hints.base,
+                                     hints.row_bytes, hints.shift, hints.h, hints.w))
+
+
+def dilate_tiles(raw_bits, shape, filtSize, count, ws, dil_bits, tile_ws, clear_raw=False, hints=None):
+    """cb_dilate_tiles: dilation + dirty-tile list + change count, no ordered index list.  `hints`
+    (:class:`PrefetchHints`): cb_dilate_compact_hinted, same outputs."""
+    B, H, W = shape
+    if hints is not None and hints.n:
+        return _dilate_hinted(raw_bits, shape, filtSize, None, count, ws, dil_bits, None, tile_ws, clear_raw,
+                              True, hints)
     check(C.cb_dilate_tiles(stream_ptr(raw_bits.device), raw_bits.data_ptr(), dil_bits.data_ptr(),
                             count.data_ptr(), ws.data_ptr(), tile_ws.data_ptr(), B, H, W,
                             (filtSize[0] - 1) // 2, (filtSize[1] - 1) // 2, int(bool(clear_raw))))
 
 
 def dilate_compact(raw_bits, shape, filtSize, idx, count, ws, dil_bits=None, dil_map=None,
-                   clear_raw=False, tile_ws=None):
+                   clear_raw=False, tile_ws=None, hints=None):
     """cb_dilate_compact: dilation by the filter footprint + ordered compaction.  With `tile_ws`
     (cb_tile_ws_bytes of zeroed int32 device memory) the dirty 8x16 output tiles are listed as well
-    (cb_dilate_compact_tiles), for :func:`conv_update_tiled`."""
+    (cb_dilate_compact_tiles), for :func:`conv_update_tiled`.  `hints` (:class:`PrefetchHints`):
+    cb_dilate_compact_hinted, same outputs."""
     B, H, W = shape
+    if hints is not None and hints.n:
+        return _dilate_hinted(raw_bits, shape, filtSize, idx, count, ws, dil_bits, dil_map, tile_ws, clear_raw,
+                              False, hints)
     if tile_ws is not None:
         check(C.cb_dilate_compact_tiles(stream_ptr(raw_bits.device), raw_bits.data_ptr(),
                                         dil_bits.data_ptr() if dil_bits is not None else None,

@@ -134,8 +134,11 @@ size_t cb_tile_ws_bytes(int B, int H, int W) { return cb::tile_ws_words(B, H, W)
 
 static int dilate_compact_impl(void* stream, const uint32_t* raw_bits, uint32_t* dil_bits, int8_t* dil_map,
                       int32_t* idx, int32_t* count, void* ws, void* tile_ws, int B, int H, int W, int kHHalf,
-                      int kWHalf, int clear_raw, int no_list = 0) {
+                      int kWHalf, int clear_raw, int no_list = 0, const cb::PrefetchHints* hints = nullptr) {
   CB_CHECK_ARG(raw_bits && (idx || no_list) && count && ws, "dilate_compact: null pointer");
+  cb::PrefetchHints ph;
+  memset(&ph, 0, sizeof(ph));
+  if (hints) ph = *hints;
   CB_CHECK_ARG(raw_bits != dil_bits, "dilate_compact: dil_bits must not alias raw_bits");
   CB_CHECK_ARG(kHHalf >= 0 && kWHalf >= 0 && kWHalf <= 31, "dilate_compact: kWHalf must be <= 31");
   CB_CHECK_ARG((long long)B * H * W < (1ll << 31), "dilate_compact: more than 2^31 pixels");
@@ -153,9 +156,40 @@ static int dilate_compact_impl(void* stream, const uint32_t* raw_bits, uint32_t*
                                                           kWHalf, (int)nwords, ntiles, 0, 0,
                                                           clear_raw ? const_cast<uint32_t*>(raw_bits) : nullptr,
                                                           (int32_t*)tile_ws, cb::tile_grid_y(H), cb::tile_grid_xp(W),
-                                                          (int)compact_coop(), no_list);
+                                                          (int)compact_coop(), no_list, ph);
   CB_CHECK_LAUNCH("dilate_compact");
   return 0;
+}
+
+int cb_dilate_compact_hinted(void* stream, const uint32_t* raw_bits, uint32_t* dil_bits, int8_t* dil_map,
+                             int32_t* idx, int32_t* count, void* ws, void* tile_ws, int B, int H, int W,
+                             int kHHalf, int kWHalf, int clear_raw, int no_list, int n_hints,
+                             const void* const* hint_base, const int* hint_row_bytes, const int* hint_shift,
+                             const int* hint_h, const int* hint_w) {
+  CB_CHECK_ARG(n_hints >= 0 && n_hints <= cb::kMaxHints, "dilate_compact_hinted: at most %d hints", cb::kMaxHints);
+  CB_CHECK_ARG(n_hints == 0 || (hint_base && hint_row_bytes && hint_shift && hint_h && hint_w),
+               "dilate_compact_hinted: null hint array");
+  CB_CHECK_ARG(!no_list || (tile_ws && dil_bits), "dilate_compact_hinted: no_list needs tile_ws and dil_bits");
+  cb::PrefetchHints ph;
+  memset(&ph, 0, sizeof(ph));
+  for (int i = 0; i < n_hints; ++i) {
+    CB_CHECK_ARG(hint_shift[i] == 0 || hint_shift[i] == 1, "dilate_compact_hinted: shift must be 0 or 1");
+    CB_CHECK_ARG(hint_base[i] && ((uintptr_t)hint_base[i] % 16) == 0 && hint_row_bytes[i] > 0 &&
+                     (hint_row_bytes[i] % 16) == 0 && hint_h[i] > 0 && hint_w[i] > 0,
+                 "dilate_compact_hinted: hint rows must be 16-byte aligned multiples of 16 bytes");
+    // (a hint never reaches beyond its map: rows are clipped to hint_h x hint_w in the kernel)
+    CB_CHECK_ARG((long long)hint_row_bytes[i] * 32 < (1ll << 31), "dilate_compact_hinted: row too large");
+    ph.base[ph.n] = (const char*)hint_base[i];
+    ph.row_bytes[ph.n] = hint_row_bytes[i];
+    ph.shift[ph.n] = hint_shift[i];
+    ph.tH[ph.n] = hint_h[i];
+    ph.tW[ph.n] = hint_w[i];
+    ++ph.n;
+  }
+  if (tile_ws && (long long)cb_bitmap_words(B, H, W) == 0)
+    cudaMemsetAsync((int32_t*)tile_ws + 1, 0, sizeof(int32_t), (cudaStream_t)stream);
+  return dilate_compact_impl(stream, raw_bits, dil_bits, dil_map, idx, count, ws, tile_ws, B, H, W, kHHalf,
+                             kWHalf, clear_raw, no_list, &ph);
 }
 
 int cb_dilate_compact(void* stream, const uint32_t* raw_bits, uint32_t* dil_bits, int8_t* dil_map,
@@ -218,7 +252,7 @@ int cb_pool_compact(void* stream, const uint32_t* in_bits, uint32_t* out_bits, i
   cb::launch_pdl(dilate_compact_kernel, ntiles, kCompactThreads, 0, s, in_bits, out_bits, nullptr, idx, count, ws,
                                                           B, oH, oW, (oW + 31) / 32, 0, 0,
                                                           (int)nwords, ntiles, H, (W + 31) / 32, nullptr,
-                                                          nullptr, 0, 0, (int)compact_coop(), 0);
+                                                          nullptr, 0, 0, (int)compact_coop(), 0, cb::PrefetchHints{});
   CB_CHECK_LAUNCH("pool_compact");
   return 0;
 }

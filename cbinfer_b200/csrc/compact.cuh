@@ -92,6 +92,46 @@ __device__ __forceinline__ unsigned pooled_word(const uint32_t* __restrict__ raw
   return d;
 }
 
+// L2 prefetch hints (extension, no reference counterpart).  The kernels that consume a change set a
+// few launches later read rows they have not touched for a frame (the next layer's state at the
+// rewritten pixels: cold in L2, a chain of dependent DRAM round trips inside a latency-bound kernel).
+// The dilation is the first kernel to know WHICH pixels those are, so it asks L2 for them while the
+// contraction in between keeps the tensor cores busy: per dilated word, one cp.async.bulk.prefetch.L2
+// per run of set bits and target (pixel-major maps: a run of pixels is one contiguous byte range).
+// shift = 1: the target has the 2x2-pooled resolution (issued from even rows).  Hints only -- no
+// architectural state changes, results are bit-identical with and without them.
+constexpr int kMaxHints = 3;
+struct PrefetchHints {
+  const char* base[kMaxHints];
+  int row_bytes[kMaxHints], shift[kMaxHints], tH[kMaxHints], tW[kMaxHints];
+  int n;
+};
+
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void prefetch_hinted_rows(const PrefetchHints& hints, unsigned d, int b, int y, int j) {
+  for (int h = 0; h < hints.n; ++h) {
+    const int sh = hints.shift[h];
+    if (sh && (y & 1)) continue;
+    const int yy = y >> sh, tH = hints.tH[h], tW = hints.tW[h], rb = hints.row_bytes[h];
+    if (yy >= tH) continue;
+    const char* row = hints.base[h] + (long long)(b * tH + yy) * tW * rb;
+    unsigned dd = d;
+    while (dd) {
+      const int x0 = __ffs(dd) - 1;
+      const unsigned inv = ~(dd >> x0);
+      const int len = inv ? __ffs(inv) - 1 : 32 - x0;        // run of set bits x0 .. x0 + len - 1
+      const int xa = (j * 32 + x0) >> sh;
+      int xb = (j * 32 + x0 + len - 1) >> sh;
+      if (xb >= tW) xb = tW - 1;
+      if (xa <= xb) prefetch_l2_bulk(row + (long long)xa * rb, (unsigned)((xb - xa + 1) * rb));
+      dd = x0 + len >= 32 ? 0u : dd & (0xffffffffu << (x0 + len));
+    }
+  }
+}
+
 // List mode: tiles are taken by ticket (atomicAdd on the header's `ticket`), not by blockIdx -- every
 // predecessor of a running tile then holds an earlier ticket, i.e. is running or finished, whatever
 // order the hardware dispatches blocks in, so the look-back cannot starve (as in CUB's single-pass
@@ -103,7 +143,7 @@ dilate_compact_kernel(const uint32_t* __restrict__ raw, uint32_t* __restrict__ d
                       int32_t* __restrict__ count, void* ws, int B, int H, int W, int Wd, int kh,
                       int kw, int nwords, int ntiles, int pool_hin, int pool_wdin,
                       uint32_t* __restrict__ clear_bits, int32_t* __restrict__ tile_ws, int tile_ty,
-                      int tile_xp, int coop, int no_list) {
+                      int tile_xp, int coop, int no_list, const PrefetchHints hints) {
   pdl_prologue();
   CompactHeader* hdr = reinterpret_cast<CompactHeader*>(ws);
   volatile unsigned long long* tstate =
@@ -160,6 +200,7 @@ dilate_compact_kernel(const uint32_t* __restrict__ raw, uint32_t* __restrict__ d
       d[i] = pool_hin ? pooled_word(raw, r / H, y, j, pool_hin, pool_wdin, W)
                       : dilated_word(win, win0, r, y, j, H, W, Wd, kh, kw);
       if (dil_bits) dil_bits[w] = d[i];
+      if (hints.n && d[i]) prefetch_hinted_rows(hints, d[i], r / H, y, j);
     }
     if (tile_ws) {
       // dirty 8 x 16 output tiles for the tiled contraction (conv_tile.cuh): a word covers four

@@ -134,6 +134,21 @@ int cb_dilate_compact_tiles(void* stream, const uint32_t* raw_bits, uint32_t* di
 int cb_dilate_tiles(void* stream, const uint32_t* raw_bits, uint32_t* dil_bits, int32_t* count, void* ws,
                     void* tile_ws, int B, int H, int W, int kHHalf, int kWHalf, int clear_raw);
 
+/* cb_dilate_compact / _tiles / cb_dilate_tiles (tile_ws may be NULL; no_list != 0 = cb_dilate_tiles, idx
+ * may then be NULL) that additionally asks L2 for rows the kernels a few launches later will read at the
+ * changed pixels -- typically the next layer's previous-input state, cold since the last time those
+ * pixels changed: for every dilated pixel (b, y, x) and hint i the bytes
+ *   hint_base[i] + (((b * hint_h[i] + (y >> s)) * hint_w[i] + (x >> s)) * hint_row_bytes[i],  s = hint_shift[i]
+ * (hint_row_bytes of them; s = 1: a map at the 2x2-pooled resolution) are prefetched with
+ * cp.async.bulk.prefetch.L2, one instruction per run of pixels.  Pure hints: every output is
+ * bit-identical to the unhinted call.  hint_base and hint_row_bytes must be multiples of 16; at most
+ * 3 hints.  No reference counterpart (the reference re-scans whole maps, conv2d.py:222-232). */
+int cb_dilate_compact_hinted(void* stream, const uint32_t* raw_bits, uint32_t* dil_bits, int8_t* dil_map,
+                             int32_t* idx, int32_t* count, void* ws, void* tile_ws, int B, int H, int W,
+                             int kHHalf, int kWHalf, int clear_raw, int no_list, int n_hints,
+                             const void* const* hint_base, const int* hint_row_bytes, const int* hint_shift,
+                             const int* hint_h, const int* hint_w);
+
 /* ---- candidate ("sparse") detection ---------------------------------------------------------
  * Same per-pixel test and state maintenance as cb_change_detect, evaluated only at the
  * `*n_candidates` pixels listed in `candidates` (indices b*H*W + y*W + x, any order); raw_bits is

@@ -158,6 +158,52 @@ def test_detect_dilate_compact(cbm, orc, dt, layout, case):
         assert int(s["count"].item()) == n
 
 
+@pytest.mark.parametrize("case", [(1, 15, 20, 3, 3), (2, 33, 65, 7, 7), (3, 40, 300, 5, 3), (8, 120, 160, 7, 7)])
+def test_hinted_dilation_is_bit_identical(cbm, case):
+    """cb_dilate_compact_hinted (L2 prefetch hints for the next layers' state rows, same resolution and
+    2x2-pooled, odd sizes, rows of 16 B .. 1 KB) returns exactly what the unhinted calls return -- bitmap,
+    ascending list, count, tile list -- in list mode and in tiles-only mode, and leaves the hinted maps
+    untouched."""
+    cg = cbm["cg"]
+    B, H, W, kH, kW = case
+    g = torch.Generator().manual_seed(sum(case))
+    raw_map = (torch.rand(B, H, W, generator=g) < 0.02).to(torch.int8).cuda()
+    raw_map[:, H // 3:H // 3 + 5, W // 4:W // 4 + 9] = 1
+    tg_same = torch.randn(B, H, W, 256, device="cuda")
+    tg_pool = torch.randn(B, (H + 1) // 2, (W + 1) // 2, 4, device="cuda")
+    tg_half = torch.randn(B, H // 2, W // 2, 64, device="cuda").to(torch.bfloat16)
+    keep = [t.clone() for t in (tg_same, tg_pool, tg_half)]
+    hints = cg.PrefetchHints([(tg_same, 0), (tg_pool, 1), (tg_half, 1)])
+    assert hints.n == 3
+    outs = []
+    for h in (None, hints):
+        s = cg.alloc_scratch((B, H, W), "cuda")
+        tws = cg.alloc_tile_ws((B, H, W), "cuda")
+        s["raw_bits"].copy_(cg._map_to_bits(raw_map)[0])
+        cg.dilate_compact(s["raw_bits"], (B, H, W), (kH, kW), s["idx"], s["count"], s["ws"],
+                          dil_bits=s["dil_bits"], tile_ws=tws, hints=h)
+        n = int(s["count"].item())
+        ntl = int(tws[1].item())
+        NT = (tws.numel() - 4) // 2
+        rec = [n, s["idx"][:n].clone(), s["dil_bits"].clone(), ntl, tws[4 + NT:4 + NT + ntl].sort().values.clone()]
+        s2 = cg.alloc_scratch((B, H, W), "cuda")
+        tws2 = cg.alloc_tile_ws((B, H, W), "cuda")
+        s2["raw_bits"].copy_(s["raw_bits"])
+        cg.dilate_tiles(s2["raw_bits"], (B, H, W), (kH, kW), s2["count"], s2["ws"], s2["dil_bits"], tws2,
+                        clear_raw=True, hints=h)
+        ntl2 = int(tws2[1].item())
+        rec += [int(s2["count"].item()), s2["dil_bits"].clone(), ntl2,
+                tws2[4 + NT:4 + NT + ntl2].sort().values.clone(), s2["raw_bits"].clone()]
+        outs.append(rec)
+    torch.cuda.synchronize()
+    assert outs[0][0] > 0 and outs[0][0] == outs[0][5] and outs[0][3] == outs[0][7]
+    for a, b in zip(*outs):
+        assert (a == b) if isinstance(a, int) else torch.equal(a, b)
+    assert int(outs[1][9].abs().sum().item()) == 0                            # clear_raw honoured
+    for t, k in zip((tg_same, tg_pool, tg_half), keep):
+        assert torch.equal(t, k)
+
+
 def test_detect_update_all_and_special_values(cbm, orc):
     cg, lib = cbm["cg"], cbm["lib"]
     x = torch.zeros(1, 1, 2, 4, device="cuda")
