@@ -472,7 +472,9 @@ def main():
                       and os.environ.get("CBINFER_FUSE_POOL", "1") != "0" and os.environ.get("CBINFER_TILES", "1") != "0")
     fused_tail = sum(1 for m in model.modules() if type(m) is cb.CBConv2d and getattr(m, '_fusedTail', None)
                      and os.environ.get("CBINFER_FUSE_TAIL", "1") != "0")
-    my_launches_per_step = 17 if args.dense_scan else 13 - fused_pools - 3 * fused_tail
+    # (... and derive their dilated bitmap + tile list themselves, cb_conv_update_tiled_self: 6 with the tail fused)
+    self_tiles = fused_pools if os.environ.get("CBINFER_SELF_TILES", "1") != "0" else 0
+    my_launches_per_step = 17 if args.dense_scan else 13 - fused_pools - 3 * fused_tail - self_tiles
 
     # one captured graph per input slot of the frame ring (the bench cycles over `nframes` device
     # buffers): a step is ONE graph launch -- first-layer detection on the slot where the frame lies
@@ -840,6 +842,8 @@ def kernel_roofline(args, model, frames, dev, tdt, step_us):
         def w(*a, **k):
             if name in ("dilate_compact", "dilate_tiles"):
                 k = dict(k, clear_raw=False)  # keep the raw bitmap: the replays must see the real input
+            if name == "conv_update_tiled" and k.get("self_list"):
+                k = dict(k, self_list=dict(k["self_list"], clear_raw=False))
             calls.append((cur["layer"], name, a, k))
             return fn(*a, **k)
         return w

@@ -30,6 +30,7 @@ SYMBOLS = [
     "cb_tile_ws_bytes", "cb_dilate_compact_tiles", "cb_conv_tiled_supported", "cb_conv_update_tiled",
     "cb_conv_tiled_pool_supported", "cb_conv_update_tiled_pool", "cb_dilate_tiles",
     "cb_tail_supported", "cb_tail_update", "cb_dilate_compact_hinted",
+    "cb_conv_tiled_self_supported", "cb_conv_update_tiled_self",
 ]
 
 
@@ -77,6 +78,11 @@ def _load():
         "cb_conv_update_tiled_pool": (i32, [vp, i32, i32, vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32,
                                             i32, i32, i32, i32, i32,
                                             vp, i64, i64, i32, i32, i32, vp, i64, i64, i32, i32, vp, vp, vp, f32, i32]),
+        "cb_conv_tiled_self_supported": (i32, [i32, i32]),
+        "cb_conv_update_tiled_self": (i32, [vp, i32, i32, vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32,
+                                            i32, i32, i32, i32, i32,
+                                            vp, i64, i64, i32, i32, i32, vp, i64, i64, i32, i32, vp, vp, vp, f32, i32,
+                                            vp, vp, vp, i32]),
         "cb_map_to_bits": (i32, [vp, vp, vp, i32, i32, i32]),
         "cb_change_detect_sparse": (i32, [vp, i32, vp, i64, i64, i64, i64, vp, i64, i64, i64, i64, i32,
                                           vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, i32, i32]),

@@ -581,7 +581,8 @@ class CBConv2d(nn.Module):
             # halo, implicit im2col through the UMMA descriptors), rows masked by the dilated bitmap
             cg.conv_update_tiled(self._inBuf, s["tile_ws"], s["dil_bits"], packed, bias32, self._outBuf,
                                  self.in_channels, self.out_channels, self.kernel_size, self.withReLU,
-                                 gemm, lo_buf=lo_buf, planes16=planes16, pool=pool_args)  # :242-251
+                                 gemm, lo_buf=lo_buf, planes16=planes16, pool=pool_args,
+                                 self_list=changeIndexes.__dict__.pop('selfList', None))  # :242-251
             if pool_args is not None:
                 changeIndexes.pooledBy = fp[0]
         else:
@@ -744,7 +745,9 @@ class CBConv2d(nn.Module):
         when the pixels last changed, so the consumer would otherwise fetch them from DRAM inside a
         latency-bound kernel; the dilation knows the pixels one contraction earlier."""
         nxt = getattr(self, '_prefetchNext', None)
-        if not nxt or os.environ.get("CBINFER_PREFETCH", "1") == "0":
+        # (opt-in: measured on the bench model the hinted L3 dilation costs 12 us more and saves the tail
+        #  kernel 2 us -- profiles/r02_experiments.md)
+        if not nxt or os.environ.get("CBINFER_PREFETCH", "0") != "1":
             return None
         tg = []
         for m, sh in nxt:
@@ -762,11 +765,23 @@ class CBConv2d(nn.Module):
             self._hintCache = hc
         return hc[1] if hc[1].n else None
 
+    def _selfTiles(self):
+        """dilation + tile list inside the tile contraction itself (cb_conv_update_tiled_self)?"""
+        return os.environ.get("CBINFER_SELF_TILES", "1") != "0" \
+            and bool(_lib.C.cb_conv_tiled_self_supported(self.kernel_size[0], self.kernel_size[1]))
+
     def _compact(self, s, B, H, W, sparse_next, tiles=False, lazy=False):
         """dilate the raw bitmap by the filter footprint and compact it to the index list."""
         if tiles and "tile_ws" not in s:
             s["tile_ws"] = cg.alloc_tile_ws((B, H, W), s["idx"].device)
         hints = self._hints(B, H, W, s["idx"].device)
+        if tiles and lazy and self._selfTiles():
+            # nothing to launch: the tile contraction dilates the raw bitmap and lists its tiles itself
+            # (cb_conv_update_tiled_self); bitmap, tile list and count exist once it has run
+            s["raw_clear"] = sparse_next
+            ci = ChangeIndexes(s["idx"], s["count"], (B, H, W), bits=s["dil_bits"], ws=s["ws"], listed=False)
+            ci.selfList = dict(raw_bits=s["raw_bits"], count=s["count"], ws=s["ws"], clear_raw=sparse_next)
+            return ci
         if tiles and lazy:
             # tiles + dilated bitmap + count only; the ordered list is compacted if somebody asks
             cg.dilate_tiles(s["raw_bits"], (B, H, W), self.kernel_size, s["count"], s["ws"], s["dil_bits"],

@@ -443,10 +443,12 @@ def conv_accumulate(planes16, changes, packed_w, out_buf, Cin, Cout, filtSize, g
 
 
 def conv_update_tiled(state_buf, tile_ws, dil_bits, packed_w, bias_f32, out_buf, Cin, Cout, filtSize,
-                      relu, gemm, lo_buf=None, planes16=None, pool=None):
+                      relu, gemm, lo_buf=None, planes16=None, pool=None, self_list=None):
     """cb_conv_update_tiled on pixel-major buffers: the contraction over the dirty 8x16 tiles listed
     in `tile_ws` (TMA-staged halo tiles, implicit im2col), writing the pixels set in `dil_bits`.
-    Operand conventions as :func:`conv_update`."""
+    Operand conventions as :func:`conv_update`.  `self_list` = dict(raw_bits, count, ws, clear_raw):
+    cb_conv_update_tiled_self -- the kernel dilates the raw bitmap and lists the tiles itself (no
+    cb_dilate_tiles launch before it); dil_bits, tile_ws and count are outputs then."""
     B, H, W, Cp = state_buf.shape
     assert out_buf.shape[:3] == state_buf.shape[:3]
     src, src_lo, pitch = state_buf, lo_buf, Cp
@@ -458,6 +460,23 @@ def conv_update_tiled(state_buf, tile_ws, dil_bits, packed_w, bias_f32, out_buf,
         pitch = src.shape[3]
     elif gemm == _lib.GEMM_TC_3X and state_buf.dtype == torch.float32 and lo_buf is None:
         src_lo = tf32_lo(state_buf)
+    if self_list is not None:
+        pa = [None, 0, 0, 0, 0, 0, None, 0, 0, 0, 0, None, None, None, 0.0, 0]
+        if pool is not None:
+            po, ns = pool["out"], pool["next_state"]
+            assert po.stride(1) == 1 and ns.stride(1) == 1 and po.shape == ns.shape, "pixel-major maps only"
+            mode, hi, lo = _aux_args(pool.get("aux"), ns)
+            pa = [po.data_ptr(), po.stride(0), po.stride(2), po.stride(3), po.size(2), po.size(3),
+                  ns.data_ptr(), ns.stride(0), ns.stride(2), ns.stride(3), mode, hi, lo,
+                  pool["next_raw_bits"].data_ptr(), float(pool["threshold"]), int(pool["mode"])]
+        check(C.cb_conv_update_tiled_self(stream_ptr(state_buf.device), dtype_code(state_buf), gemm,
+                                          src.data_ptr(), src_lo.data_ptr() if src_lo is not None else None,
+                                          pitch, tile_ws.data_ptr(), dil_bits.data_ptr(), packed_w.data_ptr(),
+                                          bias_f32.data_ptr(), out_buf.data_ptr(), out_buf.shape[3], B, H, W,
+                                          Cin, Cout, filtSize[0], filtSize[1], int(bool(relu)), *pa,
+                                          self_list["raw_bits"].data_ptr(), self_list["count"].data_ptr(),
+                                          self_list["ws"].data_ptr(), int(bool(self_list.get("clear_raw")))))
+        return
     if pool is not None:
         # pool = dict(out=pooled map view, next_state=view, next_raw_bits, threshold, mode, aux): the
         # epilogue also re-pools the touched 2x2 windows and runs the next layer's detection on them

@@ -413,7 +413,11 @@ int cb_conv_tiled_supported(int dtype, int gemm, int B, int H, int W, int Cin, i
 static int conv_update_tiled_impl(void* stream, int dtype, int gemm, const void* state, const void* state_lo,
                          int pitch_in, const void* tile_ws, const uint32_t* dil_bits,
                          const void* packed_w, const float* bias, void* out, int pitch_out, int B,
-                         int H, int W, int Cin, int Cout, int kH, int kW, int relu, const cb::PoolFuse& pf) {
+                         int H, int W, int Cin, int Cout, int kH, int kW, int relu, const cb::PoolFuse& pf,
+                         const cb::TileSelf* self = nullptr) {
+  cb::TileSelf sf;
+  memset(&sf, 0, sizeof(sf));
+  if (self) sf = *self;
   CB_CHECK_ARG(state && tile_ws && dil_bits && packed_w && bias && out, "conv_update_tiled: null pointer");
   CB_CHECK_ARG(gemm != CB_GEMM_SIMT_F32, "conv_update_tiled: tensor-core modes only");
   const int want_pitch = gemm == CB_GEMM_TC_BF16X3 ? cb::pitch16_of(Cin) : cb_channel_pitch(dtype, Cin);
@@ -424,7 +428,7 @@ static int conv_update_tiled_impl(void* stream, int dtype, int gemm, const void*
   if (B == 0 || H == 0 || W == 0) return 0;
   return cb::umma_conv_update_tiled((cudaStream_t)stream, dtype, gemm, state, state_lo, pitch_in,
                                     (const int32_t*)tile_ws, dil_bits, packed_w, bias, out, pitch_out,
-                                    B, H, W, Cout, kH, kW, relu, pf);
+                                    B, H, W, Cout, kH, kW, relu, pf, sf);
 }
 
 int cb_conv_update_tiled(void* stream, int dtype, int gemm, const void* state, const void* state_lo,
@@ -454,14 +458,14 @@ int cb_conv_tiled_pool_supported(int dtype, int gemm, int Cout) {
   return gemm != CB_GEMM_SIMT_F32 && cb::tile_pool_ok(gemm, Cout) ? 1 : 0;
 }
 
-int cb_conv_update_tiled_pool(void* stream, int dtype, int gemm, const void* state, const void* state_lo,
+static int tiled_pool_impl(void* stream, int dtype, int gemm, const void* state, const void* state_lo,
                               int pitch_in, const void* tile_ws, const uint32_t* dil_bits,
                               const void* packed_w, const float* bias, void* out, int pitch_out, int B,
                               int H, int W, int Cin, int Cout, int kH, int kW, int relu,
                               void* pool_out, long long o_sb, long long o_sy, int o_pitch, int oH, int oW,
                               void* next_state, long long n_sb, long long n_sy, int n_pitch, int aux_mode,
                               void* aux_hi, void* aux_lo, uint32_t* next_raw_bits, float threshold,
-                              int update_mode) {
+                              int update_mode, const cb::TileSelf* self) {
   CB_CHECK_ARG(pool_out && next_state && next_raw_bits, "conv_update_tiled_pool: null pointer");
   CB_CHECK_ARG(update_mode == CB_UPDATE_NONE || update_mode == CB_UPDATE_CHANGED || update_mode == CB_UPDATE_ALL,
                "conv_update_tiled_pool: bad update_mode %d", update_mode);
@@ -481,7 +485,64 @@ int cb_conv_update_tiled_pool(void* stream, int dtype, int gemm, const void* sta
   CB_DISPATCH_DTYPE(dtype, rc = cb::make_aux<T>(pf.aux, aux_mode, aux_hi, aux_lo, next_state, Cout));
   if (rc) return rc;
   return conv_update_tiled_impl(stream, dtype, gemm, state, state_lo, pitch_in, tile_ws, dil_bits, packed_w,
-                                bias, out, pitch_out, B, H, W, Cin, Cout, kH, kW, relu, pf);
+                                bias, out, pitch_out, B, H, W, Cin, Cout, kH, kW, relu, pf, self);
+}
+
+int cb_conv_update_tiled_pool(void* stream, int dtype, int gemm, const void* state, const void* state_lo,
+                              int pitch_in, const void* tile_ws, const uint32_t* dil_bits,
+                              const void* packed_w, const float* bias, void* out, int pitch_out, int B,
+                              int H, int W, int Cin, int Cout, int kH, int kW, int relu,
+                              void* pool_out, long long o_sb, long long o_sy, int o_pitch, int oH, int oW,
+                              void* next_state, long long n_sb, long long n_sy, int n_pitch, int aux_mode,
+                              void* aux_hi, void* aux_lo, uint32_t* next_raw_bits, float threshold,
+                              int update_mode) {
+  return tiled_pool_impl(stream, dtype, gemm, state, state_lo, pitch_in, tile_ws, dil_bits, packed_w, bias, out,
+                         pitch_out, B, H, W, Cin, Cout, kH, kW, relu, pool_out, o_sb, o_sy, o_pitch, oH, oW,
+                         next_state, n_sb, n_sy, n_pitch, aux_mode, aux_hi, aux_lo, next_raw_bits, threshold,
+                         update_mode, nullptr);
+}
+
+int cb_conv_tiled_self_supported(int kH, int kW) {
+  // one warp lane per raw row of a 16-row tile's window (16 + 2*kHHalf <= 32), funnel shifts up to 31
+  return kH >= 1 && kW >= 1 && (kH & 1) && (kW & 1) && (kH - 1) / 2 <= 8 && (kW - 1) / 2 <= 31 ? 1 : 0;
+}
+
+int cb_conv_update_tiled_self(void* stream, int dtype, int gemm, const void* state, const void* state_lo,
+                              int pitch_in, void* tile_ws, uint32_t* dil_bits,
+                              const void* packed_w, const float* bias, void* out, int pitch_out, int B,
+                              int H, int W, int Cin, int Cout, int kH, int kW, int relu,
+                              void* pool_out, long long o_sb, long long o_sy, int o_pitch, int oH, int oW,
+                              void* next_state, long long n_sb, long long n_sy, int n_pitch, int aux_mode,
+                              void* aux_hi, void* aux_lo, uint32_t* next_raw_bits, float threshold,
+                              int update_mode, const uint32_t* raw_bits, int32_t* count, void* ws,
+                              int clear_raw) {
+  CB_CHECK_ARG(raw_bits && count && ws && dil_bits && tile_ws, "conv_update_tiled_self: null pointer");
+  CB_CHECK_ARG(raw_bits != dil_bits, "conv_update_tiled_self: dil_bits must not alias raw_bits");
+  CB_CHECK_ARG(cb_conv_tiled_self_supported(kH, kW), "conv_update_tiled_self: filter %dx%d not supported", kH, kW);
+  CB_CHECK_ARG((long long)B * H * W < (1ll << 31) && (long long)cb_bitmap_words(B, H, W) < (1ll << 31),
+               "conv_update_tiled_self: map too large");
+  if (B == 0 || H == 0 || W == 0) {
+    cudaMemsetAsync(count, 0, sizeof(int32_t), (cudaStream_t)stream);
+    cudaMemsetAsync((int32_t*)tile_ws + 1, 0, sizeof(int32_t), (cudaStream_t)stream);
+    CB_CHECK_LAUNCH("conv_update_tiled_self(memset)");
+    return 0;
+  }
+  cb::TileSelf sf;
+  sf.raw = raw_bits;
+  sf.dil = dil_bits;
+  sf.clear = clear_raw ? const_cast<uint32_t*>(raw_bits) : nullptr;
+  sf.count = count;
+  sf.acc_pix = &reinterpret_cast<cb::CompactHeader*>(ws)->reserved;
+  if (!pool_out) {
+    cb::PoolFuse pf;
+    memset(&pf, 0, sizeof(pf));
+    return conv_update_tiled_impl(stream, dtype, gemm, state, state_lo, pitch_in, tile_ws, dil_bits, packed_w,
+                                  bias, out, pitch_out, B, H, W, Cin, Cout, kH, kW, relu, pf, &sf);
+  }
+  return tiled_pool_impl(stream, dtype, gemm, state, state_lo, pitch_in, tile_ws, dil_bits, packed_w, bias, out,
+                         pitch_out, B, H, W, Cin, Cout, kH, kW, relu, pool_out, o_sb, o_sy, o_pitch, oH, oW,
+                         next_state, n_sb, n_sy, n_pitch, aux_mode, aux_hi, aux_lo, next_raw_bits, threshold,
+                         update_mode, &sf);
 }
 
 int cb_conv_update_masked(void* stream, int dtype, int gemm, const void* state, const void* state_lo,

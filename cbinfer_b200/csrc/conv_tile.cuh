@@ -101,6 +101,106 @@ struct PoolFuse {
   int update;                    // CB_UPDATE_*
 };
 
+// Optional self-listing prologue (cb_conv_update_tiled_self): the kernel derives the dilated bitmap,
+// the dirty-tile list and the change count from the RAW change bitmap itself -- the job of
+// cb_dilate_tiles (reference: the scatter-dilate of changeDetection_kernel, cbconv2d_cg_backend.cu:62-72)
+// -- so a tile-path layer needs no dilation launch at all.  One warp per (image, tile row, bitmap word):
+// lane l loads the three raw words of row y0 - kh + l (one round of independent loads), dilates them
+// horizontally with funnel shifts; the vertical OR over 2kh + 1 rows is a chain of shuffles; lanes 0..15
+// then hold the 16 dilated words of the item: stored, counted, and folded into four tile flags with
+// ballots (a word covers four 8-pixel tiles); one atomicAdd per warp appends its dirty tiles.  A grid
+// barrier (sense-reversing, all CTAs co-resident: cooperative launch) separates the listing from the
+// contraction; the last CTA to arrive publishes the totals where cb_dilate_tiles would have left them
+// (tile_ws[1], *count) and resets the accumulators, so the workspaces stay interchangeable between the
+// two paths.  raw == nullptr: off.
+struct TileSelf {
+  const uint32_t* raw;           // raw change bitmap of this layer
+  uint32_t* dil;                 // dilated bitmap (output; the kernel's dil_bits)
+  uint32_t* clear;               // raw bitmap to zero once every CTA has consumed it, or nullptr
+  int32_t* count;                // *count = number of dilated pixels
+  unsigned* acc_pix;             // CompactHeader.reserved of the compaction workspace (0 at rest)
+};
+
+__device__ __forceinline__ void tile_self_list(const TileSelf& sf, int32_t* tws, int B, int H, int W, int Wd,
+                                               int TY, int TXp, int kh, int kw) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int NI = B * TY * Wd;
+  int32_t* list = tws + 4 + B * TY * TXp;
+  int pix = 0;
+  for (int item = blockIdx.x * nwarps + warp; item < NI; item += gridDim.x * nwarps) {
+    const int wx = item % Wd, r = item / Wd;
+    const int ty = r % TY, b = r / TY;
+    const int y0 = ty * TL_H, y = y0 - kh + lane;
+    unsigned vp = 0, vc = 0, vn = 0;
+    if (lane < TL_H + 2 * kh && y >= 0 && y < H) {
+      const uint32_t* row = sf.raw + ((long long)b * H + y) * Wd + wx;
+      vc = __ldcg(row);
+      if (wx > 0) vp = __ldcg(row - 1);
+      if (wx + 1 < Wd) vn = __ldcg(row + 1);
+    }
+    unsigned h = vc;
+    for (int dx = 1; dx <= kw; ++dx) {
+      h |= (vc << dx) | (vp >> (32 - dx));
+      h |= (vc >> dx) | (vn << (32 - dx));
+    }
+    if (wx == Wd - 1 && (W & 31)) h &= (1u << (W & 31)) - 1u;
+    unsigned v = 0;
+    for (int d = 0; d <= 2 * kh; ++d) v |= __shfl_down_sync(0xffffffffu, h, d);   // rows y0+l-kh .. y0+l+kh
+    const bool rowok = lane < TL_H && y0 + lane < H;
+    if (!rowok) v = 0u;
+    if (rowok) __stcg(sf.dil + ((long long)b * H + y0 + lane) * Wd + wx, v);
+    pix += __popc(v);
+    unsigned flags = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (__ballot_sync(0xffffffffu, ((v >> (8 * q)) & 0xffu) != 0u)) flags |= 1u << q;
+    if (flags) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(tws, __popc(flags));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (lane < 4 && ((flags >> lane) & 1u))
+        __stcg(list + base + __popc(flags & ((1u << lane) - 1u)), (b * TY + ty) * TXp + 4 * wx + lane);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) pix += __shfl_xor_sync(0xffffffffu, pix, o);
+  if (lane == 0 && pix) atomicAdd(sf.acc_pix, (unsigned)pix);
+  // ---- grid barrier: tws[2] arrivals, tws[3] generation ----------------------------------------
+  __syncthreads();
+  if (tid == 0) {
+    volatile unsigned* gen = reinterpret_cast<volatile unsigned*>(tws + 3);
+    const unsigned g0 = *gen;                                // (cannot advance before this CTA arrives)
+    __threadfence();
+    const unsigned prev = atomicAdd(reinterpret_cast<unsigned*>(tws + 2), 1u);
+    if (prev == gridDim.x - 1u) {                            // everybody has listed and counted
+      volatile int32_t* vt = tws;
+      vt[1] = vt[0];
+      vt[0] = 0;
+      *sf.count = (int32_t)*reinterpret_cast<volatile unsigned*>(sf.acc_pix);
+      *reinterpret_cast<volatile unsigned*>(sf.acc_pix) = 0u;
+      vt[2] = 0;
+      __threadfence();
+      *gen = g0 + 1u;
+    } else {
+      const long long t0 = clock64();
+      while (*gen == g0) {
+        __nanosleep(40);
+        if (clock64() - t0 > 4000000000ll) __trap();         // a CTA of the grid never arrived
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  if (sf.clear) {                                            // every CTA has read its raw windows
+    for (int item = blockIdx.x * nwarps + warp; item < NI; item += gridDim.x * nwarps) {
+      const int wx = item % Wd, r = item / Wd;
+      const int ty = r % TY, b = r / TY;
+      const int y = ty * TL_H + lane;
+      if (lane < TL_H && y < H) sf.clear[((long long)b * H + y) * Wd + wx] = 0u;
+    }
+  }
+}
+
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1,
                                             int c2, int c3, uint64_t* bar) {
   asm volatile(
@@ -124,9 +224,9 @@ __device__ __forceinline__ uint64_t tile_adesc_base(uint32_t sbo_bytes, int layo
 template <typename T, typename TO, bool SPLIT3, int BN>
 __global__ void __launch_bounds__(128 + um_epi(BN), BN <= 16 ? 4 : BN <= 64 ? 2 : 1)
 conv_tile_kernel(const __grid_constant__ CUtensorMap amap_hi, const __grid_constant__ CUtensorMap amap_lo,
-                 const __grid_constant__ CUtensorMap wmap, const int32_t* __restrict__ tile_ws,
-                 const uint32_t* __restrict__ dil_bits, const float* __restrict__ bias,
-                 TO* __restrict__ out, const TileGeom g, const PoolFuse pf) {
+                 const __grid_constant__ CUtensorMap wmap, int32_t* tile_ws,
+                 const uint32_t* dil_bits, const float* __restrict__ bias,
+                 TO* __restrict__ out, const TileGeom g, const PoolFuse pf, const TileSelf sf) {
   pdl_prologue();
 #ifdef CB_TILE_TRACE
   const long long trace_t0 = clock64();
@@ -148,8 +248,12 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap amap_hi, const __grid_const
   constexpr int ACC_COLS = MERGE ? 2 * BN : BN;                // TMEM columns of one accumulator
   constexpr int TMEM_COLS = tile_tmem_cols(SPLIT3, BN);
   constexpr int EPI = um_epi(BN);
-  // dirty tiles (cb_dilate_compact_tiles); the shuffle makes the value uniform for the compiler
-  const int ntl = __shfl_sync(0xffffffffu, tile_ws[1], 0);
+  // self-listing mode: dilation + tile list + count first, then a grid barrier (tile_self_list)
+  const bool self = sf.raw != nullptr;
+  if (self) tile_self_list(sf, tile_ws, g.B, g.H, g.W, g.Wd, g.TY, g.TXp, (g.kH - 1) / 2, (g.kW - 1) / 2);
+  // dirty tiles (cb_dilate_compact_tiles, or the prologue above: written by other CTAs of this grid,
+  // hence L2 loads); the shuffle makes the value uniform for the compiler
+  const int ntl = __shfl_sync(0xffffffffu, __ldcg(tile_ws + 1), 0);
   const int ntiles_n = g.CoutPad / BN;
   const long long total = (long long)ntl * ntiles_n;
   if ((long long)blockIdx.x >= total) return;               // CTA-uniform, before any barrier / alloc
@@ -163,7 +267,7 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap amap_hi, const __grid_const
   const bool scramble = (g.relu & 4) && (ntl % 7919) != 0;
   auto tile_at = [&](long long w) {
     const int ti = (int)(w / ntiles_n);
-    return __ldg(tiles + (scramble ? (int)(((long long)ti * 7919ll) % ntl) : ti));
+    return __ldcg(tiles + (scramble ? (int)(((long long)ti * 7919ll) % ntl) : ti));
   };
   const int halo_stage = NSPLIT * g.nblk * g.plane_bytes;
   uint8_t* bring = smem + g.nhalo * halo_stage;
@@ -393,7 +497,7 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap amap_hi, const __grid_const
       const bool inimg = y < g.H && x < g.W;
       bool on = false;
       if (inimg)
-        on = (__ldg(dil_bits + ((long long)b * g.H + y) * g.Wd + (x >> 5)) >> (x & 31)) & 1u;
+        on = (__ldcg(dil_bits + ((long long)b * g.H + y) * g.Wd + (x >> 5)) >> (x & 31)) & 1u;
       const uint32_t ab = (uint32_t)it & 1u, aph = ((uint32_t)it >> 1) & 1u;
       TO* orow = out + (((long long)b * g.H + (inimg ? y : 0)) * g.W + (inimg ? x : 0)) * g.Op;
       const unsigned onmask = __ballot_sync(0xffffffffu, on);
@@ -651,7 +755,7 @@ inline CUtensorMapDataType tmap_dtype() {
 template <typename T, typename TO, bool SPLIT3, int BN>
 int launch_conv_tile(cudaStream_t s, const void* state, const void* state_lo, const int32_t* tile_ws,
                      const uint32_t* dil_bits, const void* packed, const float* bias, void* out,
-                     const TilePlan& plan, const PoolFuse& pf) {
+                     const TilePlan& plan, const PoolFuse& pf, const TileSelf& sf) {
   const TileGeom& g = plan.g;
   auto enc = tensor_map_encoder();
   if (!enc) return fail(3, "conv_update_tiled: cuTensorMapEncodeTiled unavailable");
@@ -697,10 +801,24 @@ int launch_conv_tile(cudaStream_t s, const void* state, const void* state_lo, co
   // (the plan counts shared memory and TMEM columns; the register side is pinned by the kernel's
   //  __launch_bounds__: 4 CTAs per SM for N <= 16, 2 for N <= 64)
   long long grid = (long long)sm_count() * plan.occ;
+  if (sf.raw) {
+    // the self-listing prologue ends in a grid barrier: every CTA must be resident (cooperative launch),
+    // so the grid follows the occupancy the runtime reports for this kernel, not the plan's estimate
+    static thread_local int occ_dev = -1, occ_smem = -1, occ_act = 0;
+    if (occ_dev != dev || occ_smem != plan.smem_bytes) {
+      occ_act = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_act, kern, 128 + um_epi(BN), (size_t)plan.smem_bytes);
+      occ_dev = dev;
+      occ_smem = plan.smem_bytes;
+    }
+    if (occ_act < 1) return fail(3, "conv_update_tiled_self: kernel cannot be resident");
+    if (grid > (long long)sm_count() * occ_act) grid = (long long)sm_count() * occ_act;
+  }
   if (grid > max_items) grid = max_items;
   if (grid < 1) grid = 1;
-  cb::launch_pdl(kern, dim3((unsigned)grid), dim3(128 + um_epi(BN)), (size_t)plan.smem_bytes, s, amap[0],
-                 amap[1], wmap, tile_ws, dil_bits, bias, (TO*)out, g, pf);
+  cb::launch_cluster(kern, dim3((unsigned)grid), dim3(128 + um_epi(BN)), (size_t)plan.smem_bytes, s, 1u,
+                     sf.raw ? 1 : 0, amap[0], amap[1], wmap, const_cast<int32_t*>(tile_ws), dil_bits, bias,
+                     (TO*)out, g, pf, sf);
   CB_CHECK_LAUNCH("conv_update_tiled");
   return 0;
 }
@@ -731,7 +849,7 @@ inline int umma_conv_update_tiled(cudaStream_t s, int dtype, int gemm, const voi
                                   const void* state_lo, int Cp, const int32_t* tile_ws,
                                   const uint32_t* dil_bits, const void* packed, const float* bias,
                                   void* out, int Op, int B, int H, int W, int Cout, int kH, int kW,
-                                  int relu, const PoolFuse& pf) {
+                                  int relu, const PoolFuse& pf, const TileSelf& sf) {
   TilePlan plan;
   umma_tile_plan(plan, dtype, gemm, Cp, B, H, W, Cout, Op, kH, kW, relu);
   CB_CHECK_ARG(plan.ok, "conv_update_tiled: layer shape not supported by the tile path");
@@ -744,11 +862,11 @@ inline int umma_conv_update_tiled(cudaStream_t s, int dtype, int gemm, const voi
   CB_CHECK_ARG(!pf.out || tile_pool_ok(gemm, Cout), "conv_update_tiled: fused pooling needs Cout <= 64, a multiple of 16");
 #define CB_TBN(T_, TO_, S3_)                                                                       \
   switch (bn) {                                                                                    \
-    case 16: return launch_conv_tile<T_, TO_, S3_, 16>(s, state, state_lo, tile_ws, dil_bits, packed, bias, out, plan, pf);   \
-    case 32: return launch_conv_tile<T_, TO_, S3_, 32>(s, state, state_lo, tile_ws, dil_bits, packed, bias, out, plan, pf);   \
-    case 64: return launch_conv_tile<T_, TO_, S3_, 64>(s, state, state_lo, tile_ws, dil_bits, packed, bias, out, plan, pf);   \
-    case 128: return launch_conv_tile<T_, TO_, S3_, 128>(s, state, state_lo, tile_ws, dil_bits, packed, bias, out, plan, pf); \
-    case 256: return launch_conv_tile<T_, TO_, S3_, 256>(s, state, state_lo, tile_ws, dil_bits, packed, bias, out, plan, pf); \
+    case 16: return launch_conv_tile<T_, TO_, S3_, 16>(s, state, state_lo, tile_ws, dil_bits, packed, bias, out, plan, pf, sf);   \
+    case 32: return launch_conv_tile<T_, TO_, S3_, 32>(s, state, state_lo, tile_ws, dil_bits, packed, bias, out, plan, pf, sf);   \
+    case 64: return launch_conv_tile<T_, TO_, S3_, 64>(s, state, state_lo, tile_ws, dil_bits, packed, bias, out, plan, pf, sf);   \
+    case 128: return launch_conv_tile<T_, TO_, S3_, 128>(s, state, state_lo, tile_ws, dil_bits, packed, bias, out, plan, pf, sf); \
+    case 256: return launch_conv_tile<T_, TO_, S3_, 256>(s, state, state_lo, tile_ws, dil_bits, packed, bias, out, plan, pf, sf); \
     default: return fail(2, "conv_update_tiled: unsupported N tile %d", bn);                      \
   }
   if (bf16x3) { CB_TBN(__nv_bfloat16, float, true) }

@@ -266,6 +266,26 @@ int cb_conv_update_tiled_pool(void* stream, int dtype, int gemm, const void* sta
                               void* aux_hi, void* aux_lo, uint32_t* next_raw_bits, float threshold,
                               int update_mode);
 
+/* cb_dilate_tiles + cb_conv_update_tiled[_pool] in ONE launch: the contraction kernel first derives the
+ * dilated bitmap (dil_bits, output), the dirty-tile list (tile_ws) and *count from the RAW change bitmap
+ * itself -- the scatter-dilate of changeDetection_kernel, cbconv2d_cg_backend.cu:62-72, one warp per 16-row
+ * tile-row word -- then crosses a grid barrier (cooperative launch) and walks the tiles; raw_bits is zeroed
+ * afterwards when clear_raw != 0.  ws = the layer's cb_compact_ws_bytes() workspace (its header carries the
+ * pixel accumulator), tile_ws = cb_tile_ws_bytes(); both are left as cb_dilate_tiles leaves them, so the two
+ * paths can alternate on the same buffers.  pool_out == NULL: no pooling fusion (the pooling arguments are
+ * then ignored).  Bit-identical to the two-launch sequence.  Needs (kH - 1) / 2 <= 8
+ * (cb_conv_tiled_self_supported). */
+int cb_conv_tiled_self_supported(int kH, int kW);
+int cb_conv_update_tiled_self(void* stream, int dtype, int gemm, const void* state, const void* state_lo,
+                              int pitch_in, void* tile_ws, uint32_t* dil_bits,
+                              const void* packed_w, const float* bias, void* out, int pitch_out, int B,
+                              int H, int W, int Cin, int Cout, int kH, int kW, int relu,
+                              void* pool_out, long long o_sb, long long o_sy, int o_pitch, int oH, int oW,
+                              void* next_state, long long n_sb, long long n_sy, int n_pitch, int aux_mode,
+                              void* aux_hi, void* aux_lo, uint32_t* next_raw_bits, float threshold,
+                              int update_mode, const uint32_t* raw_bits, int32_t* count, void* ws,
+                              int clear_raw);
+
 /* cb_conv_update over a SUPERSET index list: a listed pixel is processed only if its bit is set in
  * `mask_bits` (a raw change bitmap, e.g. what cb_change_detect_sparse just wrote for a 1x1 layer
  * whose candidates were idx/count).  Layers that need no dilation can then skip the ordered

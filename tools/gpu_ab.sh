@@ -5,7 +5,7 @@ KNOB=${1:-CBINFER_PREFETCH}; OFF=${2:-0}; ON=${3:-1}
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
 PYT="python -m pytest -q --tb=short -p no:cacheprovider --timeout 600 -x"
-echo "== parity subset"; timeout 900 $PYT tests/test_gpu_modules.py tests/test_gpu_parity_baseline.py tests/test_gpu_ops.py -m gpu -k "candidate or fused or tail or pipeline or scene or parity or baseline or hint or dilate" > gpurun_out/ab_pytest.log 2>&1; echo "exit $?"; tail -4 gpurun_out/ab_pytest.log
+echo "== parity subset"; timeout 900 $PYT tests/test_gpu_tiles.py tests/test_gpu_modules.py tests/test_gpu_parity_baseline.py tests/test_gpu_ops.py -m gpu -k "${AB_TESTS:-tile or self or candidate or fused or tail or pipeline or scene or parity or baseline or hint or dilate}" > gpurun_out/ab_pytest.log 2>&1; echo "exit $?"; tail -12 gpurun_out/ab_pytest.log
 for rep in 1 2; do
   for v in $OFF $ON; do
     env $KNOB=$v timeout 600 python bench.py --steps 400 --warmup 10 --no-extras > gpurun_out/ab_${v}_$rep.json 2> gpurun_out/ab_${v}_$rep.err
