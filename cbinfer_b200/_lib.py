@@ -78,7 +78,7 @@ def _load():
         "cb_conv_update_tiled_pool": (i32, [vp, i32, i32, vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32,
                                             i32, i32, i32, i32, i32,
                                             vp, i64, i64, i32, i32, i32, vp, i64, i64, i32, i32, vp, vp, vp, f32, i32]),
-        "cb_conv_tiled_self_supported": (i32, [i32, i32]),
+        "cb_conv_tiled_self_supported": (i32, [i32] * 5),
         "cb_conv_update_tiled_self": (i32, [vp, i32, i32, vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32,
                                             i32, i32, i32, i32, i32,
                                             vp, i64, i64, i32, i32, i32, vp, i64, i64, i32, i32, vp, vp, vp, f32, i32,

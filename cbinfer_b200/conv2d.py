@@ -765,17 +765,17 @@ class CBConv2d(nn.Module):
             self._hintCache = hc
         return hc[1] if hc[1].n else None
 
-    def _selfTiles(self):
+    def _selfTiles(self, B, H, W):
         """dilation + tile list inside the tile contraction itself (cb_conv_update_tiled_self)?"""
         return os.environ.get("CBINFER_SELF_TILES", "1") != "0" \
-            and bool(_lib.C.cb_conv_tiled_self_supported(self.kernel_size[0], self.kernel_size[1]))
+            and bool(_lib.C.cb_conv_tiled_self_supported(B, H, W, self.kernel_size[0], self.kernel_size[1]))
 
     def _compact(self, s, B, H, W, sparse_next, tiles=False, lazy=False):
         """dilate the raw bitmap by the filter footprint and compact it to the index list."""
         if tiles and "tile_ws" not in s:
             s["tile_ws"] = cg.alloc_tile_ws((B, H, W), s["idx"].device)
         hints = self._hints(B, H, W, s["idx"].device)
-        if tiles and lazy and self._selfTiles():
+        if tiles and lazy and self._selfTiles(B, H, W):
             # nothing to launch: the tile contraction dilates the raw bitmap and lists its tiles itself
             # (cb_conv_update_tiled_self); bitmap, tile list and count exist once it has run
             s["raw_clear"] = sparse_next

@@ -502,9 +502,13 @@ int cb_conv_update_tiled_pool(void* stream, int dtype, int gemm, const void* sta
                          update_mode, nullptr);
 }
 
-int cb_conv_tiled_self_supported(int kH, int kW) {
-  // one warp lane per raw row of a 16-row tile's window (16 + 2*kHHalf <= 32), funnel shifts up to 31
-  return kH >= 1 && kW >= 1 && (kH & 1) && (kW & 1) && (kH - 1) / 2 <= 8 && (kW - 1) / 2 <= 31 ? 1 : 0;
+int cb_conv_tiled_self_supported(int B, int H, int W, int kH, int kW) {
+  // one warp lane per raw row of a 16-row tile's window (16 + 2*kHHalf <= 32), funnel shifts up to 31;
+  // the barrier word carries the tile count in 20 bits
+  return kH >= 1 && kW >= 1 && (kH & 1) && (kW & 1) && (kH - 1) / 2 <= 8 && (kW - 1) / 2 <= 31 &&
+                 B >= 0 && H >= 0 && W >= 0 && (long long)B * H * W < (1ll << 31) &&
+                 (long long)B * cb::tile_grid_y(H) * cb::tile_grid_xp(W) < (1ll << 20)
+             ? 1 : 0;
 }
 
 int cb_conv_update_tiled_self(void* stream, int dtype, int gemm, const void* state, const void* state_lo,
@@ -518,9 +522,8 @@ int cb_conv_update_tiled_self(void* stream, int dtype, int gemm, const void* sta
                               int clear_raw) {
   CB_CHECK_ARG(raw_bits && count && ws && dil_bits && tile_ws, "conv_update_tiled_self: null pointer");
   CB_CHECK_ARG(raw_bits != dil_bits, "conv_update_tiled_self: dil_bits must not alias raw_bits");
-  CB_CHECK_ARG(cb_conv_tiled_self_supported(kH, kW), "conv_update_tiled_self: filter %dx%d not supported", kH, kW);
-  CB_CHECK_ARG((long long)B * H * W < (1ll << 31) && (long long)cb_bitmap_words(B, H, W) < (1ll << 31),
-               "conv_update_tiled_self: map too large");
+  CB_CHECK_ARG(cb_conv_tiled_self_supported(B, H, W, kH, kW),
+               "conv_update_tiled_self: filter %dx%d / map %dx%dx%d not supported", kH, kW, B, H, W);
   if (B == 0 || H == 0 || W == 0) {
     cudaMemsetAsync(count, 0, sizeof(int32_t), (cudaStream_t)stream);
     cudaMemsetAsync((int32_t*)tile_ws + 1, 0, sizeof(int32_t), (cudaStream_t)stream);

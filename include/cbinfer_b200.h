@@ -273,9 +273,9 @@ int cb_conv_update_tiled_pool(void* stream, int dtype, int gemm, const void* sta
  * afterwards when clear_raw != 0.  ws = the layer's cb_compact_ws_bytes() workspace (its header carries the
  * pixel accumulator), tile_ws = cb_tile_ws_bytes(); both are left as cb_dilate_tiles leaves them, so the two
  * paths can alternate on the same buffers.  pool_out == NULL: no pooling fusion (the pooling arguments are
- * then ignored).  Bit-identical to the two-launch sequence.  Needs (kH - 1) / 2 <= 8
- * (cb_conv_tiled_self_supported). */
-int cb_conv_tiled_self_supported(int kH, int kW);
+ * then ignored).  Bit-identical to the two-launch sequence.  Needs (kH - 1) / 2 <= 8 and fewer than 2^20
+ * tiles (cb_conv_tiled_self_supported). */
+int cb_conv_tiled_self_supported(int B, int H, int W, int kH, int kW);
 int cb_conv_update_tiled_self(void* stream, int dtype, int gemm, const void* state, const void* state_lo,
                               int pitch_in, void* tile_ws, uint32_t* dil_bits,
                               const void* packed_w, const float* bias, void* out, int pitch_out, int B,

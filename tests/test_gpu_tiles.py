@@ -394,7 +394,7 @@ def test_self_listing_tile_contraction_is_bit_identical(cbm, case):
     cg, lib, cb = cbm["cg"], cbm["lib"], cbm["cb"]
     tdt, gemm = TORCH_DT[dt], cb.CBConv2d.GEMM_MODES[mode]
     assert cg.tiled_supported(tdt, gemm, (B, H, W), Cin, Cout, (k, k)) >= 1
-    assert lib.C.cb_conv_tiled_self_supported(k, k) == 1 and lib.C.cb_conv_tiled_self_supported(19, 3) == 0
+    assert lib.C.cb_conv_tiled_self_supported(B, H, W, k, k) == 1 and lib.C.cb_conv_tiled_self_supported(B, H, W, 19, 3) == 0
     gen = torch.Generator().manual_seed(B + 3 * H + W)
     state, sbuf = cg.pixel_major((B, Cin, H, W), tdt, "cuda", 0)
     state.copy_((torch.rand(B, Cin, H, W, generator=gen) - 0.5).to(tdt))
