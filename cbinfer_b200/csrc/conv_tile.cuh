@@ -122,14 +122,17 @@ struct TileSelf {
 };
 
 // returns the number of dirty tiles (the barrier's release word carries it: no extra load)
+// `scratch`: 40 words of shared memory (the kernel's dynamic buffer, not yet in use: static shared
+// memory would push the kernel past the 227 KB it reserves)
 __device__ __forceinline__ int tile_self_list(const TileSelf& sf, int32_t* tws, int B, int H, int W, int Wd,
-                                              int TY, int TXp, int kh, int kw) {
+                                              int TY, int TXp, int kh, int kw, int* scratch) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const int NI = B * TY * Wd;
   int32_t* list = tws + 4 + B * TY * TXp;
-  __shared__ unsigned s_flags[16];
-  __shared__ int s_pix[16];
-  __shared__ int s_base, s_ntl;
+  unsigned* s_flags = reinterpret_cast<unsigned*>(scratch);  // [16]
+  int* s_pix = scratch + 16;                                 // [16]
+  int& s_base = scratch[32];
+  int& s_ntl = scratch[33];
   // barrier word tws[3] = generation << 20 | dirty tiles of the last launch; read up front (it cannot
   // advance before this CTA arrives), needed only at the end
   volatile unsigned* gen = reinterpret_cast<volatile unsigned*>(tws + 3);
@@ -280,7 +283,9 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap amap_hi, const __grid_const
   // self-listing mode: dilation + tile list + count first, then a grid barrier (tile_self_list)
   const bool self = sf.raw != nullptr;
   int ntl_self = 0;
-  if (self) ntl_self = tile_self_list(sf, tile_ws, g.B, g.H, g.W, g.Wd, g.TY, g.TXp, (g.kH - 1) / 2, (g.kW - 1) / 2);
+  if (self)
+    ntl_self = tile_self_list(sf, tile_ws, g.B, g.H, g.W, g.Wd, g.TY, g.TXp, (g.kH - 1) / 2, (g.kW - 1) / 2,
+                              reinterpret_cast<int*>(smem));
   // dirty tiles (cb_dilate_compact_tiles, or the prologue above: written by other CTAs of this grid,
   // hence L2 loads); the shuffle makes the value uniform for the compiler
   const int ntl = __shfl_sync(0xffffffffu, self ? ntl_self : __ldcg(tile_ws + 1), 0);
