@@ -473,7 +473,8 @@ def main():
     fused_tail = sum(1 for m in model.modules() if type(m) is cb.CBConv2d and getattr(m, '_fusedTail', None)
                      and os.environ.get("CBINFER_FUSE_TAIL", "1") != "0")
     # (... and derive their dilated bitmap + tile list themselves, cb_conv_update_tiled_self: 6 with the tail fused)
-    self_tiles = fused_pools if os.environ.get("CBINFER_SELF_TILES", "1") != "0" else 0
+    self_tiles = sum(1 for m in model.modules() if type(m) is cb.CBConv2d and getattr(m, '_fusedPool', None)
+                     and m._inBuf is not None and m._selfTiles(*m._inBuf.shape[:3])) if fused_pools else 0
     my_launches_per_step = 17 if args.dense_scan else 13 - fused_pools - 3 * fused_tail - self_tiles
 
     # one captured graph per input slot of the frame ring (the bench cycles over `nframes` device

@@ -767,8 +767,13 @@ class CBConv2d(nn.Module):
 
     def _selfTiles(self, B, H, W):
         """dilation + tile list inside the tile contraction itself (cb_conv_update_tiled_self)?"""
-        return os.environ.get("CBINFER_SELF_TILES", "1") != "0" \
-            and bool(_lib.C.cb_conv_tiled_self_supported(B, H, W, self.kernel_size[0], self.kernel_size[1]))
+        # opt-in (CBINFER_SELF_TILES=1; =N > 1: only bitmaps of at most N words): bit-identical, but the
+        # runtime admits ONE block of the tile kernels per SM to a cooperative launch, and at one CTA per
+        # SM the kernel loses more than the dilation launch costs (profiles/r02_experiments.md)
+        lim = int(os.environ.get("CBINFER_SELF_TILES", "0") or 0)
+        if lim <= 0 or (lim > 1 and _lib.C.cb_bitmap_words(B, H, W) > lim):
+            return False
+        return bool(_lib.C.cb_conv_tiled_self_supported(B, H, W, self.kernel_size[0], self.kernel_size[1]))
 
     def _compact(self, s, B, H, W, sparse_next, tiles=False, lazy=False):
         """dilate the raw bitmap by the filter footprint and compact it to the index list."""

@@ -452,7 +452,7 @@ def test_self_listing_in_the_model_is_bit_identical(cbm, dt, feedback, monkeypat
     frames.insert(4, frames[3].clone())            # an unchanged frame
     runs = []
     for flag in ("1", "0"):
-        monkeypatch.setenv("CBINFER_SELF_TILES", flag)
+        monkeypatch.setenv("CBINFER_SELF_TILES", flag)     # (opt-in knob; "0" = the two-launch default)
         m = cb.convertPools(cb.convert(base, threshold=0.04))
         for c in m.modules():
             if type(c) is cb.CBConv2d:
