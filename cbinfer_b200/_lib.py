@@ -31,6 +31,7 @@ SYMBOLS = [
     "cb_conv_tiled_pool_supported", "cb_conv_update_tiled_pool", "cb_dilate_tiles",
     "cb_tail_supported", "cb_tail_update", "cb_dilate_compact_hinted",
     "cb_conv_tiled_self_supported", "cb_conv_update_tiled_self",
+    "cb_resize_ws_bytes", "cb_resize_bicubic_u8_init", "cb_resize_bicubic_u8", "cb_resize_bilinear_u8",
 ]
 
 
@@ -83,6 +84,11 @@ def _load():
                                             i32, i32, i32, i32, i32,
                                             vp, i64, i64, i32, i32, i32, vp, i64, i64, i32, i32, vp, vp, vp, f32, i32,
                                             vp, vp, vp, i32]),
+        "cb_resize_ws_bytes": (sz, [i32] * 5),
+        "cb_resize_bicubic_u8_init": (i32, [vp, vp, i32, i32, i32, i32, i32]),
+        "cb_resize_bicubic_u8": (i32, [vp, vp, i64, i64, i64, vp, i64, i64, i64, vp, i32, i32, i32, i32, i32]),
+        "cb_resize_bilinear_u8": (i32, [vp, vp, i64, i64, i64, i32, i32, vp, i64, i64, i64, i32, i32, i32,
+                                        f32, f32, f32, f32]),
         "cb_map_to_bits": (i32, [vp, vp, vp, i32, i32, i32]),
         "cb_change_detect_sparse": (i32, [vp, i32, vp, i64, i64, i64, i64, vp, i64, i64, i64, i64, i32,
                                           vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, i32, i32]),

@@ -3,6 +3,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
+#include <vector>
 
 #include "cb_common.cuh"
 #include "compact.cuh"
@@ -11,6 +12,7 @@
 #include "conv_pair.cuh"
 #include "conv_tile.cuh"
 #include "detect.cuh"
+#include "ingest.cuh"
 #include "fg.cuh"
 #include "pool.cuh"
 #include "staged.cuh"
@@ -730,6 +732,63 @@ int cb_fg_update(void* stream, const float* x, float* prev, const float* weight,
   cb::launch_pdl(fg_update_kernel, grid_for((total + 31) / 32 * 32, 256, 8), 256, 0, s, x, prev, weight, out, count, B, Cin,
                                                              Cout, H, W, kH, kW, threshold);
   CB_CHECK_LAUNCH("fg_update");
+  return 0;
+}
+
+/* ---- frame ingest: resizing on the device (ingest.cuh) -------------------------------------------- */
+size_t cb_resize_ws_bytes(int sH, int sW, int dH, int dW, int C) {
+  if (sH <= 0 || sW <= 0 || dH <= 0 || dW <= 0 || C <= 0) return 0;
+  return cb::resize_plan(sH, sW, dH, dW, C).bytes;
+}
+
+int cb_resize_bicubic_u8_init(void* stream, void* ws, int sH, int sW, int dH, int dW, int C) {
+  CB_CHECK_ARG(ws && sH > 0 && sW > 0 && dH > 0 && dW > 0 && C >= 1 && C <= 4,
+               "resize_bicubic_u8_init: bad arguments (1..4 channels)");
+  const cb::ResizePlan p = cb::resize_plan(sH, sW, dH, dW, C);
+  CB_CHECK_ARG(p.off_tmp < (1ull << 31), "resize_bicubic_u8_init: image too large");
+  // the weight tables are a function of the four sizes only: computed here in double exactly as Pillow's
+  // precompute_coeffs / normalize_coeffs_8bpc do, copied once; cb_resize_bicubic_u8 is then launch-only
+  std::vector<int32_t> host(p.off_tmp / 4, 0);
+  host[0] = p.ksize_x; host[1] = p.ksize_y; host[2] = sH; host[3] = sW; host[4] = dH; host[5] = dW; host[6] = C;
+  cb::resize_coeffs(sW, dW, p.ksize_x, host.data() + p.off_bx / 4, host.data() + p.off_kx / 4);
+  cb::resize_coeffs(sH, dH, p.ksize_y, host.data() + p.off_by / 4, host.data() + p.off_ky / 4);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cudaMemcpyAsync(ws, host.data(), p.off_tmp / 4 * 4, cudaMemcpyHostToDevice, s) != cudaSuccess ||
+      cudaStreamSynchronize(s) != cudaSuccess)
+    return cb::fail(3, "resize_bicubic_u8_init: copying the weight tables failed: %s",
+                    cudaGetErrorString(cudaGetLastError()));
+  return 0;
+}
+
+int cb_resize_bicubic_u8(void* stream, const uint8_t* src, long long s_y, long long s_x, long long s_c,
+                         uint8_t* dst, long long d_y, long long d_x, long long d_c, void* ws, int sH, int sW,
+                         int dH, int dW, int C) {
+  CB_CHECK_ARG(src && dst && ws && sH > 0 && sW > 0 && dH > 0 && dW > 0 && C >= 1 && C <= 4,
+               "resize_bicubic_u8: bad arguments (1..4 channels)");
+  const cb::ResizePlan p = cb::resize_plan(sH, sW, dH, dW, C);
+  char* w = (char*)ws;
+  uint8_t* tmp = (uint8_t*)(w + p.off_tmp);                    // [sH, dW, C] interleaved
+  cudaStream_t s = (cudaStream_t)stream;
+  cb::launch_pdl(cb::resize_pass_u8_kernel<1>, dim3((unsigned)((dW + 255) / 256), (unsigned)sH), dim3(256), 0, s, src,
+                 s_y, s_x, s_c, tmp, (long long)dW * C, (long long)C, 1ll, sH, dW, C,
+                 (const int32_t*)(w + p.off_bx), (const int32_t*)(w + p.off_kx), p.ksize_x);
+  CB_CHECK_LAUNCH("resize_bicubic_u8(horizontal)");
+  cb::launch_pdl(cb::resize_pass_u8_kernel<0>, dim3((unsigned)((dW + 255) / 256), (unsigned)dH), dim3(256), 0, s,
+                 (const uint8_t*)tmp, (long long)dW * C, (long long)C, 1ll, dst, d_y, d_x, d_c, dH, dW, C,
+                 (const int32_t*)(w + p.off_by), (const int32_t*)(w + p.off_ky), p.ksize_y);
+  CB_CHECK_LAUNCH("resize_bicubic_u8(vertical)");
+  return 0;
+}
+
+int cb_resize_bilinear_u8(void* stream, const uint8_t* src, long long s_y, long long s_x, long long s_c, int sH,
+                          int sW, float* dst, long long d_y, long long d_x, long long d_c, int dH, int dW, int C,
+                          float divisor, float cval, float clip_lo, float clip_hi) {
+  CB_CHECK_ARG(src && dst && sH > 0 && sW > 0 && dH > 0 && dW > 0 && C >= 1 && divisor != 0.f,
+               "resize_bilinear_u8: bad arguments");
+  cb::launch_pdl(cb::resize_bilinear_kernel, dim3((unsigned)((dW + 255) / 256), (unsigned)dH), dim3(256), 0,
+                 (cudaStream_t)stream, src, s_y, s_x, s_c, sH, sW, dst, d_y, d_x, d_c, dH, dW, C, (double)divisor,
+                 (double)cval, (double)clip_lo, (double)clip_hi);
+  CB_CHECK_LAUNCH("resize_bilinear_u8");
   return 0;
 }
 

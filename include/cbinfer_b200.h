@@ -394,6 +394,33 @@ int cb_conv_accumulate(void* stream, int dtype, int gemm, const void* state, con
                        void* out, int pitch_out, int B, int H, int W, int Cin, int Cout, int kH, int kW,
                        void* ws, size_t ws_bytes);
 
+/* ---- frame ingest: resizing on the device --------------------------------------------------------
+ * The step before the path: the reference's readers resize every frame on the host
+ * with third-party code before the first layer sees it.
+ *   cb_resize_bicubic_u8   replaces torchvision.transforms.Scale(boxsize, interpolation=3) =
+ *                          PIL.Image.resize(size, BICUBIC) on 8-bit images in PoseDetector.preprocess
+ *                          (poseDetection/openPose/PoseDetector.py:66-68).  Pillow's separable fixed-point
+ *                          resampler (Resample.c: horizontal pass first, 22-bit weights, 8-bit intermediate),
+ *                          BIT-EXACT.  src / dst: byte strides (row, pixel, channel): HWC, planar or pitched;
+ *                          1..4 channels.  ws = cb_resize_ws_bytes() of device memory, filled once per
+ *                          geometry by cb_resize_bicubic_u8_init (host-computed weight tables, synchronous);
+ *                          the resize call itself is two launches and capturable.  Feed dst to
+ *                          cb_change_detect_u8(divisor 256, bias -0.5): bit-identical to ToTensor() followed
+ *                          by mul_(255/256).add_(-0.5) (:69-72; util.padBottomRight returns its input).
+ *   cb_resize_bilinear_u8  replaces img.astype(float) / 255 + skimage.transform.resize(img, [776, 1040],
+ *                          mode='constant') + permute(2,0,1).float() (sceneLabeling/videoSequenceReader.py:
+ *                          64-67): order-1 interpolation at scale * (i + 0.5) - 0.5 with constant padding
+ *                          (cval), float64 arithmetic, clipped to [clip_lo, clip_hi] (skimage clips to the
+ *                          input's value range), fp32 output with ELEMENT strides (row, pixel, channel). */
+size_t cb_resize_ws_bytes(int sH, int sW, int dH, int dW, int C);
+int cb_resize_bicubic_u8_init(void* stream, void* ws, int sH, int sW, int dH, int dW, int C);
+int cb_resize_bicubic_u8(void* stream, const uint8_t* src, long long s_y, long long s_x, long long s_c,
+                         uint8_t* dst, long long d_y, long long d_x, long long d_c, void* ws, int sH, int sW,
+                         int dH, int dW, int C);
+int cb_resize_bilinear_u8(void* stream, const uint8_t* src, long long s_y, long long s_x, long long s_c, int sH,
+                          int sW, float* dst, long long d_y, long long d_x, long long d_c, int dH, int dW, int C,
+                          float divisor, float cval, float clip_lo, float clip_hi);
+
 #ifdef __cplusplus
 }
 #endif
