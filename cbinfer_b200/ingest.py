@@ -85,7 +85,9 @@ def preprocessPose(oriImg, boxsize=368, asUint8=False):
     planes = resize_bicubic_u8(oriImg, oh, ow, planar=True)
     if asUint8:
         return planes.unsqueeze(0)
-    return planes.float().div_(255.0).mul_(255.0 / 256.0).add_(-0.5)
+    # (u8 / 255) * (255 / 256) - 0.5 in fp32 equals u8 / 256 - 0.5 bit for bit for all 256 byte values
+    # (tests/test_ingest.py::test_pose_normalisation_equals_divide_by_256); 1/256 is a power of two: exact
+    return planes.float().mul_(1.0 / 256.0).add_(-0.5)
 
 
 def readSceneFrame(img, size=(776, 1040)):
