@@ -847,18 +847,14 @@ int launch_conv_tile(cudaStream_t s, const void* state, const void* state_lo, co
       occ_smem = plan.smem_bytes;
     }
     if (occ_act < 1) return fail(3, "conv_update_tiled_self: kernel cannot be resident");
-    // (CBINFER_SELF_COOP=0, experiment: plain launch of the plan's grid -- the runtime reports ONE block per
-    //  SM for these kernels whatever their shared memory and registers, the hardware runs 2-4)
-    static const bool trust_plan = [] {
-      const char* e = getenv("CBINFER_SELF_COOP");
-      return e && e[0] == '0';
-    }();
-    if (!trust_plan && grid > (long long)sm_count() * occ_act) grid = (long long)sm_count() * occ_act;
+    // (measured: launching the plan's larger grid anyway leaves CTAs waiting in the barrier for CTAs that never
+    //  become resident -- the runtime's count is the one that holds for a grid whose CTAs wait on each other)
+    if (grid > (long long)sm_count() * occ_act) grid = (long long)sm_count() * occ_act;
   }
   if (grid > max_items) grid = max_items;
   if (grid < 1) grid = 1;
   static const bool coop_self = [] {
-    const char* e = getenv("CBINFER_SELF_COOP");             // tuning knob: 0 = plain launch (single-stream use only)
+    const char* e = getenv("CBINFER_SELF_COOP");             // tuning knob: 0 = plain launch of the same (resident) grid
     return !(e && e[0] == '0');
   }();
   cb::launch_cluster(kern, dim3((unsigned)grid), dim3(128 + um_epi(BN)), (size_t)plan.smem_bytes, s, 1u,
