@@ -241,71 +241,6 @@ detect_narrow_kernel(const T* __restrict__ x, long long x_sb, long long x_sc, lo
   if (lane == 0) bits[warp] = word;
 }
 
-// Persistent, software-pipelined variant of detect_narrow_kernel (CBINFER_DETECT_PIPE=1): a warp walks the
-// bitmap words w, w + G, w + 2G, ... and issues the loads of its NEXT word before it thresholds the current one,
-// so every warp keeps two words (1.8 KB) in flight all the time instead of one block = one short burst of loads
-// (9 600 blocks of 8 warps for the bench's first layer, each alive for little more than one memory round trip).
-template <typename T, int VEC, int UPDATE>
-__global__ void __launch_bounds__(256)
-detect_narrow_pipe_kernel(const T* __restrict__ x, long long x_sb, long long x_sc, long long x_sy,
-                          long long x_sx, T* __restrict__ st, long long s_sb, long long s_sy,
-                          AuxPlanes aux, uint32_t* __restrict__ bits, int B, int H, int W, int C,
-                          int Wd, T thr) {
-  pdl_prologue();
-  const int lane = threadIdx.x & 31;
-  const unsigned nwords = (unsigned)(B * H * Wd);
-  const unsigned G = gridDim.x * (blockDim.x >> 5);
-  unsigned w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (w >= nwords) return;
-  struct Word {
-    uint4 sv;
-    T xv[VEC];
-    T* sp;
-    long long pix;
-    bool in;
-  };
-  auto fetch = [&](unsigned word, Word& o) {
-    const unsigned r = word / (unsigned)Wd;
-    const int j = (int)(word - r * (unsigned)Wd);
-    const int b = (int)(r / (unsigned)H);
-    const int y = (int)(r - (unsigned)b * (unsigned)H);
-    const int xx = j * 32 + lane;
-    o.in = xx < W;
-    o.pix = ((long long)b * H + y) * W + xx;
-    o.sp = st + b * s_sb + y * s_sy + (long long)xx * VEC;
-    if (o.in) {
-      const T* xp = x + b * x_sb + y * x_sy + xx * x_sx;
-      o.sv = ld16_stream(o.sp);
-#pragma unroll
-      for (int c = 0; c < VEC; ++c)
-        if (c < C) o.xv[c] = ld_stream(xp + c * x_sc);
-    }
-  };
-  Word cur, nxt;
-  fetch(w, cur);
-  while (true) {
-    const unsigned wn = w + G;
-    const bool more = wn < nwords;
-    if (more) fetch(wn, nxt);
-    bool f = false;
-    if (cur.in) {
-      uint4 nv = cur.sv;                       // pad lanes keep the state's (zero) value
-      T* ne = reinterpret_cast<T*>(&nv);
-#pragma unroll
-      for (int c = 0; c < VEC; ++c)
-        if (c < C) ne[c] = cur.xv[c];
-      f = Chunk<T>::changed(cur.sv, nv, thr);
-      if (UPDATE == CB_UPDATE_ALL || (UPDATE == CB_UPDATE_CHANGED && f))
-        store_state<T>(cur.sp, nv, aux, cur.pix, 0);
-    }
-    const unsigned word = __ballot_sync(0xffffffffu, f);
-    if (lane == 0) bits[w] = word;
-    if (!more) break;
-    cur = nxt;
-    w = wn;
-  }
-}
-
 // Planar x (NCHW: the pixels of a row are contiguous, any channel stride -- what a dense layer or the
 // user hands in) against a pixel-major state of more than one 16-byte chunk per pixel.  The two
 // layouts want opposite lane mappings (x coalesces across pixels, the state across channels), so a
@@ -588,11 +523,6 @@ int launch_detect(cudaStream_t stream, const void* x, long long x_sb, long long 
   const bool planar_ok = !vec_ok && !narrow_ok && x_sx == 1 && s_sc == 1 && (s_sx % VEC) == 0 && s_sx >= C &&
                          ((s_sy * es) % 16) == 0 && ((s_sb * es) % 16) == 0 && ((uintptr_t)state % 16) == 0 &&
                          s_sx < (1ll << 30) && planar_smem <= 200 * 1024;
-  // CBINFER_DETECT_PIPE=n: persistent pipelined narrow kernel with n blocks per SM (0 = one block per 8 words)
-  static const int narrow_pipe = [] {
-    const char* e = getenv("CBINFER_DETECT_PIPE");
-    return e ? atoi(e) : 0;
-  }();
   // warps per word: keep >= 4 load batches (of U*32 chunks) per warp, at most one block per word
   int wlog = 0;
   while (wlog < 3 && (32 * cpv) / (1 << (wlog + 1)) >= 4 * 4 * 32) ++wlog;
@@ -610,10 +540,6 @@ int launch_detect(cudaStream_t stream, const void* x, long long x_sb, long long 
       cb::launch_pdl(detect_vec_kernel<T, VEC, U_, 2>, grid, block, 0, stream,                             \
           (const T*)x, x_sb, x_sy, (int)x_sx, (T*)state, s_sb, s_sy, (int)s_sx, aux, bits,  \
           B, H, W, C, Wd, thr, magic, wlog);                                                   \
-  } else if (narrow_ok && narrow_pipe > 0 && blocks > (long long)sm_count() * narrow_pipe) {    \
-    cb::launch_pdl(detect_narrow_pipe_kernel<T, VEC, U_>, dim3((unsigned)(sm_count() * narrow_pipe)), block, 0, stream, \
-        (const T*)x, x_sb, x_sc, x_sy, x_sx, (T*)state, s_sb, s_sy, aux, bits, B, H, W, C,  \
-        Wd, thr);                                                                              \
   } else if (narrow_ok) {                                                                      \
     cb::launch_pdl(detect_narrow_kernel<T, VEC, U_>, grid, block, 0, stream,                               \
         (const T*)x, x_sb, x_sc, x_sy, x_sx, (T*)state, s_sb, s_sy, aux, bits, B, H, W, C,  \
