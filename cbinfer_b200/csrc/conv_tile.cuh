@@ -266,6 +266,9 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap amap_hi, const __grid_const
     unsigned long long gt;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
     if (blockIdx.x < 2048) cb_tile_trace[blockIdx.x * TL_TRACE_EV + 31] = (long long)gt;
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    if (blockIdx.x < 2048) cb_tile_trace[blockIdx.x * TL_TRACE_EV + 29] = (long long)smid + 1;
   }
 #endif
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -680,6 +683,13 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap amap_hi, const __grid_const
   tc_fence_before();
   __syncthreads();
   if (tid == 0) TL_TRACE(30);                                // all roles done
+#ifdef CB_TILE_TRACE
+  if (tid == 0 && blockIdx.x < 2048) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    cb_tile_trace[blockIdx.x * TL_TRACE_EV + 28] = (long long)gt;
+  }
+#endif
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),

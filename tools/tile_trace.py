@@ -73,6 +73,23 @@ def run(B, Cin, Cout, H, W, k, rate, cold, pool=False):
     names = ["halo issued", "halo landed", "mmas issued", "acc complete", "epilogue done", "weights landed"]
     us = lambda c: c / MHZ
     print("CTAs that ran: %d; entry spread on the global timer: %.1f us" % (len(rows), (max(ev[31] for _, ev in rows) - gt0) / 1e3))
+    # co-residency: CTAs of one SM (%smid) whose [entry, exit] intervals on the global timer overlap
+    by_sm = {}
+    for _, ev in rows:
+        if ev[29] and ev[28]:
+            by_sm.setdefault(ev[29] - 1, []).append((ev[31], ev[28]))
+    peak = []
+    for iv in by_sm.values():
+        pts = sorted([(a, 1) for a, _ in iv] + [(b, -1) for _, b in iv])
+        cur = best = 0
+        for _, d in pts:
+            cur += d
+            best = max(best, cur)
+        peak.append(best)
+    if peak:
+        print("SMs used: %d; CTAs per SM: %d..%d; peak CO-RESIDENT CTAs per SM (overlapping lifetimes): min %d  median %d  max %d"
+              % (len(by_sm), min(len(v) for v in by_sm.values()), max(len(v) for v in by_sm.values()),
+                 min(peak), sorted(peak)[len(peak) // 2], max(peak)))
     ends = sorted(us(ev[30]) for _, ev in rows if ev[30])
     print("CTA lifetime (entry -> all roles done): min %.1f  median %.1f  max %.1f us; prologue median %.2f us"
           % (ends[0], ends[len(ends) // 2], ends[-1], sorted(us(ev[0]) for _, ev in rows)[len(rows) // 2]))
@@ -88,7 +105,7 @@ def run(B, Cin, Cout, H, W, k, rate, cold, pool=False):
         print(line)
 
 
-for cold in (False, True):
-    for pool in (False, True):
+for cold in ((False,) if "--quick" in sys.argv else (False, True)):
+    for pool in ((False,) if "--quick" in sys.argv else (False, True)):
         run(8, 16, 64, 240, 320, 7, 0.05, cold, pool)
         run(8, 3, 16, 480, 640, 7, 0.05, cold, pool)
