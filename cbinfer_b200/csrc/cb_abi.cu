@@ -153,7 +153,8 @@ static int dilate_compact_impl(void* stream, const uint32_t* raw_bits, uint32_t*
   }
   CB_CHECK_ARG(nwords < (1ll << 31), "dilate_compact: bitmap too large");
   const int ntiles = (int)((nwords + kCompactTile - 1) / kCompactTile);
-  cb::launch_pdl(dilate_compact_kernel, ntiles, kCompactThreads, 0, s, raw_bits, dil_bits, dil_map, idx, count,
+  cb::launch_pdl(ph.n ? dilate_compact_kernel<true> : dilate_compact_kernel<false>, ntiles, kCompactThreads, 0, s,
+                                                          raw_bits, dil_bits, dil_map, idx, count,
                                                           ws, B, H, W, (W + 31) / 32, kHHalf,
                                                           kWHalf, (int)nwords, ntiles, 0, 0,
                                                           clear_raw ? const_cast<uint32_t*>(raw_bits) : nullptr,
@@ -251,7 +252,7 @@ int cb_pool_compact(void* stream, const uint32_t* in_bits, uint32_t* out_bits, i
   }
   CB_CHECK_ARG(nwords < (1ll << 31), "pool_compact: bitmap too large");
   const int ntiles = (int)((nwords + kCompactTile - 1) / kCompactTile);
-  cb::launch_pdl(dilate_compact_kernel, ntiles, kCompactThreads, 0, s, in_bits, out_bits, nullptr, idx, count, ws,
+  cb::launch_pdl(dilate_compact_kernel<false>, ntiles, kCompactThreads, 0, s, in_bits, out_bits, nullptr, idx, count, ws,
                                                           B, oH, oW, (oW + 31) / 32, 0, 0,
                                                           (int)nwords, ntiles, H, (W + 31) / 32, nullptr,
                                                           nullptr, 0, 0, (int)compact_coop(), 0, cb::PrefetchHints{});

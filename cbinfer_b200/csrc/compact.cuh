@@ -112,7 +112,9 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* p, unsigned bytes) 
 }
 
 __device__ __forceinline__ void prefetch_hinted_rows(const PrefetchHints& hints, unsigned d, int b, int y, int j) {
-  for (int h = 0; h < hints.n; ++h) {
+#pragma unroll
+  for (int h = 0; h < kMaxHints; ++h) {        // (constant indices: the parameter struct stays in constant memory)
+    if (h >= hints.n) break;
     const int sh = hints.shift[h];
     if (sh && (y & 1)) continue;
     const int yy = y >> sh, tH = hints.tH[h], tW = hints.tW[h], rb = hints.row_bytes[h];
@@ -137,6 +139,7 @@ __device__ __forceinline__ void prefetch_hinted_rows(const PrefetchHints& hints,
 // order the hardware dispatches blocks in, so the look-back cannot starve (as in CUB's single-pass
 // scan).  Tile-only mode has no scan across tiles and keeps blockIdx, and so do grids small enough to
 // be resident as a whole.
+template <bool HINTS>
 __global__ void __launch_bounds__(kCompactThreads)
 dilate_compact_kernel(const uint32_t* __restrict__ raw, uint32_t* __restrict__ dil_bits,
                       int8_t* __restrict__ dil_map, int32_t* __restrict__ idx,
@@ -200,7 +203,7 @@ dilate_compact_kernel(const uint32_t* __restrict__ raw, uint32_t* __restrict__ d
       d[i] = pool_hin ? pooled_word(raw, r / H, y, j, pool_hin, pool_wdin, W)
                       : dilated_word(win, win0, r, y, j, H, W, Wd, kh, kw);
       if (dil_bits) dil_bits[w] = d[i];
-      if (hints.n && d[i]) prefetch_hinted_rows(hints, d[i], r / H, y, j);
+      if (HINTS && d[i]) prefetch_hinted_rows(hints, d[i], r / H, y, j);
     }
     if (tile_ws) {
       // dirty 8 x 16 output tiles for the tiled contraction (conv_tile.cuh): a word covers four
