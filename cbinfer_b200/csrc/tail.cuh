@@ -301,10 +301,13 @@ tail_kernel(const __grid_constant__ CUtensorMap w1map, const __grid_constant__ C
       tmem_ld_wait();
       if (pix1 >= 0 && f2) {
         float* o2 = a.out2 + (long long)pix1 * a.p2;
-        for (int c = 0; c < a.C2; ++c) {
-          float t = __uint_as_float(acc[c]) + __ldg(a.bias2 + c);
-          if (a.relu2 && t <= 0.f) t = 0.f;
-          o2[c] = t;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {                       // (constant indices: acc stays in registers)
+          if (c < a.C2) {
+            float t = __uint_as_float(acc[c]) + __ldg(a.bias2 + c);
+            if (a.relu2 && t <= 0.f) t = 0.f;
+            o2[c] = t;
+          }
         }
       }
       tc_fence_before();
