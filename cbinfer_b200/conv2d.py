@@ -767,9 +767,9 @@ class CBConv2d(nn.Module):
 
     def _selfTiles(self, B, H, W):
         """dilation + tile list inside the tile contraction itself (cb_conv_update_tiled_self)?"""
-        # opt-in (CBINFER_SELF_TILES=1; =N > 1: only bitmaps of at most N words): bit-identical, but the
-        # runtime admits ONE block of the tile kernels per SM to a cooperative launch, and at one CTA per
-        # SM the kernel loses more than the dilation launch costs (profiles/r02_experiments.md)
+        # opt-in (CBINFER_SELF_TILES=1; =N > 1: only bitmaps of at most N words): bit-identical, but no faster --
+        # the runtime admits ONE block of a TMEM-allocating kernel per SM to a cooperative launch, and even
+        # at full occupancy (plain launch, CBINFER_SELF_COOP=0) the step does not gain (profiles/r02_experiments.md)
         lim = int(os.environ.get("CBINFER_SELF_TILES", "0") or 0)
         if lim <= 0 or (lim > 1 and _lib.C.cb_bitmap_words(B, H, W) > lim):
             return False

@@ -286,15 +286,39 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap amap_hi, const __grid_const
   // self-listing mode: dilation + tile list + count first, then a grid barrier (tile_self_list)
   const bool self = sf.raw != nullptr;
   int ntl_self = 0;
-  if (self)
+  TileCtrl* const ctrl0 =
+      reinterpret_cast<TileCtrl*>(smem + g.nhalo * (NSPLIT * g.nblk * g.plane_bytes) + g.nb * B_STAGE);
+  if (self) {
+    // TMEM first: the hardware starts the next CTA of a TMEM-using kernel on an SM only once the running one
+    // has relinquished its allocation permit (CTA k of an SM enters ~0.9 us after CTA k-1, r02_tile_residency.txt)
+    // -- a CTA that waited in the grid barrier BEFORE allocating kept its SM's other CTAs from ever starting
+    if ((threadIdx.x >> 5) == 2) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                       smem_u32(&ctrl0->tmem_base)),
+                   "r"((uint32_t)TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
     ntl_self = tile_self_list(sf, tile_ws, g.B, g.H, g.W, g.Wd, g.TY, g.TXp, (g.kH - 1) / 2, (g.kW - 1) / 2,
                               reinterpret_cast<int*>(smem));
+  }
   // dirty tiles (cb_dilate_compact_tiles, or the prologue above: written by other CTAs of this grid,
   // hence L2 loads); the shuffle makes the value uniform for the compiler
   const int ntl = __shfl_sync(0xffffffffu, self ? ntl_self : __ldcg(tile_ws + 1), 0);
   const int ntiles_n = g.CoutPad / BN;
   const long long total = (long long)ntl * ntiles_n;
-  if ((long long)blockIdx.x >= total) return;               // CTA-uniform, before any barrier / alloc
+  if ((long long)blockIdx.x >= total) {                      // CTA-uniform, before any barrier / alloc ...
+    if (self) {                                              // ... except the self-listing mode's early allocation
+      tc_fence_before();
+      __syncthreads();
+      tc_fence_after();
+      if ((threadIdx.x >> 5) == 2)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(ctrl0->tmem_base),
+                     "r"((uint32_t)TMEM_COLS)
+                     : "memory");
+    }
+    return;
+  }
   if (smem_u32(smem) & 1023u) __trap();
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);    // provably warp-uniform role index
@@ -329,7 +353,7 @@ conv_tile_kernel(const __grid_constant__ CUtensorMap amap_hi, const __grid_const
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) {
+  if (warp == 2 && !self) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(&ctrl->tmem_base)),
                  "r"((uint32_t)TMEM_COLS)
@@ -857,9 +881,14 @@ int launch_conv_tile(cudaStream_t s, const void* state, const void* state_lo, co
       occ_smem = plan.smem_bytes;
     }
     if (occ_act < 1) return fail(3, "conv_update_tiled_self: kernel cannot be resident");
-    // (measured: launching the plan's larger grid anyway leaves CTAs waiting in the barrier for CTAs that never
-    //  become resident -- the runtime's count is the one that holds for a grid whose CTAs wait on each other)
-    if (grid > (long long)sm_count() * occ_act) grid = (long long)sm_count() * occ_act;
+    // CBINFER_SELF_COOP=0 (experiment; needs a GPU no other grid is running on): plain launch of the plan's
+    // grid -- the CTAs do become co-resident once the TMEM allocation precedes the barrier, but the runtime
+    // will not vouch for it (it counts ONE block per SM for kernels that allocate TMEM)
+    static const bool plan_grid = [] {
+      const char* e = getenv("CBINFER_SELF_COOP");
+      return e && e[0] == '0';
+    }();
+    if (!plan_grid && grid > (long long)sm_count() * occ_act) grid = (long long)sm_count() * occ_act;
   }
   if (grid > max_items) grid = max_items;
   if (grid < 1) grid = 1;
