@@ -590,6 +590,11 @@ int cb_tail_update(void* stream, const float* x, float* state1, const void* pack
   a.count1 = count1; a.count2 = count2; a.sync = (unsigned*)sync_ws;
   a.xp = C0; a.p1 = C1; a.p2 = pitch_out2; a.C0 = C0; a.C1 = C1; a.C2 = C2;
   a.relu1 = relu1; a.relu2 = relu2; a.update = update_mode; a.thr1 = thr1; a.thr2 = thr2;
+  static const int tail_adapt = [] {
+    const char* e = getenv("CBINFER_TAIL_ADAPT");            // tuning knob: 0 = always 128 rows per tile
+    return (e && e[0] == '0') ? 0 : 1;
+  }();
+  a.adapt = tail_adapt;
   return cb::tail_update((cudaStream_t)stream, a, packed_w1, packed_w2);
 }
 

@@ -42,6 +42,7 @@ struct TailArgs {
   int C0, C1, C2;                // channels: in, mid, out
   int relu1, relu2, update;      // update: CB_UPDATE_CHANGED (feedback) or CB_UPDATE_ALL
   float thr1, thr2;
+  int adapt;                     // 1: fewer rows per tile when the candidates do not fill a wave (below)
 };
 
 struct TailCtrl {
@@ -67,7 +68,17 @@ tail_kernel(const __grid_constant__ CUtensorMap w1map, const __grid_constant__ C
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int n = __shfl_sync(0xffffffffu, *a.ncand, 0);
-  const int ntiles = (n + TAIL_ROWS - 1) / TAIL_ROWS;
+  // Rows per tile: 128 (the MMA's M) when the candidates fill the grid; with fewer, the candidates are spread
+  // over ALL CTAs in tiles of ceil(n / CTAs) rows (a multiple of 8 = one warp's rows), rows beyond that stay
+  // empty.  A CTA's time is its serial load -> MMA -> epilogue -> MMA -> store chain, whose load and store
+  // phases shrink with the rows, while the MMAs are negligible: 14 275 candidates on 148 CTAs = 138 tiles of
+  // 104 rows instead of 112 of 128 on 112 CTAs.  Per-row results do not depend on the tile's other rows.
+  int rpt = TAIL_ROWS;
+  if (a.adapt && n < (int)gridDim.x * TAIL_ROWS) {
+    rpt = (((n + (int)gridDim.x - 1) / (int)gridDim.x) + 7) & ~7;
+    rpt = rpt < 8 ? 8 : rpt > TAIL_ROWS ? TAIL_ROWS : rpt;
+  }
+  const int ntiles = (n + rpt - 1) / rpt;
   const int nkb1 = a.C0 / 64;                                // K blocks of layer 1
   // shared memory: A planes (hi: nkb1 blocks, lo: nkb1 blocks; layer 2's operand tile reuses the
   // first two blocks), W1 (hi, lo: nkb1 blocks of [N1 x 64] each), W2 (hi, lo: [16 x 64]), ctrl
@@ -136,8 +147,9 @@ tail_kernel(const __grid_constant__ CUtensorMap w1map, const __grid_constant__ C
       // batches then depend on ONE index round trip instead of one per batch
       int mypix = -1;
       {
-        const int j = tile * TAIL_ROWS + warp * RPW + lane;
-        if (lane < RPW && j < n) mypix = __ldg(a.cand + j);
+        const int rr = warp * RPW + lane;
+        const int j = tile * rpt + rr;
+        if (lane < RPW && rr < rpt && j < n) mypix = __ldg(a.cand + j);
       }
 #pragma unroll 1
       for (int r0 = 0; r0 < RPW; r0 += RB) {
